@@ -1,0 +1,79 @@
+// Shared helpers for the ddrl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ddrl_b200.h"
+
+namespace ddrl {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+extern thread_local char g_cuda_err[256];
+extern long long g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return DDRL_E_CUDA;
+}
+
+#define DDRL_CUDA(call)                                        \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) return ::ddrl::cuda_fail(_e, #call); \
+  } while (0)
+
+// after a <<<>>> launch: count it and surface launch-configuration errors
+#define DDRL_LAUNCHED(name)                                       \
+  do {                                                            \
+    ::ddrl::g_launches++;                                         \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::ddrl::cuda_fail(_e, name);    \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  scratch: >= 32 elements of shared memory.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < nw ? scratch[lane] : T(0);
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// streaming (read-once) loads/stores: keep L1 clean for the data that is reused
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+}  // namespace ddrl

@@ -1,0 +1,752 @@
+// The actor-critic engine: parameter table, packed weights, workspace, and the static kernel
+// schedules for forward (Forward module) and forward+loss+backward / clip+Adam (Backward module).
+//
+// Replaces, behind the same parameter names / shapes / order (so state_dict(), nn2redis blobs and
+// .pt checkpoints stay interchangeable, nn/base.py:60-81):
+//   AtariPreNet   USTC_lab/nn/atari_encoder.py:11-32     NavPreNet / NavPedPreNet  nn/nav_encoder.py:12-79
+//   NavPreNet1D   nn/nav_encoder.py:82-128               MLPPreNet                 nn/mlp_encoder.py:12-29
+//   CategoricalActor / GaussionActor nn/actor.py:43-101  Critic nn/critic.py:6-21
+//   PPO.forward / PPO.learn          nn/ppo.py:72-142    (tower sharing per runner/utils.py:59-170)
+//
+// Design (B200-first, not a port of autograd): no graph is recorded.  Each encoder family is a
+// fixed schedule of GEMMs (convolutions as im2col GEMMs over NHWC activations) plus streaming glue
+// kernels, run over micro-batches that keep the working set bounded; weight gradients accumulate
+// across micro-batches directly in the flat gradient buffer (or its packed twin), which is what the
+// data-parallel learner all-reduces in one NCCL call before the fused clip+Adam.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "layer_ops.h"
+
+namespace ddrl {
+
+struct TensorInfo {
+  std::string name;
+  int64_t shape[4];
+  int ndim;
+  int64_t offset, numel;
+};
+
+// One GEMM layer y[M,N] = act(x[M,K] W[N,K]^T + b): a Linear, or a Conv over its im2col matrix.
+struct Lin {
+  int N = 0, K = 0, ldw = 0;
+  int w_t = -1, b_t = -1;        // tensor-table indices
+  int I = 1, J = 0;              // packed[o, i*J + j] = ref[o, j*I + i]
+  bool packed = false;
+  int act = 0;
+  float* wp = nullptr;           // packed weight [N, ldw]   (when packed)
+  float* dwp = nullptr;          // packed weight gradient   (when packed and training)
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  float* take(size_t nfloats) {
+    const size_t bytes = (nfloats * sizeof(float) + 255) & ~size_t(255);
+    if (used + bytes > cap) return nullptr;
+    float* p = reinterpret_cast<float*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+struct Tower {
+  int arch = 0, in_ch = 0, feat = 512;
+  std::string prefix;
+  std::vector<Lin> L;            // layer order is arch specific (see build_tower)
+  ConvGeom g[5];                 // conv geometries (arch specific slots)
+  // per-micro-batch buffers
+  std::vector<float*> buf;
+  std::vector<uint8_t*> idx;
+  float* h = nullptr;            // encoder output [MB, feat]
+  float* dh = nullptr;           // its gradient
+};
+
+}  // namespace ddrl
+
+using namespace ddrl;
+
+struct ddrl_net {
+  ddrl_net_desc d;
+  std::vector<TensorInfo> T;
+  int64_t P = 0;
+  float *params = nullptr, *grads = nullptr, *am = nullptr, *av = nullptr;
+  bool dirty = true;             // packed weights stale
+  std::vector<Tower> towers;     // shared: [prenet]; unshared: [actor.pre, critic.pre]
+  int t_aw = -1, t_ab = -1, t_cw = -1, t_cb = -1, t_logstd = -1;
+  int ldA = 0;                   // padded row stride of the actor head output
+  // workspace
+  Arena ws;
+  int MB = 0;                    // micro-batch rows the workspace is sized for
+  bool ws_train = false;
+  float *logits = nullptr, *vout = nullptr, *dlogits = nullptr, *dv = nullptr, *stage = nullptr;
+  char* packed_base = nullptr;   // packed weights + packed grads arena
+  size_t packed_bytes = 0, packed_grad_off = 0, packed_grad_bytes = 0;
+  int64_t seg_begin[3];
+  int nseg = 1;
+};
+
+namespace ddrl {
+
+static int find_tensor(const ddrl_net* n, const std::string& name) {
+  for (size_t i = 0; i < n->T.size(); ++i)
+    if (n->T[i].name == name) return (int)i;
+  return -1;
+}
+
+static void add_tensor(ddrl_net* n, const std::string& name, std::initializer_list<int64_t> shape) {
+  TensorInfo t;
+  t.name = name;
+  t.ndim = (int)shape.size();
+  t.numel = 1;
+  int i = 0;
+  for (auto s : shape) { t.shape[i++] = s; t.numel *= s; }
+  for (; i < 4; ++i) t.shape[i] = 1;
+  t.offset = n->P;
+  n->P += t.numel;
+  n->T.push_back(t);
+}
+
+// reference named_parameters() order of one encoder
+static void add_encoder_tensors(ddrl_net* n, const std::string& pre, int arch, int in_ch, int feat) {
+  auto conv = [&](const char* nm, int o, int c, int kh, int kw) {
+    add_tensor(n, pre + nm + ".weight", {o, c, kh, kw});
+    add_tensor(n, pre + nm + ".bias", {o});
+  };
+  auto lin = [&](const char* nm, int o, int i) {
+    add_tensor(n, pre + nm + ".weight", {o, i});
+    add_tensor(n, pre + nm + ".bias", {o});
+  };
+  switch (arch) {
+    case DDRL_ARCH_ATARI:
+      conv("conv1", 32, in_ch, 8, 8); conv("conv2", 64, 32, 4, 4); conv("conv3", 64, 64, 3, 3); lin("linear", 512, 3136);
+      break;
+    case DDRL_ARCH_NAV:
+    case DDRL_ARCH_NAVPED:
+      conv("conv1", 64, in_ch, 3, 3); conv("conv2", 128, 64, 3, 3); conv("conv3", 256, 128, 3, 3);
+      lin("fc0.0", 512, 9216); lin("fc1.0", 512, 521); lin("fc2", 512, 512);
+      break;
+    case DDRL_ARCH_NAV1D:
+      conv("conv1", 64, in_ch, 7, 7); conv("conv2", 128, 64, 5, 5); conv("conv3", 256, 128, 3, 3);
+      add_tensor(n, pre + "conv1d1.weight", {32, 1, 5}); add_tensor(n, pre + "conv1d1.bias", {32});
+      add_tensor(n, pre + "conv1d2.weight", {32, 32, 3}); add_tensor(n, pre + "conv1d2.bias", {32});
+      lin("fc_1d.0", 256, 7616); lin("fc0.0", 512, 6400); lin("fc1.0", 512, 773); lin("fc2", 512, 512);
+      break;
+    case DDRL_ARCH_MLP:
+      lin("fc0.0", feat, in_ch);
+      break;
+  }
+}
+
+static int round4(int x) { return (x + 3) & ~3; }
+
+static Lin make_lin(ddrl_net* n, const std::string& wname, int N, int K, int I, int J, int act) {
+  Lin l;
+  l.N = N; l.K = K; l.I = I; l.J = J; l.act = act;
+  l.ldw = round4(K);
+  l.packed = (I != 1) || (l.ldw != K);
+  l.w_t = find_tensor(n, wname + ".weight");
+  l.b_t = find_tensor(n, wname + ".bias");
+  return l;
+}
+
+static ConvGeom conv_geom(int H, int W, int C, bool nchw, int KH, int KW, int stride, int pad) {
+  ConvGeom g;
+  g.H = H; g.W = W; g.C = C;
+  if (nchw) { g.sc = (long long)H * W; g.sh = W; g.sw = 1; g.sb = (long long)C * H * W; g.order = 1; }
+  else { g.sc = 1; g.sw = C; g.sh = (long long)W * C; g.sb = (long long)H * W * C; g.order = 0; }
+  g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
+  g.Ho = (H + 2 * pad - KH) / stride + 1;
+  g.Wo = (W + 2 * pad - KW) / stride + 1;
+  g.K = C * KH * KW;
+  g.ldc = round4(g.K);
+  return g;
+}
+
+static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int arch, int in_ch, int feat) {
+  t.arch = arch; t.in_ch = in_ch; t.feat = feat; t.prefix = prefix;
+  auto P = [&](const char* s) { return prefix + s; };
+  switch (arch) {
+    case DDRL_ARCH_ATARI:
+      t.g[0] = conv_geom(84, 84, in_ch, true, 8, 8, 4, 0);       // -> 20x20x32
+      t.g[1] = conv_geom(20, 20, 32, false, 4, 4, 2, 0);         // -> 9x9x64
+      t.g[2] = conv_geom(9, 9, 64, false, 3, 3, 1, 0);           // -> 7x7x64
+      t.L.push_back(make_lin(n, P("conv1"), 32, t.g[0].K, 1, t.g[0].K, ACT_LEAKY));
+      t.L.push_back(make_lin(n, P("conv2"), 64, t.g[1].K, 16, 32, ACT_LEAKY));
+      t.L.push_back(make_lin(n, P("conv3"), 64, t.g[2].K, 9, 64, ACT_LEAKY));
+      t.L.push_back(make_lin(n, P("linear"), 512, 3136, 49, 64, ACT_NONE));
+      break;
+    case DDRL_ARCH_NAV:
+    case DDRL_ARCH_NAVPED:
+      t.g[0] = conv_geom(48, 48, in_ch, true, 3, 3, 1, 1);       // -> 48x48x64 -> pool 24
+      t.g[1] = conv_geom(24, 24, 64, false, 3, 3, 1, 1);         // -> 24x24x128 -> pool 12
+      t.g[2] = conv_geom(12, 12, 128, false, 3, 3, 1, 1);        // -> 12x12x256 -> pool 6
+      t.L.push_back(make_lin(n, P("conv1"), 64, t.g[0].K, 1, t.g[0].K, ACT_RELU));
+      t.L.push_back(make_lin(n, P("conv2"), 128, t.g[1].K, 9, 64, ACT_RELU));
+      t.L.push_back(make_lin(n, P("conv3"), 256, t.g[2].K, 9, 128, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc0.0"), 512, 9216, 36, 256, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc1.0"), 512, 521, 1, 521, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc2"), 512, 512, 1, 512, ACT_NONE));
+      break;
+    case DDRL_ARCH_NAV1D:
+      t.g[0] = conv_geom(48, 48, in_ch, true, 7, 7, 1, 1);       // -> 44x44x64 -> pool 22
+      t.g[1] = conv_geom(22, 22, 64, false, 5, 5, 1, 1);         // -> 20x20x128 -> pool 10
+      t.g[2] = conv_geom(10, 10, 128, false, 3, 3, 1, 1);        // -> 10x10x256 -> pool 5
+      t.g[3] = conv_geom(1, 960, 1, true, 1, 5, 2, 0);           // laser conv1d1 -> 478 x 32
+      t.g[4] = conv_geom(1, 478, 32, false, 1, 3, 2, 0);         // laser conv1d2 -> 238 x 32
+      t.L.push_back(make_lin(n, P("conv1"), 64, t.g[0].K, 1, t.g[0].K, ACT_RELU));
+      t.L.push_back(make_lin(n, P("conv2"), 128, t.g[1].K, 25, 64, ACT_RELU));
+      t.L.push_back(make_lin(n, P("conv3"), 256, t.g[2].K, 9, 128, ACT_RELU));
+      t.L.push_back(make_lin(n, P("conv1d1"), 32, 5, 1, 5, ACT_NONE));
+      t.L.push_back(make_lin(n, P("conv1d2"), 32, 96, 3, 32, ACT_NONE));
+      t.L.push_back(make_lin(n, P("fc_1d.0"), 256, 7616, 238, 32, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc0.0"), 512, 6400, 25, 256, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc1.0"), 512, 773, 1, 773, ACT_RELU));
+      t.L.push_back(make_lin(n, P("fc2"), 512, 512, 1, 512, ACT_NONE));
+      break;
+    case DDRL_ARCH_MLP:
+      t.L.push_back(make_lin(n, P("fc0.0"), feat, in_ch, 1, in_ch, ACT_RELU));
+      break;
+  }
+}
+
+// ---- engine dispatch ------------------------------------------------------------------
+static int gemm(const ddrl_net* n, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, const float* bias, int act, int beta, int trans_c, cudaStream_t s) {
+  if (n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 && gemm_tc_supported(form, M, N, K, A, lda, B, ldb, C, ldc, trans_c))
+    return gemm_tc(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s);
+  return gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s);
+}
+
+static const float* W_of(const ddrl_net* n, const Lin& l) { return l.packed ? l.wp : n->params + n->T[l.w_t].offset; }
+static float* dW_of(const ddrl_net* n, const Lin& l) { return l.packed ? l.dwp : n->grads + n->T[l.w_t].offset; }
+static const float* b_of(const ddrl_net* n, const Lin& l) { return n->params + n->T[l.b_t].offset; }
+static float* db_of(const ddrl_net* n, const Lin& l) { return n->grads + n->T[l.b_t].offset; }
+
+#define TRY(x)                \
+  do {                        \
+    int _r = (x);             \
+    if (_r != DDRL_OK) return _r; \
+  } while (0)
+
+// y = act(x W^T + b)
+static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* y, int ldy, long long M, cudaStream_t s) {
+  return gemm(n, 0, (int)M, l.N, l.K, x, ldx, W_of(n, l), l.ldw, y, ldy, b_of(n, l), l.act, 0, 0, s);
+}
+// dy <- dy * act'(y); db += colsum(dy); dW += dy^T x; dx = dy W  (ncols_dx: leading columns of dx wanted)
+static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* dy, int ldy, const float* y, int ldy_act,
+                   float* dx, int lddx, int ncols_dx, long long M, cudaStream_t s) {
+  TRY(act_bwd(dy, ldy, y, ldy_act, M, l.N, l.act, s));
+  TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
+  // dW[N, K] += dy[M,N]^T x[M,K]: run with the larger of (N, K) on the 128-row side
+  if (l.N >= 128 || l.N >= l.K)
+    TRY(gemm(n, 2, l.N, l.K, (int)M, dy, ldy, x, ldx, dW_of(n, l), l.ldw, nullptr, 0, 1, 0, s));
+  else
+    TRY(gemm(n, 2, l.K, l.N, (int)M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, nullptr, 0, 1, 1, s));
+  if (dx) TRY(gemm(n, 1, (int)M, ncols_dx, l.N, dy, ldy, W_of(n, l), l.ldw, dx, lddx, nullptr, 0, 0, 0, s));
+  return DDRL_OK;
+}
+
+// ---- workspace ------------------------------------------------------------------------
+// per-sample float counts of a tower's buffers, in the order tower_alloc() carves them
+static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std::vector<size_t>& u8) {
+  auto cols = [&](const ConvGeom& g) { return (size_t)g.Ho * g.Wo * g.ldc; };
+  auto outp = [&](const ConvGeom& g, int Co) { return (size_t)g.Ho * g.Wo * Co; };
+  f.clear(); u8.clear();
+  switch (t.arch) {
+    case DDRL_ARCH_ATARI: {
+      // 0 cols1, 1 a1, 2 cols2, 3 a2, 4 cols3, 5 a3 | train: 6 da3, 7 dcols, 8 da2, 9 da1
+      f = {cols(t.g[0]), outp(t.g[0], 32), cols(t.g[1]), outp(t.g[1], 64), cols(t.g[2]), outp(t.g[2], 64)};
+      if (train) { f.push_back(outp(t.g[2], 64)); f.push_back(std::max(cols(t.g[1]), cols(t.g[2])));
+                   f.push_back(outp(t.g[1], 64)); f.push_back(outp(t.g[0], 32)); }
+      break;
+    }
+    case DDRL_ARCH_NAV:
+    case DDRL_ARCH_NAVPED:
+    case DDRL_ARCH_NAV1D: {
+      const int C1 = 64, C2 = 128, C3 = 256;
+      const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
+      const size_t p1 = (size_t)(g0->Ho / 2) * (g0->Wo / 2) * C1, p2 = (size_t)(g1->Ho / 2) * (g1->Wo / 2) * C2,
+                   p3 = (size_t)(g2->Ho / 2) * (g2->Wo / 2) * C3;
+      const int ldcat = t.arch == DDRL_ARCH_NAV1D ? 776 : 524;
+      // 0 cols1, 1 z1, 2 p1, 3 cols2, 4 z2, 5 p2, 6 cols3, 7 z3, 8 p3, 9 cat, 10 f1
+      f = {cols(*g0), outp(*g0, C1), p1, cols(*g1), outp(*g1, C2), p2, cols(*g2), outp(*g2, C3), p3, (size_t)ldcat, 512};
+      u8 = {p1, p2, p3};
+      // 11 colsL1, 12 l1, 13 colsL2, 14 l2   (nav1d only; zero-sized otherwise)
+      if (t.arch == DDRL_ARCH_NAV1D) { f.push_back(cols(t.g[3])); f.push_back(outp(t.g[3], 32));
+                                       f.push_back(cols(t.g[4])); f.push_back(outp(t.g[4], 32)); }
+      else { f.insert(f.end(), {0, 0, 0, 0}); }
+      // 15 staging for NavPed channel concat (navped only)
+      f.push_back(t.arch == DDRL_ARCH_NAVPED ? (size_t)t.in_ch * 48 * 48 : 0);
+      if (train) {
+        // 16 df1, 17 dcat, 18 dp3, 19 dz3, 20 dcols(max), 21 dp2, 22 dz2, 23 dp1, 24 dz1, 25 dl2, 26 dl1
+        f.push_back(512); f.push_back(ldcat); f.push_back(p3); f.push_back(outp(*g2, C3));
+        size_t dc = std::max(cols(*g1), cols(*g2));
+        if (t.arch == DDRL_ARCH_NAV1D) dc = std::max(dc, cols(t.g[4]));
+        f.push_back(dc); f.push_back(p2); f.push_back(outp(*g1, C2)); f.push_back(p1); f.push_back(outp(*g0, C1));
+        if (t.arch == DDRL_ARCH_NAV1D) { f.push_back(outp(t.g[4], 32)); f.push_back(outp(t.g[3], 32)); }
+        else { f.push_back(0); f.push_back(0); }
+      }
+      break;
+    }
+    case DDRL_ARCH_MLP:
+      break;
+  }
+}
+
+static size_t tower_bytes_per_sample(const Tower& t, bool train) {
+  std::vector<size_t> f, u8;
+  tower_sizes(t, train, f, u8);
+  size_t b = 0;
+  for (auto x : f) b += x * 4;
+  for (auto x : u8) b += x;
+  b += (size_t)t.feat * 4 * (train ? 2 : 1);
+  return b;
+}
+
+static int ensure_workspace(ddrl_net* n, int B, bool train) {
+  // micro-batch: bounded by a byte budget (DDRL_WS_GB, default 24 GiB) and DDRL_MICRO_BATCH (default 8192)
+  size_t per = 0;
+  for (auto& t : n->towers) per += tower_bytes_per_sample(t, train);
+  per += (size_t)(n->ldA * 2 + 2 + 8) * 4;
+  const char* env_gb = getenv("DDRL_WS_GB");
+  const char* env_mb = getenv("DDRL_MICRO_BATCH");
+  const double budget = (env_gb ? atof(env_gb) : 24.0) * (double)(1ull << 30);
+  int mb_cap = env_mb ? atoi(env_mb) : 8192;
+  int mb = (int)std::min<double>((double)mb_cap, budget / (double)per);
+  mb = std::max(mb, 1);
+  if (mb >= 128) mb &= ~127;
+  mb = std::min(mb, std::max(B, 1));
+  if (n->ws.base && n->MB >= mb && (n->ws_train || !train)) return DDRL_OK;
+  if (n->ws.base) { cudaDeviceSynchronize(); cudaFree(n->ws.base); n->ws.base = nullptr; }
+  n->MB = mb;
+  n->ws_train = train;
+  // total with per-buffer 256 B alignment slack
+  size_t total = 0;
+  for (auto& t : n->towers) {
+    std::vector<size_t> f, u8;
+    tower_sizes(t, train, f, u8);
+    for (auto x : f) total += ((x * mb * 4 + 255) & ~size_t(255));
+    for (auto x : u8) total += ((x * mb + 255) & ~size_t(255));
+    total += 2 * (((size_t)t.feat * mb * 4 + 255) & ~size_t(255));
+  }
+  total += 4 * (((size_t)n->ldA * mb * 4 + 255) & ~size_t(255)) + 4096;
+  if (cudaMalloc(&n->ws.base, total) != cudaSuccess) {
+    cudaGetLastError();
+    n->ws.base = nullptr; n->MB = 0;
+    return DDRL_E_NOMEM;
+  }
+  n->ws.cap = total; n->ws.used = 0;
+  for (auto& t : n->towers) {
+    std::vector<size_t> f, u8;
+    tower_sizes(t, train, f, u8);
+    t.buf.assign(f.size(), nullptr);
+    t.idx.assign(u8.size(), nullptr);
+    for (size_t i = 0; i < f.size(); ++i) if (f[i]) t.buf[i] = n->ws.take(f[i] * mb);
+    for (size_t i = 0; i < u8.size(); ++i) t.idx[i] = reinterpret_cast<uint8_t*>(n->ws.take((u8[i] * mb + 3) / 4));
+    t.h = n->ws.take((size_t)t.feat * mb);
+    t.dh = train ? n->ws.take((size_t)t.feat * mb) : nullptr;
+  }
+  n->logits = n->ws.take((size_t)n->ldA * mb);
+  n->dlogits = n->ws.take((size_t)n->ldA * mb);
+  n->vout = n->ws.take(mb);
+  n->dv = n->ws.take(mb);
+  return DDRL_OK;
+}
+
+// ---- packed weights -------------------------------------------------------------------
+static int alloc_packed(ddrl_net* n) {
+  size_t bytes = 0;
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.packed) bytes += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
+  n->packed_grad_off = bytes;
+  n->packed_grad_bytes = bytes;
+  n->packed_bytes = 2 * bytes;
+  if (!bytes) return DDRL_OK;
+  DDRL_CUDA(cudaMalloc(&n->packed_base, n->packed_bytes));
+  DDRL_CUDA(cudaMemset(n->packed_base, 0, n->packed_bytes));     // padding columns stay zero forever
+  size_t off = 0;
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.packed) {
+        l.wp = reinterpret_cast<float*>(n->packed_base + off);
+        l.dwp = reinterpret_cast<float*>(n->packed_base + n->packed_grad_off + off);
+        off += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
+      }
+  return DDRL_OK;
+}
+
+static int repack(ddrl_net* n, cudaStream_t s) {
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.packed) TRY(pack_weight(n->params + n->T[l.w_t].offset, l.wp, l.N, l.I, l.J, l.ldw, s));
+  n->dirty = false;
+  return DDRL_OK;
+}
+
+// ---- encoder schedules ------------------------------------------------------------------
+static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, float* cols, float* y, int mb,
+                      cudaStream_t s) {
+  const ConvGeom& g = t.g[gi];
+  TRY(im2col(g, x, cols, mb, s));
+  return lin_fwd(n, t.L[li], cols, g.ldc, y, t.L[li].N, (long long)mb * g.Ho * g.Wo, s);
+}
+
+static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s) {
+  auto& b = t.buf;
+  switch (t.arch) {
+    case DDRL_ARCH_ATARI: {
+      const float* x = obs[0] + row0 * t.g[0].sb;
+      TRY(conv_block(n, t, 0, 0, x, b[0], b[1], mb, s));
+      TRY(conv_block(n, t, 1, 1, b[1], b[2], b[3], mb, s));
+      TRY(conv_block(n, t, 2, 2, b[3], b[4], b[5], mb, s));
+      TRY(lin_fwd(n, t.L[3], b[5], 3136, t.h, 512, mb, s));
+      return DDRL_OK;
+    }
+    case DDRL_ARCH_NAV:
+    case DDRL_ARCH_NAVPED:
+    case DDRL_ARCH_NAV1D: {
+      const bool d1 = t.arch == DDRL_ARCH_NAV1D;
+      const int ldcat = d1 ? 776 : 524;
+      const float* img;
+      if (t.arch == DDRL_ARCH_NAV) img = obs[0] + row0 * t.g[0].sb;
+      else if (d1) img = obs[2] + row0 * t.g[0].sb;
+      else {
+        // NavPedPreNet: cat(state[0] [B,in_ch-3,48,48], state[2] [B,3,48,48]) along channels (nav_encoder.py:72)
+        const int c0 = t.in_ch - 3, hw = 48 * 48;
+        TRY(copy2d(obs[0] + row0 * c0 * hw, c0 * hw, b[15], t.in_ch * hw, mb, c0 * hw, s));
+        TRY(copy2d(obs[2] + row0 * 3 * hw, 3 * hw, b[15] + c0 * hw, t.in_ch * hw, mb, 3 * hw, s));
+        img = b[15];
+      }
+      const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
+      TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s));
+      TRY(pool_fwd(b[1], b[2], t.idx[0], mb, g0->Ho, g0->Wo, 64, s));
+      TRY(conv_block(n, t, 1, 1, b[2], b[3], b[4], mb, s));
+      TRY(pool_fwd(b[4], b[5], t.idx[1], mb, g1->Ho, g1->Wo, 128, s));
+      TRY(conv_block(n, t, 2, 2, b[5], b[6], b[7], mb, s));
+      TRY(pool_fwd(b[7], b[8], t.idx[2], mb, g2->Ho, g2->Wo, 256, s));
+      const int flat = (g2->Ho / 2) * (g2->Wo / 2) * 256;
+      const float* vec = obs[1];
+      if (d1) {
+        // laser branch: conv1d1 -> conv1d2 (no activation between, nav_encoder.py:109-110) -> fc_1d+relu -> cat[:, 0:256]
+        const float* laser = obs[0] + row0 * 960;
+        TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s));
+        TRY(conv_block(n, t, 4, 4, b[12], b[13], b[14], mb, s));
+        TRY(lin_fwd(n, t.L[5], b[14], 7616, b[9], ldcat, mb, s));
+        TRY(lin_fwd(n, t.L[6], b[8], flat, b[9] + 256, ldcat, mb, s));           // fc0 -> cat[:, 256:768]
+        TRY(copy2d(vec + row0 * 5, 5, b[9] + 768, ldcat, mb, 5, s));             // vec -> cat[:, 768:773]
+        TRY(lin_fwd(n, t.L[7], b[9], ldcat, b[10], 512, mb, s));
+        TRY(lin_fwd(n, t.L[8], b[10], 512, t.h, 512, mb, s));
+      } else {
+        TRY(lin_fwd(n, t.L[3], b[8], flat, b[9], ldcat, mb, s));                 // fc0 -> cat[:, 0:512]
+        TRY(copy2d(vec + row0 * 9, 9, b[9] + 512, ldcat, mb, 9, s));             // vec -> cat[:, 512:521]
+        TRY(lin_fwd(n, t.L[4], b[9], ldcat, b[10], 512, mb, s));
+        TRY(lin_fwd(n, t.L[5], b[10], 512, t.h, 512, mb, s));
+      }
+      return DDRL_OK;
+    }
+    case DDRL_ARCH_MLP:
+      return lin_fwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.h, t.feat, mb, s);
+  }
+  return DDRL_E_ARG;
+}
+
+// conv layer backward: dy [M, Cout] already holds dL/d(activated output); handles act', db, dW, and dx (NHWC) if wanted
+static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const float* cols, float* dy, const float* y,
+                    float* dcols, float* dx, int mb, cudaStream_t s) {
+  const ConvGeom& g = t.g[gi];
+  const Lin& l = t.L[li];
+  const long long M = (long long)mb * g.Ho * g.Wo;
+  TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, y, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, M, s));
+  if (dx) TRY(col2im(g, dcols, dx, mb, s));
+  return DDRL_OK;
+}
+
+static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long long row0, int mb, cudaStream_t s) {
+  auto& b = t.buf;
+  switch (t.arch) {
+    case DDRL_ARCH_ATARI: {
+      TRY(lin_bwd(n, t.L[3], b[5], 3136, t.dh, 512, t.h, 512, b[6], 3136, 3136, mb, s));
+      TRY(conv_bwd(n, t, 2, 2, b[4], b[6], b[5], b[7], b[8], mb, s));
+      TRY(conv_bwd(n, t, 1, 1, b[2], b[8], b[3], b[7], b[9], mb, s));
+      TRY(conv_bwd(n, t, 0, 0, b[0], b[9], b[1], nullptr, nullptr, mb, s));
+      return DDRL_OK;
+    }
+    case DDRL_ARCH_NAV:
+    case DDRL_ARCH_NAVPED:
+    case DDRL_ARCH_NAV1D: {
+      const bool d1 = t.arch == DDRL_ARCH_NAV1D;
+      const int ldcat = d1 ? 776 : 524;
+      const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
+      const int flat = (g2->Ho / 2) * (g2->Wo / 2) * 256;
+      float *df1 = b[16], *dcat = b[17], *dp3 = b[18], *dz3 = b[19], *dcols = b[20], *dp2 = b[21], *dz2 = b[22],
+            *dp1 = b[23], *dz1 = b[24];
+      const int Lfc2 = d1 ? 8 : 5, Lfc1 = d1 ? 7 : 4, Lfc0 = d1 ? 6 : 3;
+      const int img_off = d1 ? 256 : 0;
+      TRY(lin_bwd(n, t.L[Lfc2], b[10], 512, t.dh, 512, t.h, 512, df1, 512, 512, mb, s));
+      TRY(lin_bwd(n, t.L[Lfc1], b[9], ldcat, df1, 512, b[10], 512, dcat, ldcat, img_off + 512, mb, s));
+      TRY(lin_bwd(n, t.L[Lfc0], b[8], flat, dcat + img_off, ldcat, b[9] + img_off, ldcat, dp3, flat, flat, mb, s));
+      TRY(pool_bwd(dp3, t.idx[2], b[7], dz3, mb, g2->Ho, g2->Wo, 256, s));
+      // ReLU' is folded into pool_bwd (a>0 test), so the conv layers run with act = none here
+      Lin l2 = t.L[2]; l2.act = ACT_NONE;
+      Lin l1 = t.L[1]; l1.act = ACT_NONE;
+      Lin l0 = t.L[0]; l0.act = ACT_NONE;
+      {
+        const long long M = (long long)mb * g2->Ho * g2->Wo;
+        TRY(lin_bwd(n, l2, b[6], g2->ldc, dz3, 256, b[7], 256, dcols, g2->ldc, g2->ldc, M, s));
+        TRY(col2im(*g2, dcols, dp2, mb, s));
+      }
+      TRY(pool_bwd(dp2, t.idx[1], b[4], dz2, mb, g1->Ho, g1->Wo, 128, s));
+      {
+        const long long M = (long long)mb * g1->Ho * g1->Wo;
+        TRY(lin_bwd(n, l1, b[3], g1->ldc, dz2, 128, b[4], 128, dcols, g1->ldc, g1->ldc, M, s));
+        TRY(col2im(*g1, dcols, dp1, mb, s));
+      }
+      TRY(pool_bwd(dp1, t.idx[0], b[1], dz1, mb, g0->Ho, g0->Wo, 64, s));
+      {
+        const long long M = (long long)mb * g0->Ho * g0->Wo;
+        TRY(lin_bwd(n, l0, b[0], g0->ldc, dz1, 64, b[1], 64, nullptr, 0, 0, M, s));
+      }
+      if (d1) {
+        float *dl2 = b[25], *dl1 = b[26];
+        TRY(lin_bwd(n, t.L[5], b[14], 7616, dcat, ldcat, b[9], ldcat, dl2, 7616, 7616, mb, s));
+        TRY(conv_bwd(n, t, 4, 4, b[13], dl2, b[14], dcols, dl1, mb, s));
+        TRY(conv_bwd(n, t, 3, 3, b[11], dl1, b[12], nullptr, nullptr, mb, s));
+      }
+      return DDRL_OK;
+    }
+    case DDRL_ARCH_MLP:
+      return lin_bwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.dh, t.feat, t.h, t.feat, nullptr, 0, 0, mb, s);
+  }
+  return DDRL_E_ARG;
+}
+
+static int check_obs(const ddrl_net* n, const float* const* obs, int n_obs) {
+  const int need = ddrl_net_num_obs(n);
+  if (!obs || n_obs < need) return DDRL_E_ARG;
+  for (int i = 0; i < need; ++i)
+    if (!obs[i] && ddrl_net_obs_elems(n, i) > 0) return DDRL_E_ARG;
+  return DDRL_OK;
+}
+
+// encoders + heads for rows [row0, row0+mb): fills n->logits [mb, ldA], n->vout [mb]
+static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s) {
+  for (auto& t : n->towers) TRY(tower_forward(n, t, obs, row0, mb, train, s));
+  Tower& ta = n->towers[0];
+  Tower& tc = n->towers[n->d.shared ? 0 : 1];
+  const int A = n->d.act_dim, F = n->d.feat;
+  TRY(skinny_fwd(ta.h, F, n->params + n->T[n->t_aw].offset, n->params + n->T[n->t_ab].offset, mb, A, F, n->logits, n->ldA, s));
+  TRY(skinny_fwd(tc.h, F, n->params + n->T[n->t_cw].offset, n->params + n->T[n->t_cb].offset, mb, 1, F, n->vout, 1, s));
+  return DDRL_OK;
+}
+
+}  // namespace ddrl
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
+  if (!desc || !out) return DDRL_E_ARG;
+  if (desc->arch < 0 || desc->arch > DDRL_ARCH_MLP || desc->act_dim < 1 || desc->in_ch < 1) return DDRL_E_ARG;
+  if (desc->dist == DDRL_DIST_CATEGORICAL && desc->act_dim > 64) return DDRL_E_UNSUPPORTED;
+  if (desc->dist == DDRL_DIST_GAUSSIAN && desc->act_dim > 8) return DDRL_E_UNSUPPORTED;
+  if (desc->arch == DDRL_ARCH_NAVPED && desc->in_ch < 4) return DDRL_E_ARG;
+  ddrl_net* n = new ddrl_net();
+  n->d = *desc;
+  if (n->d.arch != DDRL_ARCH_MLP) n->d.feat = 512;
+  if (n->d.feat < 1) { delete n; return DDRL_E_ARG; }
+  const int F = n->d.feat;
+  // ---- parameter table: reference named_parameters() order (nn/ppo.py:26-30, actor.py:12-16,52-56, critic.py:8-12)
+  if (n->d.shared) add_encoder_tensors(n, "prenet.", n->d.arch, n->d.in_ch, F);
+  if (n->d.dist == DDRL_DIST_GAUSSIAN) add_tensor(n, "actor.log_std", {n->d.act_dim});
+  if (!n->d.shared) add_encoder_tensors(n, "actor.pre.", n->d.arch, n->d.in_ch, F);
+  add_tensor(n, "actor.actor_linear.weight", {n->d.act_dim, F});
+  add_tensor(n, "actor.actor_linear.bias", {n->d.act_dim});
+  const int64_t critic_begin = n->P;
+  add_tensor(n, "critic.critic_linear.weight", {1, F});
+  add_tensor(n, "critic.critic_linear.bias", {1});
+  if (!n->d.shared) add_encoder_tensors(n, "critic.pre.", n->d.arch, n->d.in_ch, F);
+  n->t_aw = find_tensor(n, "actor.actor_linear.weight");
+  n->t_ab = find_tensor(n, "actor.actor_linear.bias");
+  n->t_cw = find_tensor(n, "critic.critic_linear.weight");
+  n->t_cb = find_tensor(n, "critic.critic_linear.bias");
+  n->t_logstd = find_tensor(n, "actor.log_std");
+  n->ldA = round4(n->d.act_dim);
+  // Adam segments: shared -> one optimiser over everything (ppo.py:40); unshared -> actor_optim over
+  // actor.* and critic_optim over critic.* (ppo.py:41-42), contiguous in the flat order
+  if (n->d.shared) { n->nseg = 1; n->seg_begin[0] = 0; n->seg_begin[1] = n->P; }
+  else { n->nseg = 2; n->seg_begin[0] = 0; n->seg_begin[1] = critic_begin; n->seg_begin[2] = n->P; }
+  if (n->d.shared) {
+    n->towers.resize(1);
+    build_tower(n, n->towers[0], "prenet.", n->d.arch, n->d.in_ch, F);
+  } else {
+    n->towers.resize(2);
+    build_tower(n, n->towers[0], "actor.pre.", n->d.arch, n->d.in_ch, F);
+    build_tower(n, n->towers[1], "critic.pre.", n->d.arch, n->d.in_ch, F);
+  }
+  *out = n;
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_destroy(ddrl_net* n) {
+  if (!n) return DDRL_OK;
+  if (n->ws.base) cudaFree(n->ws.base);
+  if (n->packed_base) cudaFree(n->packed_base);
+  delete n;
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_num_tensors(const ddrl_net* n) { return n ? (int)n->T.size() : DDRL_E_ARG; }
+extern "C" int64_t ddrl_net_num_params(const ddrl_net* n) { return n ? n->P : DDRL_E_ARG; }
+extern "C" int ddrl_net_tensor_info(const ddrl_net* n, int i, char* name, int name_cap, int64_t* shape4, int* ndim,
+                                    int64_t* offset) {
+  if (!n || i < 0 || i >= (int)n->T.size()) return DDRL_E_ARG;
+  const TensorInfo& t = n->T[i];
+  if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (shape4) for (int k = 0; k < 4; ++k) shape4[k] = t.shape[k];
+  if (ndim) *ndim = t.ndim;
+  if (offset) *offset = t.offset;
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_bind(ddrl_net* n, float* params, float* grads, float* adam_m, float* adam_v) {
+  if (!n || !params) return DDRL_E_ARG;
+  n->params = params; n->grads = grads; n->am = adam_m; n->av = adam_v;
+  n->dirty = true;
+  if (!n->packed_base) TRY(alloc_packed(n));
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_params_changed(ddrl_net* n) {
+  if (!n) return DDRL_E_ARG;
+  n->dirty = true;
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_num_obs(const ddrl_net* n) {
+  if (!n) return DDRL_E_ARG;
+  switch (n->d.arch) {
+    case DDRL_ARCH_ATARI: case DDRL_ARCH_MLP: return 1;
+    case DDRL_ARCH_NAV: return 2;
+    default: return 3;
+  }
+}
+extern "C" int64_t ddrl_net_obs_elems(const ddrl_net* n, int slot) {
+  if (!n) return DDRL_E_ARG;
+  switch (n->d.arch) {
+    case DDRL_ARCH_ATARI: return slot == 0 ? (int64_t)n->d.in_ch * 84 * 84 : 0;
+    case DDRL_ARCH_MLP: return slot == 0 ? n->d.in_ch : 0;
+    case DDRL_ARCH_NAV: return slot == 0 ? (int64_t)n->d.in_ch * 48 * 48 : (slot == 1 ? 9 : 0);
+    case DDRL_ARCH_NAVPED: return slot == 0 ? (int64_t)(n->d.in_ch - 3) * 48 * 48 : (slot == 1 ? 9 : (slot == 2 ? 3 * 48 * 48 : 0));
+    case DDRL_ARCH_NAV1D: return slot == 0 ? 960 : (slot == 1 ? 5 : (slot == 2 ? (int64_t)n->d.in_ch * 48 * 48 : 0));
+  }
+  return 0;
+}
+extern "C" int64_t ddrl_net_workspace_bytes(const ddrl_net* n) { return n ? (int64_t)(n->ws.cap + n->packed_bytes) : 0; }
+
+extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs, int B, const float* draw, float* actions,
+                                float* logp, float* values, float* pi_out, void* stream) {
+  if (!n || B < 0) return DDRL_E_ARG;
+  if (!n->params) return DDRL_E_STATE;
+  if (B == 0) return DDRL_OK;
+  TRY(check_obs(n, obs, n_obs));
+  if (!logp || !values || !actions) return DDRL_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(ensure_workspace(n, B, n->ws_train));
+  if (n->dirty) TRY(repack(n, s));
+  const int A = n->d.act_dim;
+  for (long long r0 = 0; r0 < B; r0 += n->MB) {
+    const int mb = (int)std::min<long long>(n->MB, B - r0);
+    TRY(forward_chunk(n, obs, r0, mb, false, s));
+    if (n->d.dist == DDRL_DIST_CATEGORICAL) {
+      TRY(ddrl_categorical_head(n->logits, n->ldA, draw ? draw + r0 : nullptr, mb, A, actions + r0, logp + r0,
+                                pi_out ? pi_out + r0 * A : nullptr, s));
+    } else {
+      const float* ls = n->params + n->T[n->t_logstd].offset;
+      TRY(ddrl_gaussian_head(n->logits, n->ldA, ls, draw ? draw + r0 * A : nullptr, mb, A, actions + r0 * A, logp + r0, s));
+      if (pi_out) TRY(copy2d(n->logits, n->ldA, pi_out + r0 * A, A, mb, A, s));
+    }
+    DDRL_CUDA(cudaMemcpyAsync(values + r0, n->vout, sizeof(float) * mb, cudaMemcpyDeviceToDevice, s));
+  }
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
+                                 const float* actions, const float* old_logp, const float* adv, const float* returns,
+                                 const ddrl_ppo_hparams* hp, void* stream) {
+  if (!n || !hp || B_local < 0 || B_global < B_local || B_global < 1) return DDRL_E_ARG;
+  if (!n->params || !n->grads) return DDRL_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  // zero the flat grads (+ loss tail) and the packed grads: everything below accumulates
+  DDRL_CUDA(cudaMemsetAsync(n->grads, 0, sizeof(float) * (size_t)(n->P + 8), s));
+  if (n->packed_base) DDRL_CUDA(cudaMemsetAsync(n->packed_base + n->packed_grad_off, 0, n->packed_grad_bytes, s));
+  if (B_local == 0) return DDRL_OK;
+  TRY(check_obs(n, obs, n_obs));
+  if (!actions || !old_logp || !adv || !returns) return DDRL_E_ARG;
+  TRY(ensure_workspace(n, B_local, true));
+  if (n->dirty) TRY(repack(n, s));
+  const int A = n->d.act_dim, F = n->d.feat;
+  const float invB = 1.0f / (float)B_global;
+  float* loss_sums = n->grads + n->P;
+  Tower& ta = n->towers[0];
+  Tower& tc = n->towers[n->d.shared ? 0 : 1];
+  float* aw = n->params + n->T[n->t_aw].offset;
+  float* cw = n->params + n->T[n->t_cw].offset;
+  for (long long r0 = 0; r0 < B_local; r0 += n->MB) {
+    const int mb = (int)std::min<long long>(n->MB, B_local - r0);
+    TRY(forward_chunk(n, obs, r0, mb, true, s));
+    if (n->d.dist == DDRL_DIST_CATEGORICAL) {
+      TRY(ddrl_ppo_loss_categorical(n->logits, n->ldA, actions + r0, old_logp + r0, adv + r0, returns + r0, n->vout, mb, A,
+                                    invB, hp, n->d.shared, n->dlogits, n->ldA, n->dv, loss_sums, s));
+    } else {
+      TRY(ddrl_ppo_loss_gaussian(n->logits, n->ldA, n->params + n->T[n->t_logstd].offset, actions + r0 * A, old_logp + r0,
+                                 adv + r0, returns + r0, n->vout, mb, A, invB, hp, n->d.shared, n->dlogits, n->ldA, n->dv,
+                                 n->grads + n->T[n->t_logstd].offset, loss_sums, s));
+    }
+    // heads backward (nn/actor.py:91 actor_linear, nn/critic.py:21 critic_linear)
+    TRY(skinny_wgrad(n->dlogits, n->ldA, ta.h, F, mb, A, F, n->grads + n->T[n->t_aw].offset, n->grads + n->T[n->t_ab].offset, s));
+    TRY(skinny_wgrad(n->dv, 1, tc.h, F, mb, 1, F, n->grads + n->T[n->t_cw].offset, n->grads + n->T[n->t_cb].offset, s));
+    TRY(skinny_dgrad(n->dlogits, n->ldA, aw, mb, A, F, ta.dh, F, 0, s));
+    TRY(skinny_dgrad(n->dv, 1, cw, mb, 1, F, tc.dh, F, n->d.shared ? 1 : 0, s));
+    for (auto& t : n->towers) TRY(tower_backward(n, t, obs, r0, mb, s));
+  }
+  // packed weight grads -> reference layout
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.packed) TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
+  return DDRL_OK;
+}
+
+namespace ddrl {
+__global__ void finish_losses_kernel(const float* __restrict__ sums, float v_coef, float ent_coef, float* __restrict__ out) {
+  const float a = sums[0], v = sums[1], e = sums[2];
+  out[0] = a + v * v_coef - e * ent_coef;      // nn/ppo.py:108
+  out[1] = a; out[2] = v; out[3] = e;
+}
+}  // namespace ddrl
+
+extern "C" int ddrl_net_clip_adam(ddrl_net* n, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream) {
+  if (!n || !hp || step < 1) return DDRL_E_ARG;
+  if (!n->params || !n->grads || !n->am || !n->av) return DDRL_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (loss4_out) {
+    finish_losses_kernel<<<1, 1, 0, s>>>(n->grads + n->P, hp->v_coef, hp->ent_coef, loss4_out);
+    DDRL_LAUNCHED("finish_losses_kernel");
+  }
+  long long sb[3] = {n->seg_begin[0], n->seg_begin[1], n->seg_begin[2]};
+  float lr[2];
+  if (n->d.shared) lr[0] = hp->lr;
+  else { lr[0] = hp->lr_actor; lr[1] = hp->lr_critic; }
+  TRY(clip_adam_launch(n->params, n->grads, n->am, n->av, n->P, sb, lr, n->nseg, step, hp, nullptr, s));
+  TRY(repack(n, s));
+  return DDRL_OK;
+}
+

@@ -1,0 +1,304 @@
+"""PPO -- drop-in for USTC_lab/nn/ppo.py:17-146 running on the fused sm_100a engine.
+
+Same constructor, attributes and call contracts as the reference class:
+  * ``PPO(actor, critic, prenet, rnd, config, config_nn)``            (runner/utils.py:160)
+  * ``net(states, act=None, play_mode=False) -> ((pi, log_p), [values [B,1]])``   (ppo.py:72-75)
+  * ``net.learn(Experience)`` -> generator of ``(loss_dict, update_time, last)``   (ppo.py:77-142)
+  * ``state_dict()/load_state_dict()/named_parameters()`` names, shapes and order (App. C)
+  * ``nn2redis / updatenn_by_redis / updatenn``                         (nn/base.py:60-95)
+plus the fused entry point ``net.act(states, draw, play_mode)`` = compute body of
+``ForwardThread.run`` (server/forward.py:128-146) with the random draw supplied.
+
+What is different underneath: all parameters live in ONE flat fp32 device buffer (reference
+order); ``p.data`` of every ``nn.Parameter`` is a view into it.  Gradients, Adam m and v are flat
+buffers of the same layout, so the data-parallel learner all-reduces one buffer and the fused
+clip+Adam kernel walks it once.  No autograd graph is ever built.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+from torch.distributions.categorical import Categorical
+from torch.distributions.normal import Normal
+
+from .. import _lib, kernels
+from .._lib import DDRLError, NetDesc, check, current_stream, ptr
+from .base import Basenn
+
+
+def _cfg(obj, name, default):
+    return getattr(obj, name, default) if obj is not None else default
+
+
+class PPO(Basenn):
+    def __init__(self, actor, critic, prenet=None, rnd=None, config=None, config_nn=None):
+        super().__init__(config, config_nn)
+        if rnd is not None:
+            raise DDRLError("RND is outside the B200 hot path (off by default, config_nn.py:19); use the reference's nn/RND.py")
+        self.device = _cfg(config, "DEVICE", "cuda")
+        self.prenet = prenet            # registration order = reference (ppo.py:27-29): prenet, actor, critic
+        self.actor = actor
+        self.critic = critic
+        self._critics = [self.critic]
+        self.rnd = None
+        self.gail_critic = False
+        self.share_cnn_net = _cfg(config_nn, "SHARE_CNN_NET", prenet is not None)
+        if bool(self.share_cnn_net) != (prenet is not None):
+            raise DDRLError("SHARE_CNN_NET=%s but prenet is %s" % (self.share_cnn_net, type(prenet).__name__))
+        self.hp = kernels.make_hparams(
+            ppo_clip=_cfg(config_nn, "PPO_CLIP", 0.2), dual_clip=_cfg(config_nn, "DUEL_PPO_CLIP", 3),
+            v_coef=_cfg(config_nn, "V_LOSS_THETA", 1.0), ent_coef=_cfg(config_nn, "ENTROPY_LOSS_THETA", 0.05),
+            max_grad_norm=_cfg(config_nn, "CLIP_GRID_NUM", 0.5), clip_grad=_cfg(config_nn, "CLIP_GRID", True),
+            smooth_l1=_cfg(config_nn, "SMOOTH_L1_LOSS", False), lr=_cfg(config_nn, "LEARNING_RATE", 2e-4),
+            lr_actor=_cfg(config_nn, "ACTOR_LEARNING_RATE", 5e-5), lr_critic=_cfg(config_nn, "CRITIC_LEARNING_RATE", 1e-3))
+        self.clip_grad = bool(self.hp.clip_grad)
+        self.clip_grad_num = self.hp.max_grad_norm
+        self.v_loss_theta, self.ent_loss_theta = self.hp.v_coef, self.hp.ent_coef
+        self.ppo_clip, self.duel_ppo_clip = self.hp.ppo_clip, self.hp.dual_clip
+        self.training_iter_time = _cfg(config_nn, "TRAINING_ITER_TIME", 10)
+        self.gemm_mode = os.environ.get("DDRL_GEMM_MODE", _cfg(config_nn, "GEMM_MODE", "simt"))
+        self.update_time = 0
+        self._adam_step = 0
+        self._h = None                  # ddrl_net*
+        self._flat = self._grads = self._m = self._v = None
+        self._offsets = None
+        self._P = 0
+        self._versions = None
+        self._dp_group = None
+        self._dp_world = 1
+        self._loss4 = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _encoder(self):
+        return self.prenet if self.prenet is not None else self.actor.pre
+
+    def _spec(self):
+        enc = self._encoder()
+        if enc is None or getattr(enc, "ARCH", None) is None:
+            raise DDRLError("PPO needs a ddrl4nav_b200 encoder (AtariPreNet / NavPreNet / NavPedPreNet / NavPreNet1D / MLPPreNet)")
+        if self.prenet is None and type(self.critic.pre) is not type(enc):
+            raise DDRLError("unshared mode needs the same encoder family in actor.pre and critic.pre")
+        return dict(arch=enc.ARCH, in_ch=enc.engine_in_ch(), act_dim=self.actor.actor_linear.out_features,
+                    dist=self.actor.DIST, shared=self.prenet is not None, feat=self.actor.actor_linear.in_features)
+
+    def _destroy(self):
+        if self._h is not None:
+            _lib.load().ddrl_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def _ensure_engine(self):
+        """(Re)builds the flat buffers when needed and tells the engine about out-of-band weight edits."""
+        plist = list(self.named_parameters())
+        dev = plist[0][1].device
+        if dev.type != "cuda":
+            raise DDRLError("ddrl4nav_b200.nn.PPO needs its parameters on a CUDA device (got %s); there is no CPU "
+                            "fallback -- call .to('cuda')" % dev)
+        aliased = self._flat is not None and self._flat.device == dev and all(
+            p.data_ptr() == self._flat.data_ptr() + 4 * off for (_, p), off in zip(plist, self._offsets))
+        if self._h is None or not aliased:
+            self._build(plist, dev)
+        ver = sum(p._version for _, p in plist)
+        if ver != self._versions:
+            check(_lib.load().ddrl_net_params_changed(self._h), "ddrl_net_params_changed")
+            self._versions = ver
+
+    def _build(self, plist, dev):
+        lib = _lib.load()
+        self._destroy()
+        s = self._spec()
+        desc = NetDesc(_lib.ARCH[s["arch"]], s["in_ch"], s["act_dim"], _lib.DIST[s["dist"]], int(s["shared"]), s["feat"],
+                       _lib.GEMM_MODE[self.gemm_mode], 0)
+        h = C.c_void_p()
+        check(lib.ddrl_net_create(C.byref(desc), C.byref(h)), "ddrl_net_create")
+        self._h = h
+        nt = lib.ddrl_net_num_tensors(h)
+        P = lib.ddrl_net_num_params(h)
+        if nt != len(plist):
+            raise DDRLError("parameter table mismatch: engine has %d tensors, module has %d" % (nt, len(plist)))
+        offsets = []
+        name = C.create_string_buffer(128)
+        shape = (C.c_int64 * 4)()
+        ndim = C.c_int()
+        off = C.c_int64()
+        for i, (pname, p) in enumerate(plist):
+            check(lib.ddrl_net_tensor_info(h, i, name, 128, shape, C.byref(ndim), C.byref(off)), "ddrl_net_tensor_info")
+            eshape = tuple(shape[k] for k in range(ndim.value))
+            if name.value.decode() != pname or eshape != tuple(p.shape):
+                raise DDRLError("parameter %d mismatch: engine %s%s vs module %s%s" %
+                                (i, name.value.decode(), eshape, pname, tuple(p.shape)))
+            offsets.append(off.value)
+        with torch.cuda.device(dev):
+            flat = torch.empty(P, dtype=torch.float32, device=dev)
+            old_m, old_v = self._m, self._v
+            self._grads = torch.zeros(P + 8, dtype=torch.float32, device=dev)
+            self._m = torch.zeros(P, dtype=torch.float32, device=dev)
+            self._v = torch.zeros(P, dtype=torch.float32, device=dev)
+            if old_m is not None and old_m.numel() == P:       # keep Adam state across a .to()/re-flatten
+                self._m.copy_(old_m)
+                self._v.copy_(old_v)
+            self._loss4 = torch.zeros(4, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for (pname, p), o in zip(plist, offsets):
+                view = flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data.to(torch.float32))
+                p.data = view
+                p.grad = None
+        self._flat, self._offsets = flat, offsets
+        self._P = P
+        check(lib.ddrl_net_bind(h, ptr(flat), ptr(self._grads), ptr(self._m), ptr(self._v)), "ddrl_net_bind")
+        self._versions = sum(p._version for _, p in plist)
+        if self.prenet is None:
+            self._seg = ([0, offsets[[n for n, _ in plist].index("critic.critic_linear.weight")], P],
+                         [self.hp.lr_actor, self.hp.lr_critic])
+        else:
+            self._seg = ([0, P], [self.hp.lr])
+
+    def _weights_changed(self):
+        if self._h is not None:
+            check(_lib.load().ddrl_net_params_changed(self._h), "ddrl_net_params_changed")
+
+    def _params_to_host(self):
+        if self._flat is None:
+            return super()._params_to_host()
+        host = self._flat.detach().cpu().numpy()               # ONE D2H copy for the whole model blob
+        return [(n, host[o:o + p.numel()].reshape(tuple(p.shape))) for (n, p), o in zip(self.named_parameters(), self._offsets)]
+
+    def flat_grads(self):
+        """View of the flat gradient buffer (reference parameter order) of the last backward."""
+        return self._grads[:self._P]
+
+    def named_grads(self):
+        return {n: self._grads[o:o + p.numel()].view(p.shape) for (n, p), o in zip(self.named_parameters(), self._offsets)}
+
+    def _obs_ptrs(self, states):
+        lib = _lib.load()
+        n_obs = lib.ddrl_net_num_obs(self._h)
+        if len(states) < n_obs:
+            raise DDRLError("expected %d state slots, got %d" % (n_obs, len(states)))
+        dev = self._flat.device
+        keep, B = [], None
+        for i in range(n_obs):
+            t = states[i]
+            if not torch.is_tensor(t):
+                t = torch.as_tensor(np.asarray(t))
+            t = t.to(device=dev, dtype=torch.float32).contiguous()
+            per = lib.ddrl_net_obs_elems(self._h, i)
+            if B is None:
+                B = t.shape[0]
+            if t.shape[0] != B or (t.numel() // max(B, 1)) != per:
+                raise DDRLError("state slot %d has shape %s; expected [B=%d, %d elements/sample]" % (i, tuple(t.shape), B, per))
+            keep.append(t)
+        arr = (C.c_void_p * n_obs)(*[t.data_ptr() for t in keep])
+        return keep, arr, n_obs, B
+
+    # ------------------------------------------------------------------ Forward module
+    def act(self, states, draw=None, play_mode=False, want_pi=False):
+        """Fused compute body of ForwardThread.run (server/forward.py:128-146).
+
+        draw: uniforms [B] (categorical) or standard normals [B,A] (gaussian); generated on the device
+        when None and not play_mode.  Returns (actions [B] | [B,A], logps [B], values [V=1,B,1][, pi])."""
+        self._ensure_engine()
+        lib = _lib.load()
+        keep, arr, n_obs, B = self._obs_ptrs(states)
+        dev = self._flat.device
+        A = self.actor.actor_linear.out_features
+        gauss = self.actor.DIST == "gaussian"
+        if play_mode:
+            draw = None
+        elif draw is None:
+            draw = torch.randn(B, A, device=dev) if gauss else torch.rand(B, device=dev)
+        else:
+            draw = draw.to(device=dev, dtype=torch.float32).contiguous()
+        actions = torch.empty((B, A) if gauss else (B,), dtype=torch.float32, device=dev)
+        logps = torch.empty(B, dtype=torch.float32, device=dev)
+        values = torch.empty(B, dtype=torch.float32, device=dev)
+        pi = torch.empty((B, A), dtype=torch.float32, device=dev) if want_pi else None
+        check(lib.ddrl_net_forward(self._h, arr, n_obs, B, ptr(draw), ptr(actions), ptr(logps), ptr(values), ptr(pi),
+                                   current_stream()), "ddrl_net_forward")
+        out = (actions, logps, values.view(1, B, 1))
+        return out + (pi,) if want_pi else out
+
+    def forward(self, states, act=None, play_mode=False):
+        """Reference-shaped output: ((pi, log_p), [values [B,1]]) with pi = Categorical / Normal, or the raw
+        softmax / mu tensor in play mode (nn/actor.py:58-67,90-98)."""
+        _, _, values, pi_raw = self.act(states, draw=None, play_mode=True, want_pi=True)
+        if self.actor.DIST == "categorical":
+            pi = pi_raw if play_mode else Categorical(pi_raw)
+        else:
+            pi = pi_raw if play_mode else Normal(pi_raw, torch.exp(self.actor.log_std.detach()))
+        log_p = None
+        if act is not None:
+            if play_mode:
+                raise DDRLError("log-prob of given actions needs play_mode=False (as in the reference)")
+            log_p = self.actor.log_prob_from_distribution(pi, act.to(pi_raw.device))
+        return (pi, log_p), [values.view(-1, 1)]
+
+    # ------------------------------------------------------------------ Backward module
+    def enable_data_parallel(self, group=None):
+        """Shard each full-batch iteration over the ranks of `group` (one process per GPU): local grads are
+        pre-scaled by 1/B_global, one NCCL all-reduce(sum) of the flat grad buffer (+ loss sums) per
+        iteration, then the identical fused clip+Adam on every rank."""
+        import torch.distributed as dist
+        self._dp_group = group if group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self._dp_group)
+
+    def broadcast_parameters(self, src=0):
+        import torch.distributed as dist
+        self._ensure_engine()
+        dist.broadcast(self._flat, src=src, group=self._dp_group)
+        self._weights_changed()
+
+    def backward_only(self, states, advs, actions, old_logps, returns, b_global=None):
+        """forward + fused loss + backward for the local rows; grads (scaled 1/B_global) stay in flat_grads()."""
+        self._ensure_engine()
+        lib = _lib.load()
+        keep, arr, n_obs, B = self._obs_ptrs(states)
+        dev = self._flat.device
+        f = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        advs, actions, old_logps, returns = f(advs), f(actions), f(old_logps), f(returns)
+        if returns.dim() == 2:             # data.values is [V,B]; the PPO critic uses row 0 (ppo.py:95)
+            returns = returns[0].contiguous()
+        check(lib.ddrl_net_backward(self._h, arr, n_obs, B, int(b_global or B), ptr(actions), ptr(old_logps), ptr(advs),
+                                    ptr(returns), C.byref(self.hp), current_stream()), "ddrl_net_backward")
+        return B
+
+    def optimizer_step(self):
+        lib = _lib.load()
+        self._adam_step += 1
+        check(lib.ddrl_net_clip_adam(self._h, self._adam_step, C.byref(self.hp), ptr(self._loss4), current_stream()),
+              "ddrl_net_clip_adam")
+        return self._loss4
+
+    def learn(self, data):
+        """Generator with the reference's contract (nn/ppo.py:77-142): TRAINING_ITER_TIME full-batch iterations
+        over `data` (an Experience whose tensors are on the device), yielding
+        ({PpoTotalLoss, ActorLoss, VLoss, EntLoss, PpoBackUpTime}, update_time, True) per iteration."""
+        b_local = len(data.states[0])
+        b_global = b_local
+        if self._dp_world > 1:
+            import torch.distributed as dist
+            cnt = torch.tensor([b_local], dtype=torch.int64, device=self._flat.device if self._flat is not None else "cuda")
+            dist.all_reduce(cnt, group=self._dp_group)
+            b_global = int(cnt.item())
+        for _ in range(self.training_iter_time):
+            start_time = time.time()
+            self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global)
+            if self._dp_world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self._grads[:self._P + 4], group=self._dp_group)
+            loss4 = self.optimizer_step().tolist()          # ONE 16-byte D2H per iteration (reference: four .item())
+            self.update_time += 1
+            loss_log = {"PpoTotalLoss": loss4[0], "ActorLoss": loss4[1], "VLoss": loss4[2], "EntLoss": loss4[3],
+                        "PpoBackUpTime": time.time() - start_time}
+            yield loss_log, self.update_time, True
+
+    def add_critic(self, critic):
+        raise DDRLError("extra critics (RND/GAIL value heads) are outside the B200 hot path")

@@ -1,0 +1,187 @@
+/* ddrl_b200.h -- C ABI of the B200-native actor-learner hot path for DDRL4NAV.
+ *
+ * The reference (DRL-Navigation/DDRL4NAV) has no FFI: its "plugin API" for this path is
+ * Python duck-typing.  Each entry point below names the reference
+ * interface whose arithmetic it replaces (file:line relative to the reference root); the
+ * Python mirror in ddrl4nav_b200/ binds them through ctypes and keeps the reference's
+ * class / method names.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - return value: 0 = DDRL_OK, negative = error code (ddrl_error_string); never throws;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     DDRL_E_CUDA (and the Python mirror raises).
+ */
+#ifndef DDRL_B200_H
+#define DDRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDRL_OK 0
+#define DDRL_E_ARG (-1)        /* bad argument (null pointer, shape, enum) */
+#define DDRL_E_CUDA (-2)       /* CUDA runtime error (ddrl_last_cuda_error) */
+#define DDRL_E_STATE (-3)      /* call order (e.g. learn before bind) */
+#define DDRL_E_UNSUPPORTED (-4)
+#define DDRL_E_NOMEM (-5)
+
+enum ddrl_arch {               /* encoder family (USTC_lab/nn/__init__.py:12-18) */
+  DDRL_ARCH_ATARI = 0,         /* AtariPreNet   nn/atari_encoder.py:11-32 */
+  DDRL_ARCH_NAV = 1,           /* NavPreNet     nn/nav_encoder.py:12-43 */
+  DDRL_ARCH_NAVPED = 2,        /* NavPedPreNet  nn/nav_encoder.py:46-79 */
+  DDRL_ARCH_NAV1D = 3,         /* NavPreNet1D   nn/nav_encoder.py:82-128 */
+  DDRL_ARCH_MLP = 4            /* MLPPreNet     nn/mlp_encoder.py:12-29 */
+};
+enum ddrl_dist { DDRL_DIST_CATEGORICAL = 0, DDRL_DIST_GAUSSIAN = 1 };   /* nn/actor.py:75,43 */
+enum ddrl_gemm_mode {
+  DDRL_GEMM_SIMT_F32 = 0,      /* CUDA-core fp32 FMA (reference / fallback-free baseline) */
+  DDRL_GEMM_TC_3XTF32 = 1      /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate in TMEM */
+};
+
+typedef struct ddrl_net ddrl_net;
+
+typedef struct {
+  int32_t arch;      /* enum ddrl_arch */
+  int32_t in_ch;     /* AtariPreNet num_inputs / Nav* image_channel / MLP input_dim */
+  int32_t act_dim;   /* ACTION_OUTPUT_DIM (config/config_nn.py:12-16) */
+  int32_t dist;      /* enum ddrl_dist */
+  int32_t shared;    /* SHARE_CNN_NET (config_nn.py:57; runner/utils.py:88-135) */
+  int32_t feat;      /* AC_INPUT_DIM = 512 (MLP: last_output_dim) */
+  int32_t gemm_mode; /* enum ddrl_gemm_mode */
+  int32_t reserved;
+} ddrl_net_desc;
+
+typedef struct {     /* config/config_nn.py:27-57; torch.optim.Adam defaults */
+  float ppo_clip;        /* PPO_CLIP 0.2 */
+  float dual_clip;       /* DUEL_PPO_CLIP 3 */
+  float v_coef;          /* V_LOSS_THETA 1.0 */
+  float ent_coef;        /* ENTROPY_LOSS_THETA 0.05 */
+  float max_grad_norm;   /* CLIP_GRID_NUM 0.5 */
+  int32_t clip_grad;     /* CLIP_GRID */
+  int32_t smooth_l1;     /* SMOOTH_L1_LOSS */
+  float lr;              /* LEARNING_RATE (shared mode) */
+  float lr_actor;        /* ACTOR_LEARNING_RATE */
+  float lr_critic;       /* CRITIC_LEARNING_RATE */
+  float beta1, beta2, adam_eps;
+} ddrl_ppo_hparams;
+
+/* ---- library ------------------------------------------------------------------------- */
+int ddrl_version(void);
+const char* ddrl_error_string(int code);
+const char* ddrl_last_cuda_error(void);
+/* number of kernels this library has launched since load / since reset (bench gpu_launches) */
+int64_t ddrl_launch_count(void);
+void ddrl_launch_count_reset(void);
+
+/* ---- K5: GAE / discounted return scan -------------------------------------------------
+ * replaces Agents._accumulate_rewards (USTC_lab/agent/agent.py:124-140).
+ * values [T+1, V, N] f32 (row T = bootstrap), rewards [>=T, V, N] f32, dones [>=T, V, N] u8,
+ * gamma_host [V] f32 HOST (self.discounts), lambda (self.landa).
+ * out: ret [T, V, N] = values + g ; adv [T, N] = g of row v=0.
+ * algo: 0 = auto, 1 = sequential-per-column (bit-exact with the numpy loop), 2 = T-chunked
+ *       warp-scan (fp32 reassociation, <=1e-5 of max|adv|). */
+int ddrl_gae_f32(const float* values, const float* rewards, const uint8_t* dones,
+                 const float* gamma_host, float lambda, int T, int V, int N,
+                 float* ret, float* adv, int algo, void* stream);
+
+/* ---- K4: action sampling --------------------------------------------------------------
+ * replaces random_choice_prob_index / select_action (USTC_lab/server/utils.py:20-47) and the
+ * sample/log_prob lines of ForwardThread.run (server/forward.py:137-146).
+ * probs [B, A] (row stride ld), u [B] uniforms or NULL => play mode (first-max argmax, logp=0).
+ * action[b] = first k with fl32(sum_{j<=k} p_j) > u[b], none => 0;  logp = log(p[b,action]). */
+int ddrl_sample_categorical_probs(const float* probs, int ld, const float* u, int B, int A,
+                                  float* action, float* logp, void* stream);
+/* logits [B, A] (pre-softmax actor_linear output, nn/actor.py:91-98): softmax, Categorical
+ * re-normalisation, inverse-CDF sample, logp = log(clamp(p/sum p, eps, 1-eps))[a].
+ * probs_out may be NULL. */
+int ddrl_categorical_head(const float* logits, int ld, const float* u, int B, int A,
+                          float* action, float* logp, float* probs_out, void* stream);
+/* Gaussian head (nn/actor.py:58-70): a = mu + exp(log_std)*eps (mul, then add);
+ * logp = sum_j Normal(mu,std).log_prob(a); eps NULL => play mode (a = mu, logp = 0). */
+int ddrl_gaussian_head(const float* mu, int ld, const float* log_std, const float* eps, int B, int A,
+                       float* action, float* logp, void* stream);
+
+/* ---- K6: fused PPO loss forward + backward --------------------------------------------
+ * replaces nn/ppo.py:85-108 (+ the head part of autograd).  Per sample: dual-clip surrogate,
+ * value loss, entropy; writes d(loss)/d(logits|mu) and d(loss)/d(v); accumulates
+ * loss_sums[0..3] += {actor, v, entropy, -} contributions already scaled by inv_B_global and
+ * (gaussian) dlog_std[A].  shared=1: gradients are of actor + v_coef*v - ent_coef*ent
+ * (ppo.py:108-112); shared=0: dlogits from actor_loss only, dv from v_loss only (ppo.py:122-123).
+ * actions are fp32 (categorical: integer-valued).  returns = data.values[0,:]. */
+int ddrl_ppo_loss_categorical(const float* logits, int ld, const float* actions, const float* old_logp,
+                              const float* adv, const float* returns, const float* v, int B, int A,
+                              float inv_B_global, const ddrl_ppo_hparams* hp, int shared,
+                              float* dlogits, int ld_d, float* dv, float* loss_sums, void* stream);
+int ddrl_ppo_loss_gaussian(const float* mu, int ld, const float* log_std, const float* actions,
+                           const float* old_logp, const float* adv, const float* returns, const float* v,
+                           int B, int A, float inv_B_global, const ddrl_ppo_hparams* hp, int shared,
+                           float* dmu, int ld_d, float* dv, float* dlog_std, float* loss_sums, void* stream);
+
+/* ---- K7: fused global-norm clip + Adam ------------------------------------------------
+ * replaces torch.nn.utils.clip_grad_norm_ (nn/ppo.py:115,126) and torch.optim.Adam.step
+ * (ppo.py:117,128-129).  Flat buffers of n floats; segment s covers [seg_begin[s], seg_begin[s+1])
+ * with learning rate seg_lr[s] (host arrays, nseg+1 / nseg entries).  step >= 1 (same for all).
+ * norm_out (device, 1 float, may be NULL) receives the pre-clip global L2 norm. */
+int ddrl_clip_adam(float* params, float* grads, float* m, float* v, int64_t n,
+                   const int64_t* seg_begin_host, const float* seg_lr_host, int nseg,
+                   int step, const ddrl_ppo_hparams* hp, float* norm_out, void* stream);
+
+/* ---- GEMM building block (exposed for parity tests / roofline benches) ------------------
+ * C[M,N] (ldc) = act( A op B + bias ), fp32 in/out.
+ *  form 0 "fwd"  : C[m,n] = sum_k A[m*lda+k] * B[n*ldb+k]            (A [M,K], B [N,K])
+ *  form 1 "dgrad": C[m,n] = sum_k A[m*lda+k] * B[k*ldb+n]            (A [M,K], B [K,N])
+ *  form 2 "wgrad": C[m,n] = sum_k A[k*lda+m] * B[k*ldb+n]            (A [K,M], B [K,N])
+ * bias: NULL or [N]; act: 0 none, 1 relu, 2 leaky_relu(0.01); beta: 0 overwrite, 1 accumulate into C.
+ * mode: enum ddrl_gemm_mode. */
+int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, const float* bias, int act, int beta, void* stream);
+
+/* ---- the actor-critic net ---------------------------------------------------------------
+ * replaces PPO.forward / PPO.learn and the classes they are built from
+ * (nn/ppo.py:17-146, nn/actor.py, nn/critic.py, nn/atari_encoder.py, nn/nav_encoder.py,
+ * nn/mlp_encoder.py; construction order runner/utils.py:59-170). */
+int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out);
+int ddrl_net_destroy(ddrl_net* net);
+/* parameter table in the reference's named_parameters() order */
+int ddrl_net_num_tensors(const ddrl_net* net);
+int64_t ddrl_net_num_params(const ddrl_net* net);
+int ddrl_net_tensor_info(const ddrl_net* net, int i, char* name, int name_cap,
+                         int64_t* shape4, int* ndim, int64_t* offset);
+/* flat device buffers (reference layout/order).  grads has num_params + 8 floats: the tail
+ * [P .. P+3] carries {actor, v, entropy, unused} loss sums so one all-reduce covers both.
+ * grads/m/v may be NULL for an inference-only net. */
+int ddrl_net_bind(ddrl_net* net, float* params, float* grads, float* adam_m, float* adam_v);
+/* tell the net the flat params were changed behind its back (load_state_dict, updatenn_by_redis) */
+int ddrl_net_params_changed(ddrl_net* net);
+/* number of observation slots and per-sample element count of each (for argument checking) */
+int ddrl_net_num_obs(const ddrl_net* net);
+int64_t ddrl_net_obs_elems(const ddrl_net* net, int slot);
+
+/* Forward module compute body (server/forward.py:128-146): obs[i] fp32 device [B, ...] in the
+ * reference's NCHW/state-list order; draw = uniforms [B] (categorical) or N(0,1) [B,A]
+ * (gaussian), NULL => play mode.  Outputs: actions [B] or [B,A]; logp [B]; values [B] (the
+ * caller views it as [V=1,B,1]); pi_out (optional) probs [B,A] or mu [B,A]. */
+int ddrl_net_forward(ddrl_net* net, const float* const* obs, int n_obs, int B, const float* draw,
+                     float* actions, float* logp, float* values, float* pi_out, void* stream);
+
+/* One learn iteration, first half (nn/ppo.py:82-123): forward with act=data.actions, fused loss,
+ * backward through heads and encoders.  Leaves d(loss)/d(params) for the LOCAL B rows, scaled
+ * by 1/B_global, in the flat grads buffer and the loss sums in its tail.  In a data-parallel
+ * learner the caller all-reduces grads[0 .. P+4) (sum) before ddrl_net_clip_adam. */
+int ddrl_net_backward(ddrl_net* net, const float* const* obs, int n_obs, int B_local, int B_global,
+                      const float* actions, const float* old_logp, const float* adv, const float* returns,
+                      const ddrl_ppo_hparams* hp, void* stream);
+/* second half (nn/ppo.py:115-129): global-norm clip + the two (or one) Adam steps; then refreshes
+ * the packed weights.  loss4_out (device, 4 floats, optional) = {total, actor, v, entropy}. */
+int ddrl_net_clip_adam(ddrl_net* net, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream);
+/* bytes of device workspace currently held */
+int64_t ddrl_net_workspace_bytes(const ddrl_net* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDRL_B200_H */

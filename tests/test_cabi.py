@@ -1,0 +1,123 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/ddrl_b200.h declares; the engine's parameter table equals the reference's
+named_parameters() order (oracle.param_table, itself pinned to the live reference); the Python
+mirror registers parameters in the same order; the weight wire format round-trips."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle import restate as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from ddrl4nav_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    _lib = _ensure_built()
+    hdr = open(os.path.join(ROOT, "include", "ddrl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ddrl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "missing export: " + name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    assert lib.ddrl_version() >= 100
+    assert lib.ddrl_error_string(-1) == b"bad argument"
+
+
+@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg"])
+def test_engine_param_table_is_reference_order(kind):
+    _lib = _ensure_built()
+    lib = _lib.load()
+    spec = R.SPECS[kind]
+    desc = _lib.NetDesc(_lib.ARCH[spec.arch], spec.in_ch, spec.act_dim, _lib.DIST[spec.dist], int(spec.shared), spec.feat, 0, 0)
+    h = C.c_void_p()
+    assert lib.ddrl_net_create(C.byref(desc), C.byref(h)) == 0
+    table = R.param_table(spec)
+    assert lib.ddrl_net_num_tensors(h) == len(table)
+    name = C.create_string_buffer(128)
+    shape = (C.c_int64 * 4)()
+    ndim, off = C.c_int(), C.c_int64()
+    total = 0
+    for i, (n, shp) in enumerate(table):
+        assert lib.ddrl_net_tensor_info(h, i, name, 128, shape, C.byref(ndim), C.byref(off)) == 0
+        assert name.value.decode() == n
+        assert tuple(shape[k] for k in range(ndim.value)) == tuple(shp)
+        assert off.value == total
+        total += int(np.prod(shp))
+    assert lib.ddrl_net_num_params(h) == total == {"pong": 3371847, "navlaser": 12799685, "navimg": 5633565}[kind]
+    # argument checking without a GPU
+    assert lib.ddrl_net_backward(h, None, 0, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.ddrl_net_destroy(h) == 0
+    bad = _lib.NetDesc(99, 1, 1, 0, 0, 512, 0, 0)
+    assert lib.ddrl_net_create(C.byref(bad), C.byref(h)) == -1
+
+
+@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg"])
+def test_mirror_modules_register_reference_order(kind):
+    from ddrl4nav_b200.runner import make_net
+    net = make_net(kind, device=None)
+    got = [(n, tuple(p.shape)) for n, p in net.named_parameters()]
+    assert got == [(n, tuple(s)) for n, s in R.param_table(R.SPECS[kind])]
+    if kind == "navlaser":
+        assert float(net.actor.log_std[0]) == -0.5
+
+
+def test_wire_format_roundtrip_cpu():
+    from ddrl4nav_b200.runner import make_net
+    net = make_net("mlp", device=None)
+    blob = net.model_bytes()
+    expect = b"".join(struct.pack(">I", p.dim()) + struct.pack(">%dI" % p.dim(), *p.shape) + p.detach().numpy().tobytes()
+                      for _, p in net.named_parameters())
+    assert blob == expect
+    net2 = make_net("mlp", device=None)
+    net2.load_model_bytes(blob)
+    for (_, a), (_, b) in zip(net.named_parameters(), net2.named_parameters()):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
+def test_wire_format_matches_live_reference():
+    """Our blob is byte-identical to the reference's nn2redis payload and loads into the reference net."""
+    from ddrl4nav_b200.runner import make_net
+    ref, _, _ = ref_shim.make_ref_net("navimg")
+    params = R.init_params(R.SPECS["navimg"], seed=5)
+    ref.load_state_dict(params)
+    ours = make_net("navimg", device=None)
+    ours.load_state_dict(params)
+
+    class Pipe:
+        def __init__(self): self.kv = {}
+        def set(self, k, v): self.kv[k] = v
+        def incr(self, k): self.kv[k] = self.kv.get(k, 0) + 1
+        def execute(self): pass
+        def get(self, k): return self.kv[k]
+    p1, p2 = Pipe(), Pipe()
+    ref.nn2redis(p1, "tag")
+    ours.nn2redis(p2, "tag")
+    assert p1.kv[ref.model_key] == p2.kv[ours.model_key]
+    assert p2.kv["tag"] == 1
+    ref.updatenn_by_redis(p2, ours.model_key)      # reference decodes our blob
+
+
+def test_no_gpu_means_loud_failure():
+    from ddrl4nav_b200 import DDRLError, kernels
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(DDRLError):
+        kernels.gae(torch.zeros(3, 1, 4), torch.zeros(2, 1, 4), torch.zeros(2, 1, 4, dtype=torch.uint8), [0.99], 0.95)

@@ -1,0 +1,217 @@
+"""GPU parity tests of the whole actor-learner path (PPO.act / PPO.forward / PPO.learn through the
+C ABI) against the oracle restatement and the reference-generated golden vectors.
+
+Tolerance: fp32, allclose(rtol, atol = atol_scale * max|ref| per tensor).  Targets: forward values /
+probs 1e-5; gradients 1e-5 of the tensor's max (looser rtol 1e-3 elementwise because near-zero
+entries of a gradient carry only rounding noise); losses 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GEMM_MODE = os.environ.get("DDRL_TEST_GEMM_MODE", "simt")
+
+
+def rel_err(a, b):
+    a = a.detach().cpu().double() if torch.is_tensor(a) else torch.as_tensor(np.asarray(a)).double()
+    b = b.detach().cpu().double() if torch.is_tensor(b) else torch.as_tensor(np.asarray(b)).double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def make(kind, seed=11, **hyper):
+    from ddrl4nav_b200.runner import make_net
+    spec = R.SPECS[kind]
+    params = R.init_params(spec, seed=seed)
+    net = make_net(kind, device=None, gemm_mode=GEMM_MODE, **hyper)
+    missing = net.load_state_dict(params, strict=True)
+    return net.to(DEV), spec, params
+
+
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4)])
+def test_forward_matches_golden_and_oracle(golden_dir, kind, B):
+    g = np.load(os.path.join(golden_dir, f"net_{kind}.npz"))
+    net, spec, params = make(kind)
+    assert [n for n, _ in net.named_parameters()] == list(g["names"])
+    states = R.synth_states(kind, B, seed=5)
+    dstates = [s.to(DEV) for s in states]
+    act = torch.from_numpy(g["act"])
+    (pi, logp), values = net(dstates, act.to(DEV))
+    assert values[0].shape == (B, 1)
+    assert rel_err(torch.stack(values, 0), g["values"]) < 1e-5
+    if spec.dist == "categorical":
+        assert rel_err(pi.probs, g["probs"]) < 1e-5
+        (praw, _), _ = net(dstates, play_mode=True)
+        assert rel_err(praw, g["probs_raw"]) < 1e-5
+        assert rel_err(pi.entropy(), g["entropy"]) < 1e-5
+    else:
+        assert rel_err(pi.loc, g["mu"]) < 1e-5
+        assert rel_err(pi.scale, g["std"]) < 1e-6
+    assert rel_err(logp, g["logp"]) < 2e-5
+
+
+@pytest.mark.parametrize("kind,B", [("pong", 33), ("navimg", 9), ("navlaser", 5), ("pong", 1)])
+def test_act_matches_oracle(kind, B):
+    net, spec, params = make(kind)
+    states = R.synth_states(kind, B, seed=21)
+    gen = torch.Generator().manual_seed(4)
+    draw = torch.rand(B, generator=gen) if spec.dist == "categorical" else torch.randn(B, spec.act_dim, generator=gen)
+    ra, rlp, rv = R.forward_body(spec, params, states, draw)
+    a, lp, v, pi = net.act([s.to(DEV) for s in states], draw=draw.to(DEV), want_pi=True)
+    assert v.shape == (1, B, 1) and rel_err(v, rv) < 1e-5
+    if spec.dist == "categorical":
+        # bit-exact given the kernel's probs; vs the oracle's probs at most a rare boundary flip
+        own = R.sample_categorical(pi.cpu().numpy(), draw.numpy())
+        assert np.array_equal(a.cpu().numpy().astype(np.int64), own)
+        same = (a.cpu() == ra)
+        assert same.float().mean() >= 1 - 2.0 / max(B, 1) - 1e-9
+        assert rel_err(lp.cpu()[same], rlp[same]) < 2e-5
+    else:
+        assert rel_err(a, ra) < 1e-5 and rel_err(lp, rlp) < 2e-5
+    # play mode
+    pa, plp, pv = R.forward_body(spec, params, states, None, play_mode=True)
+    a, lp, v = net.act([s.to(DEV) for s in states], play_mode=True)
+    assert float(lp.abs().max()) == 0.0
+    if spec.dist == "categorical":
+        assert (a.cpu() == pa).float().mean() >= 1 - 1.0 / max(B, 1) - 1e-9
+    else:
+        assert rel_err(a, pa) < 1e-5
+
+
+def _learn_case(kind, B, seed=9):
+    spec = R.SPECS[kind]
+    params = R.init_params(spec, seed=11)
+    states = R.synth_states(kind, B, seed=5)
+    a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=seed)
+    return spec, params, states, a, old, adv, ret
+
+
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("pong", 40)])
+def test_backward_grads_match_oracle(kind, B):
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    st = R.LearnState(spec, params)
+    losses, raw, norm = R.learn_iteration(st, states, adv, a, old, ret, R.PPOHyper(), apply_update=False)
+    net, _, _ = make(kind)
+    net.backward_only([s.to(DEV) for s in states], adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    grads = net.named_grads()
+    worst = 0.0
+    for n, gref in raw.items():
+        e = rel_err(grads[n], gref) if float(gref.abs().max()) > 0 else float(grads[n].abs().max())
+        worst = max(worst, e)
+        assert e < 2e-5, (n, e)
+    sums = net._grads[net._P:net._P + 3].cpu().numpy()
+    assert np.allclose(sums, [losses["ActorLoss"], losses["VLoss"], losses["EntLoss"]], rtol=1e-5, atol=1e-6)
+    print(kind, B, "worst grad err / max|g| = %.2e" % worst)
+
+
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4)])
+def test_learn_matches_golden(golden_dir, kind, B):
+    g = np.load(os.path.join(golden_dir, f"net_{kind}.npz"))
+    from ddrl4nav_b200.data import Experience
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    assert np.array_equal(a.numpy(), g["learn_actions"])
+    net, _, _ = make(kind, TRAINING_ITER_TIME=1)
+    exp = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                     values=ret.numpy()[None])
+    exp.to_tensor(device=DEV)
+    out = list(net.learn(exp))
+    assert len(out) == 1 and out[0][1] == 1 and out[0][2] is True
+    l = out[0][0]
+    assert set(l) == {"PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss", "PpoBackUpTime"}
+    assert np.allclose([l["PpoTotalLoss"], l["ActorLoss"], l["VLoss"], l["EntLoss"]], g["losses"][0], rtol=1e-5, atol=1e-6)
+    # Adam deltas against the reference (step 1 is ~lr*sign(g): allow a tiny fraction of sign flips on noise-level grads)
+    sd = net.state_dict()
+    for i, n in enumerate(g["names"]):
+        d = (sd[n].cpu() - params[n]).flatten()
+        d = (d if d.numel() <= 4096 else d[::997]).numpy()
+        bad = ~np.isclose(d, g[f"delta_sample_{i}"], rtol=1e-3, atol=2e-7)
+        assert bad.mean() < 5e-3, (n, bad.mean())
+    # trajectory (loose, chaotic): 3 more iterations
+    net2, _, _ = make(kind, TRAINING_ITER_TIME=g["losses_traj"].shape[0])
+    traj = [[x["PpoTotalLoss"], x["ActorLoss"], x["VLoss"], x["EntLoss"]] for x, _, _ in net2.learn(exp)]
+    assert np.allclose(np.array(traj), g["losses_traj"], rtol=5e-3, atol=5e-4)
+    assert net2.update_time == g["losses_traj"].shape[0]
+
+
+def test_micro_batching_equals_single_shot(monkeypatch):
+    spec, params, states, a, old, adv, ret = _learn_case("pong", 21)
+    net, _, _ = make("pong")
+    ds = [s.to(DEV) for s in states]
+    net.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    g_full = net.flat_grads().clone()
+    monkeypatch.setenv("DDRL_MICRO_BATCH", "4")
+    net2, _, _ = make("pong")
+    net2.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    assert rel_err(net2.flat_grads(), g_full) < 5e-6
+    a1, l1, v1 = net.act(ds, play_mode=True)
+    a2, l2, v2 = net2.act(ds, play_mode=True)
+    assert torch.equal(a1, a2) and rel_err(v2, v1) < 1e-6
+
+
+def test_shard_sum_equals_full_batch():
+    """Data-parallel arithmetic on one GPU: two half-batches scaled by 1/B_global sum to the full-batch gradient."""
+    spec, params, states, a, old, adv, ret = _learn_case("pong", 16)
+    net, _, _ = make("pong")
+    ds = [s.to(DEV) for s in states]
+    f = lambda t: t.to(DEV)
+    net.backward_only(ds, f(adv), f(a), f(old), f(ret))
+    full = net._grads.clone()
+    net.backward_only([ds[0][:8]], f(adv[:8]), f(a[:8]), f(old[:8]), f(ret[:8]), b_global=16)
+    half = net._grads.clone()
+    net.backward_only([ds[0][8:]], f(adv[8:]), f(a[8:]), f(old[8:]), f(ret[8:]), b_global=16)
+    half += net._grads
+    assert rel_err(half[:net._P], full[:net._P]) < 5e-6
+    assert torch.allclose(half[net._P:net._P + 3], full[net._P:net._P + 3], rtol=1e-5, atol=1e-7)
+
+
+def test_state_dict_and_model_blob_roundtrip():
+    net, spec, params = make("navlaser")
+    net._ensure_engine()
+    sd = net.state_dict()
+    assert list(sd.keys()) == [n for n, _ in R.param_table(spec)]
+    for n in sd:
+        assert torch.equal(sd[n].cpu(), params[n])
+    blob = net.model_bytes()
+    import struct
+    expect = b"".join(struct.pack(">I", p.dim()) + struct.pack(">%dI" % p.dim(), *p.shape) + p.numpy().tobytes()
+                      for p in params.values())        # nn/base.py:38-45 format
+    assert blob == expect
+    net2, _, _ = make("navlaser", seed=3)
+    states = R.synth_states("navlaser", 3, seed=1)
+    ds = [s.to(DEV) for s in states]
+    before = net2.act(ds, play_mode=True)[2].clone()
+    net2.load_model_bytes(blob)                       # updatenn_by_redis path
+    after = net2.act(ds, play_mode=True)[2]
+    ref = net.act(ds, play_mode=True)[2]
+    assert not torch.equal(before, after) and torch.equal(after, ref)
+
+
+def test_cpu_module_fails_loudly():
+    from ddrl4nav_b200 import DDRLError
+    from ddrl4nav_b200.runner import make_net
+    net = make_net("pong", device=None)
+    with pytest.raises(DDRLError):
+        net.act([torch.zeros(1, 4, 84, 84)])
+
+
+def test_gae_dropin_on_experiences():
+    from types import SimpleNamespace
+    from ddrl4nav_b200.agent import accumulate_rewards
+    from ddrl4nav_b200.data import Experience
+    rng = np.random.default_rng(0)
+    T, V, N = 40, 1, 6
+    values = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+    rewards = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+    dones = (rng.random((T + 1, V, N)) < 0.1).astype(np.uint8)
+    gam = np.array([[0.99]], dtype=np.float32)
+    exps = [Experience(states=[np.zeros((N, 1))], values=values[t].copy(), dones=dones[t].copy()) for t in range(T + 1)]
+    out = accumulate_rewards(SimpleNamespace(discounts=gam, landa=0.95, model_dtype=np.float32), exps, rewards.copy())
+    ref_ret, ref_adv = R.gae(values, dones, rewards, gam, 0.95)
+    assert len(out) == T
+    assert np.allclose(np.stack([e.values for e in out]), ref_ret, rtol=1e-5, atol=1e-5)
+    assert np.allclose(np.stack([e.advs for e in out]), ref_adv, rtol=1e-5, atol=1e-5)
+    assert accumulate_rewards(SimpleNamespace(), [], rewards) == []
