@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the DDRL4NAV actor-learner hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pong|navlaser|navimg] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one Backward-module learn call on one batch = TRAINING_ITER_TIME (10) full-batch PPO
+iterations (forward + fused loss + backward + [NCCL all-reduce] + fused clip+Adam), exactly what
+BackwardTrainThread does per batch (USTC_lab/server/backward.py:182-189, nn/ppo.py:77-142).
+value   = learner sample-iterations/s over all ranks, inputs resident in HBM (metric of BASELINE.json).
+e2e     = the same through the public API (BackwardModule.train_on) from PINNED HOST buffers: H2D of the
+          batch and D2H of the losses inside the timed region, every step.
+extra   = Forward-module actions/s (PPO.act), GAE elements/s, per-kernel-class device time.
+--impl reference = the reference's CPU path (oracle port, torch CPU, all host threads), rank 0 only.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "PPO learner samples/s & batched policy actions/s at 1/2/4/8 B200"
+
+# per-GPU batch of the named BASELINE.json configs (weak scaling: fixed per GPU)
+WORKLOADS = {
+    # C4 = "8xB200 data-parallel learner: Pong PPO batch 64k, minibatch sharded" -> 8192 rows per GPU
+    "pong": dict(batch=8192, fwd_batch=32768, cpu_batch=1024, desc="Pong PPO learner, NatureCNN 4x84x84, unshared towers, "
+                 "6-way categorical (BASELINE C1/C4: 64k batch at 8 GPUs = 8192 rows/GPU)",
+                 flops_fwd=37.37e6, flops_learn=99.0e6, obs_bytes=112896),
+    # C2 = "robot-nav PPO: laser-scan + goal/vel vector, Gaussian policy" (reference shapes: 1x960 + 5 + 3x48x48)
+    "navlaser": dict(batch=1024, fwd_batch=4096, cpu_batch=128, desc="robot-nav PPO learner, NavPreNet1D laser 1x960 + vec5 + "
+                     "ped-map 3x48x48, unshared towers, 2-d Gaussian (BASELINE C2)",
+                     flops_fwd=545.3e6, flops_learn=1562.6e6, obs_bytes=31508),
+    # C5 = "nav image-env PPO (1x48x48 egocentric map), shared encoder, 28-way categorical"
+    "navimg": dict(batch=2048, fwd_batch=8192, cpu_batch=256, desc="nav image-env PPO learner, NavPreNet 1x48x48 + vec9, shared "
+                   "encoder, 28-way categorical (BASELINE C5)",
+                   flops_fwd=183.0e6, flops_learn=546.4e6, obs_bytes=9252),
+}
+ITERS = 10          # TRAINING_ITER_TIME, config/config_nn.py:45
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.index = index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synth_batch_host(kind, B, seed):
+    """Synthetic rollouts of the named observation shape, as pinned host fp32 arrays."""
+    from oracle.restate import synth_states
+    states = synth_states(kind, B, seed=seed)
+    g = torch.Generator().manual_seed(seed + 17)
+    adv = torch.randn(B, generator=g)
+    ret = torch.randn(B, generator=g)
+    return states, adv, ret
+
+
+def timed(fn, steps, warmup, dist=None):
+    """W warm-up + K timed calls bracketed by barrier + synchronize; device time by CUDA events on the current
+    stream; returns max-over-ranks seconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sec = e0.elapsed_time(e1) / 1e3
+    if dist is not None:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+def run_ours(args):
+    import ctypes as C
+    from ddrl4nav_b200 import _lib, kernels
+    from ddrl4nav_b200.data import Experience
+    from ddrl4nav_b200.runner import make_net
+    from ddrl4nav_b200.server import BackwardModule, ForwardModule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    peaks = load_peaks()
+    lib = _lib.load()
+
+    net = make_net(args.workload, device=dev, gemm_mode=args.gemm_mode, TRAINING_ITER_TIME=ITERS)
+    if dist is not None:
+        net.enable_data_parallel()
+        net.broadcast_parameters(0)
+    # ---- synthetic rollout shard of this rank (different rows per rank), host + device copies
+    states_h, adv_h, ret_h = synth_batch_host(args.workload, B, seed=100 + rank)
+    states_d = [s.to(dev) for s in states_h]
+    with torch.no_grad():
+        acts_d, logp_d, _ = net.act(states_d)                 # actions sampled from the net
+    old_d = logp_d + 0.15 * torch.randn(B, device=dev)
+    exp_dev = Experience(states=states_d, advs=adv_h.to(dev), actions=acts_d, old_logps=old_d, values=ret_h.to(dev)[None])
+    pin = lambda t: t.contiguous().pin_memory()
+    host_fields = dict(states=[pin(s) for s in states_h], advs=pin(adv_h), actions=pin(acts_d.cpu()),
+                       old_logps=pin(old_d.cpu()), values=pin(ret_h[None]))
+    h2d_bytes = sum(t.numel() * 4 for t in host_fields["states"]) + sum(
+        host_fields[k].numel() * 4 for k in ("advs", "actions", "old_logps", "values"))
+
+    # ---- headline: K learn calls, inputs resident in HBM
+    last_losses = {}
+
+    def step_resident():
+        for loss, upd, last in net.learn(exp_dev):
+            last_losses.update(loss)
+
+    sampler = ClockSampler(local)
+    kernels.launch_count_reset()
+    for _ in range(args.warmup):
+        step_resident()
+    kernels.launch_count_reset()
+    sampler.start()
+    sec = timed(step_resident, args.steps, 0, dist)
+    launches = kernels.launch_count()
+    clocks = sampler.stop()
+    value = world * B * ITERS * args.steps / sec
+
+    # ---- e2e: same metric through BackwardModule.train_on from pinned host buffers (H2D + D2H per step)
+    bm = BackwardModule(net, device=dev)
+
+    def step_e2e():
+        exp = Experience(states=list(host_fields["states"]), advs=host_fields["advs"], actions=host_fields["actions"],
+                         old_logps=host_fields["old_logps"], values=host_fields["values"])
+        logs = bm.train_on(exp)                            # H2D of the batch; 10 iterations; 16-byte D2H of the losses each
+        return logs
+
+    sec_e2e = timed(step_e2e, max(2, args.steps // 2), 1, dist)
+    e2e_value = world * B * ITERS * max(2, args.steps // 2) / sec_e2e
+
+    # ---- per-kernel-class device time of ONE learn call (separate pass: events after every launch)
+    prof = {}
+    torch.cuda.synchronize()
+    lib.ddrl_prof_start(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    step_resident()
+    buf = C.create_string_buffer(1 << 16)
+    lib.ddrl_prof_stop(buf, len(buf))
+    for line in buf.value.decode().splitlines():
+        name, ms, n, work = line.split()
+        prof[name] = dict(ms=float(ms), launches=int(n), work=float(work))
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    gemm_names = [k for k in prof if "gemm" in k]
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    if dom in gemm_names:
+        ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e12
+        roof = dict(bound="tensor", kernel=dom, achieved=round(ach, 2), peak=peaks["tensor_sustained"], unit="TFLOP/s",
+                    frac=round(ach / peaks["tensor_sustained"], 4), traffic=None,
+                    peak_note="bf16 cuBLAS sustained, of %s (no TF32/FP32 peak is in MEASURED_PEAKS.json)" % peaks["src"],
+                    share_of_step=round(prof[dom]["ms"] / tot_ms, 3), avg_launch_ms=round(prof[dom]["ms"] / prof[dom]["launches"], 4))
+    else:
+        ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e9
+        roof = dict(bound="hbm", kernel=dom, achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s",
+                    frac=round(ach / peaks["hbm"], 4), traffic=None, share_of_step=round(prof[dom]["ms"] / tot_ms, 3),
+                    avg_launch_ms=round(prof[dom]["ms"] / prof[dom]["launches"], 4))
+    kernel_shares = {k: round(v["ms"] / tot_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- Forward module: actions/s (resident) and e2e (ForwardModule.step from host arrays)
+    Bf = args.fwd_batch or wl["fwd_batch"]
+    fstates_h, _, _ = synth_batch_host(args.workload, Bf, seed=200 + rank)
+    fstates_d = [s.to(dev) for s in fstates_h]
+    sec_f = timed(lambda: net.act(fstates_d), 5, 3, dist)
+    fwd_value = world * Bf * 5 / sec_f
+    fm = ForwardModule(net, device=dev)
+    f_np = [s.numpy() for s in fstates_h]
+    sec_fe = timed(lambda: fm.step(f_np), 3, 2, dist)
+    fwd_e2e = world * Bf * 3 / sec_fe
+
+    # ---- GAE: BASELINE C3 corner 64k envs x T=2048 (2.28 GB algorithmic traffic), columns sharded over ranks
+    T, N = 2048, 65536
+    gv = torch.randn(T + 1, 1, N, device=dev)
+    gr = torch.randn(T, 1, N, device=dev)
+    gd = (torch.rand(T, 1, N, device=dev) < 0.02).to(torch.uint8)
+    sec_g = timed(lambda: kernels.gae(gv, gr, gd, [0.99], 0.95), 10, 3, dist)
+    gae_elems = world * T * N * 10 / sec_g
+    gae_gbs = 17.0 * T * N * 10 / sec_g / 1e9          # per GPU
+    del gv, gr, gd
+
+    # ---- CPU baseline beside it (rank 0 only, N=1 only): the oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(args.workload, wl["cpu_batch"], iters=2, warm=1)
+
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "learner sample-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.gemm_mode == "simt" else "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B * world, "iters_per_step": ITERS,
+                       "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode,
+                       "l2": "inputs larger than L2 (%.0f MB observations per GPU)" % (B * wl["obs_bytes"] / 1e6)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "learner sample-iterations/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 16 * ITERS},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_time_shares": kernel_shares,
+            "learner_tflops": round(value * wl["flops_learn"] / 1e12, 2),
+            "forward": {"value": round(fwd_value, 1), "unit": "actions/s", "rows_per_gpu": Bf,
+                        "e2e": round(fwd_e2e, 1), "tflops": round(fwd_value * wl["flops_fwd"] / 1e12, 2)},
+            "gae": {"value": round(gae_elems, 1), "unit": "(t*env) elements/s", "shape": "T=2048 x N=65536 per GPU",
+                    "roofline": {"bound": "hbm", "achieved": round(gae_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": round(gae_gbs / peaks["hbm"], 4)}},
+            "losses_last": {k: round(float(v), 6) for k, v in last_losses.items() if k != "PpoBackUpTime"},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_reference(kind, B, iters, warm):
+    """The reference's CPU path for the learner step (oracle port: same torch ops as nn/ppo.py:79-129) on all host
+    cores.  Returns the cpu_baseline object."""
+    from oracle import restate as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = R.SPECS[kind]
+    params = R.init_params(spec, seed=1)
+    states = R.synth_states(kind, B, seed=2)
+    a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=3)
+    st = R.LearnState(spec, params)
+    hp = R.PPOHyper()
+    for _ in range(warm):
+        R.learn_iteration(st, states, adv, a, old, ret, hp)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        R.learn_iteration(st, states, adv, a, old, ret, hp)
+    dt = time.perf_counter() - t0
+    return {"value": round(B * iters / dt, 1), "unit": "learner sample-iterations/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": "%d full-batch iterations of B=%d (%s), torch %s CPU" % (iters, B, kind, torch.__version__)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the learner step (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import restate as R
+    wl = WORKLOADS[args.workload]
+    B = wl["cpu_batch"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = R.SPECS[args.workload]
+    params = R.init_params(spec, seed=1)
+    states = R.synth_states(args.workload, B, seed=2)
+    a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=3)
+    st = R.LearnState(spec, params)
+    hp = R.PPOHyper()
+    for _ in range(args.warmup):
+        R.learn_iteration(st, states, adv, a, old, ret, hp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.learn_iteration(st, states, adv, a, old, ret, hp)
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    sample = "each step = ONE full-batch iteration of B=%d rows (bounded sample of the %d-row x %d-iteration step)" % (
+        B, wl["batch"], ITERS)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "learner sample-iterations/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "rows_per_step": B, "device": "cpu"},
+            "cpu_baseline": {"value": round(value, 1), "unit": "learner sample-iterations/s", "cores": torch.get_num_threads(),
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": "learner sample-iterations/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("DDRL_BENCH_WORKLOAD", "pong"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--fwd-batch", dest="fwd_batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            import subprocess
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+            sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ SIGNATURES = {
     "ddrl_last_cuda_error": (C.c_char_p, []),
     "ddrl_launch_count": (_L, []),
     "ddrl_launch_count_reset": (None, []),
+    "ddrl_prof_start": (_I, [_P]),
+    "ddrl_prof_stop": (_I, [C.c_char_p, _I]),
     "ddrl_gae_f32": (_I, [_P, _P, _P, C.POINTER(_F), _F, _I, _I, _I, _P, _P, _I, _P]),
     "ddrl_sample_categorical_probs": (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     "ddrl_categorical_head": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),

@@ -125,9 +125,11 @@ int clip_adam_launch(float* params, const float* grads, float* m, float* v, long
   DDRL_CUDA(cudaMemsetAsync(g_sumsq, 0, sizeof(double), s));
   const int blocks = (int)std::min<long long>(ceil_div64(n, 256 * 4), 4 * kNumSMs);
   sumsq_kernel<<<blocks, 256, 0, s>>>(grads, n, g_sumsq);
+  prof_work(4.0 * n);
   DDRL_LAUNCHED("sumsq_kernel");
   const int blocks2 = (int)std::min<long long>(ceil_div64(n, 256 * 4), 8 * kNumSMs);
   clip_adam_kernel<<<blocks2, 256, 0, s>>>(params, grads, m, v, n, segs, sc, g_sumsq, norm_out);
+  prof_work(28.0 * n);
   DDRL_LAUNCHED("clip_adam_kernel");
   return DDRL_OK;
 }

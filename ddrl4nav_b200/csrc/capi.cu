@@ -1,10 +1,37 @@
 // Library-level entry points of the C ABI (include/ddrl_b200.h).
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "layer_ops.h"
 
 namespace ddrl {
 thread_local char g_cuda_err[256] = {0};
 long long g_launches = 0;
+
+// ---- per-kernel-class device timing ------------------------------------------------------
+bool g_prof_on = false;
+double g_prof_work = 0.0;
+static cudaStream_t g_prof_stream = nullptr;
+struct ProfRec { cudaEvent_t ev; const char* name; double work; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+
+void prof_record(const char* name) {
+  ProfRec r{prof_event(), name, g_prof_work};
+  g_prof_work = 0.0;
+  cudaEventRecord(r.ev, g_prof_stream);
+  g_prof_recs.push_back(r);
+}
 }  // namespace ddrl
 
 extern "C" int ddrl_version(void) { return 100; }
@@ -24,6 +51,40 @@ extern "C" const char* ddrl_error_string(int code) {
 extern "C" const char* ddrl_last_cuda_error(void) { return ddrl::g_cuda_err; }
 extern "C" int64_t ddrl_launch_count(void) { return ddrl::g_launches; }
 extern "C" void ddrl_launch_count_reset(void) { ddrl::g_launches = 0; }
+
+extern "C" int ddrl_prof_start(void* stream) {
+  using namespace ddrl;
+  for (auto& r : g_prof_recs) g_prof_pool.push_back(r.ev);
+  g_prof_recs.clear();
+  g_prof_stream = (cudaStream_t)stream;
+  g_prof_on = true;
+  prof_record("__start__");
+  return DDRL_OK;
+}
+
+// Writes "name ms launches work\n" lines (work = sum of the algorithmic flops/bytes the launchers declared).
+extern "C" int ddrl_prof_stop(char* out, int cap) {
+  using namespace ddrl;
+  g_prof_on = false;
+  if (g_prof_recs.empty()) return DDRL_E_STATE;
+  DDRL_CUDA(cudaEventSynchronize(g_prof_recs.back().ev));
+  struct Acc { double ms = 0, work = 0; long n = 0; };
+  std::map<std::string, Acc> acc;
+  for (size_t i = 1; i < g_prof_recs.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof_recs[i - 1].ev, g_prof_recs[i].ev);
+    Acc& a = acc[g_prof_recs[i].name];
+    a.ms += ms; a.work += g_prof_recs[i].work; a.n += 1;
+  }
+  std::string s;
+  char line[256];
+  for (auto& kv : acc) {
+    snprintf(line, sizeof(line), "%s %.6f %ld %.6e\n", kv.first.c_str(), kv.second.ms, kv.second.n, kv.second.work);
+    s += line;
+  }
+  if (out && cap > 0) { strncpy(out, s.c_str(), cap - 1); out[cap - 1] = 0; }
+  return DDRL_OK;
+}
 
 extern "C" int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                              float* C, int ldc, const float* bias, int act, int beta, void* stream) {

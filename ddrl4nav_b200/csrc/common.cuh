@@ -24,12 +24,20 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     if (_e != cudaSuccess) return ::ddrl::cuda_fail(_e, #call); \
   } while (0)
 
+// Optional per-kernel-class device timing (ddrl_prof_start/stop, capi.cu): one event after every launch;
+// with the stream kept busy the gap between consecutive events is the kernel's duration.
+extern bool g_prof_on;
+extern double g_prof_work;      // algorithmic work (flops or bytes) of the NEXT recorded launch
+void prof_record(const char* name);
+inline void prof_work(double w) { if (g_prof_on) g_prof_work = w; }
+
 // after a <<<>>> launch: count it and surface launch-configuration errors
 #define DDRL_LAUNCHED(name)                                       \
   do {                                                            \
     ::ddrl::g_launches++;                                         \
     cudaError_t _e = cudaGetLastError();                          \
     if (_e != cudaSuccess) return ::ddrl::cuda_fail(_e, name);    \
+    if (::ddrl::g_prof_on) ::ddrl::prof_record(name);             \
   } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

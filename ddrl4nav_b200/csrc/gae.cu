@@ -172,6 +172,7 @@ extern "C" int ddrl_gae_f32(const float* values, const float* rewards, const uin
   if (algo == 1) {
     const int threads = 128;
     gae_seq_kernel<8><<<ceil_div(C, threads), threads, 0, s>>>(values, rewards, dones, gam, lambda, T, N, C, ret, adv);
+    prof_work(17.0 * T * (double)C);
     DDRL_LAUNCHED("gae_seq_kernel");
   } else if (algo == 2) {
     int CH = 32;
@@ -182,6 +183,7 @@ extern "C" int ddrl_gae_f32(const float* values, const float* rewards, const uin
     dim3 block(COLS, CH);
     const size_t smem = 2 * sizeof(float) * COLS * CH;
     gae_chunked_kernel<<<ceil_div(C, COLS), block, smem, s>>>(values, rewards, dones, gam, lambda, T, N, C, ret, adv);
+    prof_work(17.0 * T * (double)C);
     DDRL_LAUNCHED("gae_chunked_kernel");
   } else {
     return DDRL_E_ARG;

@@ -219,6 +219,7 @@ static int launch_bn(const GemmArgs& g, int form, bool vec, dim3 grid, cudaStrea
   } else {
     sgemm_kernel<BN, 2, 2><<<grid, 256, 0, s>>>(g);
   }
+  prof_work(2.0 * g.M * (double)g.N * g.K);
   DDRL_LAUNCHED("sgemm_kernel");
   return DDRL_OK;
 }

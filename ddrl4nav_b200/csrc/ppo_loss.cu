@@ -193,6 +193,7 @@ extern "C" int ddrl_ppo_loss_categorical(const float* logits, int ld, const floa
   ppo_loss_categorical_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
       logits, ld, actions, old_logp, adv, returns, v, B, A, make_params(hp, inv_B_global, shared), dlogits, ld_d, dv,
       loss_sums);
+  prof_work((8.0 * A + 24.0) * B);
   DDRL_LAUNCHED("ppo_loss_categorical_kernel");
   return DDRL_OK;
 }
@@ -208,6 +209,7 @@ extern "C" int ddrl_ppo_loss_gaussian(const float* mu, int ld, const float* log_
   ppo_loss_gaussian_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
       mu, ld, log_std, actions, old_logp, adv, returns, v, B, A, make_params(hp, inv_B_global, shared), dmu, ld_d, dv,
       dlog_std, loss_sums);
+  prof_work((12.0 * A + 20.0) * B);
   DDRL_LAUNCHED("ppo_loss_gaussian_kernel");
   return DDRL_OK;
 }

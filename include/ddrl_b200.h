@@ -76,6 +76,11 @@ const char* ddrl_last_cuda_error(void);
 /* number of kernels this library has launched since load / since reset (bench gpu_launches) */
 int64_t ddrl_launch_count(void);
 void ddrl_launch_count_reset(void);
+/* per-kernel-class device timing for bench.py's roofline line: between start and stop every launch
+ * on `stream` is followed by a CUDA event; stop writes "kernel_name ms launches work\n" lines
+ * (work = algorithmic flops for GEMMs, bytes for the streaming kernels that declare them). */
+int ddrl_prof_start(void* stream);
+int ddrl_prof_stop(char* out, int cap);
 
 /* ---- K5: GAE / discounted return scan -------------------------------------------------
  * replaces Agents._accumulate_rewards (USTC_lab/agent/agent.py:124-140).

@@ -265,11 +265,16 @@ def test_clip_adam_vs_torch(n, nseg):
         for o in opts:
             o.step()
         norm = kernels.clip_adam(p, grad.to(DEV), m, v, segs, lrs, step, hp)
-        assert abs(float(norm) - float(total)) <= 2e-6 * float(total)
+        # the kernel accumulates the sum of squares in fp64: tight vs the exact norm; torch's fp32 CPU
+        # reduction itself carries ~3e-5 relative error on 3.4 M elements, so only 1e-4 vs it
+        assert abs(float(norm) - float(grad.double().norm())) <= 1e-6 * float(total)
+        assert abs(float(norm) - float(total)) <= 1e-4 * float(total)
         refp = torch.cat([r.detach() for r in ref])
         d_ref = (refp - p0).double()
         d = (p.cpu() - p0).double()
-        assert float((d - d_ref).abs().max()) <= 1e-5 * float(d_ref.abs().max()) + 1e-9
+        # p itself is fp32: the update is only resolved to ~1 ulp(p) = 1.2e-7 * |p|
+        tol = 1e-5 * float(d_ref.abs().max()) + 2.4e-7 * (1.0 + p0.abs().double())
+        assert bool(((d - d_ref).abs() <= tol).all())
 
 
 # ------------------------------------------------------------------ GEMM
