@@ -1,11 +1,430 @@
-// tcgen05 3xTF32 GEMM engine -- placeholder until the kernel lands (reports "unsupported" so the
-// engine stays on the fp32 SIMT path; nothing is emulated or faked).
+// tcgen05 GEMM engine, fp32 in / fp32 out, 3xTF32 split ("parity mode", DDRL_GEMM_TC_3XTF32).
+//
+// Every Linear / Conv (as GEMM) of the reference encoders runs fp32 on the CPU (nn/atari_encoder.py,
+// nn/nav_encoder.py, autograd for backward).  A single TF32 pass (10-bit mantissa) cannot meet the 1e-5
+// parity target, so each fp32 operand x is split ON CHIP into hi = rn_tf32(x), lo = rn_tf32(x - hi) and the
+// product is accumulated as lo*hi + hi*lo + hi*hi in an fp32 TMEM accumulator (error ~2^-22 per product,
+// unbiased) -- three tcgen05.mma.kind::tf32 per K-step.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, optional split-K over grid.z):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B-swizzled) of raw fp32 A and B into a smem ring
+//   warps 4-11  splitters: rewrite each landed tile in place as hi and write lo to its twin buffer
+//               (element-wise, so the swizzled layout is preserved), fence.proxy.async, signal
+//   warp 1      MMA issuer: one elected thread issues 3 x (BK/8) tcgen05.mma per stage, tcgen05.commit frees
+//               the stage; final commit publishes the accumulator
+//   warps 4-11  epilogue: tcgen05.ld the accumulator (TMEM lane = output row), bias + activation, store
+//               (plain / transposed / atomic for split-K and gradient accumulation)
+//   warp 2      TMEM allocator
+// Operand forms (same as gemm_simt.cu): K-major operands use one TMA box [rows x 32 floats]; MN-major
+// operands (weight-gradient and data-gradient GEMMs) use 32x32 boxes with the 128B/32B-atom TMA swizzle so that
+// the shared-memory image is the canonical UMMA MN-major SWIZZLE_128B_BASE32B layout (LBO = 4096 B between
+// 32-wide groups, SBO = 512 B between 4-deep K groups).  Out-of-range rows/columns/K are zero-filled by TMA.
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "layer_ops.h"
 
 namespace ddrl {
-bool gemm_tc_supported(int, int, int, int, const float*, int, const float*, int, const float*, int, int) { return false; }
-int gemm_tc(int, int, int, int, const float*, int, const float*, int, float*, int, const float*, int, int, int, cudaStream_t) {
-  return DDRL_E_UNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                     // floats per stage along K (= 128 B = one swizzle row)
+constexpr int TC_THREADS = 384;
+constexpr int TC_SPLIT_WARPS = 8;
+
+struct TcArgs {
+  float* C;
+  const float* bias;
+  long long sCm, sCn;
+  int M, N, K;
+  int kb_per_split;                            // K blocks (of 32) per grid.z slice
+  int act, atomic;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout type [61,64): SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only layout the hardware
+// accepts for MN-major 32-bit operands: 128 B rows, 32 B swizzle atoms, pattern period 4 rows)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// The tensor core adds into its fp32 accumulator with TRUNCATION (measured on B200: all-positive tf32-exact
+// inputs lose ~1 ulp per accumulating MMA, -7e-6 relative after 128 MMAs).  To stay at fp32-FFMA accuracy the
+// main hi*hi product is accumulated in TMEM only over TC_CHUNK stages (K = 128, 16 MMAs), then drained and added
+// with round-to-nearest into fp32 registers of the splitter warps (two TMEM buffers, so the MMA pipe never waits);
+// the small lo*hi + hi*lo terms go to a third TMEM accumulator whose truncation is 2^-11 smaller.
+constexpr int TC_CHUNK = 4;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int BNS = (BN + 31) / 32 * 32;                // smem rows of the B tile
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
+  static constexpr int B_BYTES = BNS * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);    // hi(raw) + lo for A and B
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 128 : (BN <= 64 ? 256 : 512);   // main0 | main1 | corr
+  static constexpr int COLS = BN / 2;                            // accumulator columns held by one splitter warp
+};
+
+// barrier slots: [0,S) full (TMA landed)  [S,2S) split done  [2S,3S) empty (MMA consumed)
+//                [3S,3S+2) accumulator buffer ready  [3S+2,3S+4) accumulator buffer drained
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int kb_total = (g.K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(kb_total, kb0 + g.kb_per_split);
+  const int nkb = kb1 - kb0;
+  const int nchunks = (nkb + TC_CHUNK - 1) / TC_CHUNK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(bars + s), 1);
+      mbar_init(smem_u32(bars + S + s), TC_SPLIT_WARPS);
+      mbar_init(smem_u32(bars + 2 * S + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(bars + 3 * S + b), 1);
+      mbar_init(smem_u32(bars + 3 * S + 2 + b), TC_SPLIT_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(smem_u32(bars + 2 * S + s), ph ^ 1);
+        const uint32_t full = smem_u32(bars + s);
+        mbar_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const uint32_t a_dst = smem_u32(st), b_dst = smem_u32(st + 2 * Cfg::A_BYTES);
+        const int k = (kb0 + i) * TC_BK;
+        if (!A_MN) {
+          tma_load_2d(&tmA, full, a_dst, k, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(&tmA, full, a_dst + j * 4096, m0 + j * 32, k);
+        }
+        if (!B_MN) {
+          tma_load_2d(&tmB, full, b_dst, k, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * 4096, n0 + j * 32, k);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major bit15, b_major bit16,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t tmem_corr = tmem_base + 2 * BN;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (i / S) & 1;
+      const int c = i / TC_CHUNK, buf = c & 1;
+      const bool first_in_chunk = (i % TC_CHUNK) == 0;
+      if (first_in_chunk) mbar_wait(smem_u32(bars + 3 * S + 2 + buf), ((c >> 1) & 1) ^ 1);   // buffer drained
+      mbar_wait(smem_u32(bars + S + s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t b_hi = smem_u32(st + 2 * Cfg::A_BYTES), b_lo = b_hi + Cfg::B_BYTES;
+        // MN-major: 32-wide groups 4096 B apart (LBO), 4-deep K groups 512 B apart (SBO); K-major: 8-row groups 1024 B apart
+        const uint32_t lbo = 4096;
+        const uint32_t tmem_main = tmem_base + buf * BN;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_base = pass == 0 ? a_lo : a_hi;      // lo*hi, hi*lo -> corr ; hi*hi -> main[buf]
+          const uint32_t b_base = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+            const uint64_t da = umma_desc(a_base + (A_MN ? k4 * 1024 : k4 * 32), A_MN ? lbo : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+            const uint64_t db = umma_desc(b_base + (B_MN ? k4 * 1024 : k4 * 32), B_MN ? lbo : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
+            if (pass < 2) umma_tf32(tmem_corr, da, db, idesc, (i | pass | k4) != 0 ? 1u : 0u);
+            else umma_tf32(tmem_main, da, db, idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(bars + 2 * S + s));                 // stage reusable once these MMAs retire
+        if ((i % TC_CHUNK) == TC_CHUNK - 1 || i == nkb - 1) umma_commit(smem_u32(bars + 3 * S + buf));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ hi/lo splitters + fp32 accumulators
+    const int t = threadIdx.x - 128;                              // 0..255
+    const int q = warp & 3;                                       // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;                             // column half
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    constexpr int A_V4 = Cfg::A_BYTES / 16, B_V4 = Cfg::B_BYTES / 16;
+    float acc[Cfg::COLS];
+#pragma unroll
+    for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
+    int drained = 0;
+    auto drain = [&](int c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(bars + 3 * S + buf), (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + buf * BN + half * Cfg::COLS + j0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + 3 * S + 2 + buf));
+    };
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (i / S) & 1;
+      mbar_wait(smem_u32(bars + s), ph);
+      uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+#pragma unroll 4
+      for (int v = t; v < A_V4 + B_V4; v += TC_SPLIT_WARPS * 32) {
+        uint8_t* hi_p = v < A_V4 ? st + v * 16 : st + 2 * Cfg::A_BYTES + (v - A_V4) * 16;
+        uint8_t* lo_p = hi_p + (v < A_V4 ? Cfg::A_BYTES : Cfg::B_BYTES);
+        const float4 x = *reinterpret_cast<const float4*>(hi_p);
+        uint4 h, l;
+        h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
+        l.x = tf32_rn(x.x - __uint_as_float(h.x)); l.y = tf32_rn(x.y - __uint_as_float(h.y));
+        l.z = tf32_rn(x.z - __uint_as_float(h.z)); l.w = tf32_rn(x.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(hi_p) = h;
+        *reinterpret_cast<uint4*>(lo_p) = l;
+      }
+      fence_async_smem();                                         // generic-proxy writes -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + S + s));
+      // the chunk BEFORE the one whose last stage was just split has certainly been issued: drain it now
+      if ((i % TC_CHUNK) == TC_CHUNK - 1 && i / TC_CHUNK >= 1) drain(drained++);
+    }
+    while (drained < nchunks) drain(drained++);
+    // ------------------------------------------------------------ epilogue (from registers)
+    if (nkb > 0) {
+      const int row = m0 + q * 32 + lane;
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + 2 * BN + half * Cfg::COLS + j0, v);     // lo*hi + hi*lo correction
+        if (row < g.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n0 + half * Cfg::COLS + j0 + j;
+            if (col < g.N) {
+              float x = acc[j0 + j] + v[j];
+              if (g.bias != nullptr && (!g.atomic || blockIdx.z == 0)) x += g.bias[col];
+              float* p = g.C + row * g.sCm + col * g.sCn;
+              if (g.atomic) {
+                atomicAdd(p, x);
+              } else {
+                if (g.act == 1) x = fmaxf(x, 0.f);
+                else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+                *p = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return DDRL_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) return cuda_fail(e, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return DDRL_OK;
+}
+
+// 2-D fp32 tensor [outer, inner] with row stride ld (floats); box = [box_outer, 32 floats], 128B swizzle
+static int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
+                    bool mn_major) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DDRL_E_CUDA;
+  }
+  return DDRL_OK;
+}
+
+bool gemm_tc_supported(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* C,
+                       int ldc, int trans_c) {
+  if (M < 1 || N < 16 || K < 1) return false;
+  if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0) return false;
+  if (lda % 4 != 0 || ldb % 4 != 0) return false;
+  return true;
+}
+
+template <int BN>
+static int launch_tc(int form, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done[3] = {false, false, false};
+#define TC_LAUNCH(AMN, BMN)                                                                                              \
+  do {                                                                                                                   \
+    if (!attr_done[form]) {                                                                                              \
+      DDRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); \
+      attr_done[form] = true;                                                                                            \
+    }                                                                                                                    \
+    gemm_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, Cfg::SMEM, s>>>(ta, tb, g);                                         \
+  } while (0)
+  if (form == 0) TC_LAUNCH(false, false);
+  else if (form == 1) TC_LAUNCH(false, true);
+  else TC_LAUNCH(true, true);
+#undef TC_LAUNCH
+  prof_work(2.0 * g.M * (double)g.N * g.K);
+  DDRL_LAUNCHED("gemm_tc_kernel");
+  return DDRL_OK;
+}
+
+int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const float* bias, int act, int beta, int trans_c, cudaStream_t s) {
+  if (trans_c && bias) return DDRL_E_ARG;
+  int r = get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
+  CUtensorMap ta, tb;
+  // form 0: A [M,K] K-major, B [N,K] K-major | form 1: B [K,N] MN-major | form 2: A [K,M], B [K,N] MN-major
+  if (form == 2) r = make_map(&ta, A, M, K, lda, 32, true); else r = make_map(&ta, A, K, M, lda, TC_BM, false);
+  if (r != DDRL_OK) return r;
+  if (form == 0) r = make_map(&tb, B, K, N, ldb, (bn + 31) / 32 * 32, false); else r = make_map(&tb, B, N, K, ldb, 32, true);
+  if (r != DDRL_OK) return r;
+  TcArgs g;
+  g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K; g.act = act;
+  g.sCm = trans_c ? 1 : ldc; g.sCn = trans_c ? ldc : 1;
+  const int kb_total = ceil_div(K, TC_BK);
+  const int tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
+  int splits = 1;
+  if (act == 0 && kb_total >= 64 && tiles < kNumSMs) splits = std::min(std::min(ceil_div(2 * kNumSMs, tiles), kb_total / 16), 1024);
+  int kbps = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, kbps);
+  g.kb_per_split = kbps;
+  g.atomic = (splits > 1 || beta) ? 1 : 0;
+  if (splits > 1 && !beta) {
+    const int rows = trans_c ? N : M, cols = trans_c ? M : N;
+    if (ldc == cols) DDRL_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)rows * cols, s));
+    else DDRL_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * cols, rows, s));
+  }
+  dim3 grid(ceil_div(M, TC_BM), ceil_div(N, bn), splits);
+  if (grid.y > 65535 || grid.z > 65535) return DDRL_E_UNSUPPORTED;
+  switch (bn) {
+    case 128: return launch_tc<128>(form, ta, tb, g, grid, s);
+    case 64: return launch_tc<64>(form, ta, tb, g, grid, s);
+    default: return launch_tc<32>(form, ta, tb, g, grid, s);
+  }
+}
+
 }  // namespace ddrl

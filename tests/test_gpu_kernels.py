@@ -278,11 +278,17 @@ def test_clip_adam_vs_torch(n, nseg):
 
 
 # ------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("mode", ["simt"])
+@pytest.mark.parametrize("mode", ["simt", "tc"])
 @pytest.mark.parametrize("form", [0, 1, 2])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 33, 100), (1000, 512, 3136), (64, 6, 512), (4096, 32, 256), (37, 200, 9)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 33, 100), (1000, 512, 3136), (64, 6, 512), (4096, 32, 256), (37, 200, 9),
+                                   (128, 32, 32), (300, 64, 1152), (2048, 256, 1600)])
 def test_gemm_forms(mode, form, M, N, K):
     from ddrl4nav_b200 import kernels
+    if mode == "tc":
+        # the tcgen05 path needs 16-byte row strides (TMA) and N >= 16; other shapes stay on the SIMT engine
+        lds = {0: (K, K), 1: (K, N), 2: (M, N)}[form]
+        if N < 16 or lds[0] % 4 or lds[1] % 4:
+            pytest.skip("shape not eligible for the TMA/tcgen05 engine")
     g = torch.Generator().manual_seed(M + N + K + form)
     if form == 0:
         A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
@@ -302,10 +308,23 @@ def test_gemm_forms(mode, form, M, N, K):
     assert close(out2, ref + prod, rtol=1e-5, atol_scale=2e-6)
 
 
-def test_gemm_split_k_wgrad_shape():
+@pytest.mark.parametrize("mode", ["simt", "tc"])
+def test_gemm_split_k_wgrad_shape(mode):
     from ddrl4nav_b200 import kernels
     g = torch.Generator().manual_seed(5)
     K, M, N = 200000, 32, 256
     A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
-    out = kernels.gemm(2, A.to(DEV), B.to(DEV))
+    out = kernels.gemm(2, A.to(DEV), B.to(DEV), mode=mode)
     assert close(out, A.double().T @ B.double(), rtol=1e-5, atol_scale=2e-6)
+
+
+def test_gemm_tc_is_3xtf32_accurate():
+    """The tensor-core engine must be as close to the exact product as the fp32 FFMA engine (not TF32-grade 1e-3)."""
+    from ddrl4nav_b200 import kernels
+    g = torch.Generator().manual_seed(9)
+    A, B = torch.randn(512, 4096, generator=g), torch.randn(256, 4096, generator=g)
+    ref = A.double() @ B.double().T
+    e_tc = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc").cpu().double() - ref).abs().max() / ref.abs().max())
+    e_simt = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="simt").cpu().double() - ref).abs().max() / ref.abs().max())
+    print("max err / max|ref|: tc %.2e  simt %.2e" % (e_tc, e_simt))
+    assert e_tc < 2e-6 and e_simt < 2e-6
