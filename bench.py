@@ -189,6 +189,16 @@ def run_ours(args):
         for loss, upd, last in net.learn(exp_dev):
             last_losses.update(loss)
 
+    if args.profile_step:
+        for _ in range(args.warmup):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
+
     sampler = ClockSampler(local)
     kernels.launch_count_reset()
     for _ in range(args.warmup):
@@ -361,10 +371,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("DDRL_BENCH_WORKLOAD", "pong"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "tc"), choices=["simt", "tc"])
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--fwd-batch", dest="fwd_batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE learn step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -62,7 +62,7 @@ SIGNATURES = {
     "ddrl_net_num_obs": (_I, [_P]),
     "ddrl_net_obs_elems": (_L, [_P, _I]),
     "ddrl_net_forward": (_I, [_P, C.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _P]),
-    "ddrl_net_backward": (_I, [_P, C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, C.POINTER(PPOHparams), _P]),
+    "ddrl_net_backward": (_I, [_P, C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, C.POINTER(PPOHparams), _I, _P]),
     "ddrl_net_clip_adam": (_I, [_P, _I, C.POINTER(PPOHparams), _P, _P]),
     "ddrl_net_workspace_bytes": (_L, [_P]),
 }

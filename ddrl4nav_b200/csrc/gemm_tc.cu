@@ -40,6 +40,7 @@ struct TcArgs {
   int M, N, K;
   int kb_per_split;                            // K blocks (of 32) per grid.z slice
   int act, atomic;
+  int vec_store;                               // plain row-major C with 16-byte aligned rows: float4 epilogue stores
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -129,7 +130,10 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
   static constexpr int B_BYTES = BNS * TC_BK * 4;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);    // hi(raw) + lo for A and B
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  // BN = 128: one CTA per SM with a 3-deep ring; BN <= 64: two co-resident CTAs (2-deep rings) so that one CTA's
+  // prologue / epilogue overlaps the other's main loop (the conv GEMMs of this path have K <= 1600)
+  static constexpr int CTAS_PER_SM = BN <= 64 ? 2 : 1;
+  static constexpr int STAGES = BN <= 64 ? 2 : 3;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN <= 32 ? 128 : (BN <= 64 ? 256 : 512);   // main0 | main1 | corr
   static constexpr int COLS = BN / 2;                            // accumulator columns held by one splitter warp
@@ -138,7 +142,7 @@ struct TcCfg {
 // barrier slots: [0,S) full (TMA landed)  [S,2S) split done  [2S,3S) empty (MMA consumed)
 //                [3S,3S+2) accumulator buffer ready  [3S+2,3S+4) accumulator buffer drained
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
@@ -298,7 +302,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + t_lane + 2 * BN + half * Cfg::COLS + j0, v);     // lo*hi + hi*lo correction
-        if (row < g.M) {
+        const int colv = n0 + half * Cfg::COLS + j0;
+        if (row < g.M && g.vec_store && colv + 16 <= g.N) {
+          // 16 consecutive columns of this thread's row: four 16-byte stores
+          float* p = g.C + row * g.sCm + colv;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = acc[j0 + j + e] + v[j + e];
+              if (g.bias != nullptr) x += g.bias[colv + j + e];
+              if (g.act == 1) x = fmaxf(x, 0.f);
+              else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+              ov[e] = x;
+            }
+            *reinterpret_cast<float4*>(p + j) = o;
+          }
+        } else if (row < g.M) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + half * Cfg::COLS + j0 + j;
@@ -413,6 +435,7 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
   splits = ceil_div(kb_total, kbps);
   g.kb_per_split = kbps;
   g.atomic = (splits > 1 || beta) ? 1 : 0;
+  g.vec_store = (!g.atomic && !trans_c && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   if (splits > 1 && !beta) {
     const int rows = trans_c ? N : M, cols = trans_c ? M : N;
     if (ldc == cols) DDRL_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)rows * cols, s));

@@ -42,6 +42,71 @@ __global__ void __launch_bounds__(256) im2col_kernel(ConvGeom g, const float* __
   }
 }
 
+// float4 variant: 4 consecutive k of one row share their (kh,kw) tap [order 0, C % 4 == 0] or their (c,kh) and
+// cover 4 adjacent input pixels [order 1, KW % 4 == 0, sw == 1]: one 16 B load, one 16 B store, a quarter of the
+// index arithmetic.  Requires K % 4 == 0 (ldc == K) and 16 B aligned sources.
+__global__ void __launch_bounds__(256) im2col_vec4_kernel(ConvGeom g, const float* __restrict__ x, float4* __restrict__ cols,
+                                                          long long total4) {
+  const int k4n = g.ldc >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % k4n) << 2;
+    const long long row = i / k4n;
+    int c, kh, kw;
+    if (g.order == 0) { c = k % g.C; const int t = k / g.C; kw = t % g.KW; kh = t / g.KW; }
+    else { kw = k % g.KW; const int t = k / g.KW; kh = t % g.KH; c = t / g.KH; }
+    const int wo = (int)(row % g.Wo);
+    const long long t2 = row / g.Wo;
+    const int ho = (int)(t2 % g.Ho);
+    const long long b = t2 / g.Ho;
+    const int h = ho * g.stride - g.pad + kh, w = wo * g.stride - g.pad + kw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h >= 0 && h < g.H) {
+      const float* p = x + b * g.sb + h * g.sh + w * g.sw + c * g.sc;
+      if (g.order == 0) {
+        if (w >= 0 && w < g.W) v = *reinterpret_cast<const float4*>(p);
+      } else {
+        if (w >= 0 && w + 3 < g.W) v = *reinterpret_cast<const float4*>(p);
+        else {
+          if (w >= 0 && w < g.W) v.x = p[0];
+          if (w + 1 >= 0 && w + 1 < g.W) v.y = p[1];
+          if (w + 2 >= 0 && w + 2 < g.W) v.z = p[2];
+          if (w + 3 >= 0 && w + 3 < g.W) v.w = p[3];
+        }
+      }
+    }
+    cols[i] = v;
+  }
+}
+
+// float4 col2im for order-0 (NHWC, C % 4 == 0) geometries
+__global__ void __launch_bounds__(256) col2im_vec4_kernel(ConvGeom g, const float* __restrict__ dcols, float4* __restrict__ dx,
+                                                          long long total4) {
+  const int c4n = g.C >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    long long t = i / c4n;
+    const int w = (int)(t % g.W); t /= g.W;
+    const int h = (int)(t % g.H);
+    const long long b = t / g.H;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int hn = h + g.pad - kh;
+      if (hn < 0 || hn % g.stride) continue;
+      const int ho = hn / g.stride;
+      if (ho >= g.Ho) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int wn = w + g.pad - kw;
+        if (wn < 0 || wn % g.stride) continue;
+        const int wo = wn / g.stride;
+        if (wo >= g.Wo) continue;
+        const float4 v = *reinterpret_cast<const float4*>(dcols + ((b * g.Ho + ho) * g.Wo + wo) * g.ldc + (kh * g.KW + kw) * g.C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // ---------------------------------------------------------------- col2im (gather form, no atomics)
 // dx[b,h,w,c] (dense NHWC) = sum over (kh,kw) with (h+pad-kh) % stride == 0 of dcols[(b,ho,wo), (kh,kw,c)]
 __global__ void __launch_bounds__(256) col2im_kernel(ConvGeom g, const float* __restrict__ dcols, float* __restrict__ dx,
@@ -244,6 +309,16 @@ static inline int grid_for(long long total, int threads = 256) {
 int im2col(const ConvGeom& g, const float* x, float* cols, int B, cudaStream_t s) {
   const long long total = (long long)B * g.Ho * g.Wo * g.ldc;
   if (total == 0) return DDRL_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cols)) & 15) == 0 && g.ldc == g.K;
+  const bool v0 = g.order == 0 && g.C % 4 == 0;
+  const bool v1 = g.order == 1 && g.KW % 4 == 0 && g.sw == 1 && g.stride % 4 == 0 && g.pad % 4 == 0 && g.sh % 4 == 0 &&
+                  g.sc % 4 == 0 && g.sb % 4 == 0;
+  prof_work(4.0 * total + 4.0 * (double)B * g.H * g.W * g.C);      // write cols + read input once
+  if (aligned && (v0 || v1)) {
+    im2col_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(g, x, reinterpret_cast<float4*>(cols), total / 4);
+    DDRL_LAUNCHED("im2col_vec4_kernel");
+    return DDRL_OK;
+  }
   im2col_kernel<<<grid_for(total), 256, 0, s>>>(g, x, cols, total);
   DDRL_LAUNCHED("im2col_kernel");
   return DDRL_OK;
@@ -251,6 +326,12 @@ int im2col(const ConvGeom& g, const float* x, float* cols, int B, cudaStream_t s
 int col2im(const ConvGeom& g, const float* dcols, float* dx, int B, cudaStream_t s) {
   const long long total = (long long)B * g.H * g.W * g.C;
   if (total == 0) return DDRL_OK;
+  prof_work(4.0 * total + 4.0 * (double)B * g.Ho * g.Wo * g.ldc);
+  if (g.order == 0 && g.C % 4 == 0 && g.ldc % 4 == 0 && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dcols)) & 15) == 0) {
+    col2im_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(g, dcols, reinterpret_cast<float4*>(dx), total / 4);
+    DDRL_LAUNCHED("col2im_vec4_kernel");
+    return DDRL_OK;
+  }
   col2im_kernel<<<grid_for(total), 256, 0, s>>>(g, dcols, dx, total);
   DDRL_LAUNCHED("col2im_kernel");
   return DDRL_OK;

@@ -91,6 +91,9 @@ struct ddrl_net {
   size_t packed_bytes = 0, packed_grad_off = 0, packed_grad_bytes = 0;
   int64_t seg_begin[3];
   int nseg = 1;
+  // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
+  const float* cols_obs0 = nullptr;
+  int cols_rows = -1;
 };
 
 namespace ddrl {
@@ -151,7 +154,9 @@ static Lin make_lin(ddrl_net* n, const std::string& wname, int N, int K, int I, 
   Lin l;
   l.N = N; l.K = K; l.I = I; l.J = J; l.act = act;
   l.ldw = round4(K);
-  l.packed = (I != 1) || (l.ldw != K);
+  // always keep an engine-side copy: besides the layout change it guarantees the 16-byte alignment TMA needs
+  // (flat-buffer offsets of e.g. critic.pre.* are odd because of the [A,512]+[A]+[1,512]+[1] head tensors)
+  l.packed = true;
   l.w_t = find_tensor(n, wname + ".weight");
   l.b_t = find_tensor(n, wname + ".bias");
   return l;
@@ -394,18 +399,21 @@ static int repack(ddrl_net* n, cudaStream_t s) {
 
 // ---- encoder schedules ------------------------------------------------------------------
 static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, float* cols, float* y, int mb,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool cols_cached = false) {
   const ConvGeom& g = t.g[gi];
-  TRY(im2col(g, x, cols, mb, s));
+  if (!cols_cached) TRY(im2col(g, x, cols, mb, s));
   return lin_fwd(n, t.L[li], cols, g.ldc, y, t.L[li].N, (long long)mb * g.Ho * g.Wo, s);
 }
 
-static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s) {
+// reuse_obs: the im2col matrices of the layers that read the OBSERVATIONS are still valid from the previous call
+// (PPO.learn runs TRAINING_ITER_TIME iterations over the same batch, nn/ppo.py:79-82)
+static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s,
+                         bool reuse_obs = false) {
   auto& b = t.buf;
   switch (t.arch) {
     case DDRL_ARCH_ATARI: {
       const float* x = obs[0] + row0 * t.g[0].sb;
-      TRY(conv_block(n, t, 0, 0, x, b[0], b[1], mb, s));
+      TRY(conv_block(n, t, 0, 0, x, b[0], b[1], mb, s, reuse_obs));
       TRY(conv_block(n, t, 1, 1, b[1], b[2], b[3], mb, s));
       TRY(conv_block(n, t, 2, 2, b[3], b[4], b[5], mb, s));
       TRY(lin_fwd(n, t.L[3], b[5], 3136, t.h, 512, mb, s));
@@ -427,7 +435,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
         img = b[15];
       }
       const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
-      TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s));
+      TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s, reuse_obs));
       TRY(pool_fwd(b[1], b[2], t.idx[0], mb, g0->Ho, g0->Wo, 64, s));
       TRY(conv_block(n, t, 1, 1, b[2], b[3], b[4], mb, s));
       TRY(pool_fwd(b[4], b[5], t.idx[1], mb, g1->Ho, g1->Wo, 128, s));
@@ -438,7 +446,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
       if (d1) {
         // laser branch: conv1d1 -> conv1d2 (no activation between, nav_encoder.py:109-110) -> fc_1d+relu -> cat[:, 0:256]
         const float* laser = obs[0] + row0 * 960;
-        TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s));
+        TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s, reuse_obs));
         TRY(conv_block(n, t, 4, 4, b[12], b[13], b[14], mb, s));
         TRY(lin_fwd(n, t.L[5], b[14], 7616, b[9], ldcat, mb, s));
         TRY(lin_fwd(n, t.L[6], b[8], flat, b[9] + 256, ldcat, mb, s));           // fc0 -> cat[:, 256:768]
@@ -538,8 +546,9 @@ static int check_obs(const ddrl_net* n, const float* const* obs, int n_obs) {
 }
 
 // encoders + heads for rows [row0, row0+mb): fills n->logits [mb, ldA], n->vout [mb]
-static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s) {
-  for (auto& t : n->towers) TRY(tower_forward(n, t, obs, row0, mb, train, s));
+static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s,
+                         bool reuse_obs = false) {
+  for (auto& t : n->towers) TRY(tower_forward(n, t, obs, row0, mb, train, s, reuse_obs));
   Tower& ta = n->towers[0];
   Tower& tc = n->towers[n->d.shared ? 0 : 1];
   const int A = n->d.act_dim, F = n->d.feat;
@@ -662,6 +671,7 @@ extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs,
   cudaStream_t s = (cudaStream_t)stream;
   TRY(ensure_workspace(n, B, n->ws_train));
   if (n->dirty) TRY(repack(n, s));
+  n->cols_obs0 = nullptr;            // the workspace is about to be overwritten
   const int A = n->d.act_dim;
   for (long long r0 = 0; r0 < B; r0 += n->MB) {
     const int mb = (int)std::min<long long>(n->MB, B - r0);
@@ -681,7 +691,7 @@ extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs,
 
 extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
                                  const float* actions, const float* old_logp, const float* adv, const float* returns,
-                                 const ddrl_ppo_hparams* hp, void* stream) {
+                                 const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream) {
   if (!n || !hp || B_local < 0 || B_global < B_local || B_global < 1) return DDRL_E_ARG;
   if (!n->params || !n->grads) return DDRL_E_STATE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -691,8 +701,13 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   if (B_local == 0) return DDRL_OK;
   TRY(check_obs(n, obs, n_obs));
   if (!actions || !old_logp || !adv || !returns) return DDRL_E_ARG;
+  const char* ws_before = n->ws.base;
   TRY(ensure_workspace(n, B_local, true));
   if (n->dirty) TRY(repack(n, s));
+  const bool single = B_local <= n->MB;
+  const bool reuse_obs = obs_unchanged && single && ws_before == n->ws.base && n->cols_obs0 == obs[0] && n->cols_rows == B_local;
+  n->cols_obs0 = single ? obs[0] : nullptr;
+  n->cols_rows = single ? B_local : -1;
   const int A = n->d.act_dim, F = n->d.feat;
   const float invB = 1.0f / (float)B_global;
   float* loss_sums = n->grads + n->P;
@@ -702,7 +717,7 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   float* cw = n->params + n->T[n->t_cw].offset;
   for (long long r0 = 0; r0 < B_local; r0 += n->MB) {
     const int mb = (int)std::min<long long>(n->MB, B_local - r0);
-    TRY(forward_chunk(n, obs, r0, mb, true, s));
+    TRY(forward_chunk(n, obs, r0, mb, true, s, reuse_obs));
     if (n->d.dist == DDRL_DIST_CATEGORICAL) {
       TRY(ddrl_ppo_loss_categorical(n->logits, n->ldA, actions + r0, old_logp + r0, adv + r0, returns + r0, n->vout, mb, A,
                                     invB, hp, n->d.shared, n->dlogits, n->ldA, n->dv, loss_sums, s));

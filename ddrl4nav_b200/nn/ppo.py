@@ -58,7 +58,7 @@ class PPO(Basenn):
         self.v_loss_theta, self.ent_loss_theta = self.hp.v_coef, self.hp.ent_coef
         self.ppo_clip, self.duel_ppo_clip = self.hp.ppo_clip, self.hp.dual_clip
         self.training_iter_time = _cfg(config_nn, "TRAINING_ITER_TIME", 10)
-        self.gemm_mode = os.environ.get("DDRL_GEMM_MODE", _cfg(config_nn, "GEMM_MODE", "simt"))
+        self.gemm_mode = os.environ.get("DDRL_GEMM_MODE", _cfg(config_nn, "GEMM_MODE", "tc"))
         self.update_time = 0
         self._adam_step = 0
         self._h = None                  # ddrl_net*
@@ -256,7 +256,7 @@ class PPO(Basenn):
         dist.broadcast(self._flat, src=src, group=self._dp_group)
         self._weights_changed()
 
-    def backward_only(self, states, advs, actions, old_logps, returns, b_global=None):
+    def backward_only(self, states, advs, actions, old_logps, returns, b_global=None, obs_unchanged=False):
         """forward + fused loss + backward for the local rows; grads (scaled 1/B_global) stay in flat_grads()."""
         self._ensure_engine()
         lib = _lib.load()
@@ -267,7 +267,7 @@ class PPO(Basenn):
         if returns.dim() == 2:             # data.values is [V,B]; the PPO critic uses row 0 (ppo.py:95)
             returns = returns[0].contiguous()
         check(lib.ddrl_net_backward(self._h, arr, n_obs, B, int(b_global or B), ptr(actions), ptr(old_logps), ptr(advs),
-                                    ptr(returns), C.byref(self.hp), current_stream()), "ddrl_net_backward")
+                                    ptr(returns), C.byref(self.hp), int(bool(obs_unchanged)), current_stream()), "ddrl_net_backward")
         return B
 
     def optimizer_step(self):
@@ -288,9 +288,10 @@ class PPO(Basenn):
             cnt = torch.tensor([b_local], dtype=torch.int64, device=self._flat.device if self._flat is not None else "cuda")
             dist.all_reduce(cnt, group=self._dp_group)
             b_global = int(cnt.item())
-        for _ in range(self.training_iter_time):
+        for it in range(self.training_iter_time):
             start_time = time.time()
-            self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global)
+            self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global,
+                               obs_unchanged=it > 0)
             if self._dp_world > 1:
                 import torch.distributed as dist
                 dist.all_reduce(self._grads[:self._P + 4], group=self._dp_group)

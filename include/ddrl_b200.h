@@ -176,10 +176,12 @@ int ddrl_net_forward(ddrl_net* net, const float* const* obs, int n_obs, int B, c
 /* One learn iteration, first half (nn/ppo.py:82-123): forward with act=data.actions, fused loss,
  * backward through heads and encoders.  Leaves d(loss)/d(params) for the LOCAL B rows, scaled
  * by 1/B_global, in the flat grads buffer and the loss sums in its tail.  In a data-parallel
- * learner the caller all-reduces grads[0 .. P+4) (sum) before ddrl_net_clip_adam. */
+ * learner the caller all-reduces grads[0 .. P+4) (sum) before ddrl_net_clip_adam.
+ * obs_unchanged != 0: the caller guarantees obs[] hold the same bytes as in the previous backward call
+ * (iterations 2..10 of PPO.learn); observation-side staging is then reused. */
 int ddrl_net_backward(ddrl_net* net, const float* const* obs, int n_obs, int B_local, int B_global,
                       const float* actions, const float* old_logp, const float* adv, const float* returns,
-                      const ddrl_ppo_hparams* hp, void* stream);
+                      const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream);
 /* second half (nn/ppo.py:115-129): global-norm clip + the two (or one) Adam steps; then refreshes
  * the packed weights.  loss4_out (device, 4 floats, optional) = {total, actor, v, entropy}. */
 int ddrl_net_clip_adam(ddrl_net* net, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream);

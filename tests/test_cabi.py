@@ -62,7 +62,7 @@ def test_engine_param_table_is_reference_order(kind):
         total += int(np.prod(shp))
     assert lib.ddrl_net_num_params(h) == total == {"pong": 3371847, "navlaser": 12799685, "navimg": 5633565}[kind]
     # argument checking without a GPU
-    assert lib.ddrl_net_backward(h, None, 0, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.ddrl_net_backward(h, None, 0, 1, 1, None, None, None, None, None, 0, None) != 0
     assert lib.ddrl_net_destroy(h) == 0
     bad = _lib.NetDesc(99, 1, 1, 0, 0, 512, 0, 0)
     assert lib.ddrl_net_create(C.byref(bad), C.byref(h)) == -1
