@@ -23,7 +23,7 @@ import torch
 from torch.distributions.categorical import Categorical
 from torch.distributions.normal import Normal
 
-from .. import _lib, kernels
+from .. import _lib, dist, kernels
 from .._lib import DDRLError, NetDesc, check, current_stream, ptr
 from .base import Basenn
 
@@ -245,15 +245,14 @@ class PPO(Basenn):
     def enable_data_parallel(self, group=None):
         """Shard each full-batch iteration over the ranks of `group` (one process per GPU): local grads are
         pre-scaled by 1/B_global, one NCCL all-reduce(sum) of the flat grad buffer (+ loss sums) per
-        iteration, then the identical fused clip+Adam on every rank."""
-        import torch.distributed as dist
-        self._dp_group = group if group is not None else dist.group.WORLD
-        self._dp_world = dist.get_world_size(self._dp_group)
+        iteration, then the identical fused clip+Adam on every rank (ddrl4nav_b200/dist.py)."""
+        import torch.distributed as tdist
+        self._dp_group = group if group is not None else tdist.group.WORLD
+        self._dp_world = tdist.get_world_size(self._dp_group)
 
     def broadcast_parameters(self, src=0):
-        import torch.distributed as dist
         self._ensure_engine()
-        dist.broadcast(self._flat, src=src, group=self._dp_group)
+        dist.broadcast_params(self._flat, src=src, group=self._dp_group)
         self._weights_changed()
 
     def backward_only(self, states, advs, actions, old_logps, returns, b_global=None, obs_unchanged=False):
@@ -284,17 +283,14 @@ class PPO(Basenn):
         b_local = len(data.states[0])
         b_global = b_local
         if self._dp_world > 1:
-            import torch.distributed as dist
-            cnt = torch.tensor([b_local], dtype=torch.int64, device=self._flat.device if self._flat is not None else "cuda")
-            dist.all_reduce(cnt, group=self._dp_group)
-            b_global = int(cnt.item())
+            self._ensure_engine()
+            b_global = dist.global_rows(b_local, self._flat.device, self._dp_group)
         for it in range(self.training_iter_time):
             start_time = time.time()
             self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global,
                                obs_unchanged=it > 0)
             if self._dp_world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self._grads[:self._P + 4], group=self._dp_group)
+                dist.allreduce_grads(self._grads, self._P, self._dp_group)
             loss4 = self.optimizer_step().tolist()          # ONE 16-byte D2H per iteration (reference: four .item())
             self.update_time += 1
             loss_log = {"PpoTotalLoss": loss4[0], "ActorLoss": loss4[1], "VLoss": loss4[2], "EntLoss": loss4[3],
