@@ -1,4 +1,5 @@
 // Library-level entry points of the C ABI (include/ddrl_b200.h).
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -24,6 +25,13 @@ static cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEventCreate(&e);
   return e;
+}
+
+// shape-tagged kernel names (DDRL_PROF_SHAPES=1): interned so the recorded pointer stays valid
+bool g_prof_shapes = false;
+const char* prof_intern(const std::string& s) {
+  static std::map<std::string, int> pool;
+  return pool.emplace(s, 0).first->first.c_str();
 }
 
 void prof_record(const char* name) {
@@ -58,6 +66,8 @@ extern "C" int ddrl_prof_start(void* stream) {
   g_prof_recs.clear();
   g_prof_stream = (cudaStream_t)stream;
   g_prof_on = true;
+  const char* e = getenv("DDRL_PROF_SHAPES");
+  g_prof_shapes = e && e[0] == '1';
   prof_record("__start__");
   return DDRL_OK;
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <string>
+
 #include "../../include/ddrl_b200.h"
 
 namespace ddrl {
@@ -28,7 +30,9 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 // with the stream kept busy the gap between consecutive events is the kernel's duration.
 extern bool g_prof_on;
 extern double g_prof_work;      // algorithmic work (flops or bytes) of the NEXT recorded launch
+extern bool g_prof_shapes;     // DDRL_PROF_SHAPES=1: GEMM launches are recorded under a name that carries their shape
 void prof_record(const char* name);
+const char* prof_intern(const std::string& s);
 inline void prof_work(double w) { if (g_prof_on) g_prof_work = w; }
 
 // after a <<<>>> launch: count it and surface launch-configuration errors

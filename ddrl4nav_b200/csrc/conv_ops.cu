@@ -1,0 +1,181 @@
+// Convolution layers on the implicit-GEMM tcgen05 path (gemm_tc.cu: conv_tc_fwd / conv_tc_wgrad).
+//
+// The reference runs nn.Conv2d / nn.Conv1d through autograd (nn/atari_encoder.py:16-28, nn/nav_encoder.py:17-31,
+// 85-93): forward cross-correlation, and in backward the data gradient (a transposed convolution) and the weight
+// gradient.  Here all three are GEMMs whose activation operand is fetched tap by tap with 4-D TMA boxes straight
+// from the NHWC activation tensor:
+//   forward   y[pix, o]      = sum_{kh,kw,c} x[pix*s + (kh,kw) - p, c] * Wp[o, (kh,kw,c)]
+//   dgrad     dx[pix', c]    = sum over the taps that reach pix' of dy[...] * W   -- split by the parity class of
+//             (pix' + p) mod s: each class is a stride-1 convolution over dy with ceil((K - r)/s) taps per axis
+//             and its own re-packed (flipped, transposed) weights; the classes write interleaved output pixels
+//   wgrad     dWp[o, (kh,kw,c)] = sum_pix dy[pix, o] * x[pix*s + (kh,kw) - p, c]
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "layer_ops.h"
+
+namespace ddrl {
+
+// Wd[c, (th*ntx + tw)*Cout + o] = w[o, c, kh, kw]  with kh = ry + s*(nty-1-th), kw = rx + s*(ntx-1-tw)   (w: reference OIHW)
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin,
+                                                         int KH, int KW, int s, int ry, int rx, int nty, int ntx) {
+  const long long total = (long long)Cin * nty * ntx * Cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t % Cout);
+    long long r = t / Cout;
+    const int tw = (int)(r % ntx); r /= ntx;
+    const int th = (int)(r % nty);
+    const int c = (int)(r / nty);
+    const int kh = ry + s * (nty - 1 - th), kw = rx + s * (ntx - 1 - tw);
+    wd[t] = w[(((long long)o * Cin + c) * KH + kh) * KW + kw];
+  }
+}
+
+// 1-D convolutions (H == 1) are run with the pixel axis on the box's row dimension
+static void oriented(const ConvGeom& g, int& H, int& W, int& KH, int& KW, int& Ho, int& Wo) {
+  if (g.H == 1 && g.KH == 1) { H = g.W; W = 1; KH = g.KW; KW = 1; Ho = g.Wo; Wo = 1; }
+  else { H = g.H; W = g.W; KH = g.KH; KW = g.KW; Ho = g.Ho; Wo = g.Wo; }
+}
+
+ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B) {
+  ConvOp o;
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  o.a = x; o.Hin = H; o.Win = W; o.Ctot = Ctot; o.c_off = c_off; o.Cin = g.C;
+  o.KH = KH; o.KW = KW; o.sy = g.stride; o.sx = W == 1 ? 1 : g.stride; o.py = g.pad; o.px = W == 1 ? 0 : g.pad;
+  o.Yn = Ho; o.Xn = Wo; o.Bn = B;
+  return o;
+}
+
+int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out) {
+  out.clear();
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const int s = g.stride, py = g.pad, px = W == 1 ? 0 : g.pad;
+  const int sxn = W == 1 ? 1 : s;
+  for (int ry = 0; ry < s; ++ry)
+    for (int rx = 0; rx < sxn; ++rx) {
+      DgradClass c;
+      c.ry = ry; c.rx = rx;
+      c.nty = (KH - ry + s - 1) / s;
+      c.ntx = (KW - rx + sxn - 1) / sxn;
+      if (c.nty < 1 || c.ntx < 1) return DDRL_E_UNSUPPORTED;
+      c.iy0 = ((ry - py) % s + s) % s;
+      c.ix0 = ((rx - px) % sxn + sxn) % sxn;
+      if (c.iy0 >= H || c.ix0 >= W) continue;
+      c.Yn = (H - c.iy0 + s - 1) / s;
+      c.Xn = (W - c.ix0 + sxn - 1) / sxn;
+      c.pady = c.nty - 1 - (c.iy0 + py - ry) / s;
+      c.padx = c.ntx - 1 - (c.ix0 + px - rx) / sxn;
+      c.K = c.nty * c.ntx * Cout;
+      c.wd = nullptr;
+      out.push_back(c);
+    }
+  return DDRL_OK;
+}
+
+int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s) {
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const long long total = (long long)g.C * c.K;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);
+  // the reference weight is [Cout, Cin, g.KH, g.KW]; in the transposed (1-D) orientation KH/KW swap with it
+  pack_dgrad_kernel<<<blocks, 256, 0, s>>>(w_oihw, c.wd, Cout, g.C, KH, KW, g.stride, c.ry, c.rx, c.nty, c.ntx);
+  DDRL_LAUNCHED("pack_dgrad_kernel");
+  return DDRL_OK;
+}
+
+// dx (dense NHWC [B, H, W, C]) = sum over classes; every input pixel belongs to exactly one class
+int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
+                  float* dx, int act, const float* mask, int B, cudaStream_t s) {
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const int sy = g.stride, sx = W == 1 ? 1 : g.stride;
+  for (const DgradClass& c : cls) {
+    ConvOp o;
+    o.a = dy; o.Hin = Ho; o.Win = Wo; o.Ctot = dy_ctot; o.c_off = dy_coff; o.Cin = Cout;
+    o.KH = c.nty; o.KW = c.ntx; o.sy = 1; o.sx = 1; o.py = c.pady; o.px = c.padx;
+    o.Yn = c.Yn; o.Xn = c.Xn; o.Bn = B;
+    const long long off = ((long long)c.iy0 * W + c.ix0) * g.C;
+    int r = conv_tc_fwd(o, c.wd, c.K, g.C, nullptr, act, mask ? mask + off : nullptr, dx + off, (long long)H * W * g.C,
+                        (long long)sy * W * g.C, (long long)sx * g.C, s);
+    if (r != DDRL_OK) return r;
+  }
+  return DDRL_OK;
+}
+
+bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,
+                          int dy_coff, int B) {
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  if (g.order != 0 || g.C % 4 != 0) return false;
+  for (const DgradClass& c : cls) {
+    ConvOp o;
+    o.a = dy; o.Hin = Ho; o.Win = Wo; o.Ctot = dy_ctot; o.c_off = dy_coff; o.Cin = Cout;
+    o.KH = c.nty; o.KW = c.ntx; o.sy = 1; o.sx = 1; o.py = c.pady; o.px = c.padx;
+    o.Yn = c.Yn; o.Xn = c.Xn; o.Bn = B;
+    if (!conv_tc_supported(o, false)) return false;
+  }
+  return true;
+}
+
+}  // namespace ddrl
+
+// =========================================================================================
+// C ABI: stand-alone convolution entry (parity tests of the implicit-GEMM path)
+// =========================================================================================
+using namespace ddrl;
+
+extern "C" int ddrl_conv_nhwc_f32(int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
+                                  const float* dy, int act, const float* mask, float* out, void* stream) {
+  if (!d || !out || !w || op < 0 || op > 2) return DDRL_E_ARG;
+  if (d->B < 1 || d->H < 1 || d->W < 1 || d->Cin < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1 || d->stride < 1 || d->pad < 0)
+    return DDRL_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvGeom g;
+  g.H = d->H; g.W = d->W; g.C = d->Cin;
+  g.sc = 1; g.sw = d->Cin; g.sh = (long long)d->W * d->Cin; g.sb = (long long)d->H * d->W * d->Cin; g.order = 0;
+  g.KH = d->KH; g.KW = d->KW; g.stride = d->stride; g.pad = d->pad;
+  // H == 1 && KH == 1 is a Conv1d: stride / padding act on the W axis only
+  g.Ho = (d->H == 1 && d->KH == 1) ? 1 : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  g.Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  g.K = d->Cin * d->KH * d->KW; g.ldc = g.K;
+  if (g.Ho < 1 || g.Wo < 1) return DDRL_E_ARG;
+  const int taps = d->KH * d->KW;
+  int rc = DDRL_OK;
+  float* tmp = nullptr;
+  if (op == 0) {
+    if (!x) return DDRL_E_ARG;
+    DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)d->Cout * g.K));
+    rc = pack_weight(w, tmp, d->Cout, taps, d->Cin, g.K, s);
+    ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
+    if (rc == DDRL_OK && !conv_tc_supported(o, false)) rc = DDRL_E_UNSUPPORTED;
+    if (rc == DDRL_OK)
+      rc = conv_tc_fwd(o, tmp, g.K, d->Cout, bias, act, mask, out, (long long)o.Yn * o.Xn * d->Cout, (long long)o.Xn * d->Cout,
+                       d->Cout, s);
+  } else if (op == 1) {
+    if (!dy) return DDRL_E_ARG;
+    std::vector<DgradClass> cls;
+    rc = conv_dgrad_plan(g, d->Cout, cls);
+    size_t tot = 0;
+    for (auto& c : cls) tot += (size_t)g.C * c.K;
+    if (rc == DDRL_OK) DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * tot));
+    size_t off = 0;
+    for (auto& c : cls) { c.wd = tmp + off; off += (size_t)g.C * c.K; }
+    for (auto& c : cls) if (rc == DDRL_OK) rc = pack_dgrad(w, g, d->Cout, c, s);
+    if (rc == DDRL_OK && !conv_dgrad_supported(g, d->Cout, cls, dy, d->Cout, 0, d->B)) rc = DDRL_E_UNSUPPORTED;
+    if (rc == DDRL_OK) rc = conv_dgrad_tc(g, d->Cout, cls, dy, d->Cout, 0, out, act, mask, d->B, s);
+  } else {
+    if (!x || !dy) return DDRL_E_ARG;
+    DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)d->Cout * g.K));
+    DDRL_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (size_t)d->Cout * g.K, s));
+    ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
+    if (!conv_tc_supported(o, true)) rc = DDRL_E_UNSUPPORTED;
+    if (rc == DDRL_OK) rc = conv_tc_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s);
+    if (rc == DDRL_OK) rc = unpack_grad(tmp, out, d->Cout, taps, d->Cin, g.K, s);
+  }
+  cudaStreamSynchronize(s);
+  if (tmp) cudaFree(tmp);
+  return rc;
+}

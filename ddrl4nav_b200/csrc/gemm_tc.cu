@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "layer_ops.h"
@@ -36,11 +37,14 @@ constexpr int TC_SPLIT_WARPS = 8;
 struct TcArgs {
   float* C;
   const float* bias;
+  const float* mask;                           // act 3/4: C = acc * act'(mask[same address])  (fused activation backward)
   long long sCm, sCn;
   int M, N, K;
-  int kb_per_split;                            // K blocks (of 32) per grid.z slice
+  int kb_total;                                // K blocks in all (plain: ceil(K/32); wgrad taps: pixel blocks)
+  int kb_per_split;                            // K blocks per grid.z slice
   int act, atomic;
   int vec_store;                               // plain row-major C with 16-byte aligned rows: float4 epilogue stores
+  TcTap tap;                                   // tap.mode != 0: implicit-GEMM convolution operands (layer_ops.h)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -70,6 +74,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,11 +166,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-  const int kb_total = (g.K + TC_BK - 1) / TC_BK;
+  const TcTap& tp = g.tap;
+  const bool tapA = tp.mode != 0;
+  // implicit-GEMM forward / data-gradient: this CTA's M tile is a box of output pixels (nb images x ny rows x Xn)
+  int b0 = 0, y0 = 0;
+  if (tapA && !A_MN) { b0 = (blockIdx.x / tp.tpi) * tp.nb; y0 = (blockIdx.x % tp.tpi) * tp.ny; }
+  const int kb_total = g.kb_total;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(kb_total, kb0 + g.kb_per_split);
   const int nkb = kb1 - kb0;
   const int nchunks = (nkb + TC_CHUNK - 1) / TC_CHUNK;
+  // implicit-GEMM weight gradient: a K block is a box of <= 32 pixels; rows the boxes do not cover must read as zero
+  if (tapA && A_MN) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < S * Cfg::STAGE_BYTES / 16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -186,23 +211,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
+        const int kbi = kb0 + i;
         mbar_wait(smem_u32(bars + 2 * S + s), ph ^ 1);
         const uint32_t full = smem_u32(bars + s);
-        mbar_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const uint32_t a_dst = smem_u32(st), b_dst = smem_u32(st + 2 * Cfg::A_BYTES);
-        const int k = (kb0 + i) * TC_BK;
-        if (!A_MN) {
-          tma_load_2d(&tmA, full, a_dst, k, m0);
-        } else {
+        const int k = kbi * TC_BK;
+        if (!tapA) {
+          mbar_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
+          if (!A_MN) {
+            tma_load_2d(&tmA, full, a_dst, k, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(&tmA, full, a_dst + j * 4096, m0 + j * 32, k);
-        }
-        if (!B_MN) {
-          tma_load_2d(&tmB, full, b_dst, k, n0);
-        } else {
+            for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(&tmA, full, a_dst + j * 4096, m0 + j * 32, k);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmB, full, b_dst, k, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * 4096, n0 + j * 32, k);
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * 4096, n0 + j * 32, k);
+          }
+        } else if (!A_MN) {
+          // forward / data-gradient: K block = (tap, 32-channel chunk); one 4-D box of the NHWC activation tensor
+          const int tap = kbi / tp.cpb, cc = kbi - tap * tp.cpb;
+          const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+          mbar_expect_tx(full, tp.rows * 128 + Cfg::B_BYTES);
+          tma_load_4d(&tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 * tp.sy + kh - tp.py, b0);
+          if (!B_MN) {
+            tma_load_2d(&tmB, full, b_dst, k, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * 4096, n0 + j * 32, k);
+          }
+        } else {
+          // weight gradient: K block = box of pixels (image b, rows yy0..); M = 4 (tap, chunk) slices of the im2col K axis
+          const int b = kbi / tp.tpi, yy0 = (kbi - b * tp.tpi) * tp.ny;
+          int na = 0;
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j) na += (m0 / 32 + j) < tp.nslices ? 1 : 0;
+          mbar_expect_tx(full, (na + Cfg::BNS / 32) * tp.rows * 128);
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j) {
+            const int sl = m0 / 32 + j;
+            if (sl < tp.nslices) {
+              const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
+              const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+              tma_load_4d(&tmA, full, a_dst + j * 4096, tp.c_off + cc * 32, kw - tp.px, yy0 * tp.sy + kh - tp.py, b);
+            }
+          }
+          // dy as [image][pixel of the image][N]: pixel rows past the image's last row read as zero (the x boxes of
+          // those phantom rows may hold valid input pixels)
+#pragma unroll
+          for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * 4096, n0 + j * 32, yy0 * tp.Xn, b);
         }
       }
     }
@@ -213,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t tmem_corr = tmem_base + 2 * BN;
+    const int ksteps = (tapA && A_MN) ? tp.kpad / 8 : TC_BK / 8;     // pixel-box K blocks may be shorter than 32
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S;
       const uint32_t ph = (i / S) & 1;
@@ -234,6 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_base = pass == 1 ? b_lo : b_hi;
 #pragma unroll
           for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+            if (k4 >= ksteps) break;
             const uint64_t da = umma_desc(a_base + (A_MN ? k4 * 1024 : k4 * 32), A_MN ? lbo : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
             const uint64_t db = umma_desc(b_base + (B_MN ? k4 * 1024 : k4 * 32), B_MN ? lbo : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             if (pass < 2) umma_tf32(tmem_corr, da, db, idesc, (i | pass | k4) != 0 ? 1u : 0u);
@@ -297,18 +359,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     while (drained < nchunks) drain(drained++);
     // ------------------------------------------------------------ epilogue (from registers)
     if (nkb > 0) {
-      const int row = m0 + q * 32 + lane;
+      // output row of this thread: plain GEMM row, or output pixel (image, y, x) of the tile's pixel box
+      const int r = q * 32 + lane;
+      bool rvalid;
+      long long roff;
+      if (tapA && !A_MN) {
+        const int x = r % tp.Xn, t2 = r / tp.Xn;
+        const int yy = t2 % tp.ny, bb = t2 / tp.ny;
+        rvalid = r < tp.rows && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
+        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
+      } else {
+        rvalid = (m0 + r) < g.M;
+        roff = (long long)(m0 + r) * g.sCm;
+      }
+      const float neg_slope = g.act == 3 ? 0.f : 0.01f;            // act 3: relu' of mask, act 4: leaky'
 #pragma unroll
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + t_lane + 2 * BN + half * Cfg::COLS + j0, v);     // lo*hi + hi*lo correction
         const int colv = n0 + half * Cfg::COLS + j0;
-        if (row < g.M && g.vec_store && colv + 16 <= g.N) {
+        if (rvalid && g.vec_store && colv + 16 <= g.N) {
           // 16 consecutive columns of this thread's row: four 16-byte stores
-          float* p = g.C + row * g.sCm + colv;
+          float* p = g.C + roff + colv;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 o;
+            float4 o, mk = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (g.act >= 3) mk = *reinterpret_cast<const float4*>(g.mask + roff + colv + j);
+            const float* mv = reinterpret_cast<const float*>(&mk);
             float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -316,23 +393,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (g.bias != nullptr) x += g.bias[colv + j + e];
               if (g.act == 1) x = fmaxf(x, 0.f);
               else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+              else if (g.act >= 3) x = mv[e] > 0.f ? x : neg_slope * x;
               ov[e] = x;
             }
             *reinterpret_cast<float4*>(p + j) = o;
           }
-        } else if (row < g.M) {
+        } else if (rvalid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + half * Cfg::COLS + j0 + j;
             if (col < g.N) {
               float x = acc[j0 + j] + v[j];
               if (g.bias != nullptr && (!g.atomic || blockIdx.z == 0)) x += g.bias[col];
-              float* p = g.C + row * g.sCm + col * g.sCn;
+              float* p = g.C + roff + col * g.sCn;
               if (g.atomic) {
                 atomicAdd(p, x);
               } else {
                 if (g.act == 1) x = fmaxf(x, 0.f);
                 else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+                else if (g.act >= 3) x = g.mask[roff + col * g.sCn] > 0.f ? x : neg_slope * x;
                 *p = x;
               }
             }
@@ -408,6 +487,12 @@ static int launch_tc(int form, const CUtensorMap& ta, const CUtensorMap& tb, con
   else TC_LAUNCH(true, true);
 #undef TC_LAUNCH
   prof_work(2.0 * g.M * (double)g.N * g.K);
+  if (g_prof_on && g_prof_shapes) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "%s[f%d,M=%d,N=%d,K=%d,z=%d]", g.tap.mode ? "conv_tc" : "gemm_tc", form, g.M, g.N, g.K, (int)grid.z);
+    DDRL_LAUNCHED(prof_intern(nm));
+    return DDRL_OK;
+  }
   DDRL_LAUNCHED("gemm_tc_kernel");
   return DDRL_OK;
 }
@@ -425,9 +510,11 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
   if (form == 0) r = make_map(&tb, B, K, N, ldb, (bn + 31) / 32 * 32, false); else r = make_map(&tb, B, N, K, ldb, 32, true);
   if (r != DDRL_OK) return r;
   TcArgs g;
+  memset(&g, 0, sizeof(g));
   g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K; g.act = act;
   g.sCm = trans_c ? 1 : ldc; g.sCn = trans_c ? ldc : 1;
   const int kb_total = ceil_div(K, TC_BK);
+  g.kb_total = kb_total;
   const int tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
   int splits = 1;
   if (act == 0 && kb_total >= 64 && tiles < kNumSMs) splits = std::min(std::min(ceil_div(2 * kNumSMs, tiles), kb_total / 16), 1024);
@@ -447,6 +534,130 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
     case 128: return launch_tc<128>(form, ta, tb, g, grid, s);
     case 64: return launch_tc<64>(form, ta, tb, g, grid, s);
     default: return launch_tc<32>(form, ta, tb, g, grid, s);
+  }
+}
+
+// ---------------------------------------------------------------- implicit-GEMM convolutions
+// 4-D map over an NHWC tensor [Bn, H, W, C]: box = 32 channels x nx pixels (every sx-th) x ny rows (every sy-th) x nb
+static int make_map_nhwc(CUtensorMap* m, const ConvOp& o, int nx, int ny, int nb, bool mn_major) {
+  cuuint64_t dims[4] = {(cuuint64_t)o.Ctot, (cuuint64_t)o.Win, (cuuint64_t)o.Hin, (cuuint64_t)o.Bn};
+  cuuint64_t strides[3] = {(cuuint64_t)o.Ctot * 4, (cuuint64_t)o.Win * o.Ctot * 4, (cuuint64_t)o.Hin * o.Win * o.Ctot * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)((nx - 1) * o.sx + 1), (cuuint32_t)((ny - 1) * o.sy + 1), (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)o.sx, (cuuint32_t)o.sy, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.a), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(nhwc box %d x %d x %d) failed (%d)", nx, ny, nb, (int)r);
+    return DDRL_E_CUDA;
+  }
+  return DDRL_OK;
+}
+
+bool conv_tc_supported(const ConvOp& o, bool wgrad) {
+  if (o.Cin % 32 != 0 || o.Ctot % 4 != 0 || o.c_off % 4 != 0 || o.c_off + o.Cin > o.Ctot) return false;
+  if ((reinterpret_cast<uintptr_t>(o.a) & 15) != 0) return false;
+  if (o.sx < 1 || o.sx > 8 || o.sy < 1 || o.sy > 8) return false;
+  if (o.Xn < 1 || o.Yn < 1 || o.Bn < 1) return false;
+  const int cap = wgrad ? 32 : TC_BM;
+  if (o.Xn > cap) return false;
+  if ((o.Xn - 1) * o.sx + 1 > 256) return false;
+  const int ny = std::min(o.Yn, std::max(1, cap / o.Xn));
+  if ((ny - 1) * o.sy + 1 > 256) return false;
+  return true;
+}
+
+static void tap_common(TcTap& t, const ConvOp& o, int cap) {
+  memset(&t, 0, sizeof(t));
+  t.mode = 1;
+  t.Xn = o.Xn; t.Yn = o.Yn; t.Bn = o.Bn;
+  if (o.Xn * o.Yn <= cap) {                     // whole images per box
+    t.ny = o.Yn; t.nb = std::min(std::max(1, cap / (o.Xn * o.Yn)), 256); t.tpi = 1;
+  } else {                                      // row blocks of one image
+    t.ny = std::max(1, cap / o.Xn); t.nb = 1; t.tpi = ceil_div(o.Yn, t.ny);
+  }
+  t.rows = o.Xn * t.ny * t.nb;
+  t.kpad = (t.rows + 7) & ~7;
+  t.KW = o.KW; t.cpb = o.Cin / 32; t.nslices = o.KH * o.KW * t.cpb;
+  t.sx = o.sx; t.sy = o.sy; t.px = o.px; t.py = o.py; t.c_off = o.c_off;
+}
+
+int conv_tc_fwd(const ConvOp& o, const float* Wp, int ldw, int N, const float* bias, int act, const float* mask, float* out,
+                long long osb, long long osy, long long osx, cudaStream_t s) {
+  if (!conv_tc_supported(o, false) || N < 1 || ldw % 4 != 0 || (reinterpret_cast<uintptr_t>(Wp) & 15) != 0) return DDRL_E_UNSUPPORTED;
+  if (act >= 3 && !mask) return DDRL_E_ARG;
+  int r = get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
+  TcArgs g;
+  memset(&g, 0, sizeof(g));
+  tap_common(g.tap, o, TC_BM);
+  g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
+  const int K = o.KH * o.KW * o.Cin;
+  CUtensorMap ta, tb;
+  r = make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
+  if (r != DDRL_OK) return r;
+  r = make_map(&tb, Wp, K, N, ldw, (bn + 31) / 32 * 32, false);
+  if (r != DDRL_OK) return r;
+  g.C = out; g.bias = bias; g.mask = mask; g.act = act;
+  g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K;
+  g.sCm = 0; g.sCn = 1;
+  g.kb_total = g.tap.nslices; g.kb_per_split = g.kb_total;
+  g.atomic = 0;
+  g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                 (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) ? 1 : 0;
+  dim3 grid(ceil_div(o.Bn, g.tap.nb) * g.tap.tpi, ceil_div(N, bn), 1);
+  switch (bn) {
+    case 128: return launch_tc<128>(0, ta, tb, g, grid, s);
+    case 64: return launch_tc<64>(0, ta, tb, g, grid, s);
+    default: return launch_tc<32>(0, ta, tb, g, grid, s);
+  }
+}
+
+int conv_tc_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s) {
+  if (!conv_tc_supported(o, true) || N < 16 || ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return DDRL_E_UNSUPPORTED;
+  int r = get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
+  TcArgs g;
+  memset(&g, 0, sizeof(g));
+  tap_common(g.tap, o, 32);
+  if (g.tap.nb != 1) { g.tap.nb = 1; g.tap.rows = o.Xn * g.tap.ny; g.tap.kpad = (g.tap.rows + 7) & ~7; }
+  const int K = o.KH * o.KW * o.Cin;             // = M of this GEMM (the im2col K axis)
+  CUtensorMap ta, tb;
+  r = make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, true);
+  if (r != DDRL_OK) return r;
+  {
+    // dy [pixels, N] (MN-major operand): boxes of tap.rows pixel rows x 32 columns
+    const long long ipix = (long long)o.Yn * o.Xn;
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)ipix, (cuuint64_t)o.Bn};
+    cuuint64_t strides[2] = {(cuuint64_t)ldy * 4, (cuuint64_t)ipix * ldy * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)g.tap.rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = g_encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(dy box) failed (%d)", (int)cr);
+      return DDRL_E_CUDA;
+    }
+  }
+  g.C = dWp; g.bias = nullptr; g.mask = nullptr; g.act = 0;
+  g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn;
+  g.sCm = 1; g.sCn = ldw;                        // C[m = im2col k, n = cout] -> dWp[n*ldw + m]
+  g.kb_total = o.Bn * g.tap.tpi;
+  const int tiles = ceil_div(K, TC_BM) * ceil_div(N, bn);
+  int splits = std::max(1, std::min(std::min(ceil_div(2 * kNumSMs, tiles), g.kb_total / 16), 1024));
+  int kbps = ceil_div(g.kb_total, splits);
+  splits = ceil_div(g.kb_total, kbps);
+  g.kb_per_split = kbps;
+  g.atomic = 1;                                  // accumulates into the packed gradient (zeroed per backward)
+  g.vec_store = 0;
+  dim3 grid(ceil_div(K, TC_BM), ceil_div(N, bn), splits);
+  switch (bn) {
+    case 128: return launch_tc<128>(2, ta, tb, g, grid, s);
+    case 64: return launch_tc<64>(2, ta, tb, g, grid, s);
+    default: return launch_tc<32>(2, ta, tb, g, grid, s);
   }
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/ddrl_b200.h"
 
 namespace ddrl {
@@ -16,6 +18,55 @@ struct ConvGeom {
   int ldc;                       // row stride of the im2col matrix (K rounded up to 4)
   int order;                     // 0: k=(kh,kw,c)   1: k=(c,kh,kw)
 };
+
+// Implicit-GEMM operand description for the tcgen05 engine (gemm_tc.cu).  mode 0 = plain 2-D operands.
+// mode 1: the activation operand is fetched as 4-D TMA boxes (32 channels x Xn pixels x ny rows x nb images) of an
+// NHWC tensor, one box per (kernel tap, 32-channel chunk): no im2col matrix exists in memory.
+struct TcTap {
+  int mode;
+  int Xn, Yn, Bn;                // output pixel grid: Xn x Yn per image, Bn images
+  int ny, nb, tpi;               // box = nb images x ny rows x Xn pixels; boxes per image
+  int rows;                      // Xn*ny*nb   (forward/dgrad: <= 128 = the M tile; wgrad: <= 32 = one K block)
+  int kpad;                      // rows rounded up to 8 (wgrad: MMA K steps per block)
+  int KW, cpb;                   // tap index = kh*KW + kw; 32-channel chunks per tap
+  int nslices;                   // taps * cpb
+  int sx, sy, px, py;            // input coordinate = out*s + k - p
+  int c_off;                     // first channel of the operand inside the tensor's channel axis
+  long long osb, osy, osx;       // output element strides per (image, row, pixel)   (forward/dgrad)
+};
+
+// One implicit-GEMM convolution launch over an NHWC tensor a[Bn, Hin, Win, Ctot] (channels [c_off, c_off+Cin)).
+struct ConvOp {
+  const float* a;
+  int Hin, Win, Ctot, c_off, Cin;
+  int KH, KW, sy, sx, py, px;
+  int Yn, Xn, Bn;                // output pixel grid
+};
+// out[pixel, n] = epilogue( sum_{tap,c} a[pixel*s + tap - p, c] * Wp[n, (tap, c)] );  pixel -> out + b*osb + y*osy + x*osx
+// act: 0 none, 1 relu, 2 leaky, 3 multiply by relu'(mask), 4 multiply by leaky'(mask)  (mask addressed like out)
+int conv_tc_fwd(const ConvOp& o, const float* Wp, int ldw, int N, const float* bias, int act, const float* mask, float* out,
+                long long osb, long long osy, long long osx, cudaStream_t s);
+// dWp[n, (tap, c)] += sum_pixels dy[pixel, n] * a[pixel*s + tap - p, c]      (dy rows = pixels in (b, y, x) order)
+int conv_tc_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s);
+bool conv_tc_supported(const ConvOp& o, bool wgrad);
+
+// conv_ops.cu: convolution layers on the implicit-GEMM path
+struct DgradClass {              // one parity class (pix + pad) mod stride of the data gradient
+  int ry, rx;                    // class residues
+  int nty, ntx;                  // taps per axis reaching this class
+  int iy0, ix0;                  // first input pixel of the class
+  int Yn, Xn;                    // pixels of the class per image
+  int pady, padx;                // padding of the equivalent stride-1 convolution over dy
+  int K;                         // nty*ntx*Cout
+  float* wd;                     // packed weights [Cin, K]
+};
+ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B);
+int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out);
+int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s);
+int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
+                  float* dx, int act, const float* mask, int B, cudaStream_t s);
+bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,
+                          int dy_coff, int B);
 
 // GEMM engines --------------------------------------------------------------------------
 int gemm_simt(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -151,6 +151,34 @@ def gemm(form: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
+def conv_nhwc(op: int, x, w, dy=None, bias=None, stride: int = 1, pad: int = 0, act: int = 0, mask=None):
+    """Implicit-GEMM convolution on NHWC activations (ddrl_conv_nhwc_f32).  x [B,H,W,Cin] (or its shape as a tuple for
+    op 1), w [Cout,Cin,KH,KW] reference layout.  op 0: forward -> [B,Ho,Wo,Cout]; op 1: data gradient of dy -> [B,H,W,Cin];
+    op 2: weight gradient -> [Cout,Cin,KH,KW]."""
+    lib = _lib.load()
+    w = _f32c(w)
+    Cout, Cin, KH, KW = w.shape
+    B, H, W = (x.shape if torch.is_tensor(x) else x)[:3]
+    conv1d = H == 1 and KH == 1
+    Ho = 1 if conv1d else (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    d = _lib.ConvDesc(B, H, W, Cin, Cout, KH, KW, stride, pad)
+    dev = w.device
+    if op == 0:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=dev)
+    elif op == 1:
+        out = torch.zeros((B, H, W, Cin), dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty_like(w)
+    xx = _f32c(x) if torch.is_tensor(x) else None
+    dyy = _f32c(dy) if dy is not None else None
+    bb = _f32c(bias) if bias is not None else None
+    mm = _f32c(mask) if mask is not None else None
+    check(lib.ddrl_conv_nhwc_f32(op, C.byref(d), ptr(xx), ptr(w), ptr(bb), ptr(dyy), act, ptr(mm), ptr(out), current_stream()),
+          "ddrl_conv_nhwc_f32")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().ddrl_launch_count())
 

@@ -145,6 +145,22 @@ int ddrl_clip_adam(float* params, float* grads, float* m, float* v, int64_t n,
 int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, const float* bias, int act, int beta, void* stream);
 
+/* ---- convolution building block (implicit GEMM; exposed for parity tests) ----------------
+ * The conv layers of the encoders (nn.Conv2d / nn.Conv1d + autograd in nn/atari_encoder.py:16-28,
+ * nn/nav_encoder.py:17-31,85-93) on NHWC activations, with the activation operand fetched tap by
+ * tap through 4-D TMA boxes (no im2col matrix in memory).  w / dw use the reference's OIHW layout.
+ *  op 0: out[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w) + bias )                act 0/1/2 as ddrl_gemm_f32
+ *  op 1: out[B,H,W,Cin]    = conv_transpose(dy[B,Ho,Wo,Cout], w) * act'(mask)   act 0 none, 3 relu', 4 leaky'
+ *                            (mask [B,H,W,Cin] = the forward activation whose derivative is applied)
+ *  op 2: out[Cout,Cin,KH,KW] = sum_pixels dy (x) x                              (weight gradient)
+ * H == 1 && KH == 1 describes a Conv1d over W.  Needs Cin % 32 == 0 (op 0, 2) / Cout % 32 == 0 (op 1);
+ * other shapes return DDRL_E_UNSUPPORTED (the engine keeps those layers on explicit im2col). */
+typedef struct {
+  int32_t B, H, W, Cin, Cout, KH, KW, stride, pad;
+} ddrl_conv_desc;
+int ddrl_conv_nhwc_f32(int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
+                       const float* dy, int act, const float* mask, float* out, void* stream);
+
 /* ---- the actor-critic net ---------------------------------------------------------------
  * replaces PPO.forward / PPO.learn and the classes they are built from
  * (nn/ppo.py:17-146, nn/actor.py, nn/critic.py, nn/atari_encoder.py, nn/nav_encoder.py,

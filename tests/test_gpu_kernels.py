@@ -328,3 +328,66 @@ def test_gemm_tc_is_3xtf32_accurate():
     e_simt = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="simt").cpu().double() - ref).abs().max() / ref.abs().max())
     print("max err / max|ref|: tc %.2e  simt %.2e" % (e_tc, e_simt))
     assert e_tc < 2e-6 and e_simt < 2e-6
+
+
+# ------------------------------------------------------------------ implicit-GEMM convolutions (tap-TMA path)
+# (B, H, W, Cin, Cout, KH, KW, stride, pad): the inner conv layers of the three encoders + edge geometries
+CONV_CASES = [
+    (5, 20, 20, 32, 64, 4, 4, 2, 0),      # Pong conv2   (nn/atari_encoder.py:17)
+    (7, 9, 9, 64, 64, 3, 3, 1, 0),        # Pong conv3   (nn/atari_encoder.py:18)
+    (3, 24, 24, 64, 128, 3, 3, 1, 1),     # NavPreNet conv2 (nn/nav_encoder.py:18)
+    (3, 12, 12, 128, 256, 3, 3, 1, 1),    # NavPreNet conv3
+    (2, 22, 22, 64, 128, 5, 5, 1, 1),     # NavPreNet1D conv2 (nn/nav_encoder.py:86)
+    (4, 10, 10, 128, 256, 3, 3, 1, 1),    # NavPreNet1D conv3
+    (6, 1, 478, 32, 32, 1, 3, 2, 0),      # laser conv1d2 (nn/nav_encoder.py:92)
+    (1, 7, 5, 32, 32, 3, 3, 1, 1),        # single image, odd extents
+    (130, 6, 6, 32, 96, 3, 3, 2, 1),      # stride 2 with padding, many images per tile, N not a multiple of 64
+]
+
+
+def _conv_ref(x_nhwc, w, stride, pad, conv1d):
+    x = x_nhwc.permute(0, 3, 1, 2).double()
+    if conv1d:
+        return torch.nn.functional.conv2d(x, w.double(), None, stride=(1, stride), padding=(0, pad))
+    return torch.nn.functional.conv2d(x, w.double(), None, stride=stride, padding=pad)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_implicit_forward_dgrad_wgrad(case):
+    """ddrl_conv_nhwc_f32 (4-D TMA tap boxes, no im2col) == torch conv2d forward / autograd, fp32 tolerance 1e-5."""
+    from ddrl4nav_b200 import kernels
+    B, H, W, Cin, Cout, KH, KW, stride, pad = case
+    conv1d = H == 1 and KH == 1
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, KH, KW, generator=g) / (Cin * KH * KW) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y_ref = _conv_ref(xr, wr, stride, pad, conv1d)                       # [B, Cout, Ho, Wo]
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy.double())
+    # forward (+ bias + leaky relu in the epilogue)
+    y = kernels.conv_nhwc(0, x.to(DEV), w.to(DEV), bias=bias.to(DEV), stride=stride, pad=pad, act=2)
+    ref = torch.nn.functional.leaky_relu(y_ref.detach() + bias.double()[None, :, None, None], 0.01).permute(0, 2, 3, 1)
+    assert close(y, ref, rtol=1e-5, atol_scale=2e-6)
+    # data gradient, with the fused activation backward (leaky' of a mask tensor)
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
+    mask = torch.randn(B, H, W, Cin, generator=g)
+    dx = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad, act=4, mask=mask.to(DEV))
+    dx_ref = xr.grad * torch.where(mask > 0, 1.0, 0.01).double()
+    assert close(dx, dx_ref, rtol=1e-5, atol_scale=2e-6)
+    dx0 = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad)
+    assert close(dx0, xr.grad, rtol=1e-5, atol_scale=2e-6)
+    # weight gradient
+    dw = kernels.conv_nhwc(2, x.to(DEV), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad)
+    assert close(dw, wr.grad, rtol=1e-5, atol_scale=2e-6)
+
+
+def test_conv_implicit_rejects_unsupported_channels():
+    from ddrl4nav_b200 import kernels
+    from ddrl4nav_b200._lib import DDRLError
+    x = torch.randn(2, 8, 8, 4, device=DEV)
+    w = torch.randn(32, 4, 3, 3, device=DEV)
+    with pytest.raises(DDRLError):
+        kernels.conv_nhwc(0, x, w)
