@@ -498,8 +498,9 @@ static int launch_tc(int form, const CUtensorMap& ta, const CUtensorMap& tb, con
 }
 
 int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-            const float* bias, int act, int beta, int trans_c, cudaStream_t s) {
+            const float* bias, int act, int beta, int trans_c, cudaStream_t s, const float* mask) {
   if (trans_c && bias) return DDRL_E_ARG;
+  if (act >= 3 && (!mask || trans_c || beta)) return DDRL_E_ARG;
   int r = get_encode();
   if (r != DDRL_OK) return r;
   const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
@@ -511,7 +512,7 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
   if (r != DDRL_OK) return r;
   TcArgs g;
   memset(&g, 0, sizeof(g));
-  g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K; g.act = act;
+  g.C = C; g.bias = bias; g.mask = mask; g.M = M; g.N = N; g.K = K; g.act = act;
   g.sCm = trans_c ? 1 : ldc; g.sCn = trans_c ? ldc : 1;
   const int kb_total = ceil_div(K, TC_BK);
   g.kb_total = kb_total;
@@ -522,7 +523,8 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
   splits = ceil_div(kb_total, kbps);
   g.kb_per_split = kbps;
   g.atomic = (splits > 1 || beta) ? 1 : 0;
-  g.vec_store = (!g.atomic && !trans_c && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  g.vec_store = (!g.atomic && !trans_c && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                 (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) ? 1 : 0;
   if (splits > 1 && !beta) {
     const int rows = trans_c ? N : M, cols = trans_c ? M : N;
     if (ldc == cols) DDRL_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)rows * cols, s));

@@ -72,7 +72,7 @@ bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradCl
 int gemm_simt(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
               const float* bias, int act, int beta, int trans_c, cudaStream_t s);
 int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-            const float* bias, int act, int beta, int trans_c, cudaStream_t s);
+            const float* bias, int act, int beta, int trans_c, cudaStream_t s, const float* mask = nullptr);
 bool gemm_tc_supported(int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* C,
                        int ldc, int trans_c);
 

@@ -62,6 +62,9 @@ struct Tower {
   std::string prefix;
   std::vector<Lin> L;            // layer order is arch specific (see build_tower)
   ConvGeom g[5];                 // conv geometries (arch specific slots)
+  bool implicit[5] = {false, false, false, false, false};   // layer runs on the implicit-GEMM (tap-TMA) path
+  int conv_lin[5] = {-1, -1, -1, -1, -1};                   // index into L of the conv in slot g[i]
+  std::vector<DgradClass> dg[5];                            // data-gradient parity classes (+ packed weights)
   // per-micro-batch buffers
   std::vector<float*> buf;
   std::vector<uint8_t*> idx;
@@ -220,13 +223,38 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
       t.L.push_back(make_lin(n, P("fc0.0"), feat, in_ch, 1, in_ch, ACT_RELU));
       break;
   }
+  // conv slot -> layer index; inner convs (NHWC input, channel count a multiple of 32) take the implicit-GEMM path
+  const int nconv = arch == DDRL_ARCH_ATARI ? 3 : (arch == DDRL_ARCH_NAV1D ? 5 : (arch == DDRL_ARCH_MLP ? 0 : 3));
+  const char* no_implicit = getenv("DDRL_NO_IMPLICIT");
+  for (int i = 0; i < nconv; ++i) {
+    t.conv_lin[i] = i;
+    const ConvGeom& g = t.g[i];
+    const int Cout = t.L[i].N;
+    if (n->d.gemm_mode != DDRL_GEMM_TC_3XTF32 || g.order != 0 || g.C % 32 != 0 || Cout % 32 != 0) continue;
+    if (no_implicit && no_implicit[0] == '1') continue;
+    static const float* const kAligned = reinterpret_cast<const float*>(uintptr_t(256));
+    ConvOp o = conv_op_fwd(g, kAligned, g.C, 0, 1);
+    if (!conv_tc_supported(o, false) || !conv_tc_supported(o, true)) continue;
+    std::vector<DgradClass> cls;
+    if (conv_dgrad_plan(g, Cout, cls) != DDRL_OK) continue;
+    if (!conv_dgrad_supported(g, Cout, cls, kAligned, Cout, 0, 1)) continue;
+    t.implicit[i] = true;
+    t.dg[i] = cls;
+  }
 }
 
 // ---- engine dispatch ------------------------------------------------------------------
+// act 3 / 4: C = (A op B) * relu' / leaky' of mask (same shape and row stride as C)
 static int gemm(const ddrl_net* n, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                float* C, int ldc, const float* bias, int act, int beta, int trans_c, cudaStream_t s) {
+                float* C, int ldc, const float* bias, int act, int beta, int trans_c, cudaStream_t s,
+                const float* mask = nullptr) {
   if (n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 && gemm_tc_supported(form, M, N, K, A, lda, B, ldb, C, ldc, trans_c))
-    return gemm_tc(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s);
+    return gemm_tc(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s, mask);
+  if (act >= 3) {
+    int r = gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, beta, trans_c, s);
+    if (r != DDRL_OK) return r;
+    return act_bwd(C, ldc, mask, ldc, M, N, act - 2, s);
+  }
   return gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s);
 }
 
@@ -245,24 +273,29 @@ static float* db_of(const ddrl_net* n, const Lin& l) { return n->grads + n->T[l.
 static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* y, int ldy, long long M, cudaStream_t s) {
   return gemm(n, 0, (int)M, l.N, l.K, x, ldx, W_of(n, l), l.ldw, y, ldy, b_of(n, l), l.act, 0, 0, s);
 }
-// dy <- dy * act'(y); db += colsum(dy); dW += dy^T x; dx = dy W  (ncols_dx: leading columns of dx wanted)
-static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* dy, int ldy, const float* y, int ldy_act,
-                   float* dx, int lddx, int ncols_dx, long long M, cudaStream_t s) {
-  TRY(act_bwd(dy, ldy, y, ldy_act, M, l.N, l.act, s));
+// dy holds dL/d(pre-activation) of this layer (the activation derivative was applied by whoever produced dy).
+// db += colsum(dy); dW += dy^T x; dx = (dy W) * act'(mask)   (ncols_dx: leading columns of dx wanted;
+// mask_act: 0 none, 1 relu, 2 leaky -- the activation that produced x, i.e. of the layer BELOW; mask = that x)
+static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* dy, int ldy, float* dx, int lddx,
+                   int ncols_dx, int mask_act, const float* mask, long long M, cudaStream_t s) {
   TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
   // dW[N, K] += dy[M,N]^T x[M,K]: run with the larger of (N, K) on the 128-row side
   if (l.N >= 128 || l.N >= l.K)
     TRY(gemm(n, 2, l.N, l.K, (int)M, dy, ldy, x, ldx, dW_of(n, l), l.ldw, nullptr, 0, 1, 0, s));
   else
     TRY(gemm(n, 2, l.K, l.N, (int)M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, nullptr, 0, 1, 1, s));
-  if (dx) TRY(gemm(n, 1, (int)M, ncols_dx, l.N, dy, ldy, W_of(n, l), l.ldw, dx, lddx, nullptr, 0, 0, 0, s));
+  if (dx) TRY(gemm(n, 1, (int)M, ncols_dx, l.N, dy, ldy, W_of(n, l), l.ldw, dx, lddx, nullptr, mask_act ? mask_act + 2 : 0, 0, 0, s,
+                   mask_act ? mask : nullptr));
   return DDRL_OK;
 }
 
 // ---- workspace ------------------------------------------------------------------------
 // per-sample float counts of a tower's buffers, in the order tower_alloc() carves them
 static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std::vector<size_t>& u8) {
-  auto cols = [&](const ConvGeom& g) { return (size_t)g.Ho * g.Wo * g.ldc; };
+  auto cols = [&](const ConvGeom& g) {
+    const int gi = (int)(&g - &t.g[0]);
+    return t.implicit[gi] ? (size_t)0 : (size_t)g.Ho * g.Wo * g.ldc;
+  };
   auto outp = [&](const ConvGeom& g, int Co) { return (size_t)g.Ho * g.Wo * Co; };
   f.clear(); u8.clear();
   switch (t.arch) {
@@ -374,10 +407,24 @@ static int alloc_packed(ddrl_net* n) {
       if (l.packed) bytes += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
   n->packed_grad_off = bytes;
   n->packed_grad_bytes = bytes;
-  n->packed_bytes = 2 * bytes;
-  if (!bytes) return DDRL_OK;
+  // data-gradient weights of the implicit convs (one re-packed copy per parity class), after the two twin regions
+  size_t dg_bytes = 0;
+  for (auto& t : n->towers)
+    for (int i = 0; i < 5; ++i)
+      for (auto& c : t.dg[i]) dg_bytes += ((size_t)t.g[i].C * c.K * 4 + 255) & ~size_t(255);
+  n->packed_bytes = 2 * bytes + dg_bytes;
+  if (!n->packed_bytes) return DDRL_OK;
   DDRL_CUDA(cudaMalloc(&n->packed_base, n->packed_bytes));
   DDRL_CUDA(cudaMemset(n->packed_base, 0, n->packed_bytes));     // padding columns stay zero forever
+  {
+    size_t off = 2 * bytes;
+    for (auto& t : n->towers)
+      for (int i = 0; i < 5; ++i)
+        for (auto& c : t.dg[i]) {
+          c.wd = reinterpret_cast<float*>(n->packed_base + off);
+          off += ((size_t)t.g[i].C * c.K * 4 + 255) & ~size_t(255);
+        }
+  }
   size_t off = 0;
   for (auto& t : n->towers)
     for (auto& l : t.L)
@@ -393,6 +440,12 @@ static int repack(ddrl_net* n, cudaStream_t s) {
   for (auto& t : n->towers)
     for (auto& l : t.L)
       if (l.packed) TRY(pack_weight(n->params + n->T[l.w_t].offset, l.wp, l.N, l.I, l.J, l.ldw, s));
+  for (auto& t : n->towers)
+    for (int i = 0; i < 5; ++i)
+      for (auto& c : t.dg[i]) {
+        const Lin& l = t.L[t.conv_lin[i]];
+        TRY(pack_dgrad(n->params + n->T[l.w_t].offset, t.g[i], l.N, c, s));
+      }
   n->dirty = false;
   return DDRL_OK;
 }
@@ -401,6 +454,12 @@ static int repack(ddrl_net* n, cudaStream_t s) {
 static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, float* cols, float* y, int mb,
                       cudaStream_t s, bool cols_cached = false) {
   const ConvGeom& g = t.g[gi];
+  if (t.implicit[gi]) {
+    const Lin& l = t.L[li];
+    const ConvOp o = conv_op_fwd(g, x, g.C, 0, mb);
+    return conv_tc_fwd(o, W_of(n, l), l.ldw, l.N, b_of(n, l), l.act, nullptr, y, (long long)o.Yn * o.Xn * l.N,
+                       (long long)o.Xn * l.N, l.N, s);
+  }
   if (!cols_cached) TRY(im2col(g, x, cols, mb, s));
   return lin_fwd(n, t.L[li], cols, g.ldc, y, t.L[li].N, (long long)mb * g.Ho * g.Wo, s);
 }
@@ -467,14 +526,25 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
   return DDRL_E_ARG;
 }
 
-// conv layer backward: dy [M, Cout] already holds dL/d(activated output); handles act', db, dW, and dx (NHWC) if wanted
-static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const float* cols, float* dy, const float* y,
-                    float* dcols, float* dx, int mb, cudaStream_t s) {
+// conv layer backward.  dy [M, Cout] holds dL/d(pre-activation).  x: the layer's NHWC input (implicit path) / cols: its
+// im2col matrix (explicit path).  db, dW, and -- if dx -- the input gradient times act'(x) (mask_act: activation that
+// produced x; 0 = none or handled elsewhere, e.g. by pool_bwd)
+static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, const float* cols, float* dy,
+                    float* dcols, float* dx, int mask_act, int mb, cudaStream_t s) {
   const ConvGeom& g = t.g[gi];
   const Lin& l = t.L[li];
   const long long M = (long long)mb * g.Ho * g.Wo;
-  TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, y, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, M, s));
-  if (dx) TRY(col2im(g, dcols, dx, mb, s));
+  if (t.implicit[gi]) {
+    TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
+    TRY(conv_tc_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    if (dx) TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s));
+    return DDRL_OK;
+  }
+  TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, 0, nullptr, M, s));
+  if (dx) {
+    TRY(col2im(g, dcols, dx, mb, s));
+    if (mask_act) TRY(act_bwd(dx, g.C, x, g.C, (long long)mb * g.H * g.W, g.C, mask_act, s));
+  }
   return DDRL_OK;
 }
 
@@ -482,10 +552,11 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
   auto& b = t.buf;
   switch (t.arch) {
     case DDRL_ARCH_ATARI: {
-      TRY(lin_bwd(n, t.L[3], b[5], 3136, t.dh, 512, t.h, 512, b[6], 3136, 3136, mb, s));
-      TRY(conv_bwd(n, t, 2, 2, b[4], b[6], b[5], b[7], b[8], mb, s));
-      TRY(conv_bwd(n, t, 1, 1, b[2], b[8], b[3], b[7], b[9], mb, s));
-      TRY(conv_bwd(n, t, 0, 0, b[0], b[9], b[1], nullptr, nullptr, mb, s));
+      // t.dh = dL/dh (linear has no activation); every conv output went through leaky_relu (atari_encoder.py:26-28)
+      TRY(lin_bwd(n, t.L[3], b[5], 3136, t.dh, 512, b[6], 3136, 3136, ACT_LEAKY, b[5], mb, s));
+      TRY(conv_bwd(n, t, 2, 2, b[3], b[4], b[6], b[7], b[8], ACT_LEAKY, mb, s));
+      TRY(conv_bwd(n, t, 1, 1, b[1], b[2], b[8], b[7], b[9], ACT_LEAKY, mb, s));
+      TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], b[9], nullptr, nullptr, 0, mb, s));
       return DDRL_OK;
     }
     case DDRL_ARCH_NAV:
@@ -499,40 +570,30 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
             *dp1 = b[23], *dz1 = b[24];
       const int Lfc2 = d1 ? 8 : 5, Lfc1 = d1 ? 7 : 4, Lfc0 = d1 ? 6 : 3;
       const int img_off = d1 ? 256 : 0;
-      TRY(lin_bwd(n, t.L[Lfc2], b[10], 512, t.dh, 512, t.h, 512, df1, 512, 512, mb, s));
-      TRY(lin_bwd(n, t.L[Lfc1], b[9], ldcat, df1, 512, b[10], 512, dcat, ldcat, img_off + 512, mb, s));
-      TRY(lin_bwd(n, t.L[Lfc0], b[8], flat, dcat + img_off, ldcat, b[9] + img_off, ldcat, dp3, flat, flat, mb, s));
+      // fc2 (no activation) <- relu(fc1) <- relu(cat parts): each data gradient is multiplied by relu' of its target
+      TRY(lin_bwd(n, t.L[Lfc2], b[10], 512, t.dh, 512, df1, 512, 512, ACT_RELU, b[10], mb, s));
+      TRY(lin_bwd(n, t.L[Lfc1], b[9], ldcat, df1, 512, dcat, ldcat, img_off + 512, ACT_RELU, b[9], mb, s));
+      TRY(lin_bwd(n, t.L[Lfc0], b[8], flat, dcat + img_off, ldcat, dp3, flat, flat, 0, nullptr, mb, s));
+      // ReLU' of the conv outputs is folded into pool_bwd (a > 0 test)
       TRY(pool_bwd(dp3, t.idx[2], b[7], dz3, mb, g2->Ho, g2->Wo, 256, s));
-      // ReLU' is folded into pool_bwd (a>0 test), so the conv layers run with act = none here
-      Lin l2 = t.L[2]; l2.act = ACT_NONE;
-      Lin l1 = t.L[1]; l1.act = ACT_NONE;
-      Lin l0 = t.L[0]; l0.act = ACT_NONE;
-      {
-        const long long M = (long long)mb * g2->Ho * g2->Wo;
-        TRY(lin_bwd(n, l2, b[6], g2->ldc, dz3, 256, b[7], 256, dcols, g2->ldc, g2->ldc, M, s));
-        TRY(col2im(*g2, dcols, dp2, mb, s));
-      }
+      TRY(conv_bwd(n, t, 2, 2, b[5], b[6], dz3, dcols, dp2, 0, mb, s));
       TRY(pool_bwd(dp2, t.idx[1], b[4], dz2, mb, g1->Ho, g1->Wo, 128, s));
-      {
-        const long long M = (long long)mb * g1->Ho * g1->Wo;
-        TRY(lin_bwd(n, l1, b[3], g1->ldc, dz2, 128, b[4], 128, dcols, g1->ldc, g1->ldc, M, s));
-        TRY(col2im(*g1, dcols, dp1, mb, s));
-      }
+      TRY(conv_bwd(n, t, 1, 1, b[2], b[3], dz2, dcols, dp1, 0, mb, s));
       TRY(pool_bwd(dp1, t.idx[0], b[1], dz1, mb, g0->Ho, g0->Wo, 64, s));
-      {
-        const long long M = (long long)mb * g0->Ho * g0->Wo;
-        TRY(lin_bwd(n, l0, b[0], g0->ldc, dz1, 64, b[1], 64, nullptr, 0, 0, M, s));
-      }
+      TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], dz1, nullptr, nullptr, 0, mb, s));
       if (d1) {
+        // laser branch: fc_1d+relu <- conv1d2 <- conv1d1, no activation between the convs (nav_encoder.py:109-110)
         float *dl2 = b[25], *dl1 = b[26];
-        TRY(lin_bwd(n, t.L[5], b[14], 7616, dcat, ldcat, b[9], ldcat, dl2, 7616, 7616, mb, s));
-        TRY(conv_bwd(n, t, 4, 4, b[13], dl2, b[14], dcols, dl1, mb, s));
-        TRY(conv_bwd(n, t, 3, 3, b[11], dl1, b[12], nullptr, nullptr, mb, s));
+        TRY(lin_bwd(n, t.L[5], b[14], 7616, dcat, ldcat, dl2, 7616, 7616, 0, nullptr, mb, s));
+        TRY(conv_bwd(n, t, 4, 4, b[12], b[13], dl2, dcols, dl1, 0, mb, s));
+        TRY(conv_bwd(n, t, 3, 3, nullptr, b[11], dl1, nullptr, nullptr, 0, mb, s));
       }
       return DDRL_OK;
     }
-    case DDRL_ARCH_MLP:
-      return lin_bwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.dh, t.feat, t.h, t.feat, nullptr, 0, 0, mb, s);
+    case DDRL_ARCH_MLP: {
+      TRY(act_bwd(t.dh, t.feat, t.h, t.feat, mb, t.feat, ACT_RELU, s));
+      return lin_bwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.dh, t.feat, nullptr, 0, 0, 0, nullptr, mb, s);
+    }
   }
   return DDRL_E_ARG;
 }
