@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
 
 ARCH = {"atari": 0, "nav": 1, "navped": 2, "nav1d": 3, "mlp": 4}
 DIST = {"categorical": 0, "gaussian": 1}
-GEMM_MODE = {"simt": 0, "tc": 1}
+GEMM_MODE = {"simt": 0, "tc": 1, "tc2": 2}
 
 _P = C.c_void_p
 _I = C.c_int
@@ -56,7 +56,7 @@ SIGNATURES = {
     "ddrl_ppo_loss_gaussian": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _F, C.POINTER(PPOHparams), _I, _P, _I, _P, _P, _P, _P]),
     "ddrl_clip_adam": (_I, [_P, _P, _P, _P, _L, C.POINTER(_L), C.POINTER(_F), _I, _I, C.POINTER(PPOHparams), _P, _P]),
     "ddrl_gemm_f32": (_I, [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
-    "ddrl_conv_nhwc_f32": (_I, [_I, C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P, _P]),
+    "ddrl_conv_nhwc_f32": (_I, [_I, _I, C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P, _P]),
     "ddrl_net_create": (_I, [C.POINTER(NetDesc), C.POINTER(_P)]),
     "ddrl_net_destroy": (_I, [_P]),
     "ddrl_net_num_tensors": (_I, [_P]),

@@ -107,6 +107,27 @@ extern "C" int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const floa
     if (!gemm_tc_supported(form, M, N, K, A, lda, B, ldb, C, ldc, 0)) return DDRL_E_UNSUPPORTED;
     return gemm_tc(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, 0, s);
   }
+  if (mode == DDRL_GEMM_TC2_TMEM) {
+    if (form == 2) {
+      // C[m,n] (+)= sum_k A[k,m] B[k,n]: the engine's weight-gradient form with dy := A, x := B (output row = dy column)
+      if (bias || act) return DDRL_E_UNSUPPORTED;
+      if (!beta) DDRL_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
+      return tc2_wgrad(N, M, K, B, ldb, A, lda, C, ldc, s);
+    }
+    if (beta) return DDRL_E_UNSUPPORTED;
+    const size_t nb = (size_t)(form == 0 ? N : K) * ldb;
+    const size_t nb4 = (nb + 3) & ~size_t(3);
+    float* tmp = nullptr;
+    DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * 3 * nb4));
+    int r = DDRL_OK;
+    if (cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * nb4, s) != cudaSuccess ||
+        cudaMemcpyAsync(tmp, B, sizeof(float) * nb, cudaMemcpyDeviceToDevice, s) != cudaSuccess) r = DDRL_E_CUDA;
+    if (r == DDRL_OK) r = split_hi_lo(tmp, tmp + nb4, tmp + 2 * nb4, (long long)nb4, s);
+    if (r == DDRL_OK) r = tc2_gemm(form, M, N, K, A, lda, tmp + nb4, tmp + 2 * nb4, ldb, C, ldc, bias, act, nullptr, s);
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    return r;
+  }
   if (mode != DDRL_GEMM_SIMT_F32) return DDRL_E_ARG;
   return gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, 0, s);
 }

@@ -69,7 +69,7 @@ int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out) {
       c.pady = c.nty - 1 - (c.iy0 + py - ry) / s;
       c.padx = c.ntx - 1 - (c.ix0 + px - rx) / sxn;
       c.K = c.nty * c.ntx * Cout;
-      c.wd = nullptr;
+      c.wd = c.wd_hi = c.wd_lo = nullptr;
       out.push_back(c);
     }
   return DDRL_OK;
@@ -88,7 +88,7 @@ int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClas
 
 // dx (dense NHWC [B, H, W, C]) = sum over classes; every input pixel belongs to exactly one class
 int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
-                  float* dx, int act, const float* mask, int B, cudaStream_t s) {
+                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine) {
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const int sy = g.stride, sx = W == 1 ? 1 : g.stride;
@@ -98,8 +98,13 @@ int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cl
     o.KH = c.nty; o.KW = c.ntx; o.sy = 1; o.sx = 1; o.py = c.pady; o.px = c.padx;
     o.Yn = c.Yn; o.Xn = c.Xn; o.Bn = B;
     const long long off = ((long long)c.iy0 * W + c.ix0) * g.C;
-    int r = conv_tc_fwd(o, c.wd, c.K, g.C, nullptr, act, mask ? mask + off : nullptr, dx + off, (long long)H * W * g.C,
-                        (long long)sy * W * g.C, (long long)sx * g.C, s);
+    int r;
+    if (tmem_engine)
+      r = tc2_conv_fwd(o, c.wd_hi, c.wd_lo, c.K, g.C, nullptr, act, mask ? mask + off : nullptr, dx + off,
+                       (long long)H * W * g.C, (long long)sy * W * g.C, (long long)sx * g.C, s);
+    else
+      r = conv_tc_fwd(o, c.wd, c.K, g.C, nullptr, act, mask ? mask + off : nullptr, dx + off, (long long)H * W * g.C,
+                      (long long)sy * W * g.C, (long long)sx * g.C, s);
     if (r != DDRL_OK) return r;
   }
   return DDRL_OK;
@@ -127,9 +132,11 @@ bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradCl
 // =========================================================================================
 using namespace ddrl;
 
-extern "C" int ddrl_conv_nhwc_f32(int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
+extern "C" int ddrl_conv_nhwc_f32(int mode, int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
                                   const float* dy, int act, const float* mask, float* out, void* stream) {
   if (!d || !out || !w || op < 0 || op > 2) return DDRL_E_ARG;
+  if (mode != DDRL_GEMM_TC_3XTF32 && mode != DDRL_GEMM_TC2_TMEM) return DDRL_E_ARG;
+  const bool v2 = mode == DDRL_GEMM_TC2_TMEM;
   if (d->B < 1 || d->H < 1 || d->W < 1 || d->Cin < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1 || d->stride < 1 || d->pad < 0)
     return DDRL_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -147,32 +154,41 @@ extern "C" int ddrl_conv_nhwc_f32(int op, const ddrl_conv_desc* d, const float* 
   float* tmp = nullptr;
   if (op == 0) {
     if (!x) return DDRL_E_ARG;
-    DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)d->Cout * g.K));
+    const size_t nw = ((size_t)d->Cout * g.K + 3) & ~size_t(3);
+    DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * 3 * nw));
+    DDRL_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * 3 * nw, s));
     rc = pack_weight(w, tmp, d->Cout, taps, d->Cin, g.K, s);
     ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
     if (rc == DDRL_OK && !conv_tc_supported(o, false)) rc = DDRL_E_UNSUPPORTED;
-    if (rc == DDRL_OK)
-      rc = conv_tc_fwd(o, tmp, g.K, d->Cout, bias, act, mask, out, (long long)o.Yn * o.Xn * d->Cout, (long long)o.Xn * d->Cout,
-                       d->Cout, s);
+    if (rc == DDRL_OK && v2) rc = split_hi_lo(tmp, tmp + nw, tmp + 2 * nw, (long long)nw, s);
+    if (rc == DDRL_OK) {
+      if (v2)
+        rc = tc2_conv_fwd(o, tmp + nw, tmp + 2 * nw, g.K, d->Cout, bias, act, mask, out, (long long)o.Yn * o.Xn * d->Cout,
+                          (long long)o.Xn * d->Cout, d->Cout, s);
+      else
+        rc = conv_tc_fwd(o, tmp, g.K, d->Cout, bias, act, mask, out, (long long)o.Yn * o.Xn * d->Cout,
+                         (long long)o.Xn * d->Cout, d->Cout, s);
+    }
   } else if (op == 1) {
     if (!dy) return DDRL_E_ARG;
     std::vector<DgradClass> cls;
     rc = conv_dgrad_plan(g, d->Cout, cls);
     size_t tot = 0;
-    for (auto& c : cls) tot += (size_t)g.C * c.K;
-    if (rc == DDRL_OK) DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * tot));
+    for (auto& c : cls) tot += (size_t)g.C * c.K;                 // Cout % 32 == 0 on this path: multiples of 4
+    if (rc == DDRL_OK) DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * 3 * tot));
     size_t off = 0;
-    for (auto& c : cls) { c.wd = tmp + off; off += (size_t)g.C * c.K; }
+    for (auto& c : cls) { c.wd = tmp + off; c.wd_hi = c.wd + tot; c.wd_lo = c.wd + 2 * tot; off += (size_t)g.C * c.K; }
     for (auto& c : cls) if (rc == DDRL_OK) rc = pack_dgrad(w, g, d->Cout, c, s);
     if (rc == DDRL_OK && !conv_dgrad_supported(g, d->Cout, cls, dy, d->Cout, 0, d->B)) rc = DDRL_E_UNSUPPORTED;
-    if (rc == DDRL_OK) rc = conv_dgrad_tc(g, d->Cout, cls, dy, d->Cout, 0, out, act, mask, d->B, s);
+    if (rc == DDRL_OK && v2) rc = split_hi_lo(tmp, tmp + tot, tmp + 2 * tot, (long long)tot, s);
+    if (rc == DDRL_OK) rc = conv_dgrad_tc(g, d->Cout, cls, dy, d->Cout, 0, out, act, mask, d->B, s, v2);
   } else {
     if (!x || !dy) return DDRL_E_ARG;
     DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)d->Cout * g.K));
     DDRL_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (size_t)d->Cout * g.K, s));
     ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
     if (!conv_tc_supported(o, true)) rc = DDRL_E_UNSUPPORTED;
-    if (rc == DDRL_OK) rc = conv_tc_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s);
+    if (rc == DDRL_OK) rc = v2 ? tc2_conv_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s) : conv_tc_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s);
     if (rc == DDRL_OK) rc = unpack_grad(tmp, out, d->Cout, taps, d->Cin, g.K, s);
   }
   cudaStreamSynchronize(s);

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "tc_ptx.cuh"
 
 namespace ddrl {
 
@@ -46,90 +47,6 @@ struct TcArgs {
   int vec_store;                               // plain row-major C with 16-byte aligned rows: float4 epilogue stores
   TcTap tap;                                   // tap.mode != 0: implicit-GEMM convolution operands (layer_ops.h)
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
-// | layout type [61,64): SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only layout the hardware
-// accepts for MN-major 32-bit operands: 128 B rows, 32 B swizzle atoms, pattern period 4 rows)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-__device__ __forceinline__ uint32_t tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 
 // The tensor core adds into its fp32 accumulator with TRUNCATION (measured on B200: all-positive tf32-exact
 // inputs lose ~1 ulp per accumulating MMA, -7e-6 relative after 128 MMAs).  To stay at fp32-FFMA accuracy the
@@ -434,7 +351,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-static int get_encode() {
+int tc_get_encode() {
   if (g_encode) return DDRL_OK;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -445,8 +362,8 @@ static int get_encode() {
 }
 
 // 2-D fp32 tensor [outer, inner] with row stride ld (floats); box = [box_outer, 32 floats], 128B swizzle
-static int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
-                    bool mn_major) {
+int tc_make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer,
+                bool mn_major) {
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
@@ -501,14 +418,14 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
             const float* bias, int act, int beta, int trans_c, cudaStream_t s, const float* mask) {
   if (trans_c && bias) return DDRL_E_ARG;
   if (act >= 3 && (!mask || trans_c || beta)) return DDRL_E_ARG;
-  int r = get_encode();
+  int r = tc_get_encode();
   if (r != DDRL_OK) return r;
   const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
   CUtensorMap ta, tb;
   // form 0: A [M,K] K-major, B [N,K] K-major | form 1: B [K,N] MN-major | form 2: A [K,M], B [K,N] MN-major
-  if (form == 2) r = make_map(&ta, A, M, K, lda, 32, true); else r = make_map(&ta, A, K, M, lda, TC_BM, false);
+  if (form == 2) r = tc_make_map(&ta, A, M, K, lda, 32, true); else r = tc_make_map(&ta, A, K, M, lda, TC_BM, false);
   if (r != DDRL_OK) return r;
-  if (form == 0) r = make_map(&tb, B, K, N, ldb, (bn + 31) / 32 * 32, false); else r = make_map(&tb, B, N, K, ldb, 32, true);
+  if (form == 0) r = tc_make_map(&tb, B, K, N, ldb, (bn + 31) / 32 * 32, false); else r = tc_make_map(&tb, B, N, K, ldb, 32, true);
   if (r != DDRL_OK) return r;
   TcArgs g;
   memset(&g, 0, sizeof(g));
@@ -541,7 +458,7 @@ int gemm_tc(int form, int M, int N, int K, const float* A, int lda, const float*
 
 // ---------------------------------------------------------------- implicit-GEMM convolutions
 // 4-D map over an NHWC tensor [Bn, H, W, C]: box = 32 channels x nx pixels (every sx-th) x ny rows (every sy-th) x nb
-static int make_map_nhwc(CUtensorMap* m, const ConvOp& o, int nx, int ny, int nb, bool mn_major) {
+int tc_make_map_nhwc(CUtensorMap* m, const ConvOp& o, int nx, int ny, int nb, bool mn_major) {
   cuuint64_t dims[4] = {(cuuint64_t)o.Ctot, (cuuint64_t)o.Win, (cuuint64_t)o.Hin, (cuuint64_t)o.Bn};
   cuuint64_t strides[3] = {(cuuint64_t)o.Ctot * 4, (cuuint64_t)o.Win * o.Ctot * 4, (cuuint64_t)o.Hin * o.Win * o.Ctot * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)((nx - 1) * o.sx + 1), (cuuint32_t)((ny - 1) * o.sy + 1), (cuuint32_t)nb};
@@ -551,6 +468,23 @@ static int make_map_nhwc(CUtensorMap* m, const ConvOp& o, int nx, int ny, int nb
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(nhwc box %d x %d x %d) failed (%d)", nx, ny, nb, (int)r);
+    return DDRL_E_CUDA;
+  }
+  return DDRL_OK;
+}
+
+// dy [image][pixel of the image][N] (MN-major operand): boxes of `rows` pixel rows x 32 columns; rows past the image's
+// last pixel read as zero
+int tc_make_map_dy3(CUtensorMap* m, const float* dy, int ldy, int N, long long ipix, int Bn, int rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)ipix, (cuuint64_t)Bn};
+  cuuint64_t strides[2] = {(cuuint64_t)ldy * 4, (cuuint64_t)ipix * ldy * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(dy box) failed (%d)", (int)cr);
     return DDRL_E_CUDA;
   }
   return DDRL_OK;
@@ -569,7 +503,7 @@ bool conv_tc_supported(const ConvOp& o, bool wgrad) {
   return true;
 }
 
-static void tap_common(TcTap& t, const ConvOp& o, int cap) {
+void tc_tap_common(TcTap& t, const ConvOp& o, int cap) {
   memset(&t, 0, sizeof(t));
   t.mode = 1;
   t.Xn = o.Xn; t.Yn = o.Yn; t.Bn = o.Bn;
@@ -588,18 +522,18 @@ int conv_tc_fwd(const ConvOp& o, const float* Wp, int ldw, int N, const float* b
                 long long osb, long long osy, long long osx, cudaStream_t s) {
   if (!conv_tc_supported(o, false) || N < 1 || ldw % 4 != 0 || (reinterpret_cast<uintptr_t>(Wp) & 15) != 0) return DDRL_E_UNSUPPORTED;
   if (act >= 3 && !mask) return DDRL_E_ARG;
-  int r = get_encode();
+  int r = tc_get_encode();
   if (r != DDRL_OK) return r;
   const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
   TcArgs g;
   memset(&g, 0, sizeof(g));
-  tap_common(g.tap, o, TC_BM);
+  tc_tap_common(g.tap, o, TC_BM);
   g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
   const int K = o.KH * o.KW * o.Cin;
   CUtensorMap ta, tb;
-  r = make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
+  r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
   if (r != DDRL_OK) return r;
-  r = make_map(&tb, Wp, K, N, ldw, (bn + 31) / 32 * 32, false);
+  r = tc_make_map(&tb, Wp, K, N, ldw, (bn + 31) / 32 * 32, false);
   if (r != DDRL_OK) return r;
   g.C = out; g.bias = bias; g.mask = mask; g.act = act;
   g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K;
@@ -618,32 +552,19 @@ int conv_tc_fwd(const ConvOp& o, const float* Wp, int ldw, int N, const float* b
 
 int conv_tc_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s) {
   if (!conv_tc_supported(o, true) || N < 16 || ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return DDRL_E_UNSUPPORTED;
-  int r = get_encode();
+  int r = tc_get_encode();
   if (r != DDRL_OK) return r;
   const int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
   TcArgs g;
   memset(&g, 0, sizeof(g));
-  tap_common(g.tap, o, 32);
+  tc_tap_common(g.tap, o, 32);
   if (g.tap.nb != 1) { g.tap.nb = 1; g.tap.rows = o.Xn * g.tap.ny; g.tap.kpad = (g.tap.rows + 7) & ~7; }
   const int K = o.KH * o.KW * o.Cin;             // = M of this GEMM (the im2col K axis)
   CUtensorMap ta, tb;
-  r = make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, true);
+  r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, true);
   if (r != DDRL_OK) return r;
-  {
-    // dy [pixels, N] (MN-major operand): boxes of tap.rows pixel rows x 32 columns
-    const long long ipix = (long long)o.Yn * o.Xn;
-    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)ipix, (cuuint64_t)o.Bn};
-    cuuint64_t strides[2] = {(cuuint64_t)ldy * 4, (cuuint64_t)ipix * ldy * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)g.tap.rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult cr = g_encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-      snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(dy box) failed (%d)", (int)cr);
-      return DDRL_E_CUDA;
-    }
-  }
+  r = tc_make_map_dy3(&tb, dy, ldy, N, (long long)o.Yn * o.Xn, o.Bn, g.tap.rows);
+  if (r != DDRL_OK) return r;
   g.C = dWp; g.bias = nullptr; g.mask = nullptr; g.act = 0;
   g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn;
   g.sCm = 1; g.sCn = ldw;                        // C[m = im2col k, n = cout] -> dWp[n*ldw + m]

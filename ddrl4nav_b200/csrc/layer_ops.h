@@ -50,6 +50,17 @@ int conv_tc_fwd(const ConvOp& o, const float* Wp, int ldw, int N, const float* b
 int conv_tc_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s);
 bool conv_tc_supported(const ConvOp& o, bool wgrad);
 
+// tc2.cu: persistent TMEM-operand engine (pre-split weights Bhi / Blo = split_hi_lo of the packed weights)
+bool tc2_gemm_supported(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb);
+int tc2_gemm(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb, float* C,
+             int ldc, const float* bias, int act, const float* mask, cudaStream_t s);
+int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, int N, const float* bias, int act,
+                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s);
+int tc2_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, float* dW, int ldw,
+              cudaStream_t s);
+int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s);
+int split_hi_lo(const float* w, float* hi, float* lo, long long n, cudaStream_t s);
+
 // conv_ops.cu: convolution layers on the implicit-GEMM path
 struct DgradClass {              // one parity class (pix + pad) mod stride of the data gradient
   int ry, rx;                    // class residues
@@ -59,12 +70,13 @@ struct DgradClass {              // one parity class (pix + pad) mod stride of t
   int pady, padx;                // padding of the equivalent stride-1 convolution over dy
   int K;                         // nty*ntx*Cout
   float* wd;                     // packed weights [Cin, K]
+  float *wd_hi, *wd_lo;          // their tf32 hi / lo split (tc2 engine)
 };
 ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B);
 int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out);
 int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s);
 int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
-                  float* dx, int act, const float* mask, int B, cudaStream_t s);
+                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine = false);
 bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,
                           int dy_coff, int B);
 

@@ -1,0 +1,579 @@
+// Second-generation tcgen05 engine: persistent, warp-specialised, activation operand split into TENSOR MEMORY.
+//
+// Same arithmetic as gemm_tc.cu (fp32 in / fp32 out, 3xTF32: lo*hi + hi*lo + hi*hi, the hi*hi term accumulated in
+// TMEM only over 16 MMAs and then added round-to-nearest into fp32 registers), re-organised around what the narrow
+// GEMMs of this path (N = 32 / 64 output channels, K = 256..1600) are bound by: shared-memory bandwidth and per-tile
+// fixed cost, not the MMA rate.
+//   * the activation operand A (128 rows x 32 k) is read from shared memory ONCE per K block by the splitter warps,
+//     split into hi / lo in registers and written to TMEM (tcgen05.st); all three MMA passes read A from TMEM
+//     (tcgen05.mma with a TMEM A operand), so the tensor core only reads the small B tile from shared memory;
+//   * the weight operand B is split once per optimiser step on the device (split_hi_lo) and arrives by TMA as two
+//     ready-made tiles; nothing is rewritten in shared memory on the forward / data-gradient path;
+//   * CTAs are persistent (one per SM) and loop over output tiles; dedicated epilogue warps drain the accumulators,
+//     so the stores of tile t overlap the MMAs of tile t+1;
+//   * weight gradient: A^T is what the MMA needs (M = im2col K axis, reduction over pixels); the transposition is free
+//     because each splitter thread gathers one k column of the landed [pixels x 32 k] box into its TMEM lane.
+// Warp roles: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 splitters (TMEM lane quadrant = warp % 4) |
+// 8.. epilogue (4 warps for BN <= 64, 8 for BN = 128).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "layer_ops.h"
+#include "tc_ptx.cuh"
+
+namespace ddrl {
+
+constexpr int T2_BM = 128;
+constexpr int T2_BK = 32;
+constexpr int T2_CHUNK = 4;                   // K blocks per TMEM main-accumulator chunk (16 accumulating MMAs)
+
+struct Tc2Args {
+  float* C;
+  const float* bias;
+  const float* mask;
+  long long sCm, sCn;
+  int M, N, K;
+  int kb_total, kb_per_split;
+  int act, atomic, vec_store;
+  int m_tiles, n_tiles;                       // mode 0: persistent tile space
+  TcTap tap;
+};
+
+template <int BN>
+struct T2Cfg {
+  static constexpr int BNS = (BN + 31) / 32 * 32;
+  static constexpr int A_BYTES = T2_BM * T2_BK * 4;              // 16 KB raw activation tile (or 4 transposed slices)
+  static constexpr int B_BYTES = BNS * T2_BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;      // A raw | B hi | B lo
+  static constexpr int STAGES = BN <= 32 ? 6 : (BN <= 64 ? 5 : 4);
+  static constexpr int SA = BN <= 64 ? 4 : 2;                    // TMEM A slots (64 columns each: hi | lo)
+  static constexpr int NEPI = BN <= 64 ? 4 : 8;
+  static constexpr int THREADS = 256 + NEPI * 32;
+  static constexpr int COLS = BN / (NEPI / 4);                   // accumulator columns per epilogue thread
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = BN, TM_CORR = 2 * BN, TM_A = 3 * BN;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + NBARS * 8 + 16;
+  static_assert(3 * BN + SA * 64 <= 512, "TMEM budget");
+};
+
+// MODE 0: C[M,N] = epi(A[M,K] . B)   A K-major (plain 2-D or tap boxes), B = pre-split weights (K-major or MN-major)
+// MODE 1: C[m,n] += sum_r A[r,m] * B[r,n]   (weight gradient; A = activations [rows, k], B = dy [rows, n], both raw)
+template <int BN, int MODE, bool B_MN>
+__global__ void __launch_bounds__(T2Cfg<BN>::THREADS, 1)
+tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+           const __grid_constant__ CUtensorMap tmBlo, Tc2Args g) {
+  using Cfg = T2Cfg<BN>;
+  constexpr int S = Cfg::STAGES, SA = Cfg::SA;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* bar_full = bars;                  // [S]  TMA landed
+  uint64_t* bar_empty = bars + S;             // [S]  MMAs that read the stage retired
+  uint64_t* bar_aready = bars + 2 * S;        // [SA] TMEM A slot written
+  uint64_t* bar_afree = bars + 2 * S + SA;    // [SA] MMAs that read the slot retired
+  uint64_t* bar_mfull = bars + 2 * S + 2 * SA;      // [2] main accumulator chunk complete
+  uint64_t* bar_mfree = bar_mfull + 2;              // [2] drained
+  uint64_t* bar_cfull = bar_mfull + 4;              // correction accumulator complete (tile end)
+  uint64_t* bar_cfree = bar_mfull + 5;              // read by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcTap& tp = g.tap;
+  const bool tapA = tp.mode != 0;
+
+  if (MODE == 1 && tapA) {
+    // pixel-box K blocks shorter than 32 rows: the rows no box covers must read as zero
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < S * Cfg::STAGE_BYTES / 16; i += Cfg::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
+    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
+    mbar_init(smem_u32(bar_cfull), 1);
+    mbar_init(smem_u32(bar_cfree), Cfg::NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work enumeration, identical in every role --------------------------------------------------------------
+  // MODE 0: tiles blockIdx.x, +gridDim.x, ... of the (m_tiles x n_tiles) space, full K each
+  // MODE 1: one unit per CTA: (blockIdx.x = M block, blockIdx.y = N tile, blockIdx.z = K split)
+  const int total_tiles = MODE == 0 ? g.m_tiles * g.n_tiles : 1;
+  const int tile_step = MODE == 0 ? (int)gridDim.x : 1;
+  const int tile_first = MODE == 0 ? (int)blockIdx.x : 0;
+  int kb0 = 0, nkb = g.kb_total;
+  if (MODE == 1) {
+    kb0 = blockIdx.z * g.kb_per_split;
+    nkb = min(g.kb_total, kb0 + g.kb_per_split) - kb0;
+  }
+  const int ksteps = (MODE == 1 && tapA) ? tp.kpad / 8 : T2_BK / 8;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
+        const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
+        const int m0 = mt * T2_BM, n0 = nt * BN;
+        int b0 = 0, y0 = 0;
+        if (MODE == 0 && tapA) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny; }
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % S;
+          const int kbi = kb0 + i;
+          mbar_wait(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1);
+          const uint32_t full = smem_u32(bar_full + s);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          const uint32_t a_dst = smem_u32(st), bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
+          const int k = kbi * T2_BK;
+          if (MODE == 0) {
+            if (!tapA) {
+              mbar_expect_tx(full, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+              tma_load_2d(&tmA, full, a_dst, k, m0);
+            } else {
+              const int tap = kbi / tp.cpb, cc = kbi - tap * tp.cpb;
+              const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+              mbar_expect_tx(full, tp.rows * 128 + 2 * Cfg::B_BYTES);
+              tma_load_4d(&tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 * tp.sy + kh - tp.py, b0);
+            }
+            if (!B_MN) {
+              tma_load_2d(&tmBhi, full, bh_dst, k, n0);
+              tma_load_2d(&tmBlo, full, bl_dst, k, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::BNS / 32; ++j) {
+                tma_load_2d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, k);
+                tma_load_2d(&tmBlo, full, bl_dst + j * 4096, n0 + j * 32, k);
+              }
+            }
+          } else if (!tapA) {
+            // A slices: [32 rows x 32 k] boxes of x[rows, Kx] at k = m0 + 32 j; B: dy[rows, N] boxes of 32 rows x 32 n
+            mbar_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(&tmA, full, a_dst + j * 4096, m0 + j * 32, k);
+#pragma unroll
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, k);
+          } else {
+            const int b = kbi / tp.tpi, yy0 = (kbi - b * tp.tpi) * tp.ny;
+            int na = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) na += (m0 / 32 + j) < tp.nslices ? 1 : 0;
+            mbar_expect_tx(full, (na + Cfg::BNS / 32) * tp.rows * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int sl = m0 / 32 + j;
+              if (sl < tp.nslices) {
+                const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
+                const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+                tma_load_4d(&tmA, full, a_dst + j * 4096, tp.c_off + cc * 32, kw - tp.px, yy0 * tp.sy + kh - tp.py, b);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_3d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, yy0 * tp.Xn, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(T2_BM >> 4) << 24);
+    uint32_t it = 0, ch = 0, tl = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % S, a = it % SA;
+        const int buf = ch & 1;
+        const bool first_in_chunk = (i % T2_CHUNK) == 0;
+        const bool last_in_chunk = (i % T2_CHUNK) == T2_CHUNK - 1 || i == nkb - 1;
+        if (i == 0) mbar_wait(smem_u32(bar_cfree), (tl & 1) ^ 1);
+        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
+        mbar_wait(smem_u32(bar_aready + a), (it / SA) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          const uint32_t b_hi = smem_u32(st) + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
+          const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
+          const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+          for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
+            if (k4 >= ksteps) break;
+            const uint64_t dbh = B_MN ? umma_desc(b_hi + k4 * 1024, 4096, 512, 1) : umma_desc(b_hi + k4 * 32, 16, 1024, 2);
+            const uint64_t dbl = B_MN ? umma_desc(b_lo + k4 * 1024, 4096, 512, 1) : umma_desc(b_lo + k4 * 32, 16, 1024, 2);
+            umma_tf32_ts(t_corr, a_lo + k4 * 8, dbh, idesc, (i | k4) != 0 ? 1u : 0u);
+            umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl, idesc, 1u);
+          }
+        }
+        __syncwarp();
+        // the previous user of this main buffer (two chunks ago) must have been drained; by now 8 MMAs are queued
+        if (first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          const uint32_t b_hi = smem_u32(st) + Cfg::A_BYTES;
+          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64;
+          const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+          for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
+            if (k4 >= ksteps) break;
+            const uint64_t dbh = B_MN ? umma_desc(b_hi + k4 * 1024, 4096, 512, 1) : umma_desc(b_hi + k4 * 32, 16, 1024, 2);
+            umma_tf32_ts(t_main, a_hi + k4 * 8, dbh, idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(bar_empty + s));
+          umma_commit(smem_u32(bar_afree + a));
+          if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+          if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
+        }
+        __syncwarp();
+        if (last_in_chunk) ++ch;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================================================ splitters: smem A -> hi / lo -> TMEM
+    const int q = warp - 4;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % S, a = it % SA;
+        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
+        const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        uint32_t hi[32], lo[32];
+        if (MODE == 0) {
+          // thread = tile row; its 32 k values are the row's eight 16-byte chunks (128B swizzle: chunk ^ (row & 7))
+          const int row = q * 32 + lane;
+          const uint8_t* rp = st + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[c * 4 + e] = tf32_rn(x[e]);
+              lo[c * 4 + e] = tf32_rn(x[e] - __uint_as_float(hi[c * 4 + e]));
+            }
+          }
+        } else {
+          // thread = k column `lane` of slice q; it gathers that column over the (<= 32) pixel rows of the box
+          const uint8_t* sp = st + q * 4096 + (lane & 3) * 4;
+#pragma unroll
+          for (int p = 0; p < 32; ++p) {
+            const float x = *reinterpret_cast<const float*>(sp + p * 128 + (((lane >> 2) ^ (p & 7)) << 4));
+            hi[p] = tf32_rn(x);
+            lo[p] = tf32_rn(x - __uint_as_float(hi[p]));
+          }
+          // dy tile: split in place (hi) + twin (lo); element-wise, so the TMA swizzle is preserved
+          uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
+          for (int v = threadIdx.x - 128; v < Cfg::B_BYTES / 16; v += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(bh + v * 16);
+            uint4 h, l;
+            h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
+            l.x = tf32_rn(x.x - __uint_as_float(h.x)); l.y = tf32_rn(x.y - __uint_as_float(h.y));
+            l.z = tf32_rn(x.z - __uint_as_float(h.z)); l.w = tf32_rn(x.w - __uint_as_float(h.w));
+            *reinterpret_cast<uint4*>(bh + v * 16) = h;
+            *reinterpret_cast<uint4*>(bh + Cfg::B_BYTES + v * 16) = l;
+          }
+          fence_async_smem();
+        }
+        mbar_wait(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 16, hi + 16);
+        tmem_st16(ta + 32, lo);
+        tmem_st16(ta + 48, lo + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
+      }
+    }
+  } else if (warp >= 8) {
+    // ============================================================ drain + epilogue
+    const int e = warp - 8;
+    const int q = e & 3, half = e >> 2;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const uint32_t col0 = half * Cfg::COLS;
+    uint32_t ch = 0, tl = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
+      const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
+      const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
+      const int m0 = mt * T2_BM, n0 = nt * BN;
+      float acc[Cfg::COLS];
+#pragma unroll
+      for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
+      const int nch = (nkb + T2_CHUNK - 1) / T2_CHUNK;
+      for (int c = 0; c < nch; ++c, ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(smem_u32(bar_mfull + buf), (ch >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
+      }
+      mbar_wait(smem_u32(bar_cfull), tl & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
+      // ---- stores
+      const int r = q * 32 + lane;
+      bool rvalid;
+      long long roff;
+      if (MODE == 0 && tapA) {
+        const int b0 = (mt / tp.tpi) * tp.nb, y0 = (mt % tp.tpi) * tp.ny;
+        const int x = r % tp.Xn, t2 = r / tp.Xn;
+        const int yy = t2 % tp.ny, bb = t2 / tp.ny;
+        rvalid = r < tp.rows && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
+        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
+      } else {
+        rvalid = (m0 + r) < g.M;
+        roff = (long long)(m0 + r) * g.sCm;
+      }
+      if (!rvalid) continue;
+      const float neg_slope = g.act == 3 ? 0.f : 0.01f;
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 4) {
+        const int colv = n0 + col0 + j0;
+        if (MODE == 0 && g.vec_store && colv + 4 <= g.N) {
+          float4 o, mk = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (g.act >= 3) mk = *reinterpret_cast<const float4*>(g.mask + roff + colv);
+          const float* mv = reinterpret_cast<const float*>(&mk);
+          float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float x = acc[j0 + k];
+            if (g.bias != nullptr) x += g.bias[colv + k];
+            if (g.act == 1) x = fmaxf(x, 0.f);
+            else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+            else if (g.act >= 3) x = mv[k] > 0.f ? x : neg_slope * x;
+            ov[k] = x;
+          }
+          *reinterpret_cast<float4*>(g.C + roff + colv) = o;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int col = colv + k;
+            if (col < g.N) {
+              float x = acc[j0 + k];
+              float* p = g.C + roff + col * g.sCn;
+              if (g.atomic) {
+                atomicAdd(p, x);
+              } else {
+                if (g.bias != nullptr) x += g.bias[col];
+                if (g.act == 1) x = fmaxf(x, 0.f);
+                else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+                else if (g.act >= 3) x = g.mask[roff + col * g.sCn] > 0.f ? x : neg_slope * x;
+                *p = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+template <int BN, int MODE, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const Tc2Args& g, dim3 grid,
+                   cudaStream_t s) {
+  using Cfg = T2Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DDRL_CUDA(cudaFuncSetAttribute(tc2_kernel<BN, MODE, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  tc2_kernel<BN, MODE, B_MN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tbh, tbl, g);
+  prof_work(2.0 * g.M * (double)g.N * g.K);
+  if (g_prof_on && g_prof_shapes) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "%s2[%s,M=%d,N=%d,K=%d,g=%d]", g.tap.mode ? "conv_tc" : "gemm_tc",
+             MODE ? "wgrad" : (B_MN ? "dgrad" : "fwd"), g.M, g.N, g.K, (int)(grid.x * grid.y * grid.z));
+    DDRL_LAUNCHED(prof_intern(nm));
+    return DDRL_OK;
+  }
+  DDRL_LAUNCHED("tc2_kernel");
+  return DDRL_OK;
+}
+
+template <int MODE, bool B_MN>
+static int launch2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const Tc2Args& g, dim3 grid,
+                      cudaStream_t s) {
+  switch (bn) {
+    case 128: return launch2<128, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
+    case 64: return launch2<64, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
+    default: return launch2<32, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
+  }
+}
+
+static inline int pick_bn(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool tc2_gemm_supported(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb) {
+  if (form != 0 && form != 1) return false;
+  if (M < 1 || N < 1 || K < 1) return false;
+  if (!al16(A) || !al16(Bhi) || !al16(Blo) || lda % 4 != 0 || ldb % 4 != 0) return false;
+  return true;
+}
+
+// forward / data-gradient GEMM with pre-split weights.  form 0: B [N,K] K-major; form 1: B [K,N] MN-major.
+int tc2_gemm(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb, float* C,
+             int ldc, const float* bias, int act, const float* mask, cudaStream_t s) {
+  if (!tc2_gemm_supported(form, M, N, K, A, lda, Bhi, Blo, ldb)) return DDRL_E_UNSUPPORTED;
+  if (act >= 3 && !mask) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn(N);
+  const int bns = (bn + 31) / 32 * 32;
+  CUtensorMap ta, tbh, tbl;
+  r = tc_make_map(&ta, A, K, M, lda, T2_BM, false);
+  if (r != DDRL_OK) return r;
+  if (form == 0) { r = tc_make_map(&tbh, Bhi, K, N, ldb, bns, false); if (r == DDRL_OK) r = tc_make_map(&tbl, Blo, K, N, ldb, bns, false); }
+  else { r = tc_make_map(&tbh, Bhi, N, K, ldb, 32, true); if (r == DDRL_OK) r = tc_make_map(&tbl, Blo, N, K, ldb, 32, true); }
+  if (r != DDRL_OK) return r;
+  Tc2Args g;
+  memset(&g, 0, sizeof(g));
+  g.C = C; g.bias = bias; g.mask = mask; g.act = act;
+  g.M = M; g.N = N; g.K = K; g.sCm = ldc; g.sCn = 1;
+  g.kb_total = ceil_div(K, T2_BK); g.kb_per_split = g.kb_total;
+  g.m_tiles = ceil_div(M, T2_BM); g.n_tiles = ceil_div(N, bn);
+  g.vec_store = (ldc % 4 == 0 && al16(C) && (!mask || al16(mask))) ? 1 : 0;
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  return form == 0 ? launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s) : launch2_bn<0, true>(bn, ta, tbh, tbl, g, grid, s);
+}
+
+int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, int N, const float* bias, int act,
+                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s) {
+  if (!conv_tc_supported(o, false) || N < 1 || ldw % 4 != 0 || !al16(Whi) || !al16(Wlo)) return DDRL_E_UNSUPPORTED;
+  if (act >= 3 && !mask) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn(N);
+  const int bns = (bn + 31) / 32 * 32;
+  Tc2Args g;
+  memset(&g, 0, sizeof(g));
+  tc_tap_common(g.tap, o, T2_BM);
+  g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
+  const int K = o.KH * o.KW * o.Cin;
+  CUtensorMap ta, tbh, tbl;
+  r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
+  if (r == DDRL_OK) r = tc_make_map(&tbh, Whi, K, N, ldw, bns, false);
+  if (r == DDRL_OK) r = tc_make_map(&tbl, Wlo, K, N, ldw, bns, false);
+  if (r != DDRL_OK) return r;
+  g.C = out; g.bias = bias; g.mask = mask; g.act = act;
+  g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K; g.sCm = 0; g.sCn = 1;
+  g.kb_total = g.tap.nslices; g.kb_per_split = g.kb_total;
+  g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi; g.n_tiles = ceil_div(N, bn);
+  g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && al16(out) && (!mask || al16(mask))) ? 1 : 0;
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  return launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s);
+}
+
+static void wgrad_splits(Tc2Args& g, int tiles) {
+  int splits = std::max(1, std::min(std::min(ceil_div(2 * kNumSMs, tiles), g.kb_total / 8), 1024));
+  int kbps = ceil_div(g.kb_total, splits);
+  g.kb_per_split = kbps;
+}
+
+// dW[n*ldw + k] += sum_r dy[r, n] * x[r, k]     (x [rows, Kx], dy [rows, N]; accumulates atomically)
+int tc2_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, float* dW, int ldw,
+              cudaStream_t s) {
+  if (Kx < 1 || N < 1 || rows < 1 || !al16(x) || !al16(dy) || ldx % 4 != 0 || ldy % 4 != 0 || rows > 0x7fffffffLL)
+    return DDRL_E_UNSUPPORTED;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn(N);
+  CUtensorMap ta, tb;
+  r = tc_make_map(&ta, x, Kx, rows, ldx, 32, false);             // [32 rows x 32 k] boxes, plain 128B swizzle
+  if (r == DDRL_OK) r = tc_make_map(&tb, dy, N, rows, ldy, 32, true);
+  if (r != DDRL_OK) return r;
+  Tc2Args g;
+  memset(&g, 0, sizeof(g));
+  g.C = dW; g.M = Kx; g.N = N; g.K = (int)rows; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
+  g.kb_total = (int)ceil_div64(rows, T2_BK);
+  const int tiles = ceil_div(Kx, T2_BM) * ceil_div(N, bn);
+  wgrad_splits(g, tiles);
+  dim3 grid(ceil_div(Kx, T2_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  return launch2_bn<1, true>(bn, ta, tb, tb, g, grid, s);
+}
+
+int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s) {
+  if (!conv_tc_supported(o, true) || N < 1 || ldy % 4 != 0 || !al16(dy)) return DDRL_E_UNSUPPORTED;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn(N);
+  Tc2Args g;
+  memset(&g, 0, sizeof(g));
+  tc_tap_common(g.tap, o, 32);
+  if (g.tap.nb != 1) { g.tap.nb = 1; g.tap.rows = o.Xn * g.tap.ny; g.tap.kpad = (g.tap.rows + 7) & ~7; }
+  const int K = o.KH * o.KW * o.Cin;
+  CUtensorMap ta, tb;
+  r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, false);
+  if (r == DDRL_OK) r = tc_make_map_dy3(&tb, dy, ldy, N, o.Yn * o.Xn, o.Bn, g.tap.rows);
+  if (r != DDRL_OK) return r;
+  g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
+  g.kb_total = o.Bn * g.tap.tpi;
+  const int tiles = ceil_div(K, T2_BM) * ceil_div(N, bn);
+  wgrad_splits(g, tiles);
+  dim3 grid(ceil_div(K, T2_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  return launch2_bn<1, true>(bn, ta, tb, tb, g, grid, s);
+}
+
+// hi = rn_tf32(w), lo = rn_tf32(w - hi): the weight operand's split, once per optimiser step
+__global__ void __launch_bounds__(256) split_hi_lo_kernel(const float4* __restrict__ w, uint4* __restrict__ hi,
+                                                          uint4* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = w[i];
+    uint4 h, l;
+    h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
+    l.x = tf32_rn(x.x - __uint_as_float(h.x)); l.y = tf32_rn(x.y - __uint_as_float(h.y));
+    l.z = tf32_rn(x.z - __uint_as_float(h.z)); l.w = tf32_rn(x.w - __uint_as_float(h.w));
+    hi[i] = h; lo[i] = l;
+  }
+}
+int split_hi_lo(const float* w, float* hi, float* lo, long long n, cudaStream_t s) {
+  if (n % 4 != 0 || !al16(w) || !al16(hi) || !al16(lo)) return DDRL_E_ARG;
+  if (n == 0) return DDRL_OK;
+  const long long n4 = n / 4;
+  const int blocks = (int)std::min<long long>((n4 + 255) / 256, 8LL * kNumSMs);
+  split_hi_lo_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(w), reinterpret_cast<uint4*>(hi),
+                                            reinterpret_cast<uint4*>(lo), n4);
+  DDRL_LAUNCHED("split_hi_lo_kernel");
+  return DDRL_OK;
+}
+
+}  // namespace ddrl

@@ -151,7 +151,7 @@ def gemm(form: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def conv_nhwc(op: int, x, w, dy=None, bias=None, stride: int = 1, pad: int = 0, act: int = 0, mask=None):
+def conv_nhwc(op: int, x, w, dy=None, bias=None, stride: int = 1, pad: int = 0, act: int = 0, mask=None, mode: str = "tc"):
     """Implicit-GEMM convolution on NHWC activations (ddrl_conv_nhwc_f32).  x [B,H,W,Cin] (or its shape as a tuple for
     op 1), w [Cout,Cin,KH,KW] reference layout.  op 0: forward -> [B,Ho,Wo,Cout]; op 1: data gradient of dy -> [B,H,W,Cin];
     op 2: weight gradient -> [Cout,Cin,KH,KW]."""
@@ -174,7 +174,7 @@ def conv_nhwc(op: int, x, w, dy=None, bias=None, stride: int = 1, pad: int = 0, 
     dyy = _f32c(dy) if dy is not None else None
     bb = _f32c(bias) if bias is not None else None
     mm = _f32c(mask) if mask is not None else None
-    check(lib.ddrl_conv_nhwc_f32(op, C.byref(d), ptr(xx), ptr(w), ptr(bb), ptr(dyy), act, ptr(mm), ptr(out), current_stream()),
+    check(lib.ddrl_conv_nhwc_f32(_lib.GEMM_MODE[mode], op, C.byref(d), ptr(xx), ptr(w), ptr(bb), ptr(dyy), act, ptr(mm), ptr(out), current_stream()),
           "ddrl_conv_nhwc_f32")
     return out
 

@@ -39,7 +39,9 @@ enum ddrl_arch {               /* encoder family (USTC_lab/nn/__init__.py:12-18)
 enum ddrl_dist { DDRL_DIST_CATEGORICAL = 0, DDRL_DIST_GAUSSIAN = 1 };   /* nn/actor.py:75,43 */
 enum ddrl_gemm_mode {
   DDRL_GEMM_SIMT_F32 = 0,      /* CUDA-core fp32 FMA (reference / fallback-free baseline) */
-  DDRL_GEMM_TC_3XTF32 = 1      /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate in TMEM */
+  DDRL_GEMM_TC_3XTF32 = 1,     /* tcgen05 kind::tf32, hi/lo split in shared memory, one tile per CTA (gemm_tc.cu) */
+  DDRL_GEMM_TC2_TMEM = 2       /* same arithmetic; persistent CTAs, activation operand split into TMEM, weights
+                                  pre-split per optimiser step (tc2.cu).  Shapes it does not take run on mode 1. */
 };
 
 typedef struct ddrl_net ddrl_net;
@@ -141,7 +143,7 @@ int ddrl_clip_adam(float* params, float* grads, float* m, float* v, int64_t n,
  *  form 1 "dgrad": C[m,n] = sum_k A[m*lda+k] * B[k*ldb+n]            (A [M,K], B [K,N])
  *  form 2 "wgrad": C[m,n] = sum_k A[k*lda+m] * B[k*ldb+n]            (A [K,M], B [K,N])
  * bias: NULL or [N]; act: 0 none, 1 relu, 2 leaky_relu(0.01); beta: 0 overwrite, 1 accumulate into C.
- * mode: enum ddrl_gemm_mode. */
+ * mode: enum ddrl_gemm_mode (mode 2 takes beta = 1 only for form 2 and splits B on the fly). */
 int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, const float* bias, int act, int beta, void* stream);
 
@@ -158,7 +160,7 @@ int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const float* A, int l
 typedef struct {
   int32_t B, H, W, Cin, Cout, KH, KW, stride, pad;
 } ddrl_conv_desc;
-int ddrl_conv_nhwc_f32(int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
+int ddrl_conv_nhwc_f32(int mode /* 1 or 2: enum ddrl_gemm_mode */, int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
                        const float* dy, int act, const float* mask, float* out, void* stream);
 
 /* ---- the actor-critic net ---------------------------------------------------------------

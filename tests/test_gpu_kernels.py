@@ -278,14 +278,14 @@ def test_clip_adam_vs_torch(n, nseg):
 
 
 # ------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", ["simt", "tc", "tc2"])
 @pytest.mark.parametrize("form", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 33, 100), (1000, 512, 3136), (64, 6, 512), (4096, 32, 256), (37, 200, 9),
                                    (128, 32, 32), (300, 64, 1152), (2048, 256, 1600)])
 def test_gemm_forms(mode, form, M, N, K):
     from ddrl4nav_b200 import kernels
-    if mode == "tc":
-        # the tcgen05 path needs 16-byte row strides (TMA) and N >= 16; other shapes stay on the SIMT engine
+    if mode in ("tc", "tc2"):
+        # the tcgen05 paths need 16-byte row strides (TMA) and N >= 16; other shapes stay on the SIMT engine
         lds = {0: (K, K), 1: (K, N), 2: (M, N)}[form]
         if N < 16 or lds[0] % 4 or lds[1] % 4:
             pytest.skip("shape not eligible for the TMA/tcgen05 engine")
@@ -300,15 +300,24 @@ def test_gemm_forms(mode, form, M, N, K):
         A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
         ref = A.double().T @ B.double()
     bias = torch.randn(N, generator=g)
-    out = kernels.gemm(form, A.to(DEV), B.to(DEV), bias.to(DEV), act=2, mode=mode)
     prod = ref
+    if mode == "tc2" and form == 2:
+        # the TMEM engine's transposed-operand form is the weight gradient: no bias / activation, accumulates
+        out = kernels.gemm(form, A.to(DEV), B.to(DEV), None, act=0, mode=mode)
+        assert close(out, prod, rtol=1e-5, atol_scale=2e-6)
+        out2 = kernels.gemm(form, A.to(DEV), B.to(DEV), None, act=0, mode=mode, out=out.clone(), beta=1)
+        assert close(out2, 2 * prod, rtol=1e-5, atol_scale=2e-6)
+        return
+    out = kernels.gemm(form, A.to(DEV), B.to(DEV), bias.to(DEV), act=2, mode=mode)
     ref = torch.nn.functional.leaky_relu(prod + bias.double(), 0.01)
     assert close(out, ref, rtol=1e-5, atol_scale=2e-6)
+    if mode == "tc2":
+        return                       # accumulate-into-C exists only for the weight-gradient form on this engine
     out2 = kernels.gemm(form, A.to(DEV), B.to(DEV), None, act=0, mode=mode, out=out.clone(), beta=1)   # C += A op B
     assert close(out2, ref + prod, rtol=1e-5, atol_scale=2e-6)
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", ["simt", "tc", "tc2"])
 def test_gemm_split_k_wgrad_shape(mode):
     from ddrl4nav_b200 import kernels
     g = torch.Generator().manual_seed(5)
@@ -325,9 +334,10 @@ def test_gemm_tc_is_3xtf32_accurate():
     A, B = torch.randn(512, 4096, generator=g), torch.randn(256, 4096, generator=g)
     ref = A.double() @ B.double().T
     e_tc = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc").cpu().double() - ref).abs().max() / ref.abs().max())
+    e_tc2 = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc2").cpu().double() - ref).abs().max() / ref.abs().max())
     e_simt = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="simt").cpu().double() - ref).abs().max() / ref.abs().max())
-    print("max err / max|ref|: tc %.2e  simt %.2e" % (e_tc, e_simt))
-    assert e_tc < 2e-6 and e_simt < 2e-6
+    print("max err / max|ref|: tc %.2e  tc2 %.2e  simt %.2e" % (e_tc, e_tc2, e_simt))
+    assert e_tc < 2e-6 and e_tc2 < 2e-6 and e_simt < 2e-6
 
 
 # ------------------------------------------------------------------ implicit-GEMM convolutions (tap-TMA path)
@@ -352,8 +362,9 @@ def _conv_ref(x_nhwc, w, stride, pad, conv1d):
     return torch.nn.functional.conv2d(x, w.double(), None, stride=stride, padding=pad)
 
 
+@pytest.mark.parametrize("mode", ["tc", "tc2"])
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_implicit_forward_dgrad_wgrad(case):
+def test_conv_implicit_forward_dgrad_wgrad(case, mode):
     """ddrl_conv_nhwc_f32 (4-D TMA tap boxes, no im2col) == torch conv2d forward / autograd, fp32 tolerance 1e-5."""
     from ddrl4nav_b200 import kernels
     B, H, W, Cin, Cout, KH, KW, stride, pad = case
@@ -368,19 +379,20 @@ def test_conv_implicit_forward_dgrad_wgrad(case):
     dy = torch.randn(y_ref.shape, generator=g)
     y_ref.backward(dy.double())
     # forward (+ bias + leaky relu in the epilogue)
-    y = kernels.conv_nhwc(0, x.to(DEV), w.to(DEV), bias=bias.to(DEV), stride=stride, pad=pad, act=2)
+    y = kernels.conv_nhwc(0, x.to(DEV), w.to(DEV), bias=bias.to(DEV), stride=stride, pad=pad, act=2, mode=mode)
     ref = torch.nn.functional.leaky_relu(y_ref.detach() + bias.double()[None, :, None, None], 0.01).permute(0, 2, 3, 1)
     assert close(y, ref, rtol=1e-5, atol_scale=2e-6)
     # data gradient, with the fused activation backward (leaky' of a mask tensor)
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
     mask = torch.randn(B, H, W, Cin, generator=g)
-    dx = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad, act=4, mask=mask.to(DEV))
+    dx = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad, act=4, mask=mask.to(DEV),
+                           mode=mode)
     dx_ref = xr.grad * torch.where(mask > 0, 1.0, 0.01).double()
     assert close(dx, dx_ref, rtol=1e-5, atol_scale=2e-6)
-    dx0 = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad)
+    dx0 = kernels.conv_nhwc(1, (B, H, W), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad, mode=mode)
     assert close(dx0, xr.grad, rtol=1e-5, atol_scale=2e-6)
     # weight gradient
-    dw = kernels.conv_nhwc(2, x.to(DEV), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad)
+    dw = kernels.conv_nhwc(2, x.to(DEV), w.to(DEV), dy=dy_nhwc.to(DEV), stride=stride, pad=pad, mode=mode)
     assert close(dw, wr.grad, rtol=1e-5, atol_scale=2e-6)
 
 
