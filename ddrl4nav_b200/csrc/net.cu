@@ -40,6 +40,7 @@ struct Lin {
   bool packed = false;
   int act = 0;
   float* wp = nullptr;           // packed weight [N, ldw]   (when packed)
+  float *wp_hi = nullptr, *wp_lo = nullptr;   // its tf32 hi / lo split (tc2 engine), refreshed with wp
   float* dwp = nullptr;          // packed weight gradient   (when packed and training)
 };
 
@@ -91,6 +92,7 @@ struct ddrl_net {
   bool ws_train = false;
   float *logits = nullptr, *vout = nullptr, *dlogits = nullptr, *dv = nullptr, *stage = nullptr;
   char* packed_base = nullptr;   // packed weights + packed grads arena
+  char* split_base = nullptr;    // tc2 engine: [hi mirror of the packed arena | lo mirror]
   size_t packed_bytes = 0, packed_grad_off = 0, packed_grad_bytes = 0;
   int64_t seg_begin[3];
   int nseg = 1;
@@ -100,6 +102,20 @@ struct ddrl_net {
 };
 
 namespace ddrl {
+
+static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM; }
+static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC2_TMEM; }
+// hi / lo mirrors of a pointer into the packed arena
+static inline const float* hi_of(const ddrl_net* n, const float* p) {
+  return reinterpret_cast<const float*>(n->split_base + (reinterpret_cast<const char*>(p) - n->packed_base));
+}
+static inline const float* lo_of(const ddrl_net* n, const float* p) {
+  return reinterpret_cast<const float*>(n->split_base + n->packed_bytes + (reinterpret_cast<const char*>(p) - n->packed_base));
+}
+static inline bool in_packed(const ddrl_net* n, const float* p) {
+  const char* c = reinterpret_cast<const char*>(p);
+  return n->packed_base && c >= n->packed_base && c < n->packed_base + n->packed_bytes;
+}
 
 static int find_tensor(const ddrl_net* n, const std::string& name) {
   for (size_t i = 0; i < n->T.size(); ++i)
@@ -230,7 +246,7 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
     t.conv_lin[i] = i;
     const ConvGeom& g = t.g[i];
     const int Cout = t.L[i].N;
-    if (n->d.gemm_mode != DDRL_GEMM_TC_3XTF32 || g.order != 0 || g.C % 32 != 0 || Cout % 32 != 0) continue;
+    if (!tc_mode(n) || g.order != 0 || g.C % 32 != 0 || Cout % 32 != 0) continue;
     if (no_implicit && no_implicit[0] == '1') continue;
     static const float* const kAligned = reinterpret_cast<const float*>(uintptr_t(256));
     ConvOp o = conv_op_fwd(g, kAligned, g.C, 0, 1);
@@ -248,7 +264,11 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
 static int gemm(const ddrl_net* n, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const float* bias, int act, int beta, int trans_c, cudaStream_t s,
                 const float* mask = nullptr) {
-  if (n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 && gemm_tc_supported(form, M, N, K, A, lda, B, ldb, C, ldc, trans_c))
+  // tc2: forward / dgrad GEMMs whose B operand is a packed weight (pre-split mirrors exist)
+  if (tc2_mode(n) && form != 2 && !beta && !trans_c && in_packed(n, B) &&
+      tc2_gemm_supported(form, M, N, K, A, lda, hi_of(n, B), lo_of(n, B), ldb))
+    return tc2_gemm(form, M, N, K, A, lda, hi_of(n, B), lo_of(n, B), ldb, C, ldc, bias, act, mask, s);
+  if (tc_mode(n) && gemm_tc_supported(form, M, N, K, A, lda, B, ldb, C, ldc, trans_c))
     return gemm_tc(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, trans_c, s, mask);
   if (act >= 3) {
     int r = gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, beta, trans_c, s);
@@ -279,8 +299,12 @@ static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
 static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* dy, int ldy, float* dx, int lddx,
                    int ncols_dx, int mask_act, const float* mask, long long M, cudaStream_t s) {
   TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
-  // dW[N, K] += dy[M,N]^T x[M,K]: run with the larger of (N, K) on the 128-row side
-  if (l.N >= 128 || l.N >= l.K)
+  // dW[N, K] += dy[M,N]^T x[M,K]
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 && ldx % 4 == 0 && ldy % 4 == 0;
+  if (tc2_mode(n) && al && l.K >= 32)
+    TRY(tc2_wgrad(l.K, l.N, M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, s));
+  // older engines: run with the larger of (N, K) on the 128-row side
+  else if (l.N >= 128 || l.N >= l.K)
     TRY(gemm(n, 2, l.N, l.K, (int)M, dy, ldy, x, ldx, dW_of(n, l), l.ldw, nullptr, 0, 1, 0, s));
   else
     TRY(gemm(n, 2, l.K, l.N, (int)M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, nullptr, 0, 1, 1, s));
@@ -416,12 +440,20 @@ static int alloc_packed(ddrl_net* n) {
   if (!n->packed_bytes) return DDRL_OK;
   DDRL_CUDA(cudaMalloc(&n->packed_base, n->packed_bytes));
   DDRL_CUDA(cudaMemset(n->packed_base, 0, n->packed_bytes));     // padding columns stay zero forever
+  if (tc2_mode(n)) {
+    DDRL_CUDA(cudaMalloc(&n->split_base, 2 * n->packed_bytes));
+    DDRL_CUDA(cudaMemset(n->split_base, 0, 2 * n->packed_bytes));
+  }
   {
     size_t off = 2 * bytes;
     for (auto& t : n->towers)
       for (int i = 0; i < 5; ++i)
         for (auto& c : t.dg[i]) {
           c.wd = reinterpret_cast<float*>(n->packed_base + off);
+          if (n->split_base) {
+            c.wd_hi = reinterpret_cast<float*>(n->split_base + off);
+            c.wd_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
+          }
           off += ((size_t)t.g[i].C * c.K * 4 + 255) & ~size_t(255);
         }
   }
@@ -431,6 +463,10 @@ static int alloc_packed(ddrl_net* n) {
       if (l.packed) {
         l.wp = reinterpret_cast<float*>(n->packed_base + off);
         l.dwp = reinterpret_cast<float*>(n->packed_base + n->packed_grad_off + off);
+        if (n->split_base) {
+          l.wp_hi = reinterpret_cast<float*>(n->split_base + off);
+          l.wp_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
+        }
         off += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
       }
   return DDRL_OK;
@@ -446,6 +482,16 @@ static int repack(ddrl_net* n, cudaStream_t s) {
         const Lin& l = t.L[t.conv_lin[i]];
         TRY(pack_dgrad(n->params + n->T[l.w_t].offset, t.g[i], l.N, c, s));
       }
+  if (n->split_base) {
+    // tf32 hi / lo mirrors of the forward weights [0, grad_off) and of the data-gradient weights [2*grad_off, end)
+    const size_t fwd = n->packed_grad_off, dg0 = 2 * n->packed_grad_off, dgn = n->packed_bytes - dg0;
+    char* hi = n->split_base;
+    char* lo = n->split_base + n->packed_bytes;
+    if (fwd) TRY(split_hi_lo(reinterpret_cast<float*>(n->packed_base), reinterpret_cast<float*>(hi), reinterpret_cast<float*>(lo),
+                             (long long)(fwd / 4), s));
+    if (dgn) TRY(split_hi_lo(reinterpret_cast<float*>(n->packed_base + dg0), reinterpret_cast<float*>(hi + dg0),
+                             reinterpret_cast<float*>(lo + dg0), (long long)(dgn / 4), s));
+  }
   n->dirty = false;
   return DDRL_OK;
 }
@@ -457,6 +503,9 @@ static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const f
   if (t.implicit[gi]) {
     const Lin& l = t.L[li];
     const ConvOp o = conv_op_fwd(g, x, g.C, 0, mb);
+    if (tc2_mode(n))
+      return tc2_conv_fwd(o, l.wp_hi, l.wp_lo, l.ldw, l.N, b_of(n, l), l.act, nullptr, y, (long long)o.Yn * o.Xn * l.N,
+                          (long long)o.Xn * l.N, l.N, s);
     return conv_tc_fwd(o, W_of(n, l), l.ldw, l.N, b_of(n, l), l.act, nullptr, y, (long long)o.Yn * o.Xn * l.N,
                        (long long)o.Xn * l.N, l.N, s);
   }
@@ -536,8 +585,10 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
   const long long M = (long long)mb * g.Ho * g.Wo;
   if (t.implicit[gi]) {
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
-    TRY(conv_tc_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
-    if (dx) TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s));
+    if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    else TRY(conv_tc_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    if (dx) TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s,
+                              tc2_mode(n)));
     return DDRL_OK;
   }
   TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, 0, nullptr, M, s));
@@ -670,6 +721,7 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   if (!n) return DDRL_OK;
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
+  if (n->split_base) cudaFree(n->split_base);
   delete n;
   return DDRL_OK;
 }

@@ -13,8 +13,10 @@
 //     so the stores of tile t overlap the MMAs of tile t+1;
 //   * weight gradient: A^T is what the MMA needs (M = im2col K axis, reduction over pixels); the transposition is free
 //     because each splitter thread gathers one k column of the landed [pixels x 32 k] box into its TMEM lane.
-// Warp roles: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 splitters (TMEM lane quadrant = warp % 4) |
-// 8.. epilogue (4 warps for BN <= 64, 8 for BN = 128).
+// Warp roles: 0 TMA producer | 1 MMA issuer for the chunked accumulators | 3 MMA issuer for the whole-tile correction
+// accumulator (two independent in-order MMA streams: one thread can only issue a tf32 MMA every ~45 cycles) |
+// 2 TMEM allocator | splitter groups of 4 warps (TMEM lane quadrant = warp % 4; groups alternate K blocks) |
+// epilogue warps (4 for BN <= 64, 8 for BN = 128).
 #include <cuda.h>
 
 #include <algorithm>
@@ -49,15 +51,23 @@ struct T2Cfg {
   static constexpr int B_BYTES = BNS * T2_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;      // A raw | B hi | B lo
   static constexpr int STAGES = BN <= 32 ? 6 : (BN <= 64 ? 5 : 4);
-  static constexpr int SA = BN <= 64 ? 4 : 2;                    // TMEM A slots (64 columns each: hi | lo)
+  // BN <= 64: hi*hi and hi*lo are ONE MMA of N' = 2 BN (B hi | B lo tiles are adjacent in shared memory) writing the
+  // adjacent accumulators [main | corrB] of the current chunk buffer; lo*hi goes to corrA.  2 MMAs per k step instead
+  // of 3 (every tf32 MMA with N <= 64 occupies the tensor pipe for ~45 cycles regardless of N, scratch/mma_bench.cu).
+  static constexpr bool FOLD = BN <= 64;
+  static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
   static constexpr int NEPI = BN <= 64 ? 4 : 8;
-  static constexpr int THREADS = 256 + NEPI * 32;
+  static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
+  static constexpr int EPI0 = 4 + 4 * NSG;                       // first epilogue warp
+  static constexpr int THREADS = (EPI0 + NEPI) * 32;
   static constexpr int COLS = BN / (NEPI / 4);                   // accumulator columns per epilogue thread
-  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = BN, TM_CORR = 2 * BN, TM_A = 3 * BN;
+  // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN,
+                       TM_A = FOLD ? 5 * BN : 3 * BN;
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + NBARS * 8 + 16;
-  static_assert(3 * BN + SA * 64 <= 512, "TMEM budget");
+  static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
 };
 
 // MODE 0: C[M,N] = epi(A[M,K] . B)   A K-major (plain 2-D or tap boxes), B = pre-split weights (K-major or MN-major)
@@ -91,8 +101,9 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     fence_async_smem();
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
-    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 1); }
+    // stages and A slots are released by BOTH MMA issuers' commits
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
+    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 2); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
     mbar_init(smem_u32(bar_cfree), Cfg::NEPI);
@@ -123,31 +134,47 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
   if (warp == 0) {
     // ============================================================ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
-        const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
-        const int m0 = mt * T2_BM, n0 = nt * BN;
-        int b0 = 0, y0 = 0;
-        if (MODE == 0 && tapA) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny; }
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % S;
-          const int kbi = kb0 + i;
-          mbar_wait(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1);
+    // The whole warp runs the loop convergently; one elected lane issues (keeps every operand in uniform registers).
+    // Tap / pixel-block coordinates advance incrementally: no integer division per K block.
+    uint32_t it = 0;
+    // weight gradient, implicit operand: the 4 (tap, chunk) slices of this CTA's M block are fixed
+    int sl_c[4] = {0, 0, 0, 0}, sl_x[4] = {0, 0, 0, 0}, sl_y[4] = {0, 0, 0, 0}, na = 0;
+    if (MODE == 1 && tapA) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sl = (int)blockIdx.x * 4 + j;
+        if (sl < tp.nslices) {
+          const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
+          const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+          sl_c[j] = tp.c_off + cc * 32; sl_x[j] = kw - tp.px; sl_y[j] = kh - tp.py;
+          na = j + 1;
+        }
+      }
+    }
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
+      const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
+      const int m0 = mt * T2_BM, n0 = nt * BN;
+      int b0 = 0, y0 = 0;
+      if (MODE == 0 && tapA) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny * tp.sy - tp.py; }
+      int cc = 0, kw = 0, kh = 0;                     // forward taps: K block = (kh, kw, chunk), chunk fastest
+      int pb = 0, pj = 0;                             // wgrad pixel blocks: image, row block within the image
+      if (MODE == 1 && tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S;
+        mbar_wait(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1);
+        if (elect_one()) {
           const uint32_t full = smem_u32(bar_full + s);
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t a_dst = smem_u32(st), bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
-          const int k = kbi * T2_BK;
+          const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES,
+                         bl_dst = bh_dst + Cfg::B_BYTES;
+          const int k = (kb0 + i) * T2_BK;
           if (MODE == 0) {
             if (!tapA) {
               mbar_expect_tx(full, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
               tma_load_2d(&tmA, full, a_dst, k, m0);
             } else {
-              const int tap = kbi / tp.cpb, cc = kbi - tap * tp.cpb;
-              const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
               mbar_expect_tx(full, tp.rows * 128 + 2 * Cfg::B_BYTES);
-              tma_load_4d(&tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 * tp.sy + kh - tp.py, b0);
+              tma_load_4d(&tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
             }
             if (!B_MN) {
               tma_load_2d(&tmBhi, full, bh_dst, k, n0);
@@ -167,87 +194,86 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, k);
           } else {
-            const int b = kbi / tp.tpi, yy0 = (kbi - b * tp.tpi) * tp.ny;
-            int na = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) na += (m0 / 32 + j) < tp.nslices ? 1 : 0;
+            const int yy0 = pj * tp.ny;
             mbar_expect_tx(full, (na + Cfg::BNS / 32) * tp.rows * 128);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int sl = m0 / 32 + j;
-              if (sl < tp.nslices) {
-                const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
-                const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
-                tma_load_4d(&tmA, full, a_dst + j * 4096, tp.c_off + cc * 32, kw - tp.px, yy0 * tp.sy + kh - tp.py, b);
-              }
-            }
+            for (int j = 0; j < 4; ++j)
+              if (j < na) tma_load_4d(&tmA, full, a_dst + j * 4096, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
 #pragma unroll
-            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_3d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, yy0 * tp.Xn, b);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(T2_BM >> 4) << 24);
-    uint32_t it = 0, ch = 0, tl = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
-      for (int i = 0; i < nkb; ++i, ++it) {
-        const int s = it % S, a = it % SA;
-        const int buf = ch & 1;
-        const bool first_in_chunk = (i % T2_CHUNK) == 0;
-        const bool last_in_chunk = (i % T2_CHUNK) == T2_CHUNK - 1 || i == nkb - 1;
-        if (i == 0) mbar_wait(smem_u32(bar_cfree), (tl & 1) ^ 1);
-        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
-        mbar_wait(smem_u32(bar_aready + a), (it / SA) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t b_hi = smem_u32(st) + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
-          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
-          const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
-          const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
-#pragma unroll
-          for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
-            if (k4 >= ksteps) break;
-            const uint64_t dbh = B_MN ? umma_desc(b_hi + k4 * 1024, 4096, 512, 1) : umma_desc(b_hi + k4 * 32, 16, 1024, 2);
-            const uint64_t dbl = B_MN ? umma_desc(b_lo + k4 * 1024, 4096, 512, 1) : umma_desc(b_lo + k4 * 32, 16, 1024, 2);
-            umma_tf32_ts(t_corr, a_lo + k4 * 8, dbh, idesc, (i | k4) != 0 ? 1u : 0u);
-            umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl, idesc, 1u);
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_3d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, yy0 * tp.Xn, pb);
           }
         }
         __syncwarp();
-        // the previous user of this main buffer (two chunks ago) must have been drained; by now 8 MMAs are queued
-        if (first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1);
+        if (MODE == 0) { if (++cc == tp.cpb) { cc = 0; if (++kw == tp.KW) { kw = 0; ++kh; } } }
+        else if (++pj == tp.tpi) { pj = 0; ++pb; }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers (one elected thread each)
+    // warp 1: chunk buffers   main (+)= A_hi . B_hi          [FOLD: [main | corrB] (+)= A_hi . [B_hi ; B_lo], N' = 2 BN]
+    // warp 3: whole tile      corr  += A_lo . B_hi           [!FOLD: ... + A_hi . B_lo]
+    // The two streams write disjoint accumulators, so they need no ordering between them.
+    const bool chunk_role = warp == 1;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(T2_BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)((2 * BN) >> 3) << 17) |
+                            ((uint32_t)(T2_BM >> 4) << 24);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
+    constexpr uint32_t kstep = B_MN ? (1024 >> 4) : (32 >> 4);      // start-address field increment per k step
+    uint32_t it = 0, ch = 0, tl = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S, a = it % SA;
+        const uint32_t buf = ch & 1;
+        const bool first_in_chunk = (i % T2_CHUNK) == 0;
+        const bool last_in_chunk = (i % T2_CHUNK) == T2_CHUNK - 1 || i == nkb - 1;
+        if (chunk_role) { if (first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1); }
+        else if (i == 0) mbar_wait(smem_u32(bar_cfree), (tl & 1) ^ 1);
+        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
+        mbar_wait(smem_u32(bar_aready + a), (it / SA) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t b_hi = smem_u32(st) + Cfg::A_BYTES;
-          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64;
-          const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+        if (elect_one()) {
+          const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
+          const uint64_t dbh0 = B_MN ? umma_desc(b_hi, 4096, 512, 1) : umma_desc(b_hi, 16, 1024, 2);
+          if (chunk_role) {
+            const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
 #pragma unroll
-          for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
-            if (k4 >= ksteps) break;
-            const uint64_t dbh = B_MN ? umma_desc(b_hi + k4 * 1024, 4096, 512, 1) : umma_desc(b_hi + k4 * 32, 16, 1024, 2);
-            umma_tf32_ts(t_main, a_hi + k4 * 8, dbh, idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+            for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_tf32_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * kstep, Cfg::FOLD ? idesc2 : idesc,
+                           (!first_in_chunk || k4 != 0) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(bar_empty + s));
+            umma_commit(smem_u32(bar_afree + a));
+            if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+          } else {
+            const uint64_t dbl0 = B_MN ? umma_desc(b_lo, 4096, 512, 1) : umma_desc(b_lo, 16, 1024, 2);
+#pragma unroll
+            for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_tf32_ts(t_corr, a_lo + k4 * 8, dbh0 + k4 * kstep, idesc, (i | k4) != 0 ? 1u : 0u);
+              if (!Cfg::FOLD) umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * kstep, idesc, 1u);
+            }
+            umma_commit(smem_u32(bar_empty + s));
+            umma_commit(smem_u32(bar_afree + a));
+            if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
           }
-          umma_commit(smem_u32(bar_empty + s));
-          umma_commit(smem_u32(bar_afree + a));
-          if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
-          if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
         }
         __syncwarp();
         if (last_in_chunk) ++ch;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < Cfg::EPI0) {
     // ============================================================ splitters: smem A -> hi / lo -> TMEM
-    const int q = warp - 4;
+    const int q = (warp - 4) & 3, grp = (warp - 4) >> 2;
+    const int st_tid = (threadIdx.x - 128) & 127;                // thread index within the group
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       for (int i = 0; i < nkb; ++i, ++it) {
+        if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
         const int s = it % S, a = it % SA;
         mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
@@ -275,9 +301,11 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             hi[p] = tf32_rn(x);
             lo[p] = tf32_rn(x - __uint_as_float(hi[p]));
           }
-          // dy tile: split in place (hi) + twin (lo); element-wise, so the TMA swizzle is preserved
+        }
+        if (MODE == 1) {
+          // raw dy tile: hi in place + lo twin; element-wise, so the TMA swizzle is preserved
           uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
-          for (int v = threadIdx.x - 128; v < Cfg::B_BYTES / 16; v += 128) {
+          for (int v = st_tid; v < Cfg::B_BYTES / 16; v += 128) {
             const float4 x = *reinterpret_cast<const float4*>(bh + v * 16);
             uint4 h, l;
             h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
@@ -301,9 +329,9 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= Cfg::EPI0) {
     // ============================================================ drain + epilogue
-    const int e = warp - 8;
+    const int e = warp - Cfg::EPI0;
     const int q = e & 3, half = e >> 2;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const uint32_t col0 = half * Cfg::COLS;
@@ -326,6 +354,12 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           tmem_ld16(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+          if (Cfg::FOLD) {
+            // the hi*lo term of this chunk sits BN columns further (second half of the folded N' = 2 BN MMA)
+            tmem_ld16(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+          }
         }
         tc_fence_before();
         __syncwarp();

@@ -102,6 +102,33 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One elected lane of a CONVERGENT warp.  Unlike `lane == 0`, ptxas knows the elected region is single-threaded and
+// warp-uniform: addresses / descriptors computed inside it stay in uniform registers (no per-instruction R2UR loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// Convergent-issue variants: EVERY lane of the warp executes the surrounding code (so the operands stay warp-uniform
+// and live in uniform registers); only the lane with leader != 0 issues the tcgen05 instruction.
+__device__ __forceinline__ void umma_tf32_ts_lead(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 e, %5, 0;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_lead(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "setp.ne.b32 e, %1, 0;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}" ::"r"(bar), "r"(leader) : "memory");
+}
 // 16 consecutive columns of this thread's TMEM lane (no wait: follow with tcgen05.wait::st)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(

@@ -14,7 +14,16 @@ from oracle import restate as R
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-GEMM_MODE = os.environ.get("DDRL_TEST_GEMM_MODE", "simt")
+# every engine is checked against the same oracle: CUDA-core fp32, tcgen05 (smem split), tcgen05 (TMEM operand)
+GEMM_MODES = os.environ.get("DDRL_TEST_GEMM_MODE", "simt,tc,tc2").split(",")
+GEMM_MODE = GEMM_MODES[0]
+
+
+@pytest.fixture(autouse=True, params=GEMM_MODES)
+def engine(request):
+    global GEMM_MODE
+    GEMM_MODE = request.param
+    yield request.param
 
 
 def rel_err(a, b):
