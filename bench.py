@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("DDRL_BENCH_WORKLOAD", "pong"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "tc"), choices=["simt", "tc", "tc2"])
+    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "tc2"), choices=["simt", "tc", "tc2"])
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--fwd-batch", dest="fwd_batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -853,6 +853,16 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   return DDRL_OK;
 }
 
+// debugging aid (not part of the public header): copies workspace buffer `idx` of tower `tower` to `out`
+extern "C" int ddrl_net_debug_buffer(ddrl_net* n, int tower, int idx, float* out, int64_t nfloats, void* stream) {
+  if (!n || tower < 0 || tower >= (int)n->towers.size()) return DDRL_E_ARG;
+  Tower& t = n->towers[tower];
+  const float* src = idx == -1 ? t.h : (idx == -2 ? t.dh : (idx >= 0 && idx < (int)t.buf.size() ? t.buf[idx] : nullptr));
+  if (!src) return DDRL_E_ARG;
+  DDRL_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * nfloats, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return DDRL_OK;
+}
+
 namespace ddrl {
 __global__ void finish_losses_kernel(const float* __restrict__ sums, float v_coef, float ent_coef, float* __restrict__ out) {
   const float a = sums[0], v = sums[1], e = sums[2];

@@ -287,10 +287,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
             const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[c * 4 + e] = tf32_rn(x[e]);
-              lo[c * 4 + e] = tf32_rn(x[e] - __uint_as_float(hi[c * 4 + e]));
-            }
+            for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[c * 4 + e], lo[c * 4 + e]);
           }
         } else {
           // thread = k column `lane` of slice q; it gathers that column over the (<= 32) pixel rows of the box
@@ -298,8 +295,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
           for (int p = 0; p < 32; ++p) {
             const float x = *reinterpret_cast<const float*>(sp + p * 128 + (((lane >> 2) ^ (p & 7)) << 4));
-            hi[p] = tf32_rn(x);
-            lo[p] = tf32_rn(x - __uint_as_float(hi[p]));
+            split_tf32(x, hi[p], lo[p]);
           }
         }
         if (MODE == 1) {
@@ -308,9 +304,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           for (int v = st_tid; v < Cfg::B_BYTES / 16; v += 128) {
             const float4 x = *reinterpret_cast<const float4*>(bh + v * 16);
             uint4 h, l;
-            h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
-            l.x = tf32_rn(x.x - __uint_as_float(h.x)); l.y = tf32_rn(x.y - __uint_as_float(h.y));
-            l.z = tf32_rn(x.z - __uint_as_float(h.z)); l.w = tf32_rn(x.w - __uint_as_float(h.w));
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
             *reinterpret_cast<uint4*>(bh + v * 16) = h;
             *reinterpret_cast<uint4*>(bh + Cfg::B_BYTES + v * 16) = l;
           }

@@ -102,6 +102,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Activation-operand split for the TMEM engine, 3 ALU ops per element (cvt.rna.tf32 is a ~5-instruction sequence on
+// sm_100 and the splitter warps are the busiest role):  hi = x rounded to nearest tf32 (ties away, = cvt.rna for finite
+// x) by integer add + mask;  lo = x - hi, exact in fp32 and left un-rounded: the tensor core drops its bits below tf32
+// precision itself (<= 2^-10 |lo| <= 2^-21 |x|).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
 // One elected lane of a CONVERGENT warp.  Unlike `lane == 0`, ptxas knows the elected region is single-threaded and
 // warp-uniform: addresses / descriptors computed inside it stay in uniform registers (no per-instruction R2UR loops).
 __device__ __forceinline__ bool elect_one() {

@@ -148,17 +148,52 @@ def _lin(p, pre, name, x):
     return F.linear(x, p[pre + name + ".weight"], p[pre + name + ".bias"])
 
 
+# Activation ties.  relu / leaky_relu are not differentiable at 0; the reference takes slope 0 (relu) / 0.01 (leaky) at
+# exactly 0, but a pre-activation that is zero only to within fp32 rounding (|z| ~ 1e-8) lands on
+# either side depending on the summation order of whoever computes it -- torch CPU, torch CUDA and the kernels here
+# all differ there.  TIE_HOOK lets the parity tests (a) record every pre-activation and (b) re-run the backward with
+# the branch of chosen tie elements flipped, so that "equal up to measure-zero ties" can be asserted exactly.
+TIE_HOOK = None      # callable(layer_name, z, a, slope_neg) -> a'   (test infrastructure only)
+
+
+def _act(name, z, slope):
+    a = F.leaky_relu(z, slope) if slope else F.relu(z)
+    return TIE_HOOK(name, z, a, slope) if TIE_HOOK is not None else a
+
+
+class TieRecorder:
+    """Records pre-activations; optionally flips the backward slope of given flat indices per layer (forward value kept)."""
+
+    def __init__(self, flips=None):
+        self.z = {}
+        self.flips = flips or {}
+
+    def __call__(self, name, z, a, slope):
+        self.z[name] = z.detach()
+        idx = self.flips.get(name)
+        if idx is None or len(idx) == 0:
+            return a
+        zf = z.reshape(-1)
+        sel = torch.zeros_like(zf)
+        sel[torch.as_tensor(idx, dtype=torch.long)] = 1.0
+        cur = torch.where(zf.detach() > 0, torch.ones_like(zf), torch.full_like(zf, slope))
+        new = torch.where(zf.detach() > 0, torch.full_like(zf, slope), torch.ones_like(zf))
+        # zero-valued term whose gradient replaces slope `cur` by slope `new` on the selected elements
+        return a + (sel * (new - cur) * (zf - zf.detach())).reshape(a.shape)
+
+
 def _conv_relu_pool(p, pre, name, x, pad):
     # nn/nav_encoder.py:29-31,100-102: max_pool2d(relu(conv(x)), 2, stride=2)
-    return F.max_pool2d(F.relu(F.conv2d(x, p[pre + name + ".weight"], p[pre + name + ".bias"], padding=pad)), 2, stride=2)
+    z = F.conv2d(x, p[pre + name + ".weight"], p[pre + name + ".bias"], padding=pad)
+    return F.max_pool2d(_act(pre + name, z, 0.0), 2, stride=2)
 
 
 def encoder_forward(arch: str, p: Dict[str, Tensor], pre: str, states: Sequence[Tensor]) -> Tensor:
     if arch == "atari":
         # nn/atari_encoder.py:25-32 -- leaky_relu(0.01) x3, C-major flatten, linear WITHOUT activation
-        x = F.leaky_relu(F.conv2d(states[0], p[pre + "conv1.weight"], p[pre + "conv1.bias"], stride=4))
-        x = F.leaky_relu(F.conv2d(x, p[pre + "conv2.weight"], p[pre + "conv2.bias"], stride=2))
-        x = F.leaky_relu(F.conv2d(x, p[pre + "conv3.weight"], p[pre + "conv3.bias"], stride=1))
+        x = _act(pre + "conv1", F.conv2d(states[0], p[pre + "conv1.weight"], p[pre + "conv1.bias"], stride=4), 0.01)
+        x = _act(pre + "conv2", F.conv2d(x, p[pre + "conv2.weight"], p[pre + "conv2.bias"], stride=2), 0.01)
+        x = _act(pre + "conv3", F.conv2d(x, p[pre + "conv3.weight"], p[pre + "conv3.bias"], stride=1), 0.01)
         return _lin(p, pre, "linear", x.reshape(x.shape[0], -1))
     if arch in ("nav", "navped"):
         # nn/nav_encoder.py:28-43 (NavPreNet) / :64-79 (NavPedPreNet: image = cat(state[0], state[2]))
@@ -166,24 +201,24 @@ def encoder_forward(arch: str, p: Dict[str, Tensor], pre: str, states: Sequence[
         x = _conv_relu_pool(p, pre, "conv1", img, 1)
         x = _conv_relu_pool(p, pre, "conv2", x, 1)
         x = _conv_relu_pool(p, pre, "conv3", x, 1)
-        x = F.relu(_lin(p, pre, "fc0.0", x.reshape(x.shape[0], -1)))
+        x = _act(pre + "fc0", _lin(p, pre, "fc0.0", x.reshape(x.shape[0], -1)), 0.0)
         x = torch.cat((x, states[1]), dim=1)
-        x = F.relu(_lin(p, pre, "fc1.0", x))
+        x = _act(pre + "fc1", _lin(p, pre, "fc1.0", x), 0.0)
         return _lin(p, pre, "fc2", x)
     if arch == "nav1d":
         # nn/nav_encoder.py:99-128 -- laser: conv1d,conv1d (NO activation between), fc_1d+relu
         l = F.conv1d(states[0], p[pre + "conv1d1.weight"], p[pre + "conv1d1.bias"], stride=2)
         l = F.conv1d(l, p[pre + "conv1d2.weight"], p[pre + "conv1d2.bias"], stride=2)
-        l = F.relu(_lin(p, pre, "fc_1d.0", l.reshape(l.shape[0], -1)))
+        l = _act(pre + "fc_1d", _lin(p, pre, "fc_1d.0", l.reshape(l.shape[0], -1)), 0.0)
         x = _conv_relu_pool(p, pre, "conv1", states[2], 1)
         x = _conv_relu_pool(p, pre, "conv2", x, 1)
         x = _conv_relu_pool(p, pre, "conv3", x, 1)
-        x = F.relu(_lin(p, pre, "fc0.0", x.reshape(x.shape[0], -1)))
+        x = _act(pre + "fc0", _lin(p, pre, "fc0.0", x.reshape(x.shape[0], -1)), 0.0)
         x = torch.cat((l, x, states[1]), dim=1)
-        x = F.relu(_lin(p, pre, "fc1.0", x))
+        x = _act(pre + "fc1", _lin(p, pre, "fc1.0", x), 0.0)
         return _lin(p, pre, "fc2", x)
     if arch == "mlp":
-        return F.relu(_lin(p, pre, "fc0.0", states[0]))    # nn/mlp_encoder.py:21-27
+        return _act(pre + "fc0", _lin(p, pre, "fc0.0", states[0]), 0.0)    # nn/mlp_encoder.py:21-27
     raise ValueError(arch)
 
 
