@@ -10,6 +10,7 @@
 //             and its own re-packed (flipped, transposed) weights; the classes write interleaved output pixels
 //   wgrad     dWp[o, (kh,kw,c)] = sum_pix dy[pix, o] * x[pix*s + (kh,kw) - p, c]
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -110,6 +111,101 @@ int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cl
   return DDRL_OK;
 }
 
+// ---- fused parity classes (tc2 engine) ----------------------------------------------------------------------------
+// Wd[(cy*ncx + cx)*Cin + c, (th*ntx + tw)*Cout + o] = w[o, c, kh, kw],  kh = cy + s*(q0y[cy] + pady - th) (0 if no such tap)
+__global__ void __launch_bounds__(256) pack_dgrad_fused_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout,
+                                                               int Cin, int KH, int KW, int s, int sx, int ncx, int nty, int ntx,
+                                                               int pady, int padx, int q0y0, int q0y1, int q0x0, int q0x1,
+                                                               long long total) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t % Cout);
+    long long r = t / Cout;
+    const int tw = (int)(r % ntx); r /= ntx;
+    const int th = (int)(r % nty); r /= nty;
+    const int c = (int)(r % Cin); r /= Cin;
+    const int cx = (int)(r % ncx), cy = (int)(r / ncx);
+    const int uy = (cy ? q0y1 : q0y0) + pady - th, ux = (cx ? q0x1 : q0x0) + padx - tw;
+    const int kh = cy + s * uy, kw = cx + sx * ux;
+    float v = 0.f;
+    if (uy >= 0 && ux >= 0 && kh < KH && kw < KW) v = w[(((long long)o * Cin + c) * KH + kh) * KW + kw];
+    wd[t] = v;
+  }
+}
+
+int conv_dgrad_fused_plan(const ConvGeom& g, int Cout, DgradFused& f) {
+  memset(&f, 0, sizeof(f));
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const int s = g.stride, sx = W == 1 ? 1 : s;
+  const int py = g.pad, px = W == 1 ? 0 : g.pad;
+  if (s < 2 || s > 2) return DDRL_E_UNSUPPORTED;                // stride 1 has a single class: the plain path
+  if (g.order != 0 || g.C % 4 != 0 || Cout % 32 != 0) return DDRL_E_UNSUPPORTED;
+  f.s = s; f.ncy = s; f.ncx = sx;
+  int pady = 0, padx = 0, topy = 0, topx = 0;
+  for (int r = 0; r < s; ++r) {
+    const int nt = (KH - r + s - 1) / s;
+    if (nt < 1) return DDRL_E_UNSUPPORTED;
+    f.iy0[r] = ((r - py) % s + s) % s;
+    f.q0y[r] = (f.iy0[r] + py - r) / s;
+    pady = std::max(pady, nt - 1 - f.q0y[r]);
+    topy = std::max(topy, f.q0y[r]);
+  }
+  for (int r = 0; r < sx; ++r) {
+    const int nt = (KW - r + sx - 1) / sx;
+    if (nt < 1) return DDRL_E_UNSUPPORTED;
+    f.ix0[r] = ((r - px) % sx + sx) % sx;
+    f.q0x[r] = (f.ix0[r] + px - r) / sx;
+    padx = std::max(padx, nt - 1 - f.q0x[r]);
+    topx = std::max(topx, f.q0x[r]);
+  }
+  f.pady = pady; f.padx = padx;
+  f.nty = topy + pady + 1; f.ntx = topx + padx + 1;
+  f.Jy = (H + s - 1) / s; f.Jx = (W + sx - 1) / sx;
+  f.K = f.nty * f.ntx * Cout;
+  f.N = f.ncy * f.ncx * g.C;
+  if (f.N > 256) return DDRL_E_UNSUPPORTED;
+  ConvOp o;
+  o.a = reinterpret_cast<const float*>(uintptr_t(256)); o.Hin = Ho; o.Win = Wo; o.Ctot = Cout; o.c_off = 0; o.Cin = Cout;
+  o.KH = f.nty; o.KW = f.ntx; o.sy = 1; o.sx = 1; o.py = f.pady; o.px = f.padx; o.Yn = f.Jy; o.Xn = f.Jx; o.Bn = 1;
+  if (!conv_tc_supported(o, false)) return DDRL_E_UNSUPPORTED;
+  f.on = true;
+  return DDRL_OK;
+}
+
+int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const DgradFused& f, cudaStream_t s) {
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const long long total = (long long)f.N * f.K;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);
+  pack_dgrad_fused_kernel<<<blocks, 256, 0, s>>>(w_oihw, f.wd, Cout, g.C, KH, KW, f.s, W == 1 ? 1 : f.s, f.ncx, f.nty, f.ntx,
+                                                 f.pady, f.padx, f.q0y[0], f.q0y[1], f.q0x[0], f.q0x[1], total);
+  DDRL_LAUNCHED("pack_dgrad_fused_kernel");
+  return DDRL_OK;
+}
+
+int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
+                         const float* mask, int B, cudaStream_t s) {
+  int H, W, KH, KW, Ho, Wo;
+  oriented(g, H, W, KH, KW, Ho, Wo);
+  const int sx = W == 1 ? 1 : f.s;
+  ConvOp o;
+  o.a = dy; o.Hin = Ho; o.Win = Wo; o.Ctot = Cout; o.c_off = 0; o.Cin = Cout;
+  o.KH = f.nty; o.KW = f.ntx; o.sy = 1; o.sx = 1; o.py = f.pady; o.px = f.padx;
+  o.Yn = f.Jy; o.Xn = f.Jx; o.Bn = B;
+  TcTap cls;
+  memset(&cls, 0, sizeof(cls));
+  cls.ncls = f.ncy * f.ncx; cls.cls_cols = g.C; cls.out_s = f.s; cls.out_H = H; cls.out_W = W;
+  for (int cy = 0; cy < f.ncy; ++cy)
+    for (int cx = 0; cx < f.ncx; ++cx) {
+      const int q = cy * f.ncx + cx;
+      cls.cls_iy[q] = f.iy0[cy]; cls.cls_ix[q] = f.ix0[cx];
+      cls.cls_off[q] = ((long long)f.iy0[cy] * W + f.ix0[cx]) * g.C;
+    }
+  // tile pixel (jy, jx) -> base input pixel (s*jy, sx*jx); out_s scales both axes, so a 1-D layer (W == 1) keeps x = 0
+  return tc2_conv_fwd(o, f.wd_hi, f.wd_lo, f.K, f.N, nullptr, act, mask, dx, (long long)H * W * g.C, (long long)f.s * W * g.C,
+                      (long long)sx * g.C, s, &cls);
+}
+
 bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,
                           int dy_coff, int B) {
   int H, W, KH, KW, Ho, Wo;
@@ -171,6 +267,18 @@ extern "C" int ddrl_conv_nhwc_f32(int mode, int op, const ddrl_conv_desc* d, con
     }
   } else if (op == 1) {
     if (!dy) return DDRL_E_ARG;
+    DgradFused fz;
+    if (v2 && conv_dgrad_fused_plan(g, d->Cout, fz) == DDRL_OK) {
+      const size_t tot = (size_t)fz.N * fz.K;
+      DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * 3 * tot));
+      fz.wd = tmp; fz.wd_hi = tmp + tot; fz.wd_lo = tmp + 2 * tot;
+      rc = pack_dgrad_fused(w, g, d->Cout, fz, s);
+      if (rc == DDRL_OK) rc = split_hi_lo(tmp, tmp + tot, tmp + 2 * tot, (long long)tot, s);
+      if (rc == DDRL_OK) rc = conv_dgrad_fused_tc2(g, d->Cout, fz, dy, out, act, mask, d->B, s);
+      cudaStreamSynchronize(s);
+      cudaFree(tmp);
+      return rc;
+    }
     std::vector<DgradClass> cls;
     rc = conv_dgrad_plan(g, d->Cout, cls);
     size_t tot = 0;

@@ -33,6 +33,11 @@ struct TcTap {
   int sx, sy, px, py;            // input coordinate = out*s + k - p
   int c_off;                     // first channel of the operand inside the tensor's channel axis
   long long osb, osy, osx;       // output element strides per (image, row, pixel)   (forward/dgrad)
+  // fused stride-parity data gradient: the N axis is ncls groups of cls_cols channels; group q writes the input pixel
+  // (out_s*y + cls_iy[q], out_s*x + cls_ix[q]) of its tile pixel (y, x)  [ncls == 0: plain channel axis]
+  int ncls, cls_cols, out_s, out_H, out_W;
+  int cls_iy[4], cls_ix[4];
+  long long cls_off[4];
 };
 
 // One implicit-GEMM convolution launch over an NHWC tensor a[Bn, Hin, Win, Ctot] (channels [c_off, c_off+Cin)).
@@ -55,7 +60,8 @@ bool tc2_gemm_supported(int form, int M, int N, int K, const float* A, int lda, 
 int tc2_gemm(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb, float* C,
              int ldc, const float* bias, int act, const float* mask, cudaStream_t s);
 int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, int N, const float* bias, int act,
-                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s);
+                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s,
+                 const TcTap* cls = nullptr);     // cls: only its ncls.. fields are read (fused data gradient)
 int tc2_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, float* dW, int ldw,
               cudaStream_t s);
 int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s);
@@ -72,6 +78,19 @@ struct DgradClass {              // one parity class (pix + pad) mod stride of t
   float* wd;                     // packed weights [Cin, K]
   float *wd_hi, *wd_lo;          // their tf32 hi / lo split (tc2 engine)
 };
+struct DgradFused {              // all parity classes of a strided data gradient as ONE GEMM (tc2 engine)
+  bool on;
+  int s, ncy, ncx;               // stride, classes per axis
+  int nty, ntx, pady, padx;      // unified taps / padding of the stride-1 convolution over dy
+  int Jy, Jx;                    // unified pixel grid per image (ceil(H/s), ceil(W/s))
+  int K, N;                      // nty*ntx*Cout, ncy*ncx*Cin
+  int iy0[2], ix0[2], q0y[2], q0x[2];
+  float *wd, *wd_hi, *wd_lo;     // [N, K] (class-major rows), zero where a class has no tap
+};
+int conv_dgrad_fused_plan(const ConvGeom& g, int Cout, DgradFused& f);
+int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const DgradFused& f, cudaStream_t s);
+int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
+                         const float* mask, int B, cudaStream_t s);
 ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B);
 int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out);
 int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s);

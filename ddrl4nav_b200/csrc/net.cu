@@ -66,6 +66,7 @@ struct Tower {
   bool implicit[5] = {false, false, false, false, false};   // layer runs on the implicit-GEMM (tap-TMA) path
   int conv_lin[5] = {-1, -1, -1, -1, -1};                   // index into L of the conv in slot g[i]
   std::vector<DgradClass> dg[5];                            // data-gradient parity classes (+ packed weights)
+  DgradFused df[5] = {};                                    // tc2: all classes of a strided layer as one GEMM
   // per-micro-batch buffers
   std::vector<float*> buf;
   std::vector<uint8_t*> idx;
@@ -256,6 +257,7 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
     if (!conv_dgrad_supported(g, Cout, cls, kAligned, Cout, 0, 1)) continue;
     t.implicit[i] = true;
     t.dg[i] = cls;
+    if (tc2_mode(n) && g.stride > 1) conv_dgrad_fused_plan(g, Cout, t.df[i]);    // leaves df.on = false if unsupported
   }
 }
 
@@ -436,6 +438,9 @@ static int alloc_packed(ddrl_net* n) {
   for (auto& t : n->towers)
     for (int i = 0; i < 5; ++i)
       for (auto& c : t.dg[i]) dg_bytes += ((size_t)t.g[i].C * c.K * 4 + 255) & ~size_t(255);
+  for (auto& t : n->towers)
+    for (int i = 0; i < 5; ++i)
+      if (t.df[i].on) dg_bytes += ((size_t)t.df[i].N * t.df[i].K * 4 + 255) & ~size_t(255);
   n->packed_bytes = 2 * bytes + dg_bytes;
   if (!n->packed_bytes) return DDRL_OK;
   DDRL_CUDA(cudaMalloc(&n->packed_base, n->packed_bytes));
@@ -455,6 +460,15 @@ static int alloc_packed(ddrl_net* n) {
             c.wd_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
           }
           off += ((size_t)t.g[i].C * c.K * 4 + 255) & ~size_t(255);
+        }
+    for (auto& t : n->towers)
+      for (int i = 0; i < 5; ++i)
+        if (t.df[i].on) {
+          DgradFused& f = t.df[i];
+          f.wd = reinterpret_cast<float*>(n->packed_base + off);
+          f.wd_hi = reinterpret_cast<float*>(n->split_base + off);
+          f.wd_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
+          off += ((size_t)f.N * f.K * 4 + 255) & ~size_t(255);
         }
   }
   size_t off = 0;
@@ -481,6 +495,12 @@ static int repack(ddrl_net* n, cudaStream_t s) {
       for (auto& c : t.dg[i]) {
         const Lin& l = t.L[t.conv_lin[i]];
         TRY(pack_dgrad(n->params + n->T[l.w_t].offset, t.g[i], l.N, c, s));
+      }
+  for (auto& t : n->towers)
+    for (int i = 0; i < 5; ++i)
+      if (t.df[i].on) {
+        const Lin& l = t.L[t.conv_lin[i]];
+        TRY(pack_dgrad_fused(n->params + n->T[l.w_t].offset, t.g[i], l.N, t.df[i], s));
       }
   if (n->split_base) {
     // tf32 hi / lo mirrors of the forward weights [0, grad_off) and of the data-gradient weights [2*grad_off, end)
@@ -587,8 +607,11 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
     if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
     else TRY(conv_tc_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
-    if (dx) TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s,
-                              tc2_mode(n)));
+    if (dx && t.df[gi].on)
+      TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s));
+    else if (dx)
+      TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s,
+                        tc2_mode(n)));
     return DDRL_OK;
   }
   TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, 0, nullptr, M, s));

@@ -387,12 +387,27 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
       if (!rvalid) continue;
       const float neg_slope = g.act == 3 ? 0.f : 0.01f;
+      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
+      const bool fused = MODE == 0 && tapA && tp.ncls > 1;
+      int py = 0, px = 0;
+      if (fused) {
+        const int y0 = (mt % tp.tpi) * tp.ny;
+        px = (r % tp.Xn) * tp.out_s;
+        py = (y0 + (r / tp.Xn) % tp.ny) * tp.out_s;
+      }
 #pragma unroll
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 4) {
-        const int colv = n0 + col0 + j0;
+        int colv = n0 + col0 + j0;
+        long long coff = roff;
+        if (fused) {
+          if (colv >= g.N) continue;
+          const int q = colv / tp.cls_cols;
+          if (py + tp.cls_iy[q] >= tp.out_H || px + tp.cls_ix[q] >= tp.out_W) continue;
+          coff += tp.cls_off[q] - (long long)q * tp.cls_cols;       // column colv of group q lands at channel colv - q*cls_cols
+        }
         if (MODE == 0 && g.vec_store && colv + 4 <= g.N) {
           float4 o, mk = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (g.act >= 3) mk = *reinterpret_cast<const float4*>(g.mask + roff + colv);
+          if (g.act >= 3) mk = *reinterpret_cast<const float4*>(g.mask + coff + colv);
           const float* mv = reinterpret_cast<const float*>(&mk);
           float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
@@ -404,21 +419,21 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             else if (g.act >= 3) x = mv[k] > 0.f ? x : neg_slope * x;
             ov[k] = x;
           }
-          *reinterpret_cast<float4*>(g.C + roff + colv) = o;
+          *reinterpret_cast<float4*>(g.C + coff + colv) = o;
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int col = colv + k;
             if (col < g.N) {
               float x = acc[j0 + k];
-              float* p = g.C + roff + col * g.sCn;
+              float* p = g.C + coff + col * g.sCn;
               if (g.atomic) {
                 atomicAdd(p, x);
               } else {
                 if (g.bias != nullptr) x += g.bias[col];
                 if (g.act == 1) x = fmaxf(x, 0.f);
                 else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
-                else if (g.act >= 3) x = g.mask[roff + col * g.sCn] > 0.f ? x : neg_slope * x;
+                else if (g.act >= 3) x = g.mask[coff + col * g.sCn] > 0.f ? x : neg_slope * x;
                 *p = x;
               }
             }
@@ -505,7 +520,8 @@ int tc2_gemm(int form, int M, int N, int K, const float* A, int lda, const float
 }
 
 int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, int N, const float* bias, int act,
-                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s) {
+                 const float* mask, float* out, long long osb, long long osy, long long osx, cudaStream_t s,
+                 const TcTap* cls) {
   if (!conv_tc_supported(o, false) || N < 1 || ldw % 4 != 0 || !al16(Whi) || !al16(Wlo)) return DDRL_E_UNSUPPORTED;
   if (act >= 3 && !mask) return DDRL_E_ARG;
   int r = tc_get_encode();
@@ -516,6 +532,15 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   memset(&g, 0, sizeof(g));
   tc_tap_common(g.tap, o, T2_BM);
   g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
+  if (cls && cls->ncls > 1) {
+    if (cls->ncls > 4 || N != cls->ncls * cls->cls_cols || cls->cls_cols % 4 != 0) return DDRL_E_ARG;
+    g.tap.ncls = cls->ncls; g.tap.cls_cols = cls->cls_cols; g.tap.out_s = cls->out_s; g.tap.out_H = cls->out_H;
+    g.tap.out_W = cls->out_W;
+    for (int q = 0; q < cls->ncls; ++q) {
+      g.tap.cls_iy[q] = cls->cls_iy[q]; g.tap.cls_ix[q] = cls->cls_ix[q]; g.tap.cls_off[q] = cls->cls_off[q];
+      if (cls->cls_off[q] % 4 != 0) return DDRL_E_ARG;
+    }
+  }
   const int K = o.KH * o.KW * o.Cin;
   CUtensorMap ta, tbh, tbl;
   r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
