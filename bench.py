@@ -233,7 +233,7 @@ def run_ours(args):
         name, ms, n, work = line.split()
         prof[name] = dict(ms=float(ms), launches=int(n), work=float(work))
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    gemm_names = [k for k in prof if "gemm" in k]
+    gemm_names = [k for k in prof if "gemm" in k or "tc2" in k or "conv_tc" in k]
     dom = max(prof, key=lambda k: prof[k]["ms"])
     if dom in gemm_names:
         ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e12

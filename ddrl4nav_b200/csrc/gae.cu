@@ -10,17 +10,20 @@
 // [V,N] row per env step), so a warp reading 32 consecutive columns of one time row is one
 // 128 B coalesced request.  HBM-bound: 17 B per (t, column): r 4 + V 4 + done 1 in, ret 4 + adv 4 out.
 //
-// Two schedules:
-//  * gae_seq_kernel: one thread per column walks time backwards with the loads of the next
-//    kUnroll steps in flight (they do not depend on the recurrence).  Every step uses the
-//    reference's exact rounding sequence (__fmul_rn/__fadd_rn, no FMA contraction), so the
-//    result is BIT-EXACT with the numpy loop.  Used when there are enough columns to fill the GPU.
-//  * gae_chunked_kernel: for few columns the time axis is split into CH chunks per column tile.
-//    Pass 1 folds each chunk into one affine map g_out = a*g_in + b; the CH maps of a column are
-//    then combined by a warp-level associative (Hillis-Steele, shuffle) suffix scan over time;
-//    pass 2 replays each chunk from its exact carry-in with the reference's rounding sequence and
-//    writes the outputs (re-read served by L2).  Only the carry-in is reassociated; it is
-//    damped by gamma*lam per step, measured error <= 1e-6 of max|adv|.
+// Schedules (algo argument of ddrl_gae_f32):
+//  * gae_seq_kernel (1) / gae_seq_vec_kernel (4): one thread per column (per 2 adjacent columns) walks time backwards
+//    with the loads of the next steps in flight (they do not depend on the recurrence).  Every step uses the reference's
+//    exact rounding sequence (__fmul_rn/__fadd_rn, no FMA contraction), so the result is BIT-EXACT with the numpy loop.
+//  * gae_tiled_kernel (3/5/7, the default): single pass, time-parallel.  Each thread keeps LC steps of VEC columns in
+//    registers, folds them into an affine map, the maps of a column are combined by a warp-level associative scan
+//    (Hillis-Steele over shuffles), and the steps are replayed from registers with the exact rounding sequence.  Only
+//    the carry-in of each chunk is reassociated (damped by gamma*lam per step; measured <= 3e-7 of max|adv|).
+//    Measured on B200 (profiles/r1_gae_sweep.json): what decides the achieved HBM fraction is the number of
+//    CONTIGUOUS bytes a warp requests per time row (rows are N*4 bytes apart, every request opens another DRAM page):
+//    128 B/warp-row (VEC=1) tops out at 0.59-0.68 of the copy peak, 512 B/warp-row (VEC=4) reaches 0.88.
+//  * gae_chunked_kernel (2): two-pass predecessor of the tiled schedule (fold, scan, replay from L2); kept for A/B.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ddrl {
@@ -79,6 +82,239 @@ __global__ void __launch_bounds__(256) gae_seq_kernel(const float* __restrict__ 
     }
     t -= kUnroll;
   }
+}
+
+
+// Vectorised bit-exact schedule: one thread walks VEC adjacent columns (16-byte loads for VEC = 4), so a warp touches
+// 32*VEC*4 contiguous bytes of every time row (DRAM-page friendly) and carries VEC independent recurrences (ILP).
+// Double-buffered: the loads of batch k+1 are issued BEFORE batch k is consumed (two register buffers of U steps), so a
+// thread always has U..2U steps of independent loads in flight while it walks the dependent chain.  Requires N % VEC == 0 (the VEC columns share one value row / gamma).
+template <int VEC> struct GaeVec;
+template <> struct GaeVec<2> { using F = float2; using B = uint16_t; };
+
+template <int VEC, int U>
+__global__ void __launch_bounds__(64) gae_seq_vec_kernel(const float* __restrict__ values, const float* __restrict__ rewards,
+                                                         const uint8_t* __restrict__ dones, GaeGammas gam, float lam,
+                                                         int T, int N, int C, float* __restrict__ ret,
+                                                         float* __restrict__ adv) {
+  using F = typename GaeVec<VEC>::F;
+  using B = typename GaeVec<VEC>::B;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (c >= C) return;
+  const int vrow = c / N;
+  const float gamma = gam.g[vrow];
+  const float gl = __fmul_rn(gamma, lam);
+  float g[VEC], nv[VEC];
+  {
+    const F b = *reinterpret_cast<const F*>(values + (size_t)T * C + c);
+    const float* bp = reinterpret_cast<const float*>(&b);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { g[k] = 0.f; nv[k] = bp[k]; }
+  }
+  F rA[U], vA[U], rB[U], vB[U];
+  B dA[U], dB[U];
+#define GAE_LOADV(R, V, D, tt)                                                 \
+  _Pragma("unroll") for (int i = 0; i < U; ++i) {                              \
+    const int ti = (tt)-1 - i;                                                 \
+    if (ti >= 0) {                                                             \
+      const size_t o = (size_t)ti * C + c;                                     \
+      R[i] = __ldcs(reinterpret_cast<const F*>(rewards + o));                  \
+      V[i] = __ldcs(reinterpret_cast<const F*>(values + o));                   \
+      D[i] = __ldcs(reinterpret_cast<const B*>(dones + o));                    \
+    }                                                                          \
+  }
+#define GAE_CONSUMEV(R, V, D, tt)                                              \
+  _Pragma("unroll") for (int i = 0; i < U; ++i) {                              \
+    const int ti = (tt)-1 - i;                                                 \
+    if (ti >= 0) {                                                             \
+      const float* rp = reinterpret_cast<const float*>(&R[i]);                 \
+      const float* vp = reinterpret_cast<const float*>(&V[i]);                 \
+      const uint32_t dw = D[i];                                                \
+      F orr, oa;                                                               \
+      float* orp = reinterpret_cast<float*>(&orr);                             \
+      float* oap = reinterpret_cast<float*>(&oa);                              \
+      _Pragma("unroll") for (int k = 0; k < VEC; ++k) {                        \
+        g[k] = gae_step(g[k], gl, gamma, nv[k], vp[k], rp[k], not_done((uint8_t)(dw >> (8 * k)))); \
+        nv[k] = vp[k];                                                         \
+        orp[k] = __fadd_rn(vp[k], g[k]);                                       \
+        oap[k] = g[k];                                                         \
+      }                                                                        \
+      const size_t o = (size_t)ti * C + c;                                     \
+      __stcs(reinterpret_cast<F*>(ret + o), orr);                              \
+      if (vrow == 0) __stcs(reinterpret_cast<F*>(adv + (size_t)ti * N + c), oa); \
+    }                                                                          \
+  }
+  GAE_LOADV(rA, vA, dA, T)
+  for (int t = T; t > 0; t -= 2 * U) {
+    GAE_LOADV(rB, vB, dB, t - U)
+    GAE_CONSUMEV(rA, vA, dA, t)
+    GAE_LOADV(rA, vA, dA, t - 2 * U)
+    GAE_CONSUMEV(rB, vB, dB, t - U)
+  }
+#undef GAE_LOADV
+#undef GAE_CONSUMEV
+}
+
+// Time-parallel single-pass schedule: blockDim = (COLS, CH), COLS*CH = 256.  The block walks the time axis backwards
+// in super-chunks of CH*LC steps.  Thread (x, ch) owns LC consecutive steps of VEC adjacent columns, kept in REGISTERS:
+//   load (all LC steps independent, in flight together; 16-byte loads for VEC = 4, so a warp touches 512 contiguous
+//   bytes of every time row) -> fold into one affine map g_out = a g_in + b per column ->
+//   warp-level associative scan (Hillis-Steele over shuffles) of the CH maps of each column, seeded with the carry of
+//   the previous super-chunk -> replay the LC steps from registers with the reference's exact rounding sequence.
+// HBM sees every input byte once (17 B per (t, column)) for any T; only the carry-in of each chunk is reassociated.
+template <int VEC> struct GaeTile;
+template <> struct GaeTile<1> { using F = float; using B = uint8_t; };
+template <> struct GaeTile<4> { using F = float4; using B = uint32_t; };
+
+template <int VEC, int LC>
+__global__ void __launch_bounds__(256, 2) gae_tiled_kernel(const float* __restrict__ values, const float* __restrict__ rewards,
+                                                           const uint8_t* __restrict__ dones, GaeGammas gam, float lam,
+                                                           int T, int N, int C, float* __restrict__ ret,
+                                                           float* __restrict__ adv) {
+  using F = typename GaeTile<VEC>::F;
+  using B = typename GaeTile<VEC>::B;
+  extern __shared__ float sm[];
+  const int COLS = blockDim.x, CH = blockDim.y, W = COLS * VEC, LD = W + 4;
+  float* sa = sm;                  // [CH][LD]
+  float* sb = sm + CH * LD;        // [CH][LD]  maps, then carry-ins
+  float* sc = sm + 2 * CH * LD;    // [W]       g carried across super-chunks
+  const int x = threadIdx.x, ch = threadIdx.y;
+  const int c = (blockIdx.x * COLS + x) * VEC;
+  const bool live = c < C;
+  int vrow = 0;
+  float gamma = 0.f, gl = 0.f;
+  if (live) {
+    vrow = c / N;
+    gamma = gam.g[vrow];
+    gl = __fmul_rn(gamma, lam);
+  }
+  if (ch == 0) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) sc[x * VEC + k] = 0.f;
+  }
+  const int tid = ch * COLS + x;
+  const int scol = tid / CH, sk = tid % CH;       // scan role: CH consecutive lanes = the chunks of one column
+  const int S = CH * LC;
+  for (int tend = T; tend > 0; tend -= S) {
+    const int t1 = tend - ch * LC;                // this thread's steps: t1-1, t1-2, ..., t1-LC (those >= 0)
+    const bool work = live && t1 > 0;
+    F v[LC], r[LC];
+    B dn[LC];
+    float nv0[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) nv0[k] = 0.f;
+    if (work) {
+      const F b0 = __ldg(reinterpret_cast<const F*>(values + (size_t)t1 * C + c));
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) nv0[k] = reinterpret_cast<const float*>(&b0)[k];
+#pragma unroll
+      for (int i = 0; i < LC; ++i) {
+        const int t = t1 - 1 - i;
+        if (t >= 0) {
+          const size_t o = (size_t)t * C + c;
+          v[i] = __ldcs(reinterpret_cast<const F*>(values + o));
+          r[i] = __ldcs(reinterpret_cast<const F*>(rewards + o));
+          dn[i] = __ldcs(reinterpret_cast<const B*>(dones + o));
+        }
+      }
+    }
+    float a[VEC], b[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { a[k] = 1.f; b[k] = 0.f; }
+    if (work) {
+      float nv[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) nv[k] = nv0[k];
+#pragma unroll
+      for (int i = 0; i < LC; ++i) {
+        if (t1 - 1 - i >= 0) {
+          const uint32_t dw = dn[i];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float nd = not_done((uint8_t)(dw >> (8 * k)));
+            const float vk = reinterpret_cast<const float*>(&v[i])[k], rk = reinterpret_cast<const float*>(&r[i])[k];
+            const float A = gl * nd;
+            const float Bt = (gamma * nv[k]) * nd - vk + rk;
+            b[k] = fmaf(A, b[k], Bt);
+            a[k] = A * a[k];
+            nv[k] = vk;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      sa[ch * LD + x * VEC + k] = a[k];
+      sb[ch * LD + x * VEC + k] = b[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      // P_j = F_j o ... o F_0 (chunk 0 is the latest in time and is applied first)
+      const int col = scol * VEC + k;
+      float pa = sa[sk * LD + col], pb = sb[sk * LD + col];
+      for (int off = 1; off < CH; off <<= 1) {
+        const float qa = __shfl_up_sync(0xffffffffu, pa, off, CH);
+        const float qb = __shfl_up_sync(0xffffffffu, pb, off, CH);
+        if (sk >= off) {
+          pb = fmaf(pa, qb, pb);
+          pa = pa * qa;
+        }
+      }
+      const float g0 = sc[col];
+      const float ua = __shfl_up_sync(0xffffffffu, pa, 1, CH);
+      const float ub = __shfl_up_sync(0xffffffffu, pb, 1, CH);
+      sb[sk * LD + col] = sk == 0 ? g0 : fmaf(ua, g0, ub);      // carry-in of chunk sk
+    }
+    __syncthreads();
+    if (work) {
+      float g[VEC], nv[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { g[k] = sb[ch * LD + x * VEC + k]; nv[k] = nv0[k]; }
+#pragma unroll
+      for (int i = 0; i < LC; ++i) {
+        const int t = t1 - 1 - i;
+        if (t >= 0) {
+          const uint32_t dw = dn[i];
+          F orr, oa;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float vk = reinterpret_cast<const float*>(&v[i])[k], rk = reinterpret_cast<const float*>(&r[i])[k];
+            g[k] = gae_step(g[k], gl, gamma, nv[k], vk, rk, not_done((uint8_t)(dw >> (8 * k))));
+            nv[k] = vk;
+            reinterpret_cast<float*>(&orr)[k] = __fadd_rn(vk, g[k]);
+            reinterpret_cast<float*>(&oa)[k] = g[k];
+          }
+          const size_t o = (size_t)t * C + c;
+          __stcs(reinterpret_cast<F*>(ret + o), orr);
+          if (vrow == 0) __stcs(reinterpret_cast<F*>(adv + (size_t)t * N + c), oa);
+        }
+      }
+      if (ch == CH - 1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) sc[x * VEC + k] = g[k];
+      }
+    }
+  }
+}
+
+template <int VEC, int LC>
+static int launch_tiled(const float* values, const float* rewards, const uint8_t* dones, const GaeGammas& gam, float lambda, int T,
+                        int N, int C, float* ret, float* adv, cudaStream_t s) {
+  const int cols = C / VEC;
+  static int min_blocks = -1;
+  if (min_blocks < 0) { const char* e = getenv("DDRL_GAE_MINBLOCKS"); min_blocks = e ? atoi(e) : kNumSMs; }
+  int COLS = 32;
+  while (COLS > 8 && ceil_div(cols, COLS) < min_blocks) COLS >>= 1;
+  int CH = 256 / COLS;
+  while (CH > 1 && (CH / 2) * LC >= T) CH >>= 1;     // no more chunks than the time axis has
+  while (COLS * CH < 32) CH <<= 1;
+  dim3 block(COLS, CH);
+  const size_t smem = sizeof(float) * (2 * CH * (COLS * VEC + 4) + COLS * VEC);
+  gae_tiled_kernel<VEC, LC><<<ceil_div(cols, COLS), block, smem, s>>>(values, rewards, dones, gam, lambda, T, N, C, ret, adv);
+  prof_work(17.0 * T * (double)C);
+  DDRL_LAUNCHED("gae_tiled_kernel");
+  return DDRL_OK;
 }
 
 // blockDim = (COLS, CH); CH power of two <= 32; COLS*CH multiple of 32.
@@ -168,12 +404,28 @@ extern "C" int ddrl_gae_f32(const float* values, const float* rewards, const uin
   for (int i = 0; i < kMaxV; ++i) gam.g[i] = i < V ? gamma_host[i] : 0.f;
   const int C = V * N;
   cudaStream_t s = (cudaStream_t)stream;
-  if (algo == 0) algo = (C >= 32768 || T < 8) ? 1 : 2;
+  // algo: 0 auto | 1 sequential scalar (bit-exact) | 2 two-pass chunked | 3 time-parallel single pass, widest vector that fits |
+  //       4 sequential vectorised (bit-exact) | 5 time-parallel VEC=1 | 7 time-parallel VEC=4
+  const bool al16 = (reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(rewards) | reinterpret_cast<uintptr_t>(ret) |
+                     reinterpret_cast<uintptr_t>(adv)) % 16 == 0 && reinterpret_cast<uintptr_t>(dones) % 4 == 0;
+  if (algo == 0) algo = T < 8 ? 1 : 3;
+  if (algo == 3) algo = (N % 4 == 0 && al16 && C >= 8192) ? 7 : 5;
+  if (algo == 4 && (N % 2 != 0 || !al16)) algo = 1;
   if (algo == 1) {
     const int threads = 128;
     gae_seq_kernel<8><<<ceil_div(C, threads), threads, 0, s>>>(values, rewards, dones, gam, lambda, T, N, C, ret, adv);
     prof_work(17.0 * T * (double)C);
     DDRL_LAUNCHED("gae_seq_kernel");
+  } else if (algo == 4) {
+    const int threads = 64, cols = C / 2;
+    gae_seq_vec_kernel<2, 8><<<ceil_div(cols, threads), threads, 0, s>>>(values, rewards, dones, gam, lambda, T, N, C, ret, adv);
+    prof_work(17.0 * T * (double)C);
+    DDRL_LAUNCHED("gae_seq_vec_kernel");
+  } else if (algo == 5) {
+    return launch_tiled<1, 16>(values, rewards, dones, gam, lambda, T, N, C, ret, adv, s);
+  } else if (algo == 7) {
+    if (N % 4 != 0 || !al16) return DDRL_E_UNSUPPORTED;
+    return launch_tiled<4, 8>(values, rewards, dones, gam, lambda, T, N, C, ret, adv, s);
   } else if (algo == 2) {
     int CH = 32;
     while (CH > 1 && CH * 4 > T) CH >>= 1;       // at least ~4 steps per chunk

@@ -89,8 +89,11 @@ int ddrl_prof_stop(char* out, int cap);
  * values [T+1, V, N] f32 (row T = bootstrap), rewards [>=T, V, N] f32, dones [>=T, V, N] u8,
  * gamma_host [V] f32 HOST (self.discounts), lambda (self.landa).
  * out: ret [T, V, N] = values + g ; adv [T, N] = g of row v=0.
- * algo: 0 = auto, 1 = sequential-per-column (bit-exact with the numpy loop), 2 = T-chunked
- *       warp-scan (fp32 reassociation, <=1e-5 of max|adv|). */
+ * algo: 0 = auto (3, or 1 when T < 8); 1 = sequential per column and 4 = sequential, 2 columns per thread
+ *       (both bit-exact with the numpy loop); 3 = single-pass time-parallel warp scan with the widest vector
+ *       the shape allows (5 = scalar columns, 7 = 4 columns per thread: needs N % 4 == 0 and 16-byte aligned
+ *       pointers, else DDRL_E_UNSUPPORTED); 2 = two-pass chunked warp scan.  2/3/5/7 reassociate only the
+ *       carry-in of a time chunk (<= 1e-5 of max|adv|, measured 3e-7). */
 int ddrl_gae_f32(const float* values, const float* rewards, const uint8_t* dones,
                  const float* gamma_host, float lambda, int T, int V, int N,
                  float* ret, float* adv, int algo, void* stream);

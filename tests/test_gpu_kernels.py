@@ -32,7 +32,7 @@ def _gae_inputs(T, V, N, seed, p_done=0.02):
     values = rng.standard_normal((T + 1, V, N)).astype(np.float32)
     rewards = rng.standard_normal((T + 1, V, N)).astype(np.float32)
     dones = (rng.random((T + 1, V, N)) < p_done).astype(np.uint8)
-    gam = np.array([0.99, 0.999, 0.9][:V], dtype=np.float32).reshape(V, 1)
+    gam = (np.array([0.99, 0.999, 0.9][:V], dtype=np.float32) if V <= 3 else np.linspace(0.9, 0.999, V).astype(np.float32)).reshape(V, 1)
     return values, rewards, dones, gam
 
 
@@ -50,20 +50,26 @@ def test_gae_golden(golden_dir):
         ret, adv = _run_gae(v, r, d, gam, 1)
         assert np.array_equal(ret, g[f"{tag}_returns"]), tag        # bit-exact
         assert np.array_equal(adv, g[f"{tag}_advs"]), tag
-        ret2, adv2 = _run_gae(v, r, d, gam, 2)
-        assert close(ret2, g[f"{tag}_returns"]) and close(adv2, g[f"{tag}_advs"]), tag
+        ret4, adv4 = _run_gae(v, r, d, gam, 4)                      # double-buffered sequential schedule: bit-exact too
+        assert np.array_equal(ret4, g[f"{tag}_returns"]) and np.array_equal(adv4, g[f"{tag}_advs"]), tag
+        for algo in (2, 3, 5) + ((7,) if v.shape[-1] % 4 == 0 else ()):   # time-parallel schedules: carry-in reassociated
+            ret2, adv2 = _run_gae(v, r, d, gam, algo)
+            assert close(ret2, g[f"{tag}_returns"]) and close(adv2, g[f"{tag}_advs"]), (tag, algo)
         ret0, adv0 = _run_gae(v, r, d, gam, 0)
         assert close(ret0, g[f"{tag}_returns"]) and close(adv0, g[f"{tag}_advs"]), tag
 
 
-@pytest.mark.parametrize("T,V,N", [(1, 1, 1), (2, 1, 3), (7, 1, 33), (128, 1, 1024), (300, 2, 77), (513, 1, 40), (64, 3, 1000)])
+@pytest.mark.parametrize("T,V,N", [(1, 1, 1), (2, 1, 3), (7, 1, 33), (128, 1, 1024), (300, 2, 77), (513, 1, 40), (64, 3, 1000),
+                                   (1025, 1, 300), (33, 2, 5000), (16, 1, 9), (17, 8, 3), (260, 2, 4096), (70, 1, 16388)])
 def test_gae_vs_oracle(T, V, N):
     v, r, d, gam = _gae_inputs(T, V, N, seed=T * 31 + N)
     ref_ret, ref_adv = R.gae(v, d, r, gam, 0.95)
-    ret, adv = _run_gae(v, r, d, gam, 1)
-    assert np.array_equal(ret, ref_ret) and np.array_equal(adv, ref_adv)
-    ret, adv = _run_gae(v, r, d, gam, 2)
-    assert close(ret, ref_ret) and close(adv, ref_adv)
+    for algo in (1, 4):
+        ret, adv = _run_gae(v, r, d, gam, algo)
+        assert np.array_equal(ret, ref_ret) and np.array_equal(adv, ref_adv), algo
+    for algo in (0, 2, 3, 5) + ((7,) if N % 4 == 0 else ()):
+        ret, adv = _run_gae(v, r, d, gam, algo)
+        assert close(ret, ref_ret) and close(adv, ref_adv), algo
 
 
 def test_gae_empty_and_done_everywhere():
@@ -73,9 +79,21 @@ def test_gae_empty_and_done_everywhere():
     assert ret.shape == (0, 1, 5) and adv.shape == (0, 5)
     v, r, d, gam = _gae_inputs(50, 1, 64, 3)
     d[:] = 1                                     # every step terminal: adv = r - v exactly
-    for algo in (1, 2):
+    for algo in (1, 2, 3, 4, 5, 7):
         ret, adv = _run_gae(v, r, d, gam, algo)
         assert np.array_equal(adv, (r[:50, 0] - v[:50, 0]).astype(np.float32) + np.float32(0)) or close(adv, r[:50, 0] - v[:50, 0])
+
+
+def test_gae_vector_schedule_rejects_ragged_rows():
+    """VEC=4 needs N % 4 == 0 (the 4 columns of a thread share one value row): explicit request fails loudly, auto falls back."""
+    from ddrl4nav_b200 import kernels
+    from ddrl4nav_b200._lib import DDRLError
+    v, r, d, gam = _gae_inputs(40, 2, 8191, 5)
+    with pytest.raises(DDRLError):
+        _run_gae(v, r, d, gam, 7)
+    ref_ret, ref_adv = R.gae(v, d, r, gam, 0.95)
+    ret, adv = _run_gae(v, r, d, gam, 0)
+    assert close(ret, ref_ret) and close(adv, ref_adv)
 
 
 def test_gae_full_size_properties():
@@ -91,6 +109,15 @@ def test_gae_full_size_properties():
     scale = adv1.abs().max()
     assert float((adv1 - adv2).abs().max() / scale) < 1e-5
     assert float((ret1 - ret2).abs().max() / ret1.abs().max()) < 1e-5
+    del ret2, adv2
+    for algo in (5, 7):
+        ret3, adv3 = kernels.gae(values, rewards, dones, [0.99], 0.95, algo)
+        assert float((adv1 - adv3).abs().max() / scale) < 1e-5
+        assert float((ret1 - ret3).abs().max() / ret1.abs().max()) < 1e-5
+        del ret3, adv3
+    ret5, adv5 = kernels.gae(values, rewards, dones, [0.99], 0.95, 4)
+    assert torch.equal(adv5, adv1) and torch.equal(ret5, ret1)          # both sequential schedules are bit-identical
+    del ret5, adv5
     ret4, adv4 = kernels.gae(values * 4, rewards * 4, dones, [0.99], 0.95, 1)
     assert torch.equal(adv4, adv1 * 4) and torch.equal(ret4, ret1 * 4)
     # ret - adv == values (row 0) up to one rounding
