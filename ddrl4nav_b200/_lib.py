@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddrl_b200.so")
+# DDRL_LIB_PATH: development override (e.g. an instrumented build); the product path is the in-tree library
+LIB_PATH = os.environ.get("DDRL_LIB_PATH") or os.path.join(_HERE, "libddrl_b200.so")
 
 
 class DDRLError(RuntimeError):

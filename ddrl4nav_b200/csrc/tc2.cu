@@ -32,6 +32,24 @@ constexpr int T2_BM = 128;
 constexpr int T2_BK = 32;
 constexpr int T2_CHUNK = 4;                   // K blocks per TMEM main-accumulator chunk (16 accumulating MMAs)
 
+// Optional role-level wait accounting (build with -DTC2_TIMING): cycles each warp role spends blocked on each of its
+// mbarriers, accumulated over every launch; read with ddrl_tc2_timing_read.  [role*4 + k], k = 3 is the role's lifetime.
+// roles: 0 TMA producer {empty} | 1 chunk MMA {mfree, full, aready} | 2 corr MMA {cfree, full, aready} |
+//        3 splitter warp 4 {full, afree} | 4 epilogue warp 0 {mfull, cfull, stores}
+__device__ unsigned long long g_tc2_wait[32];
+#ifdef TC2_TIMING
+#define T2_WAIT(bar, par, acc) do { const long long _t0 = clock64(); mbar_wait(bar, par); acc += clock64() - _t0; } while (0)
+#define T2_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0; const long long role_t0 = clock64();
+#define T2_ROLE_END(role, cond) do { if ((cond) && lane == 0) { \
+    atomicAdd(&g_tc2_wait[(role) * 4 + 0], (unsigned long long)w0); atomicAdd(&g_tc2_wait[(role) * 4 + 1], (unsigned long long)w1); \
+    atomicAdd(&g_tc2_wait[(role) * 4 + 2], (unsigned long long)w2); \
+    atomicAdd(&g_tc2_wait[(role) * 4 + 3], (unsigned long long)(clock64() - role_t0)); } } while (0)
+#else
+#define T2_WAIT(bar, par, acc) mbar_wait(bar, par)
+#define T2_ROLE_BEGIN
+#define T2_ROLE_END(role, cond)
+#endif
+
 struct Tc2Args {
   float* C;
   const float* bias;
@@ -66,7 +84,10 @@ struct T2Cfg {
                        TM_A = FOLD ? 5 * BN : 3 * BN;
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + NBARS * 8 + 16;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES + 256;      // epilogue staging: one swizzled 32 x 32 fp32 panel per warp
+  static constexpr int SMEM = 1024 + STG_OFF + NEPI * 4096;
+  static_assert(NBARS * 8 + 16 <= 256, "barrier block");
+  static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
 };
 
@@ -137,6 +158,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // The whole warp runs the loop convergently; one elected lane issues (keeps every operand in uniform registers).
     // Tap / pixel-block coordinates advance incrementally: no integer division per K block.
     uint32_t it = 0;
+    T2_ROLE_BEGIN
     // weight gradient, implicit operand: the 4 (tap, chunk) slices of this CTA's M block are fixed
     int sl_c[4] = {0, 0, 0, 0}, sl_x[4] = {0, 0, 0, 0}, sl_y[4] = {0, 0, 0, 0}, na = 0;
     if (MODE == 1 && tapA) {
@@ -162,7 +184,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (MODE == 1 && tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
       for (int i = 0; i < nkb; ++i, ++it) {
         const uint32_t s = it % S;
-        mbar_wait(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1);
+        T2_WAIT(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1, w0);
         if (elect_one()) {
           const uint32_t full = smem_u32(bar_full + s);
           const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES,
@@ -208,6 +230,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         else if (++pj == tp.tpi) { pj = 0; ++pb; }
       }
     }
+    T2_ROLE_END(0, true);
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers (one elected thread each)
     // warp 1: chunk buffers   main (+)= A_hi . B_hi          [FOLD: [main | corrB] (+)= A_hi . [B_hi ; B_lo], N' = 2 BN]
@@ -222,16 +245,17 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
     constexpr uint32_t kstep = B_MN ? (1024 >> 4) : (32 >> 4);      // start-address field increment per k step
     uint32_t it = 0, ch = 0, tl = 0;
+    T2_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
       for (int i = 0; i < nkb; ++i, ++it) {
         const uint32_t s = it % S, a = it % SA;
         const uint32_t buf = ch & 1;
         const bool first_in_chunk = (i % T2_CHUNK) == 0;
         const bool last_in_chunk = (i % T2_CHUNK) == T2_CHUNK - 1 || i == nkb - 1;
-        if (chunk_role) { if (first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1); }
-        else if (i == 0) mbar_wait(smem_u32(bar_cfree), (tl & 1) ^ 1);
-        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
-        mbar_wait(smem_u32(bar_aready + a), (it / SA) & 1);
+        if (chunk_role) { if (first_in_chunk) T2_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0); }
+        else if (i == 0) T2_WAIT(smem_u32(bar_cfree), (tl & 1) ^ 1, w0);
+        T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w1);
+        T2_WAIT(smem_u32(bar_aready + a), (it / SA) & 1, w2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
@@ -265,19 +289,24 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (last_in_chunk) ++ch;
       }
     }
+    T2_ROLE_END(chunk_role ? 1 : 2, true);
   } else if (warp >= 4 && warp < Cfg::EPI0) {
     // ============================================================ splitters: smem A -> hi / lo -> TMEM
     const int q = (warp - 4) & 3, grp = (warp - 4) >> 2;
     const int st_tid = (threadIdx.x - 128) & 127;                // thread index within the group
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t it = 0;
+    T2_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       for (int i = 0; i < nkb; ++i, ++it) {
         if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
         const int s = it % S, a = it % SA;
-        mbar_wait(smem_u32(bar_full + s), (it / S) & 1);
+        T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         uint32_t hi[32], lo[32];
+#ifdef TC2_TIMING
+        const long long sp0 = clock64();
+#endif
         if (MODE == 0) {
           // thread = tile row; its 32 k values are the row's eight 16-byte chunks (128B swizzle: chunk ^ (row & 7))
           const int row = q * 32 + lane;
@@ -310,7 +339,10 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           }
           fence_async_smem();
         }
-        mbar_wait(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1);
+#ifdef TC2_TIMING
+        w2 += clock64() - sp0;
+#endif
+        T2_WAIT(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1, w1);
         tc_fence_after();
         const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
         tmem_st16(ta, hi);
@@ -323,6 +355,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
       }
     }
+    T2_ROLE_END(3, warp == 4);
   } else if (warp >= Cfg::EPI0) {
     // ============================================================ drain + epilogue
     const int e = warp - Cfg::EPI0;
@@ -330,6 +363,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const uint32_t col0 = half * Cfg::COLS;
     uint32_t ch = 0, tl = 0;
+    T2_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
       const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
       const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
@@ -340,7 +374,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const int nch = (nkb + T2_CHUNK - 1) / T2_CHUNK;
       for (int c = 0; c < nch; ++c, ++ch) {
         const int buf = ch & 1;
-        mbar_wait(smem_u32(bar_mfull + buf), (ch >> 1) & 1);
+        T2_WAIT(smem_u32(bar_mfull + buf), (ch >> 1) & 1, w0);
         tc_fence_after();
 #pragma unroll
         for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
@@ -359,7 +393,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
       }
-      mbar_wait(smem_u32(bar_cfull), tl & 1);
+      T2_WAIT(smem_u32(bar_cfull), tl & 1, w1);
       tc_fence_after();
 #pragma unroll
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
@@ -372,6 +406,9 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
       // ---- stores
+#ifdef TC2_TIMING
+      const long long st0 = clock64();
+#endif
       const int r = q * 32 + lane;
       bool rvalid;
       long long roff;
@@ -385,7 +422,6 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         rvalid = (m0 + r) < g.M;
         roff = (long long)(m0 + r) * g.sCm;
       }
-      if (!rvalid) continue;
       const float neg_slope = g.act == 3 ? 0.f : 0.01f;
       // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
       const bool fused = MODE == 0 && tapA && tp.ncls > 1;
@@ -395,32 +431,97 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         px = (r % tp.Xn) * tp.out_s;
         py = (y0 + (r / tp.Xn) % tp.ny) * tp.out_s;
       }
+      if (MODE == 0 && g.vec_store) {
+        // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
+        // (and activation-mask load) instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+        float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
+        const int cidx = lane & 7, rsub = lane >> 3;
+        const int pyx = (py << 16) | px;
 #pragma unroll
-      for (int j0 = 0; j0 < Cfg::COLS; j0 += 4) {
-        int colv = n0 + col0 + j0;
-        long long coff = roff;
-        if (fused) {
-          if (colv >= g.N) continue;
-          const int q = colv / tp.cls_cols;
-          if (py + tp.cls_iy[q] >= tp.out_H || px + tp.cls_ix[q] >= tp.out_W) continue;
-          coff += tp.cls_off[q] - (long long)q * tp.cls_cols;       // column colv of group q lands at channel colv - q*cls_cols
-        }
-        if (MODE == 0 && g.vec_store && colv + 4 <= g.N) {
-          float4 o, mk = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (g.act >= 3) mk = *reinterpret_cast<const float4*>(g.mask + coff + colv);
-          const float* mv = reinterpret_cast<const float*>(&mk);
-          float* ov = reinterpret_cast<float*>(&o);
+        for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float x = acc[j0 + k];
-            if (g.bias != nullptr) x += g.bias[colv + k];
-            if (g.act == 1) x = fmaxf(x, 0.f);
-            else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
-            else if (g.act >= 3) x = mv[k] > 0.f ? x : neg_slope * x;
-            ov[k] = x;
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                make_float4(acc[p0 + 4 * c], acc[p0 + 4 * c + 1], acc[p0 + 4 * c + 2], acc[p0 + 4 * c + 3]);
+          __syncwarp();
+          const int colv = n0 + col0 + p0 + cidx * 4;
+          const bool cok = colv < g.N;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (colv + k < g.N) bv[k] = g.bias[colv + k];
           }
-          *reinterpret_cast<float4*>(g.C + coff + colv) = o;
-        } else {
+          long long cadd = 0;
+          int ciy = 0, cix = 0;
+          if (fused && cok) {
+            const int qq = colv / tp.cls_cols;
+            ciy = tp.cls_iy[qq]; cix = tp.cls_ix[qq];
+            cadd = tp.cls_off[qq] - (long long)qq * tp.cls_cols;     // column colv of group qq lands at channel colv - qq*cls_cols
+          }
+          // pass 1: addresses + all activation-mask loads of the panel in flight together (the mask may alias nothing
+          // the compiler can prove, so loads interleaved with the stores would serialise on L2 latency)
+          long long off[8];
+          float4 mk[8];
+          uint32_t okm = 0;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rr = i8 * 4 + rsub;
+            const int ok = __shfl_sync(0xffffffffu, (int)rvalid, rr);
+            const long long ro = __shfl_sync(0xffffffffu, roff, rr);
+            const int ryx = __shfl_sync(0xffffffffu, pyx, rr);
+            bool live = ok && cok;
+            if (fused && ((ryx >> 16) + ciy >= tp.out_H || (ryx & 0xffff) + cix >= tp.out_W)) live = false;
+            off[i8] = ro + cadd + colv;
+            mk[i8] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (live) {
+              okm |= 1u << i8;
+              if (g.act >= 3) {
+                if (colv + 4 <= g.N) mk[i8] = __ldg(reinterpret_cast<const float4*>(g.mask + off[i8]));
+                else {
+                  float* mv = reinterpret_cast<float*>(&mk[i8]);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) if (colv + k < g.N) mv[k] = __ldg(g.mask + off[i8] + k);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            if (!((okm >> i8) & 1u)) continue;
+            const int rr = i8 * 4 + rsub;
+            const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cidx ^ (rr & 7)) << 2));
+            const float xv[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float* mv = reinterpret_cast<const float*>(&mk[i8]);
+            float4 o;
+            float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float x = xv[k] + bv[k];
+              if (g.act == 1) x = fmaxf(x, 0.f);
+              else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+              else if (g.act >= 3) x = mv[k] > 0.f ? x : neg_slope * x;
+              ov[k] = x;
+            }
+            if (colv + 4 <= g.N) {
+              *reinterpret_cast<float4*>(g.C + off[i8]) = o;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) if (colv + k < g.N) g.C[off[i8] + k] = ov[k];
+            }
+          }
+          __syncwarp();
+        }
+      } else if (rvalid) {
+#pragma unroll
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 4) {
+          const int colv = n0 + col0 + j0;
+          long long coff = roff;
+          if (fused) {
+            if (colv >= g.N) continue;
+            const int qq = colv / tp.cls_cols;
+            if (py + tp.cls_iy[qq] >= tp.out_H || px + tp.cls_ix[qq] >= tp.out_W) continue;
+            coff += tp.cls_off[qq] - (long long)qq * tp.cls_cols;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int col = colv + k;
@@ -440,7 +541,11 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           }
         }
       }
+#ifdef TC2_TIMING
+      w2 += clock64() - st0;
+#endif
     }
+    T2_ROLE_END(4, warp == Cfg::EPI0);
   }
   tc_fence_before();
   __syncthreads();
@@ -630,3 +735,13 @@ int split_hi_lo(const float* w, float* hi, float* lo, long long n, cudaStream_t 
 }
 
 }  // namespace ddrl
+
+// debugging aid (not part of the public header): role wait counters of the tc2 engine (all zero unless built -DTC2_TIMING)
+extern "C" int ddrl_tc2_timing_read(unsigned long long* out32, int reset) {
+  if (out32) DDRL_CUDA(cudaMemcpyFromSymbol(out32, ddrl::g_tc2_wait, sizeof(unsigned long long) * 32));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    DDRL_CUDA(cudaMemcpyToSymbol(ddrl::g_tc2_wait, z, sizeof(z)));
+  }
+  return DDRL_OK;
+}
