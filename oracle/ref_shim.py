@@ -146,10 +146,11 @@ def make_ref_net(kind: str):
 
     kind: 'pong' (C1, unshared AtariPreNet x2, 6-way categorical),
           'navlaser' (C2, unshared NavPreNet1D x2, 2-d Gaussian),
-          'navimg' (C5, shared NavPreNet, 28-way categorical).
+          'navimg' (C5, shared NavPreNet, 28-way categorical),
+          'navped' (shared NavPedPreNet on cat(map, 3-ch ped-map), 28-way categorical).
     """
     import_reference()
-    from USTC_lab.nn import (PPO, AtariPreNet, NavPreNet, NavPreNet1D, Critic)
+    from USTC_lab.nn import (PPO, AtariPreNet, NavPreNet, NavPedPreNet, NavPreNet1D, Critic)
     if kind == "pong":
         cfg, cnn = make_ref_configs(True, 6, share=False)
         pa, pc = AtariPreNet(4, last_output_dim=512, device="cpu"), AtariPreNet(4, last_output_dim=512, device="cpu")
@@ -170,5 +171,12 @@ def make_ref_net(kind: str):
                                 nn_dtype=cnn.MODULE_TENSOR_DTYPE)
         critic = Critic(device="cpu", last_input_dim=512)
         prenet = NavPreNet(image_channel=1, last_output_dim=512)
+        return PPO(actor, critic, prenet, None, cfg, cnn), cfg, cnn
+    if kind == "navped":
+        cfg, cnn = make_ref_configs(True, 28, share=True, env_type="robot_nav")
+        actor = cnn.ACTOR_CLASS(action_output_dim=28, device="cpu", soft_max_grid=True, last_input_dim=512,
+                                nn_dtype=cnn.MODULE_TENSOR_DTYPE)
+        critic = Critic(device="cpu", last_input_dim=512)
+        prenet = NavPedPreNet(image_channel=4, last_output_dim=512)
         return PPO(actor, critic, prenet, None, cfg, cnn), cfg, cnn
     raise ValueError(kind)

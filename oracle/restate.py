@@ -51,6 +51,7 @@ SPECS = {
     "pong": NetSpec("atari", 4, 6, "categorical", False),       # BASELINE config C1
     "navlaser": NetSpec("nav1d", 3, 2, "gaussian", False),      # C2
     "navimg": NetSpec("nav", 1, 28, "categorical", True),       # C5
+    "navped": NetSpec("navped", 4, 28, "categorical", True),    # C5 "+ scan" variant: NavPedPreNet, cat(map, ped-map)
 }
 
 
@@ -471,6 +472,12 @@ def synth_states(kind: str, B: int, seed: int = 0) -> List[Tensor]:
         return [laser, vec, torch.cat([occ, vel], dim=1)]
     if kind == "navimg":
         return [torch.rand(B, 1, 48, 48, generator=g), torch.randn(B, 9, generator=g)]
+    if kind == "navped":
+        img = torch.rand(B, 1, 48, 48, generator=g)
+        vec = torch.randn(B, 9, generator=g)
+        occ = (torch.rand(B, 1, 48, 48, generator=g) < 0.03).float()
+        vel = (torch.rand(B, 2, 48, 48, generator=g) - 0.5) * occ
+        return [img, vec, torch.cat([occ, vel], dim=1)]
     raise ValueError(kind)
 
 

@@ -175,10 +175,12 @@ def golden_net(kind: str, B: int, iters: int = 4):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    golden_gae()
-    golden_sampling()
-    golden_net("pong", 8)
-    golden_net("navimg", 6)
-    golden_net("navlaser", 4)
+    only = set(sys.argv[1:])          # e.g. `make_golden.py navped` regenerates one fixture
+    todo = [("gae", golden_gae), ("sampling", golden_sampling), ("pong", lambda: golden_net("pong", 8)),
+            ("navimg", lambda: golden_net("navimg", 6)), ("navlaser", lambda: golden_net("navlaser", 4)),
+            ("navped", lambda: golden_net("navped", 5))]
+    for name, fn in todo:
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

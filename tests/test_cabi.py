@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
     assert lib.ddrl_error_string(-1) == b"bad argument"
 
 
-@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg"])
+@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg", "navped"])
 def test_engine_param_table_is_reference_order(kind):
     _lib = _ensure_built()
     lib = _lib.load()
@@ -60,7 +60,7 @@ def test_engine_param_table_is_reference_order(kind):
         assert tuple(shape[k] for k in range(ndim.value)) == tuple(shp)
         assert off.value == total
         total += int(np.prod(shp))
-    assert lib.ddrl_net_num_params(h) == total == {"pong": 3371847, "navlaser": 12799685, "navimg": 5633565}[kind]
+    assert lib.ddrl_net_num_params(h) == total == {"pong": 3371847, "navlaser": 12799685, "navimg": 5633565, "navped": 5635293}[kind]
     # argument checking without a GPU
     assert lib.ddrl_net_backward(h, None, 0, 1, 1, None, None, None, None, None, 0, None) != 0
     assert lib.ddrl_net_destroy(h) == 0
@@ -68,7 +68,7 @@ def test_engine_param_table_is_reference_order(kind):
     assert lib.ddrl_net_create(C.byref(bad), C.byref(h)) == -1
 
 
-@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg"])
+@pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg", "navped"])
 def test_mirror_modules_register_reference_order(kind):
     from ddrl4nav_b200.runner import make_net
     net = make_net(kind, device=None)

@@ -41,7 +41,7 @@ def make(kind, seed=11, **hyper):
     return net.to(DEV), spec, params
 
 
-@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4)])
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("navped", 5)])
 def test_forward_matches_golden_and_oracle(golden_dir, kind, B):
     g = np.load(os.path.join(golden_dir, f"net_{kind}.npz"))
     net, spec, params = make(kind)
@@ -63,7 +63,7 @@ def test_forward_matches_golden_and_oracle(golden_dir, kind, B):
     assert rel_err(logp, g["logp"]) < 2e-5
 
 
-@pytest.mark.parametrize("kind,B", [("pong", 33), ("navimg", 9), ("navlaser", 5), ("pong", 1)])
+@pytest.mark.parametrize("kind,B", [("pong", 33), ("navimg", 9), ("navlaser", 5), ("pong", 1), ("navped", 7)])
 def test_act_matches_oracle(kind, B):
     net, spec, params = make(kind)
     states = R.synth_states(kind, B, seed=21)
@@ -114,7 +114,7 @@ def _oracle_grads(spec, params, states, adv, a, old, ret, flips=None):
 TIE_EPS = 1e-6      # an activation with |z| < TIE_EPS * max|z| of its layer is zero to within fp32 rounding: a tie
 
 
-@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("pong", 40)])
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("pong", 40), ("navped", 5)])
 def test_backward_grads_match_oracle(kind, B):
     """Every parameter gradient within 2e-5 of its tensor's max.  relu / leaky_relu are not differentiable at 0, and a
     pre-activation that is zero to fp32 rounding (|z| < 1e-6 max|z|) may take either branch depending on summation
@@ -153,7 +153,7 @@ def test_backward_grads_match_oracle(kind, B):
     print(kind, B, "worst grad err / max|g| = %.2e" % worst)
 
 
-@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4)])
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("navped", 5)])
 def test_learn_matches_golden(golden_dir, kind, B):
     g = np.load(os.path.join(golden_dir, f"net_{kind}.npz"))
     from ddrl4nav_b200.data import Experience
