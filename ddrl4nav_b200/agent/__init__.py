@@ -1,3 +1,3 @@
-from .gae import accumulate_rewards, GAE
+from .gae import accumulate_rewards, accumulate_tempo_rewards, GAE
 
-__all__ = ["accumulate_rewards", "GAE"]
+__all__ = ["accumulate_rewards", "accumulate_tempo_rewards", "GAE"]

@@ -46,3 +46,30 @@ def accumulate_rewards(self, experiences: List, rewards_step: np.ndarray) -> Lis
         experiences[t].values = ret[t]
         experiences[t].advs = adv[t]
     return experiences[:-1]
+
+
+def accumulate_tempo_rewards(self, experiences: List) -> List:
+    """Drop-in for ``Agents._accumulate_tempo_rewards`` (USTC_lab/agent/agent.py:142-160): per-step discount
+    ``self.tempo_discounts[experiences[t].durations[0]]`` (float64 table), rewards from ``experiences[t].rewards``.
+    ``self`` needs ``tempo_discounts`` and ``landa``.  Results are float64 arrays, as in the reference."""
+    if len(experiences) == 0:
+        return []
+    T = len(experiences) - 1
+    if T == 0:
+        return experiences[:-1]
+    dev = torch.device("cuda")
+    values = np.stack([np.asarray(e.values, dtype=np.float32) for e in experiences])              # [T+1,V,N]
+    V, N = values.shape[1], values.shape[2]
+    dones = np.stack([np.asarray(experiences[t].dones, dtype=np.uint8) for t in range(T)]).reshape(T, -1, N)
+    rewards = np.stack([np.asarray(experiences[t].rewards, dtype=np.float32) for t in range(T)]).reshape(T, -1, N)
+    durations = np.array([int(experiences[t].durations[0]) for t in range(T)], dtype=np.int32)
+    dones = np.ascontiguousarray(np.broadcast_to(dones, (T, V, N)))
+    rewards = np.ascontiguousarray(np.broadcast_to(rewards, (T, V, N)))
+    ret, adv = kernels.gae_tempo(torch.from_numpy(values).to(dev), torch.from_numpy(rewards).to(dev),
+                                 torch.from_numpy(dones).to(dev), torch.from_numpy(durations).to(dev),
+                                 np.asarray(self.tempo_discounts, dtype=np.float64), float(self.landa), out_f64=True)
+    ret, adv = ret.cpu().numpy(), adv.cpu().numpy()
+    for t in range(T):
+        experiences[t].values = ret[t]
+        experiences[t].advs = adv[t]
+    return experiences[:-1]

@@ -391,6 +391,89 @@ __global__ void __launch_bounds__(1024) gae_chunked_kernel(const float* __restri
   }
 }
 
+
+// ---- tempo-GAE: Agents._accumulate_tempo_rewards (USTC_lab/agent/agent.py:142-160) ------------------------------------
+// Per-step discount td[t] = tempo_discounts[durations[t]] from the float64 table np.logspace(0, 100, 101, base=gamma)
+// (agent.py:119).  td is an np.float64 scalar, so under NumPy-2 promotion the whole recurrence runs in float64 in the
+// reference; this kernel does the same (explicit __dmul_rn/__dadd_rn, no FMA contraction) => BIT-EXACT f64 results.
+// One thread per column walks time backwards with kUnroll steps of loads in flight.  OUT = double (the reference's
+// arrays) or float (one final rounding, what Experience.to_tensor does downstream; halves the write traffic).
+struct TempoTable { double d[101]; };
+
+template <typename OUT, int kUnroll>
+__global__ void __launch_bounds__(128) gae_tempo_kernel(const float* __restrict__ values, const float* __restrict__ rewards,
+                                                        const uint8_t* __restrict__ dones, const int* __restrict__ durations,
+                                                        const __grid_constant__ TempoTable table, double lam, int T, int N,
+                                                        int C, OUT* __restrict__ ret, OUT* __restrict__ adv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const bool row0 = c < N;
+  double g = 0.0;
+  double nv = (double)values[(size_t)T * C + c];
+  int t = T;
+  while (t > 0) {
+    float rr[kUnroll], vv[kUnroll];
+    uint8_t dd[kUnroll];
+    int du[kUnroll];
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const int ti = t - 1 - i;
+      if (ti >= 0) {
+        const size_t o = (size_t)ti * C + c;
+        rr[i] = ld_stream(rewards + o);
+        vv[i] = ld_stream(values + o);
+        dd[i] = __ldg(dones + o);
+        du[i] = __ldg(durations + ti);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const int ti = t - 1 - i;
+      if (ti >= 0) {
+        const double td = table.d[du[i]];
+        const double nd = (double)(uint8_t)(1 - dd[i]);
+        const double v = (double)vv[i];
+        g = __dmul_rn(g, nd);
+        const double x = __dmul_rn(__dmul_rn(td, lam), g);
+        double y = __dmul_rn(__dmul_rn(td, nv), nd);
+        y = __dsub_rn(y, v);
+        y = __dadd_rn(y, (double)rr[i]);
+        g = __dadd_rn(x, y);
+        nv = v;
+        const size_t o = (size_t)ti * C + c;
+        ret[o] = (OUT)__dadd_rn(v, g);
+        if (row0) adv[(size_t)ti * N + c] = (OUT)g;
+      }
+    }
+    t -= kUnroll;
+  }
+}
+
+}  // namespace ddrl
+
+extern "C" int ddrl_gae_tempo(const float* values, const float* rewards, const uint8_t* dones, const int* durations,
+                              const double* table_host, int table_len, double lambda, int T, int V, int N, void* ret,
+                              void* adv, int out_f64, void* stream) {
+  using namespace ddrl;
+  if (T < 0 || V < 1 || N < 0 || !table_host || table_len < 1 || table_len > 101) return DDRL_E_ARG;
+  if (T == 0 || N == 0) return DDRL_OK;      // empty rollout: agent.py:143-144 returns []
+  if (!values || !rewards || !dones || !durations || !ret || !adv) return DDRL_E_ARG;
+  TempoTable tab;
+  for (int i = 0; i < 101; ++i) tab.d[i] = table_host[i < table_len ? i : table_len - 1];
+  const int C = V * N, threads = 128;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_f64)
+    gae_tempo_kernel<double, 8><<<ceil_div(C, threads), threads, 0, s>>>(values, rewards, dones, durations, tab, lambda, T, N, C,
+                                                                         (double*)ret, (double*)adv);
+  else
+    gae_tempo_kernel<float, 8><<<ceil_div(C, threads), threads, 0, s>>>(values, rewards, dones, durations, tab, lambda, T, N, C,
+                                                                        (float*)ret, (float*)adv);
+  prof_work((out_f64 ? 25.0 : 17.0) * T * (double)C);
+  DDRL_LAUNCHED("gae_tempo_kernel");
+  return DDRL_OK;
+}
+
+namespace ddrl {
 }  // namespace ddrl
 
 extern "C" int ddrl_gae_f32(const float* values, const float* rewards, const uint8_t* dones,

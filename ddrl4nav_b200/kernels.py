@@ -44,6 +44,33 @@ def gae(values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, gamma:
     return ret, adv
 
 
+def gae_tempo(values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, durations: torch.Tensor, table,
+              lam: float, out_f64: bool = True):
+    """values [T+1,V,N] f32, rewards/dones [>=T,V,N], durations [>=T] int32, table [<=101] float64 (host)
+    -> (returns [T,V,N], advs [T,N]) float64 (or float32).  Agents._accumulate_tempo_rewards (agent/agent.py:142-160)."""
+    lib = _lib.load()
+    values = _f32c(values)
+    rewards = _f32c(rewards)
+    require_cuda(dones)
+    require_cuda(durations)
+    if dones.dtype != torch.uint8 or not dones.is_contiguous():
+        dones = dones.to(torch.uint8).contiguous()
+    if durations.dtype != torch.int32 or not durations.is_contiguous():
+        durations = durations.to(torch.int32).contiguous()
+    Tp1, V, N = values.shape
+    T = Tp1 - 1
+    assert rewards.shape[0] >= T and dones.shape[0] >= T and durations.shape[0] >= T and tuple(rewards.shape[1:]) == (V, N)
+    tab = [float(x) for x in table]
+    assert 1 <= len(tab) <= 101
+    dt = torch.float64 if out_f64 else torch.float32
+    ret = torch.empty((T, V, N), dtype=dt, device=values.device)
+    adv = torch.empty((T, N), dtype=dt, device=values.device)
+    check(lib.ddrl_gae_tempo(ptr(values), ptr(rewards), ptr(dones), ptr(durations), (C.c_double * len(tab))(*tab), len(tab),
+                             C.c_double(float(lam)), T, V, N, ptr(ret), ptr(adv), int(out_f64), current_stream()),
+          "ddrl_gae_tempo")
+    return ret, adv
+
+
 def sample_categorical_probs(probs: torch.Tensor, u: Optional[torch.Tensor]):
     """(probs [B,A], u [B] | None) -> (action [B] f32, logp [B] f32); server/utils.py:20-47."""
     lib = _lib.load()

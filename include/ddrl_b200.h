@@ -98,6 +98,16 @@ int ddrl_gae_f32(const float* values, const float* rewards, const uint8_t* dones
                  const float* gamma_host, float lambda, int T, int V, int N,
                  float* ret, float* adv, int algo, void* stream);
 
+/* tempo-GAE: replaces Agents._accumulate_tempo_rewards (USTC_lab/agent/agent.py:142-160).
+ * Per-step discount table_host[durations[t]] (table = self.tempo_discounts, float64 np.logspace(0,100,101,base=gamma),
+ * agent.py:119; durations [>=T] int32 DEVICE = experiences[t].durations[0]).  The np.float64 table entry promotes the
+ * reference's recurrence to float64; the kernel computes in float64 with the same operation order (bit-exact).
+ * out_f64 != 0: ret [T,V,N] / adv [T,N] are double (the reference's arrays); 0: float (rounded once, what
+ * Experience.to_tensor makes of them).  values / rewards / dones as for ddrl_gae_f32; lambda = self.landa. */
+int ddrl_gae_tempo(const float* values, const float* rewards, const uint8_t* dones, const int* durations,
+                   const double* table_host, int table_len, double lambda, int T, int V, int N,
+                   void* ret, void* adv, int out_f64, void* stream);
+
 /* ---- K4: action sampling --------------------------------------------------------------
  * replaces random_choice_prob_index / select_action (USTC_lab/server/utils.py:20-47) and the
  * sample/log_prob lines of ForwardThread.run (server/forward.py:137-146).

@@ -65,6 +65,35 @@ def golden_gae():
     np.savez_compressed(os.path.join(HERE, "gae.npz"), **out)
 
 
+def golden_gae_tempo():
+    """Agents._accumulate_tempo_rewards (agent/agent.py:142-160) run unbound on the unmodified reference."""
+    ref_shim.import_reference()
+    from USTC_lab.agent import Agents
+    from USTC_lab.data import Experience
+    out = {}
+    cases = [("a", 16, 1, 8, 0), ("b", 67, 1, 33, 1), ("c", 37, 2, 5, 2), ("d", 1, 1, 4, 3)]
+    for tag, T, V, N, seed in cases:
+        rng = np.random.default_rng(100 + seed)
+        values = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+        rewards = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+        dones = (rng.random((T + 1, V, N)) < 0.1).astype(np.uint8)
+        durations = rng.integers(0, 12, size=T + 1).astype(np.int32)
+        durations[0] = 100 if T > 1 else durations[0]          # last table entry
+        fake_self = SimpleNamespace(tempo_discounts=np.logspace(0, 100, 101, base=0.99), landa=0.95, model_dtype=np.float32)
+        exps = [Experience(states=[np.zeros((N, 1))], values=values[t].copy(), dones=dones[t].copy(),
+                           rewards=rewards[t].copy(), durations=[int(durations[t])] * 2) for t in range(T + 1)]
+        done = Agents._accumulate_tempo_rewards(fake_self, exps)
+        assert len(done) == T
+        out[tag + "_values"], out[tag + "_rewards"], out[tag + "_dones"] = values, rewards, dones
+        out[tag + "_durations"] = durations
+        out[tag + "_returns"] = np.stack([e.values for e in done])     # float64 (np.float64 table entry promotes)
+        out[tag + "_advs"] = np.stack([e.advs for e in done])
+        assert out[tag + "_returns"].dtype == np.float64 and out[tag + "_advs"].dtype == np.float64
+    out["cases"] = np.array([c[0] for c in cases])
+    assert Agents._accumulate_tempo_rewards(SimpleNamespace(), []) == []
+    np.savez_compressed(os.path.join(HERE, "gae_tempo.npz"), **out)
+
+
 def golden_sampling():
     ref_shim.import_reference()
     import USTC_lab.server.utils as su
@@ -176,7 +205,7 @@ def golden_net(kind: str, B: int, iters: int = 4):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `make_golden.py navped` regenerates one fixture
-    todo = [("gae", golden_gae), ("sampling", golden_sampling), ("pong", lambda: golden_net("pong", 8)),
+    todo = [("gae", golden_gae), ("gae_tempo", golden_gae_tempo), ("sampling", golden_sampling), ("pong", lambda: golden_net("pong", 8)),
             ("navimg", lambda: golden_net("navimg", 6)), ("navlaser", lambda: golden_net("navlaser", 4)),
             ("navped", lambda: golden_net("navped", 5))]
     for name, fn in todo:

@@ -72,6 +72,57 @@ def test_gae_vs_oracle(T, V, N):
         assert close(ret, ref_ret) and close(adv, ref_adv), algo
 
 
+def test_gae_tempo_golden_and_oracle(golden_dir):
+    """Agents._accumulate_tempo_rewards: float64 recurrence, per-step discount from the logspace table -- bit-exact."""
+    from ddrl4nav_b200 import kernels
+    table = np.logspace(0, 100, 101, base=0.99)
+    g = np.load(os.path.join(golden_dir, "gae_tempo.npz"))
+
+    def run(v, r, d, du, f64=True):
+        T = v.shape[0] - 1
+        ret, adv = kernels.gae_tempo(torch.from_numpy(v).to(DEV), torch.from_numpy(r[:max(T, 0)]).to(DEV),
+                                     torch.from_numpy(d[:max(T, 0)]).to(DEV), torch.from_numpy(du[:max(T, 0)]).to(DEV),
+                                     table, 0.95, out_f64=f64)
+        return ret.cpu().numpy(), adv.cpu().numpy()
+
+    for tag in g["cases"]:
+        v, r, d, du = g[f"{tag}_values"], g[f"{tag}_rewards"], g[f"{tag}_dones"], g[f"{tag}_durations"]
+        ret, adv = run(v, r, d, du)
+        assert ret.dtype == np.float64
+        assert np.array_equal(ret, g[f"{tag}_returns"]) and np.array_equal(adv, g[f"{tag}_advs"]), tag
+        ret32, adv32 = run(v, r, d, du, f64=False)                 # one final rounding (Experience.to_tensor)
+        assert np.array_equal(ret32, g[f"{tag}_returns"].astype(np.float32)), tag
+        assert np.array_equal(adv32, g[f"{tag}_advs"].astype(np.float32)), tag
+    for T, V, N in [(1, 1, 1), (9, 1, 130), (300, 2, 77), (130, 1, 5000), (2050, 1, 64)]:
+        rng = np.random.default_rng(T + N)
+        v = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+        r = rng.standard_normal((T + 1, V, N)).astype(np.float32)
+        d = (rng.random((T + 1, V, N)) < 0.05).astype(np.uint8)
+        du = rng.integers(0, 101, size=T + 1).astype(np.int32)
+        ref_ret, ref_adv = R.gae_tempo(v, d, r, du, 0.99, 0.95)
+        ret, adv = run(v, r, d, du)
+        assert np.array_equal(ret, ref_ret) and np.array_equal(adv, ref_adv), (T, V, N)
+
+
+def test_accumulate_tempo_rewards_dropin(golden_dir):
+    """agent-level mirror: same signature / side effects as the reference method (agent.py:142-160)."""
+    from types import SimpleNamespace
+    from ddrl4nav_b200.agent import accumulate_tempo_rewards
+    from ddrl4nav_b200.data import Experience
+    g = np.load(os.path.join(golden_dir, "gae_tempo.npz"))
+    me = SimpleNamespace(tempo_discounts=np.logspace(0, 100, 101, base=0.99), landa=0.95, model_dtype=np.float32)
+    assert accumulate_tempo_rewards(me, []) == []
+    for tag in g["cases"]:
+        v, r, d, du = g[f"{tag}_values"], g[f"{tag}_rewards"], g[f"{tag}_dones"], g[f"{tag}_durations"]
+        T = v.shape[0] - 1
+        exps = [Experience(states=[np.zeros((v.shape[2], 1))], values=v[t].copy(), dones=d[t].copy(), rewards=r[t].copy(),
+                           durations=[int(du[t])]) for t in range(T + 1)]
+        out = accumulate_tempo_rewards(me, exps)
+        assert len(out) == T
+        assert np.array_equal(np.stack([e.values for e in out]), g[f"{tag}_returns"]), tag
+        assert np.array_equal(np.stack([e.advs for e in out]), g[f"{tag}_advs"]), tag
+
+
 def test_gae_empty_and_done_everywhere():
     from ddrl4nav_b200 import kernels
     ret, adv = kernels.gae(torch.zeros(1, 1, 5, device=DEV), torch.zeros(0, 1, 5, device=DEV),
