@@ -183,11 +183,15 @@ int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const Dgr
   return DDRL_OK;
 }
 
+// out_ctot / out_coff: dx (and the mask, addressed like dx) are channels [out_coff, out_coff + C) of an out_ctot-wide
+// NHWC tensor (0 = dense [B, H, W, C])
 int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
-                         const float* mask, int B, cudaStream_t s) {
+                         const float* mask, int B, cudaStream_t s, int out_ctot, int out_coff) {
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const int sx = W == 1 ? 1 : f.s;
+  const long long ct = out_ctot > 0 ? out_ctot : g.C;
+  if (out_ctot > 0) { dx += out_coff; if (mask) mask += out_coff; }
   ConvOp o;
   o.a = dy; o.Hin = Ho; o.Win = Wo; o.Ctot = Cout; o.c_off = 0; o.Cin = Cout;
   o.KH = f.nty; o.KW = f.ntx; o.sy = 1; o.sx = 1; o.py = f.pady; o.px = f.padx;
@@ -199,11 +203,11 @@ int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const
     for (int cx = 0; cx < f.ncx; ++cx) {
       const int q = cy * f.ncx + cx;
       cls.cls_iy[q] = f.iy0[cy]; cls.cls_ix[q] = f.ix0[cx];
-      cls.cls_off[q] = ((long long)f.iy0[cy] * W + f.ix0[cx]) * g.C;
+      cls.cls_off[q] = ((long long)f.iy0[cy] * W + f.ix0[cx]) * ct;
     }
   // tile pixel (jy, jx) -> base input pixel (s*jy, sx*jx); out_s scales both axes, so a 1-D layer (W == 1) keeps x = 0
-  return tc2_conv_fwd(o, f.wd_hi, f.wd_lo, f.K, f.N, nullptr, act, mask, dx, (long long)H * W * g.C, (long long)f.s * W * g.C,
-                      (long long)sx * g.C, s, &cls);
+  return tc2_conv_fwd(o, f.wd_hi, f.wd_lo, f.K, f.N, nullptr, act, mask, dx, (long long)H * W * ct, (long long)f.s * W * ct,
+                      (long long)sx * ct, s, &cls);
 }
 
 bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__
     if (v2 > best) { best = v2; bi = 2; }
     if (v3 > best) { best = v3; bi = 3; }
     out[i] = best;
-    if (idx) idx[i] = (uint8_t)bi;
+    if (idx) idx[i] = (uint8_t)(best > 0.f ? bi : 4);       // 4: window maximum <= 0, ReLU passes no gradient
   }
 }
 
@@ -175,9 +175,60 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
     if (ho < Ho && wo < Wo) {
       const long long o = ((b * Ho + ho) * Wo + wo) * C + c;
       const int me = (h & 1) * 2 + (w & 1);
-      if (idx[o] == me && a[i] > 0.f) v = dout[o];
+      if (idx[o] == me) v = dout[o];                          // idx == 4 encodes relu'(max) == 0
     }
     da[i] = v;
+  }
+}
+
+// float4 variants (C % 4 == 0, H and W even, < 2^31 pooled elements): one thread per (pooled pixel, 4 channels).
+// The ReLU derivative is folded into the index (4 = "no gradient": the window maximum is <= 0), so the backward pass
+// reads only dout (a quarter of da) and one index byte per element -- 21 B per 4 da elements instead of 37.
+__global__ void __launch_bounds__(256) pool_fwd_vec4_kernel(const float4* __restrict__ a, float4* __restrict__ out,
+                                                            uchar4* __restrict__ idx, int H, int W, int C4, unsigned total) {
+  const int Ho = H / 2, Wo = W / 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % C4;
+    unsigned t = i / C4;
+    const unsigned wo = t % Wo; t /= Wo;
+    const unsigned ho = t % Ho;
+    const unsigned b = t / Ho;
+    const float4* p = a + ((size_t)(b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const float4 v0 = p[0], v1 = p[C4], v2 = p[(size_t)W * C4], v3 = p[(size_t)W * C4 + C4];
+    float4 best;
+    uchar4 bi;
+#define DDRL_POOL1(f)                                           \
+    {                                                           \
+      float m = v0.f; int k = 0;                                \
+      if (v1.f > m) { m = v1.f; k = 1; }                        \
+      if (v2.f > m) { m = v2.f; k = 2; }                        \
+      if (v3.f > m) { m = v3.f; k = 3; }                        \
+      best.f = m; bi.f = (unsigned char)(m > 0.f ? k : 4);      \
+    }
+    DDRL_POOL1(x) DDRL_POOL1(y) DDRL_POOL1(z) DDRL_POOL1(w)
+#undef DDRL_POOL1
+    out[i] = best;
+    if (idx) idx[i] = bi;
+  }
+}
+__global__ void __launch_bounds__(256) pool_bwd_vec4_kernel(const float4* __restrict__ dout, const uchar4* __restrict__ idx,
+                                                            float4* __restrict__ da, int H, int W, int C4, unsigned total) {
+  const int Ho = H / 2, Wo = W / 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % C4;
+    unsigned t = i / C4;
+    const unsigned wo = t % Wo; t /= Wo;
+    const unsigned ho = t % Ho;
+    const unsigned b = t / Ho;
+    const float4 g = dout[i];
+    const uchar4 k = idx[i];
+    float4* p = da + ((size_t)(b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+#define DDRL_SEL(pos) make_float4(k.x == pos ? g.x : 0.f, k.y == pos ? g.y : 0.f, k.z == pos ? g.z : 0.f, k.w == pos ? g.w : 0.f)
+    p[0] = DDRL_SEL(0);
+    p[C4] = DDRL_SEL(1);
+    p[(size_t)W * C4] = DDRL_SEL(2);
+    p[(size_t)W * C4 + C4] = DDRL_SEL(3);
+#undef DDRL_SEL
   }
 }
 
@@ -301,6 +352,155 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------- space-to-depth (first-layer strided convs)
+// A valid (pad 0) convolution of an NCHW observation whose kernel extents and image extents are multiples of its stride s
+// (NatureCNN conv1: 8x8 stride 4 on 84x84, nn/atari_encoder.py:16) equals a stride-1 convolution with a (KH/s) x (KW/s)
+// kernel over the space-to-depth tensor  X2[b, Y, X, (i*s + j)*C + c] = x[b, c, s*Y + i, s*X + j]  -- an NHWC tensor of
+// exactly the observation's size (the im2col matrix it replaces is KH*KW/s^2 times larger), which the implicit-GEMM
+// (tap-TMA) path consumes directly.  One block per (b, Y) band: coalesced row reads -> shared memory -> one contiguous
+// W2*C2 run of the output.
+__global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int H, int W,
+                                                  int s, long long sb, long long bands) {
+  extern __shared__ float band[];                       // [C][s][W]
+  const int H2 = H / s, W2 = W / s, C2 = s * s * C;
+  const int n_in = C * s * W;
+  for (long long bd = blockIdx.x; bd < bands; bd += gridDim.x) {
+    const long long b = bd / H2;
+    const int Y = (int)(bd - b * H2);
+    const float* xb = x + b * sb + (long long)Y * s * W;
+    for (int e = threadIdx.x; e < n_in; e += blockDim.x) {
+      const int w = e % W, ci = e / W;                  // ci = c*s + i
+      const int c = ci / s, i = ci - c * s;
+      band[e] = xb[(long long)c * H * W + (long long)i * W + w];
+    }
+    __syncthreads();
+    float* ob = out + bd * (long long)W2 * C2;
+    for (int e = threadIdx.x; e < W2 * C2; e += blockDim.x) {
+      const int ch = e % C2, X = e / C2;
+      const int c = ch % C, ij = ch / C;
+      const int j = ij % s, i = ij / s;
+      ob[e] = band[(c * s + i) * W + X * s + j];
+    }
+    __syncthreads();
+  }
+}
+// packed[o*ld + ((a*KW2 + b)*s*s + i*s + j)*C + c] = w[o, c, s*a + i, s*b + j]      (w: reference OIHW)
+__global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ w, float* __restrict__ dst, int O, int C, int KH,
+                                                       int KW, int s, int ld, int unpack) {
+  const long long total = (long long)O * C * KH * KW;
+  const int KW2 = KW / s;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(t % KW);
+    long long r = t / KW;
+    const int kh = (int)(r % KH); r /= KH;
+    const int c = (int)(r % C);
+    const long long o = r / C;
+    const int a = kh / s, i = kh - a * s, b = kw / s, j = kw - b * s;
+    const long long pk = o * ld + ((long long)(a * KW2 + b) * s * s + i * s + j) * C + c;
+    if (unpack) dst[t] = w[pk]; else dst[pk] = w[t];
+  }
+}
+
+// ---------------------------------------------------------------- thin-K layers (first convs on 1..4-channel maps)
+// y[m, n] = act(sum_k x[m, k] W[n, k] + b[n]) and dW[n, k] += sum_m dy[m, n] x[m, k] for K <= 36 (K4 = ldx/4 float4 per
+// row), N = 4*NC4 <= 64.  These layers are pure HBM streams (y / dy are 64 floats per row, x is 12): a tensor-core tile
+// would spend one whole K block and a full epilogue on 9 useful k values.  Thread = (row lane, 4 output channels); its
+// 4 x K weights (forward) or 4 x K partial sums (weight gradient) live in registers for the whole launch.
+template <int K4, int NC4>
+__global__ void __launch_bounds__(256) thin_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ W, int ldw,
+                                                       const float* __restrict__ bias, float4* __restrict__ y, long long M,
+                                                       int K, int act) {
+  constexpr int RL = 256 / NC4;                         // rows in flight per block
+  const int c4 = threadIdx.x % NC4, rl = threadIdx.x / NC4;
+  float w[4][K4 * 4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K4 * 4; ++k) w[j][k] = k < K ? W[(size_t)(c4 * 4 + j) * ldw + k] : 0.f;
+  const float4 b = bias ? make_float4(bias[c4 * 4], bias[c4 * 4 + 1], bias[c4 * 4 + 2], bias[c4 * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // UR rows per thread and iteration: all their x loads are issued before the first FMA (memory-level parallelism; with
+  // ~60 live registers only 3-4 blocks fit an SM, so one row in flight per thread leaves HBM idle)
+  constexpr int UR = K4 <= 3 ? 4 : 2;
+  const long long step = (long long)gridDim.x * RL;
+  for (long long m0 = (long long)blockIdx.x * RL + rl; m0 < M; m0 += step * UR) {
+    float4 v[UR][K4];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const long long m = m0 + u * step;
+#pragma unroll
+      for (int q = 0; q < K4; ++q) v[u][q] = m < M ? __ldg(x + m * K4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const long long m = m0 + u * step;
+      if (m >= M) break;
+      float4 acc = b;
+#pragma unroll
+      for (int q = 0; q < K4; ++q) {
+        const float xv[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc.x = fmaf(xv[e], w[0][q * 4 + e], acc.x); acc.y = fmaf(xv[e], w[1][q * 4 + e], acc.y);
+          acc.z = fmaf(xv[e], w[2][q * 4 + e], acc.z); acc.w = fmaf(xv[e], w[3][q * 4 + e], acc.w);
+        }
+      }
+      if (act == 1) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      else if (act == 2) {
+        acc.x = acc.x > 0.f ? acc.x : 0.01f * acc.x; acc.y = acc.y > 0.f ? acc.y : 0.01f * acc.y;
+        acc.z = acc.z > 0.f ? acc.z : 0.01f * acc.z; acc.w = acc.w > 0.f ? acc.w : 0.01f * acc.w;
+      }
+      y[m * NC4 + c4] = acc;
+    }
+  }
+}
+template <int K4, int NC4>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                         float* __restrict__ dW, int ldw, long long M, int K) {
+  constexpr int RL = 256 / NC4;
+  __shared__ float red[NC4 * 4 * K4 * 4];
+  const int c4 = threadIdx.x % NC4, rl = threadIdx.x / NC4;
+  float acc[4][K4 * 4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K4 * 4; ++k) acc[j][k] = 0.f;
+  for (int i = threadIdx.x; i < NC4 * 4 * K4 * 4; i += 256) red[i] = 0.f;
+  __syncthreads();
+  constexpr int UR = K4 <= 3 ? 4 : 2;
+  const long long step = (long long)gridDim.x * RL;
+  for (long long m0 = (long long)blockIdx.x * RL + rl; m0 < M; m0 += step * UR) {
+    float4 v[UR][K4], g[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const long long m = m0 + u * step;
+      g[u] = m < M ? __ldg(dy + m * NC4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < K4; ++q) v[u][q] = m < M ? __ldg(x + m * K4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+#pragma unroll
+      for (int q = 0; q < K4; ++q) {
+        const float xv[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[0][q * 4 + e] = fmaf(g[u].x, xv[e], acc[0][q * 4 + e]); acc[1][q * 4 + e] = fmaf(g[u].y, xv[e], acc[1][q * 4 + e]);
+          acc[2][q * 4 + e] = fmaf(g[u].z, xv[e], acc[2][q * 4 + e]); acc[3][q * 4 + e] = fmaf(g[u].w, xv[e], acc[3][q * 4 + e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K4 * 4; ++k) atomicAdd(&red[(c4 * 4 + j) * (K4 * 4) + k], acc[j][k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NC4 * 4 * K4 * 4; i += 256) {
+    const int n = i / (K4 * 4), k = i % (K4 * 4);
+    if (k < K) atomicAdd(dW + (size_t)n * ldw + k, red[i]);
+  }
+}
+
 // ---------------------------------------------------------------- launchers
 static inline int grid_for(long long total, int threads = 256) {
   return (int)std::min<long long>((total + threads - 1) / threads, 32LL * kNumSMs);
@@ -336,16 +536,37 @@ int col2im(const ConvGeom& g, const float* dcols, float* dx, int B, cudaStream_t
   DDRL_LAUNCHED("col2im_kernel");
   return DDRL_OK;
 }
+static inline bool pool_vec_ok(const void* p0, const void* p1, const void* p2, int H, int W, int C, long long total) {
+  return C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && total / 4 < 0x7fffffffLL &&
+         ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p2) & 3) == 0;
+}
 int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s) {
   const long long total = (long long)B * (H / 2) * (W / 2) * C;
   if (total == 0) return DDRL_OK;
+  prof_work(4.0 * (double)B * H * W * C + 5.0 * total);
+  if (pool_vec_ok(a, out, idx, H, W, C, total)) {
+    pool_fwd_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<float4*>(out),
+                                                             reinterpret_cast<uchar4*>(idx), H, W, C / 4, (unsigned)(total / 4));
+    DDRL_LAUNCHED("pool_fwd_kernel");
+    return DDRL_OK;
+  }
   pool_fwd_kernel<<<grid_for(total), 256, 0, s>>>(a, out, idx, H, W, C, total);
   DDRL_LAUNCHED("pool_fwd_kernel");
   return DDRL_OK;
 }
+// `a` (the pooled layer's input) is no longer read: relu'(a) at the argmax is encoded in idx by pool_fwd
 int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s) {
   const long long total = (long long)B * H * W * C;
   if (total == 0) return DDRL_OK;
+  const long long pooled = (long long)B * (H / 2) * (W / 2) * C;
+  prof_work(4.0 * (double)total + 5.0 * pooled);
+  if (pool_vec_ok(dout, da, idx, H, W, C, pooled)) {
+    pool_bwd_vec4_kernel<<<grid_for(pooled / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(dout),
+                                                              reinterpret_cast<const uchar4*>(idx), reinterpret_cast<float4*>(da),
+                                                              H, W, C / 4, (unsigned)(pooled / 4));
+    DDRL_LAUNCHED("pool_bwd_kernel");
+    return DDRL_OK;
+  }
   pool_bwd_kernel<<<grid_for(total), 256, 0, s>>>(dout, idx, a, da, H, W, C, total);
   DDRL_LAUNCHED("pool_bwd_kernel");
   return DDRL_OK;
@@ -373,6 +594,57 @@ int pack_weight(const float* src, float* dst, int O, int I, int J, int ld, cudaS
 }
 int unpack_grad(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s) {
   unpack_kernel<<<grid_for((long long)O * I * J), 256, 0, s>>>(src, dst, O, I, J, ld);
+  DDRL_LAUNCHED("unpack_kernel");
+  return DDRL_OK;
+}
+bool thin_supported(long long M, int N, int K, const float* x, int ldx, const float* y, int ldy) {
+  if (M < 1 || ldy != N || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return false;
+  const int k4 = ldx / 4, nc4 = N / 4;
+  if (ldx % 4 != 0 || N % 4 != 0 || K > ldx) return false;
+  return (nc4 == 16 && (k4 == 3 || k4 == 9)) || (nc4 == 8 && k4 == 2);
+}
+#define DDRL_THIN_DISPATCH(KERNEL, ...)                                                        \
+  do {                                                                                         \
+    const int k4 = ldx / 4, nc4 = N / 4;                                                       \
+    const int grid = (int)std::min<long long>((M + 256 / nc4 - 1) / (256 / nc4), 8LL * kNumSMs); \
+    if (nc4 == 16 && k4 == 3) KERNEL<3, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);                \
+    else if (nc4 == 16 && k4 == 9) KERNEL<9, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);           \
+    else KERNEL<2, 8><<<grid, 256, 0, s>>>(__VA_ARGS__);                                      \
+  } while (0)
+int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias, float* y, long long M, int N, int K, int act,
+             cudaStream_t s) {
+  if (!thin_supported(M, N, K, x, ldx, y, N)) return DDRL_E_UNSUPPORTED;
+  prof_work(4.0 * (double)M * (ldx + N));
+  DDRL_THIN_DISPATCH(thin_fwd_kernel, reinterpret_cast<const float4*>(x), W, ldw, bias, reinterpret_cast<float4*>(y), M, K, act);
+  DDRL_LAUNCHED("thin_fwd_kernel");
+  return DDRL_OK;
+}
+int thin_wgrad(const float* x, int ldx, const float* dy, float* dW, int ldw, long long M, int N, int K, cudaStream_t s) {
+  if (!thin_supported(M, N, K, x, ldx, dy, N)) return DDRL_E_UNSUPPORTED;
+  prof_work(4.0 * (double)M * (ldx + N));
+  DDRL_THIN_DISPATCH(thin_wgrad_kernel, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), dW, ldw, M, K);
+  DDRL_LAUNCHED("thin_wgrad_kernel");
+  return DDRL_OK;
+}
+#undef DDRL_THIN_DISPATCH
+int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s) {
+  if (g.order != 1 || g.sw != 1 || g.stride < 1 || g.H % g.stride || g.W % g.stride) return DDRL_E_ARG;
+  const long long bands = (long long)B * (g.H / g.stride);
+  if (bands == 0) return DDRL_OK;
+  const size_t smem = sizeof(float) * (size_t)g.C * g.stride * g.W;
+  if (smem > 48 * 1024) return DDRL_E_UNSUPPORTED;
+  prof_work(8.0 * (double)B * g.C * g.H * g.W);
+  s2d_kernel<<<(int)std::min<long long>(bands, 16LL * kNumSMs), 256, smem, s>>>(x, out, g.C, g.H, g.W, g.stride, g.sb, bands);
+  DDRL_LAUNCHED("s2d_kernel");
+  return DDRL_OK;
+}
+int pack_weight_s2d(const float* w_oihw, float* dst, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s) {
+  pack_s2d_kernel<<<grid_for((long long)O * C * KH * KW), 256, 0, s>>>(w_oihw, dst, O, C, KH, KW, stride, ld, 0);
+  DDRL_LAUNCHED("pack_kernel");
+  return DDRL_OK;
+}
+int unpack_grad_s2d(const float* src, float* dst_oihw, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s) {
+  pack_s2d_kernel<<<grid_for((long long)O * C * KH * KW), 256, 0, s>>>(src, dst_oihw, O, C, KH, KW, stride, ld, 1);
   DDRL_LAUNCHED("unpack_kernel");
   return DDRL_OK;
 }

@@ -90,7 +90,7 @@ struct DgradFused {              // all parity classes of a strided data gradien
 int conv_dgrad_fused_plan(const ConvGeom& g, int Cout, DgradFused& f);
 int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const DgradFused& f, cudaStream_t s);
 int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
-                         const float* mask, int B, cudaStream_t s);
+                         const float* mask, int B, cudaStream_t s, int out_ctot = 0, int out_coff = 0);
 ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B);
 int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out);
 int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s);
@@ -116,6 +116,15 @@ int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int 
 int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s);
 int pack_weight(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s);
 int unpack_grad(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s);
+// thin-K layers (K <= 36, N <= 64): register-resident weights / partial sums, HBM-streaming (layer_ops.cu)
+bool thin_supported(long long M, int N, int K, const float* x, int ldx, const float* y, int ldy);
+int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias, float* y, long long M, int N, int K, int act,
+             cudaStream_t s);
+int thin_wgrad(const float* x, int ldx, const float* dy, float* dW, int ldw, long long M, int N, int K, cudaStream_t s);
+// first-layer strided valid convs as stride-1 convs over the space-to-depth observation (layer_ops.cu)
+int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s);
+int pack_weight_s2d(const float* w_oihw, float* dst, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s);
+int unpack_grad_s2d(const float* src, float* dst_oihw, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s);
 int copy2d(const float* src, int ld_s, float* dst, int ld_d, long long rows, int colsN, cudaStream_t s);
 int skinny_fwd(const float* x, int ldx, const float* W, const float* bias, int B, int N, int K, float* y, int ldy,
                cudaStream_t s);

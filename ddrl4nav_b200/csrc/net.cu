@@ -42,6 +42,7 @@ struct Lin {
   float* wp = nullptr;           // packed weight [N, ldw]   (when packed)
   float *wp_hi = nullptr, *wp_lo = nullptr;   // its tf32 hi / lo split (tc2 engine), refreshed with wp
   float* dwp = nullptr;          // packed weight gradient   (when packed and training)
+  int s2d_s = 0, s2d_C = 0, s2d_KH = 0, s2d_KW = 0;   // space-to-depth first layer: packing follows pack_weight_s2d
 };
 
 struct Arena {
@@ -67,6 +68,11 @@ struct Tower {
   int conv_lin[5] = {-1, -1, -1, -1, -1};                   // index into L of the conv in slot g[i]
   std::vector<DgradClass> dg[5];                            // data-gradient parity classes (+ packed weights)
   DgradFused df[5] = {};                                    // tc2: all classes of a strided layer as one GEMM
+  // cross-tower fusion of the first conv (unshared towers read the same observation): 0 none, 1 owner of the shared
+  // im2col / a1 / da1 buffers (tower 0), 2 borrower.  conv slot 1 then reads channels [in1_coff, +C) of a in1_ctot-wide tensor.
+  int fuse_role = 0, in1_ctot = 0, in1_coff = 0;
+  bool s2d0 = false;                                        // conv slot 0 runs on the space-to-depth observation
+  ConvGeom gs = {};                                         // its stride-1 NHWC geometry (buf[0] holds the s2d tensor)
   // per-micro-batch buffers
   std::vector<float*> buf;
   std::vector<uint8_t*> idx;
@@ -97,6 +103,8 @@ struct ddrl_net {
   size_t packed_bytes = 0, packed_grad_off = 0, packed_grad_bytes = 0;
   int64_t seg_begin[3];
   int nseg = 1;
+  bool fuse0 = false;            // both towers' first conv as ONE GEMM over the shared im2col matrix (N = 2 x Cout)
+  float* bias0c = nullptr;       // its concatenated bias [2 x Cout]
   // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
   const float* cols_obs0 = nullptr;
   int cols_rows = -1;
@@ -259,6 +267,28 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
     t.dg[i] = cls;
     if (tc2_mode(n) && g.stride > 1) conv_dgrad_fused_plan(g, Cout, t.df[i]);    // leaves df.on = false if unsupported
   }
+  // first layer on the raw NCHW observation: a strided valid conv whose extents divide by the stride becomes a stride-1
+  // implicit conv over the space-to-depth tensor (same size as the observation; no im2col matrix)
+  // Measured on B200 (profiles/r1c_tc2_experiments.md): with N = 32 the implicit kernels are bound by per-tile / per-K-block
+  // pipeline cost, not by HBM, and the 78 %-filled 6x20-pixel tiles make conv1 forward 822 us vs 596 us on the cached im2col
+  // matrix -- so this path is opt-in (DDRL_S2D=1) until the N = 32 tile cost drops.
+  const char* use_s2d = getenv("DDRL_S2D");
+  if (nconv > 0 && tc_mode(n) && !(no_implicit && no_implicit[0] == '1') && use_s2d && use_s2d[0] == '1') {
+    const ConvGeom& g = t.g[0];
+    const int st = g.stride, Cout = t.L[0].N;
+    if (g.order == 1 && g.sw == 1 && g.pad == 0 && st > 1 && g.KH % st == 0 && g.KW % st == 0 && g.H % st == 0 &&
+        g.W % st == 0 && (st * st * g.C) % 32 == 0 && Cout % 32 == 0 && (size_t)g.C * st * g.W * 4 <= 48 * 1024) {
+      ConvGeom gs = conv_geom(g.H / st, g.W / st, st * st * g.C, false, g.KH / st, g.KW / st, 1, 0);
+      static const float* const kAligned = reinterpret_cast<const float*>(uintptr_t(256));
+      ConvOp o = conv_op_fwd(gs, kAligned, gs.C, 0, 1);
+      if (gs.Ho == g.Ho && gs.Wo == g.Wo && gs.K == g.K && conv_tc_supported(o, false) && conv_tc_supported(o, true)) {
+        t.s2d0 = true;
+        t.gs = gs;
+        Lin& l = t.L[0];
+        l.s2d_s = st; l.s2d_C = g.C; l.s2d_KH = g.KH; l.s2d_KW = g.KW;
+      }
+    }
+  }
 }
 
 // ---- engine dispatch ------------------------------------------------------------------
@@ -293,6 +323,8 @@ static float* db_of(const ddrl_net* n, const Lin& l) { return n->grads + n->T[l.
 
 // y = act(x W^T + b)
 static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* y, int ldy, long long M, cudaStream_t s) {
+  if (l.K <= 36 && l.act <= 2 && thin_supported(M, l.N, l.K, x, ldx, y, ldy))
+    return thin_fwd(x, ldx, W_of(n, l), l.ldw, b_of(n, l), y, M, l.N, l.K, l.act, s);
   return gemm(n, 0, (int)M, l.N, l.K, x, ldx, W_of(n, l), l.ldw, y, ldy, b_of(n, l), l.act, 0, 0, s);
 }
 // dy holds dL/d(pre-activation) of this layer (the activation derivative was applied by whoever produced dy).
@@ -303,7 +335,9 @@ static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
   TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
   // dW[N, K] += dy[M,N]^T x[M,K]
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 && ldx % 4 == 0 && ldy % 4 == 0;
-  if (tc2_mode(n) && al && l.K >= 32)
+  if (l.K <= 36 && thin_supported(M, l.N, l.K, x, ldx, dy, ldy))
+    TRY(thin_wgrad(x, ldx, dy, dW_of(n, l), l.ldw, M, l.N, l.K, s));
+  else if (tc2_mode(n) && al && l.K >= 32)
     TRY(tc2_wgrad(l.K, l.N, M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, s));
   // older engines: run with the larger of (N, K) on the 128-row side
   else if (l.N >= 128 || l.N >= l.K)
@@ -320,6 +354,7 @@ static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
 static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std::vector<size_t>& u8) {
   auto cols = [&](const ConvGeom& g) {
     const int gi = (int)(&g - &t.g[0]);
+    if (gi == 0 && t.s2d0) return (size_t)g.C * g.H * g.W;         // the space-to-depth observation
     return t.implicit[gi] ? (size_t)0 : (size_t)g.Ho * g.Wo * g.ldc;
   };
   auto outp = [&](const ConvGeom& g, int Co) { return (size_t)g.Ho * g.Wo * Co; };
@@ -327,9 +362,11 @@ static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std:
   switch (t.arch) {
     case DDRL_ARCH_ATARI: {
       // 0 cols1, 1 a1, 2 cols2, 3 a2, 4 cols3, 5 a3 | train: 6 da3, 7 dcols, 8 da2, 9 da1
-      f = {cols(t.g[0]), outp(t.g[0], 32), cols(t.g[1]), outp(t.g[1], 64), cols(t.g[2]), outp(t.g[2], 64)};
+      // fused first conv: tower 0 owns cols1 and the 2x-wide a1 / da1, tower 1 borrows them
+      const size_t k0 = t.fuse_role == 2 ? 0 : 1, k1 = t.fuse_role == 2 ? 0 : (t.fuse_role == 1 ? 2 : 1);
+      f = {k0 * cols(t.g[0]), k1 * outp(t.g[0], 32), cols(t.g[1]), outp(t.g[1], 64), cols(t.g[2]), outp(t.g[2], 64)};
       if (train) { f.push_back(outp(t.g[2], 64)); f.push_back(std::max(cols(t.g[1]), cols(t.g[2])));
-                   f.push_back(outp(t.g[1], 64)); f.push_back(outp(t.g[0], 32)); }
+                   f.push_back(outp(t.g[1], 64)); f.push_back(k1 * outp(t.g[0], 32)); }
       break;
     }
     case DDRL_ARCH_NAV:
@@ -418,6 +455,11 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     t.h = n->ws.take((size_t)t.feat * mb);
     t.dh = train ? n->ws.take((size_t)t.feat * mb) : nullptr;
   }
+  if (n->fuse0) {
+    Tower &t0 = n->towers[0], &t1 = n->towers[1];
+    t1.buf[0] = t0.buf[0]; t1.buf[1] = t0.buf[1];
+    if (train) t1.buf[9] = t0.buf[9];
+  }
   n->logits = n->ws.take((size_t)n->ldA * mb);
   n->dlogits = n->ws.take((size_t)n->ldA * mb);
   n->vout = n->ws.take(mb);
@@ -426,11 +468,24 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
 }
 
 // ---- packed weights -------------------------------------------------------------------
+// packed layers in arena order; with the fused first conv the two towers' conv1 weights (and gradients) are adjacent, so
+// [2 x Cout, K] is one GEMM operand
+static std::vector<Lin*> packed_order(ddrl_net* n) {
+  std::vector<Lin*> v;
+  if (n->fuse0) { v.push_back(&n->towers[0].L[0]); v.push_back(&n->towers[1].L[0]); }
+  for (auto& t : n->towers)
+    for (size_t i = 0; i < t.L.size(); ++i)
+      if (t.L[i].packed && !(n->fuse0 && i == 0)) v.push_back(&t.L[i]);
+  return v;
+}
+
 static int alloc_packed(ddrl_net* n) {
   size_t bytes = 0;
-  for (auto& t : n->towers)
-    for (auto& l : t.L)
-      if (l.packed) bytes += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
+  for (Lin* l : packed_order(n)) bytes += ((size_t)l->N * l->ldw * 4 + 255) & ~size_t(255);
+  if (n->fuse0) {
+    if (((size_t)n->towers[0].L[0].N * n->towers[0].L[0].ldw * 4) % 256 != 0) return DDRL_E_STATE;   // rows must abut
+    DDRL_CUDA(cudaMalloc(&n->bias0c, sizeof(float) * 2 * n->towers[0].L[0].N));
+  }
   n->packed_grad_off = bytes;
   n->packed_grad_bytes = bytes;
   // data-gradient weights of the implicit convs (one re-packed copy per parity class), after the two twin regions
@@ -472,24 +527,26 @@ static int alloc_packed(ddrl_net* n) {
         }
   }
   size_t off = 0;
-  for (auto& t : n->towers)
-    for (auto& l : t.L)
-      if (l.packed) {
-        l.wp = reinterpret_cast<float*>(n->packed_base + off);
-        l.dwp = reinterpret_cast<float*>(n->packed_base + n->packed_grad_off + off);
-        if (n->split_base) {
-          l.wp_hi = reinterpret_cast<float*>(n->split_base + off);
-          l.wp_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
-        }
-        off += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
-      }
+  for (Lin* lp : packed_order(n)) {
+    Lin& l = *lp;
+    l.wp = reinterpret_cast<float*>(n->packed_base + off);
+    l.dwp = reinterpret_cast<float*>(n->packed_base + n->packed_grad_off + off);
+    if (n->split_base) {
+      l.wp_hi = reinterpret_cast<float*>(n->split_base + off);
+      l.wp_lo = reinterpret_cast<float*>(n->split_base + n->packed_bytes + off);
+    }
+    off += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
+  }
   return DDRL_OK;
 }
 
 static int repack(ddrl_net* n, cudaStream_t s) {
   for (auto& t : n->towers)
     for (auto& l : t.L)
-      if (l.packed) TRY(pack_weight(n->params + n->T[l.w_t].offset, l.wp, l.N, l.I, l.J, l.ldw, s));
+      if (l.packed) {
+        if (l.s2d_s) TRY(pack_weight_s2d(n->params + n->T[l.w_t].offset, l.wp, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
+        else TRY(pack_weight(n->params + n->T[l.w_t].offset, l.wp, l.N, l.I, l.J, l.ldw, s));
+      }
   for (auto& t : n->towers)
     for (int i = 0; i < 5; ++i)
       for (auto& c : t.dg[i]) {
@@ -502,6 +559,11 @@ static int repack(ddrl_net* n, cudaStream_t s) {
         const Lin& l = t.L[t.conv_lin[i]];
         TRY(pack_dgrad_fused(n->params + n->T[l.w_t].offset, t.g[i], l.N, t.df[i], s));
       }
+  if (n->fuse0) {
+    const Lin &l0 = n->towers[0].L[0], &l1 = n->towers[1].L[0];
+    DDRL_CUDA(cudaMemcpyAsync(n->bias0c, b_of(n, l0), sizeof(float) * l0.N, cudaMemcpyDeviceToDevice, s));
+    DDRL_CUDA(cudaMemcpyAsync(n->bias0c + l0.N, b_of(n, l1), sizeof(float) * l1.N, cudaMemcpyDeviceToDevice, s));
+  }
   if (n->split_base) {
     // tf32 hi / lo mirrors of the forward weights [0, grad_off) and of the data-gradient weights [2*grad_off, end)
     const size_t fwd = n->packed_grad_off, dg0 = 2 * n->packed_grad_off, dgn = n->packed_bytes - dg0;
@@ -519,10 +581,13 @@ static int repack(ddrl_net* n, cudaStream_t s) {
 // ---- encoder schedules ------------------------------------------------------------------
 static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, float* cols, float* y, int mb,
                       cudaStream_t s, bool cols_cached = false) {
-  const ConvGeom& g = t.g[gi];
-  if (t.implicit[gi]) {
+  const bool s2d = gi == 0 && t.s2d0;
+  if (s2d && !cols_cached) TRY(space_to_depth(t.g[0], x, cols, mb, s));
+  const ConvGeom& g = s2d ? t.gs : t.g[gi];
+  if (s2d || t.implicit[gi]) {
     const Lin& l = t.L[li];
-    const ConvOp o = conv_op_fwd(g, x, g.C, 0, mb);
+    const bool sub = gi == 1 && t.in1_ctot;
+    const ConvOp o = conv_op_fwd(g, s2d ? cols : x, sub ? t.in1_ctot : g.C, sub ? t.in1_coff : 0, mb);
     if (tc2_mode(n))
       return tc2_conv_fwd(o, l.wp_hi, l.wp_lo, l.ldw, l.N, b_of(n, l), l.act, nullptr, y, (long long)o.Yn * o.Xn * l.N,
                           (long long)o.Xn * l.N, l.N, s);
@@ -541,7 +606,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
   switch (t.arch) {
     case DDRL_ARCH_ATARI: {
       const float* x = obs[0] + row0 * t.g[0].sb;
-      TRY(conv_block(n, t, 0, 0, x, b[0], b[1], mb, s, reuse_obs));
+      if (!t.fuse_role) TRY(conv_block(n, t, 0, 0, x, b[0], b[1], mb, s, reuse_obs));     // else: fused_conv0_fwd ran it
       TRY(conv_block(n, t, 1, 1, b[1], b[2], b[3], mb, s));
       TRY(conv_block(n, t, 2, 2, b[3], b[4], b[5], mb, s));
       TRY(lin_fwd(n, t.L[3], b[5], 3136, t.h, 512, mb, s));
@@ -600,15 +665,24 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
 // produced x; 0 = none or handled elsewhere, e.g. by pool_bwd)
 static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const float* x, const float* cols, float* dy,
                     float* dcols, float* dx, int mask_act, int mb, cudaStream_t s) {
-  const ConvGeom& g = t.g[gi];
+  const bool s2d = gi == 0 && t.s2d0;
+  const ConvGeom& g = s2d ? t.gs : t.g[gi];
   const Lin& l = t.L[li];
   const long long M = (long long)mb * g.Ho * g.Wo;
-  if (t.implicit[gi]) {
+  if (s2d) {                                       // first layer: no data gradient; x2 = the cached space-to-depth tensor
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
-    if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
-    else TRY(conv_tc_wgrad(conv_op_fwd(g, x, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    if (tc2_mode(n)) return tc2_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
+    return conv_tc_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
+  }
+  if (t.implicit[gi]) {
+    const bool sub = gi == 1 && t.in1_ctot;
+    const int ctot = sub ? t.in1_ctot : g.C, coff = sub ? t.in1_coff : 0;
+    TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
+    if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    else TRY(conv_tc_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
     if (dx && t.df[gi].on)
-      TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s));
+      TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s, ctot, coff));
+    else if (dx && sub) return DDRL_E_STATE;
     else if (dx)
       TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s,
                         tc2_mode(n)));
@@ -630,7 +704,7 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
       TRY(lin_bwd(n, t.L[3], b[5], 3136, t.dh, 512, b[6], 3136, 3136, ACT_LEAKY, b[5], mb, s));
       TRY(conv_bwd(n, t, 2, 2, b[3], b[4], b[6], b[7], b[8], ACT_LEAKY, mb, s));
       TRY(conv_bwd(n, t, 1, 1, b[1], b[2], b[8], b[7], b[9], ACT_LEAKY, mb, s));
-      TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], b[9], nullptr, nullptr, 0, mb, s));
+      if (!t.fuse_role) TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], b[9], nullptr, nullptr, 0, mb, s));   // else: fused_conv0_bwd
       return DDRL_OK;
     }
     case DDRL_ARCH_NAV:
@@ -680,9 +754,32 @@ static int check_obs(const ddrl_net* n, const float* const* obs, int n_obs) {
   return DDRL_OK;
 }
 
+// First conv of both unshared towers in one pass over the shared im2col matrix: a1c[M, 2 Cout] = act(cols W01^T + b01)
+// (rows 0..Cout-1 of W01 = actor tower, the rest = critic tower; each tower's conv2 reads its channel half).
+static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0, int mb, cudaStream_t s, bool cols_cached) {
+  Tower& t0 = n->towers[0];
+  const ConvGeom& g = t0.g[0];
+  const Lin& l = t0.L[0];
+  if (!cols_cached) TRY(im2col(g, obs[0] + row0 * g.sb, t0.buf[0], mb, s));
+  return gemm(n, 0, (int)((long long)mb * g.Ho * g.Wo), 2 * l.N, l.K, t0.buf[0], g.ldc, l.wp, l.ldw, t0.buf[1], 2 * l.N, n->bias0c,
+              l.act, 0, 0, s);
+}
+// ... and its backward: da1c [M, 2 Cout] holds both towers' dL/d(pre-activation) side by side
+static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
+  Tower &t0 = n->towers[0], &t1 = n->towers[1];
+  const ConvGeom& g = t0.g[0];
+  const Lin &l0 = t0.L[0], &l1 = t1.L[0];
+  const long long M = (long long)mb * g.Ho * g.Wo;
+  float* dy = t0.buf[9];
+  TRY(colsum_add(dy, 2 * l0.N, M, l0.N, db_of(n, l0), s));
+  TRY(colsum_add(dy + l0.N, 2 * l0.N, M, l1.N, db_of(n, l1), s));
+  return tc2_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, l0.dwp, l0.ldw, s);
+}
+
 // encoders + heads for rows [row0, row0+mb): fills n->logits [mb, ldA], n->vout [mb]
 static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s,
                          bool reuse_obs = false) {
+  if (n->fuse0) TRY(fused_conv0_fwd(n, obs, row0, mb, s, reuse_obs));
   for (auto& t : n->towers) TRY(tower_forward(n, t, obs, row0, mb, train, s, reuse_obs));
   Tower& ta = n->towers[0];
   Tower& tc = n->towers[n->d.shared ? 0 : 1];
@@ -735,6 +832,16 @@ extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
     n->towers.resize(2);
     build_tower(n, n->towers[0], "actor.pre.", n->d.arch, n->d.in_ch, F);
     build_tower(n, n->towers[1], "critic.pre.", n->d.arch, n->d.in_ch, F);
+    // unshared towers read the same observation: run their first (explicit-im2col) conv as one N = 2 x Cout GEMM
+    Tower &t0 = n->towers[0], &t1 = n->towers[1];
+    const char* nf = getenv("DDRL_NO_FUSE0");
+    if (n->d.arch == DDRL_ARCH_ATARI && tc2_mode(n) && !(nf && nf[0] == '1') && !t0.s2d0 && !t0.implicit[0] && t0.implicit[1] &&
+        t0.df[1].on && t1.df[1].on && t0.L[0].N % 32 == 0 && 2 * t0.L[0].N <= 128 && t0.g[0].ldc % 4 == 0) {
+      n->fuse0 = true;
+      t0.fuse_role = 1; t1.fuse_role = 2;
+      t0.in1_ctot = t1.in1_ctot = 2 * t0.L[0].N;
+      t0.in1_coff = 0; t1.in1_coff = t0.L[0].N;
+    }
   }
   *out = n;
   return DDRL_OK;
@@ -745,6 +852,7 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
   if (n->split_base) cudaFree(n->split_base);
+  if (n->bias0c) cudaFree(n->bias0c);
   delete n;
   return DDRL_OK;
 }
@@ -868,11 +976,15 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
     TRY(skinny_dgrad(n->dlogits, n->ldA, aw, mb, A, F, ta.dh, F, 0, s));
     TRY(skinny_dgrad(n->dv, 1, cw, mb, 1, F, tc.dh, F, n->d.shared ? 1 : 0, s));
     for (auto& t : n->towers) TRY(tower_backward(n, t, obs, r0, mb, s));
+    if (n->fuse0) TRY(fused_conv0_bwd(n, mb, s));
   }
   // packed weight grads -> reference layout
   for (auto& t : n->towers)
     for (auto& l : t.L)
-      if (l.packed) TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
+      if (l.packed) {
+        if (l.s2d_s) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
+        else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
+      }
   return DDRL_OK;
 }
 

@@ -16,10 +16,12 @@
 // Warp roles: 0 TMA producer | 1 MMA issuer for the chunked accumulators | 3 MMA issuer for the whole-tile correction
 // accumulator (two independent in-order MMA streams: one thread can only issue a tf32 MMA every ~45 cycles) |
 // 2 TMEM allocator | splitter groups of 4 warps (TMEM lane quadrant = warp % 4; groups alternate K blocks) |
-// epilogue warps (4 for BN <= 64, 8 for BN = 128).
+// epilogue warps (4 for BN = 32, 8 otherwise: the epilogue is ~2000 dependent instructions per 64-column tile and
+// warp -- with one warp per scheduler it, not the MMA stream, bounded the N = 64 layers; profiles/r1b_ncu_tc2.md).
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -50,6 +52,13 @@ __device__ unsigned long long g_tc2_wait[32];
 #define T2_ROLE_END(role, cond)
 #endif
 
+// Timing experiments (scratch/tc2_exp.py; WRONG RESULTS, never defined in the product build): -DT2_EXP=<bitmask>
+//   1 wgrad: skip the dy (B) tile split   2 wgrad: skip the A gather loads   4 fwd: skip the epilogue's global stores
+//   8 fwd: skip the splitter's smem loads   16 skip tcgen05.wait::st   32 fwd: skip the chunk drains' FADDs
+#ifndef T2_EXP
+#define T2_EXP 0
+#endif
+
 struct Tc2Args {
   float* C;
   const float* bias;
@@ -74,7 +83,7 @@ struct T2Cfg {
   // of 3 (every tf32 MMA with N <= 64 occupies the tensor pipe for ~45 cycles regardless of N, scratch/mma_bench.cu).
   static constexpr bool FOLD = BN <= 64;
   static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
-  static constexpr int NEPI = BN <= 64 ? 4 : 8;
+  static constexpr int NEPI = BN <= 32 ? 4 : 8;                  // 32 accumulator columns per epilogue thread (64 for BN = 128)
   static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
   static constexpr int EPI0 = 4 + 4 * NSG;                       // first epilogue warp
   static constexpr int THREADS = (EPI0 + NEPI) * 32;
@@ -303,31 +312,10 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int s = it % S, a = it % SA;
         T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        uint32_t hi[32], lo[32];
 #ifdef TC2_TIMING
         const long long sp0 = clock64();
 #endif
-        if (MODE == 0) {
-          // thread = tile row; its 32 k values are the row's eight 16-byte chunks (128B swizzle: chunk ^ (row & 7))
-          const int row = q * 32 + lane;
-          const uint8_t* rp = st + row * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-            const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[c * 4 + e], lo[c * 4 + e]);
-          }
-        } else {
-          // thread = k column `lane` of slice q; it gathers that column over the (<= 32) pixel rows of the box
-          const uint8_t* sp = st + q * 4096 + (lane & 3) * 4;
-#pragma unroll
-          for (int p = 0; p < 32; ++p) {
-            const float x = *reinterpret_cast<const float*>(sp + p * 128 + (((lane >> 2) ^ (p & 7)) << 4));
-            split_tf32(x, hi[p], lo[p]);
-          }
-        }
-        if (MODE == 1) {
+        if (MODE == 1 && !(T2_EXP & 1)) {
           // raw dy tile: hi in place + lo twin; element-wise, so the TMA swizzle is preserved
           uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
           for (int v = st_tid; v < Cfg::B_BYTES / 16; v += 128) {
@@ -339,17 +327,45 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           }
           fence_async_smem();
         }
-#ifdef TC2_TIMING
-        w2 += clock64() - sp0;
-#endif
-        T2_WAIT(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1, w1);
-        tc_fence_after();
         const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 16, hi + 16);
-        tmem_st16(ta + 32, lo);
-        tmem_st16(ta + 48, lo + 16);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // two halves of 16 k values (keeps the live split registers at 32: the CTA runs 640 threads for BN = 64)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hi[16], lo[16];
+          if (MODE == 0) {
+            // thread = tile row; its 32 k values are the row's eight 16-byte chunks (128B swizzle: chunk ^ (row & 7))
+            const int row = q * 32 + lane;
+            const uint8_t* rp = st + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = (T2_EXP & 8) ? make_float4(1.f, 2.f, 3.f, (float)it)
+                                            : *reinterpret_cast<const float4*>(rp + (((hf * 4 + c) ^ (row & 7)) << 4));
+              const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[c * 4 + e], lo[c * 4 + e]);
+            }
+          } else {
+            // thread = k column `lane` of slice q; it gathers that column over the (<= 32) pixel rows of the box
+            const uint8_t* sp = st + q * 4096 + (lane & 3) * 4;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int pp = hf * 16 + p;
+              const float x = (T2_EXP & 2) ? (float)(it + pp)
+                                           : *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
+              split_tf32(x, hi[p], lo[p]);
+            }
+          }
+          if (hf == 0) {
+#ifdef TC2_TIMING
+            w2 += clock64() - sp0;
+#endif
+            T2_WAIT(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1, w1);
+            tc_fence_after();
+          }
+          tmem_st16(ta + hf * 16, hi);
+          tmem_st16(ta + 32 + hf * 16, lo);
+        }
+        if (!(T2_EXP & 16)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
@@ -377,16 +393,16 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         T2_WAIT(smem_u32(bar_mfull + buf), (ch >> 1) & 1, w0);
         tc_fence_after();
 #pragma unroll
-        for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+          for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
           if (Cfg::FOLD) {
             // the hi*lo term of this chunk sits BN columns further (second half of the folded N' = 2 BN MMA)
-            tmem_ld16(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
+            tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+            for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
           }
         }
         tc_fence_before();
@@ -396,11 +412,11 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       T2_WAIT(smem_u32(bar_cfull), tl & 1, w1);
       tc_fence_after();
 #pragma unroll
-      for (int j0 = 0; j0 < Cfg::COLS; j0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j0 + j] += v[j];
+        for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
       }
       tc_fence_before();
       __syncwarp();
@@ -431,7 +447,9 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         px = (r % tp.Xn) * tp.out_s;
         py = (y0 + (r / tp.Xn) % tp.ny) * tp.out_s;
       }
-      if (MODE == 0 && g.vec_store) {
+      if (T2_EXP & 4) {
+        if (acc[0] == 123.456f) g.C[0] = acc[1];
+      } else if (MODE == 0 && g.vec_store) {
         // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
         // (and activation-mask load) instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
         float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
@@ -589,6 +607,16 @@ static int launch2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tbh, con
 }
 
 static inline int pick_bn(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+// Implicit convolutions with a short K loop are bounded by the epilogue (one 64-column pass per warp and tile), not by
+// the MMA stream: DDRL_TC2_CONV_MAXBN=64 runs their N = 128 layers as two 64-wide tiles (twice the epilogue warps per
+// output column, FOLD MMAs) at the price of splitting the activation tile twice.
+static inline int pick_bn_conv(int N, int kb_total) {
+  static const int maxbn = [] { const char* e = getenv("DDRL_TC2_CONV_MAXBN"); return e ? atoi(e) : 128; }();
+  static const int maxkb = [] { const char* e = getenv("DDRL_TC2_CONV_MAXBN_KB"); return e ? atoi(e) : 1 << 30; }();
+  int bn = pick_bn(N);
+  if (bn > maxbn && kb_total <= maxkb && maxbn >= 32) bn = maxbn;
+  return bn;
+}
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool tc2_gemm_supported(int form, int M, int N, int K, const float* A, int lda, const float* Bhi, const float* Blo, int ldb) {
@@ -631,7 +659,7 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   if (act >= 3 && !mask) return DDRL_E_ARG;
   int r = tc_get_encode();
   if (r != DDRL_OK) return r;
-  const int bn = pick_bn(N);
+  const int bn = pick_bn_conv(N, o.KH * o.KW * (o.Cin / 32));
   const int bns = (bn + 31) / 32 * 32;
   Tc2Args g;
   memset(&g, 0, sizeof(g));
@@ -661,10 +689,21 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   return launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s);
 }
 
+// K splits of the weight gradient: one CTA per (tile, split) and one CTA per SM at a time, so the launch runs in
+// ceil(tiles*splits / 148) waves of equal-length CTAs.  Pick the split count whose last wave is fullest (a grid of 300
+// CTAs is THREE waves: 148 + 148 + 4), preferring fewer splits (less atomic traffic) among near-equals; every split keeps
+// >= 8 K blocks so the pipeline prologue stays amortised.
 static void wgrad_splits(Tc2Args& g, int tiles) {
-  int splits = std::max(1, std::min(std::min(ceil_div(2 * kNumSMs, tiles), g.kb_total / 8), 1024));
-  int kbps = ceil_div(g.kb_total, splits);
-  g.kb_per_split = kbps;
+  const int max_splits = std::max(1, std::min(g.kb_total / 8, 1024));
+  int best = 1;
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= max_splits && (long long)tiles * sp <= 4LL * kNumSMs; ++sp) {
+    const int kbps = ceil_div(g.kb_total, sp);
+    const int waves = ceil_div(tiles * ceil_div(g.kb_total, kbps), kNumSMs);
+    const double cost = (double)waves * (kbps + 6);                 // K blocks per CTA + fixed prologue/epilogue
+    if (cost < best_cost * 0.98) { best_cost = cost; best = sp; }
+  }
+  g.kb_per_split = ceil_div(g.kb_total, best);
 }
 
 // dW[n*ldw + k] += sum_r dy[r, n] * x[r, k]     (x [rows, Kx], dy [rows, N]; accumulates atomically)

@@ -197,6 +197,25 @@ def test_micro_batching_equals_single_shot(monkeypatch):
     assert torch.equal(a1, a2) and rel_err(v2, v1) < 1e-6
 
 
+@pytest.mark.parametrize("env", [{"DDRL_S2D": "1"}, {"DDRL_NO_FUSE0": "1"}, {"DDRL_NO_IMPLICIT": "1"}])
+def test_engine_layer_variants_agree(monkeypatch, env):
+    """Alternative layer lowerings of the same net (space-to-depth conv1, un-fused first convs, explicit im2col for
+    every conv) must give the default lowering's forward values and gradients to fp32 rounding."""
+    spec, params, states, a, old, adv, ret = _learn_case("pong", 19)
+    ds = [s.to(DEV) for s in states]
+    net, _, _ = make("pong")
+    net.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    g0 = net.flat_grads().clone()
+    _, _, v0 = net.act(ds, play_mode=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    net2, _, _ = make("pong")
+    net2.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    assert rel_err(net2.flat_grads(), g0) < 1e-5
+    _, _, v2 = net2.act(ds, play_mode=True)
+    assert rel_err(v2, v0) < 1e-5
+
+
 def test_shard_sum_equals_full_batch():
     """Data-parallel arithmetic on one GPU: two half-batches scaled by 1/B_global sum to the full-batch gradient."""
     spec, params, states, a, old, adv, ret = _learn_case("pong", 16)
