@@ -108,6 +108,17 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this same workload (profiles/ncu_traffic.json; null when there is no capture for it)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d[workload][kernel]["bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def synth_batch_host(kind, B, seed):
     """Synthetic rollouts of the named observation shape, as pinned host fp32 arrays."""
     from oracle.restate import synth_states
@@ -213,14 +224,28 @@ def run_ours(args):
     # ---- e2e: same metric through BackwardModule.train_on from pinned host buffers (H2D + D2H per step)
     bm = BackwardModule(net, device=dev)
 
+    def host_exp():
+        return Experience(states=list(host_fields["states"]), advs=host_fields["advs"], actions=host_fields["actions"],
+                          old_logps=host_fields["old_logps"], values=host_fields["values"])
+
+    pending = [None]
+
     def step_e2e():
-        exp = Experience(states=list(host_fields["states"]), advs=host_fields["advs"], actions=host_fields["actions"],
-                         old_logps=host_fields["old_logps"], values=host_fields["values"])
-        logs = bm.train_on(exp)                            # H2D of the batch; 10 iterations; 16-byte D2H of the losses each
+        # every step copies ONE batch host->device inside the timed region: the NEXT step's batch, on the copy stream,
+        # while this step's batch trains (BackwardModule.prefetch = the reference's concurrent BackwardGetDataThread);
+        # the first batch was copied by the warm-up step, the last prefetched one is never trained on: K copies, K steps
+        cur = pending[0]
+        if cur is None:
+            cur = host_exp()
+        nxt = host_exp()
+        bm.prefetch(nxt)
+        logs = bm.train_on(cur)                            # 10 iterations; 16-byte D2H of the losses each
+        pending[0] = nxt
         return logs
 
     sec_e2e = timed(step_e2e, max(2, args.steps // 2), 1, dist)
     e2e_value = world * B * ITERS * max(2, args.steps // 2) / sec_e2e
+    pending[0] = None
 
     # ---- per-kernel-class device time of ONE learn call (separate pass: events after every launch)
     prof = {}
@@ -238,7 +263,7 @@ def run_ours(args):
     if dom in gemm_names:
         ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e12
         roof = dict(bound="tensor", kernel=dom, achieved=round(ach, 2), peak=peaks["tensor_sustained"], unit="TFLOP/s",
-                    frac=round(ach / peaks["tensor_sustained"], 4), traffic=None,
+                    frac=round(ach / peaks["tensor_sustained"], 4), traffic=ncu_traffic(args.workload, dom),
                     peak_note="bf16 cuBLAS sustained, of %s (no TF32/FP32 peak is in MEASURED_PEAKS.json)" % peaks["src"],
                     share_of_step=round(prof[dom]["ms"] / tot_ms, 3), avg_launch_ms=round(prof[dom]["ms"] / prof[dom]["launches"], 4))
     else:
@@ -268,6 +293,15 @@ def run_ours(args):
     gae_elems = world * T * N * 10 / sec_g
     gae_gbs = 17.0 * T * N * 10 / sec_g / 1e9          # per GPU
     del gv, gr, gd
+
+    # ---- the other named single-GPU configurations (BASELINE configs[1] / [4]), short runs, N=1 only
+    others = {}
+    if world == 1 and not args.no_others:
+        del net, exp_dev, states_d, fstates_d, bm, fm
+        torch.cuda.empty_cache()
+        for other in [w for w in ("navlaser", "navimg", "pong") if w != args.workload]:
+            others[other] = quick_workload(other, args.gemm_mode, dev, dist)
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0 only, N=1 only): the oracle port on the host cores, bounded sample
     cpu = None
@@ -300,11 +334,39 @@ def run_ours(args):
                                  "frac": round(gae_gbs / peaks["hbm"], 4)}},
             "losses_last": {k: round(float(v), 6) for k, v in last_losses.items() if k != "PpoBackUpTime"},
         }
+        if others:
+            line["other_workloads"] = others
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def quick_workload(kind, gemm_mode, dev, dist):
+    """Learner sample-iterations/s (3 warm-up + 2 timed learn calls, inputs resident) and Forward actions/s of another
+    named configuration, same definitions as the headline numbers."""
+    from ddrl4nav_b200.data import Experience
+    from ddrl4nav_b200.runner import make_net
+    wl = WORKLOADS[kind]
+    B, Bf = wl["batch"], wl["fwd_batch"]
+    net = make_net(kind, device=dev, gemm_mode=gemm_mode, TRAINING_ITER_TIME=ITERS)
+    states_h, adv_h, ret_h = synth_batch_host(kind, B, seed=100)
+    states_d = [s.to(dev) for s in states_h]
+    with torch.no_grad():
+        acts_d, logp_d, _ = net.act(states_d)
+    old_d = logp_d + 0.15 * torch.randn(B, device=dev)
+    exp = Experience(states=states_d, advs=adv_h.to(dev), actions=acts_d, old_logps=old_d, values=ret_h.to(dev)[None])
+
+    def step():
+        for _ in net.learn(exp):
+            pass
+    sec = timed(step, 2, 3, dist)
+    fstates_d = [s.to(dev) for s in synth_batch_host(kind, Bf, seed=200)[0]]
+    sec_f = timed(lambda: net.act(fstates_d), 5, 3, dist)
+    return {"workload": wl["desc"], "rows_per_gpu": B, "value": round(B * ITERS * 2 / sec, 1), "unit": "learner sample-iterations/s",
+            "ms_per_step": round(sec / 2 * 1e3, 3), "learner_tflops": round(B * ITERS * 2 / sec * wl["flops_learn"] / 1e12, 2),
+            "forward_actions_per_s": round(Bf * 5 / sec_f, 1), "forward_rows": Bf}
 
 
 def cpu_reference(kind, B, iters, warm):
@@ -375,6 +437,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--fwd-batch", dest="fwd_batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", dest="no_others", action="store_true", help="skip the short runs of the other named workloads")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE learn step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -503,7 +503,7 @@ bool conv_tc_supported(const ConvOp& o, bool wgrad) {
   return true;
 }
 
-void tc_tap_common(TcTap& t, const ConvOp& o, int cap) {
+void tc_tap_common(TcTap& t, const ConvOp& o, int cap, bool two_phase) {
   memset(&t, 0, sizeof(t));
   t.mode = 1;
   t.Xn = o.Xn; t.Yn = o.Yn; t.Bn = o.Bn;
@@ -511,6 +511,33 @@ void tc_tap_common(TcTap& t, const ConvOp& o, int cap) {
     t.ny = o.Yn; t.nb = std::min(std::max(1, cap / (o.Xn * o.Yn)), 256); t.tpi = 1;
   } else {                                      // row blocks of one image
     t.ny = std::max(1, cap / o.Xn); t.nb = 1; t.tpi = ceil_div(o.Yn, t.ny);
+  }
+  t.tiles1 = 0x7fffffff;
+  if (two_phase) {
+    // tiles per image of the plan above, against: k full blocks of ny_a rows (nb_a images per box) + one box class for
+    // the remaining rows
+    // (taller boxes first: a plan must beat the incumbent by 5 % to replace it, so equal tile counts keep the more
+    // local one)
+    double best = (double)t.tpi / t.nb;
+    for (int ny_a = o.Yn; ny_a >= 1; --ny_a) {
+      const int nb_a = std::min(cap / (o.Xn * ny_a), 256);
+      if (nb_a < 1) continue;
+      if ((ny_a - 1) * o.sy + 1 > 256) continue;
+      const int k = o.Yn / ny_a, rem = o.Yn - k * ny_a;
+      if (rem == 0) {
+        const double c = (double)k / nb_a;
+        if (c < best * 0.95) { best = c; t.ny = ny_a; t.nb = nb_a; t.tpi = k; t.y2 = 0; t.ny2 = 0; t.nb2 = 0; }
+        continue;
+      }
+      const int nb_b = std::min(cap / (o.Xn * rem), 256);
+      if (nb_b < 1 || (rem - 1) * o.sy + 1 > 256) continue;
+      const double c = (double)k / nb_a + 1.0 / nb_b;
+      if (c < best * 0.95) { best = c; t.ny = ny_a; t.nb = nb_a; t.tpi = k; t.y2 = k * ny_a; t.ny2 = rem; t.nb2 = nb_b; }
+    }
+    if (t.ny2 > 0) {
+      t.tiles1 = ceil_div(o.Bn, t.nb) * t.tpi;
+      t.rows2 = o.Xn * t.ny2 * t.nb2;
+    }
   }
   t.rows = o.Xn * t.ny * t.nb;
   t.kpad = (t.rows + 7) & ~7;

@@ -27,6 +27,10 @@ struct TcTap {
   int Xn, Yn, Bn;                // output pixel grid: Xn x Yn per image, Bn images
   int ny, nb, tpi;               // box = nb images x ny rows x Xn pixels; boxes per image
   int rows;                      // Xn*ny*nb   (forward/dgrad: <= 128 = the M tile; wgrad: <= 32 = one K block)
+  // two-phase tiling (tc2 forward/dgrad): tiles [0, tiles1) are phase-1 boxes (rows [0, y2) of each image in blocks of ny,
+  // nb images per box); tiles >= tiles1 cover the remaining rows [y2, Yn) with nb2 images per box (their own tensor map).
+  // 9x9 images: 7 rows x 2 images + 2 rows x 7 images = 126-row tiles instead of one 81-row image per 128-row tile.
+  int tiles1, y2, ny2, nb2, rows2;
   int kpad;                      // rows rounded up to 8 (wgrad: MMA K steps per block)
   int KW, cpb;                   // tap index = kh*KW + kw; 32-channel chunks per tap
   int nslices;                   // taps * cpb

@@ -105,7 +105,7 @@ struct T2Cfg {
 template <int BN, int MODE, bool B_MN>
 __global__ void __launch_bounds__(T2Cfg<BN>::THREADS, 1)
 tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-           const __grid_constant__ CUtensorMap tmBlo, Tc2Args g) {
+           const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmA2, Tc2Args g) {
   using Cfg = T2Cfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
@@ -187,7 +187,11 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
       const int m0 = mt * T2_BM, n0 = nt * BN;
       int b0 = 0, y0 = 0;
-      if (MODE == 0 && tapA) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny * tp.sy - tp.py; }
+      const bool ph2 = MODE == 0 && tapA && mt >= tp.tiles1;       // second tiling phase: the images' remaining rows
+      if (MODE == 0 && tapA) {
+        if (!ph2) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny * tp.sy - tp.py; }
+        else { b0 = (mt - tp.tiles1) * tp.nb2; y0 = tp.y2 * tp.sy - tp.py; }
+      }
       int cc = 0, kw = 0, kh = 0;                     // forward taps: K block = (kh, kw, chunk), chunk fastest
       int pb = 0, pj = 0;                             // wgrad pixel blocks: image, row block within the image
       if (MODE == 1 && tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
@@ -204,8 +208,8 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               mbar_expect_tx(full, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
               tma_load_2d(&tmA, full, a_dst, k, m0);
             } else {
-              mbar_expect_tx(full, tp.rows * 128 + 2 * Cfg::B_BYTES);
-              tma_load_4d(&tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
+              mbar_expect_tx(full, (ph2 ? tp.rows2 : tp.rows) * 128 + 2 * Cfg::B_BYTES);
+              tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
             }
             if (!B_MN) {
               tma_load_2d(&tmBhi, full, bh_dst, k, n0);
@@ -429,10 +433,12 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       bool rvalid;
       long long roff;
       if (MODE == 0 && tapA) {
-        const int b0 = (mt / tp.tpi) * tp.nb, y0 = (mt % tp.tpi) * tp.ny;
+        const bool ph2 = mt >= tp.tiles1;
+        const int b0 = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb, y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        const int nyp = ph2 ? tp.ny2 : tp.ny;
         const int x = r % tp.Xn, t2 = r / tp.Xn;
-        const int yy = t2 % tp.ny, bb = t2 / tp.ny;
-        rvalid = r < tp.rows && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
+        const int yy = t2 % nyp, bb = t2 / nyp;
+        rvalid = r < (ph2 ? tp.rows2 : tp.rows) && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
         roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
       } else {
         rvalid = (m0 + r) < g.M;
@@ -443,9 +449,10 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const bool fused = MODE == 0 && tapA && tp.ncls > 1;
       int py = 0, px = 0;
       if (fused) {
-        const int y0 = (mt % tp.tpi) * tp.ny;
+        const bool ph2 = mt >= tp.tiles1;
+        const int y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
         px = (r % tp.Xn) * tp.out_s;
-        py = (y0 + (r / tp.Xn) % tp.ny) * tp.out_s;
+        py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
       }
       if (T2_EXP & 4) {
         if (acc[0] == 123.456f) g.C[0] = acc[1];
@@ -576,14 +583,14 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 // ---------------------------------------------------------------- host side
 template <int BN, int MODE, bool B_MN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const Tc2Args& g, dim3 grid,
-                   cudaStream_t s) {
+                   cudaStream_t s, const CUtensorMap* ta2 = nullptr) {
   using Cfg = T2Cfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
     DDRL_CUDA(cudaFuncSetAttribute(tc2_kernel<BN, MODE, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  tc2_kernel<BN, MODE, B_MN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tbh, tbl, g);
+  tc2_kernel<BN, MODE, B_MN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tbh, tbl, ta2 ? *ta2 : ta, g);
   prof_work(2.0 * g.M * (double)g.N * g.K);
   if (g_prof_on && g_prof_shapes) {
     char nm[96];
@@ -598,11 +605,11 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensor
 
 template <int MODE, bool B_MN>
 static int launch2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const Tc2Args& g, dim3 grid,
-                      cudaStream_t s) {
+                      cudaStream_t s, const CUtensorMap* ta2 = nullptr) {
   switch (bn) {
-    case 128: return launch2<128, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
-    case 64: return launch2<64, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
-    default: return launch2<32, MODE, B_MN>(ta, tbh, tbl, g, grid, s);
+    case 128: return launch2<128, MODE, B_MN>(ta, tbh, tbl, g, grid, s, ta2);
+    case 64: return launch2<64, MODE, B_MN>(ta, tbh, tbl, g, grid, s, ta2);
+    default: return launch2<32, MODE, B_MN>(ta, tbh, tbl, g, grid, s, ta2);
   }
 }
 
@@ -663,7 +670,8 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   const int bns = (bn + 31) / 32 * 32;
   Tc2Args g;
   memset(&g, 0, sizeof(g));
-  tc_tap_common(g.tap, o, T2_BM);
+  static const bool one_phase = [] { const char* e = getenv("DDRL_TC2_ONE_PHASE"); return e && e[0] == '1'; }();
+  tc_tap_common(g.tap, o, T2_BM, !one_phase);
   g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
   if (cls && cls->ncls > 1) {
     if (cls->ncls > 4 || N != cls->ncls * cls->cls_cols || cls->cls_cols % 4 != 0) return DDRL_E_ARG;
@@ -675,18 +683,21 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
     }
   }
   const int K = o.KH * o.KW * o.Cin;
-  CUtensorMap ta, tbh, tbl;
+  CUtensorMap ta, tbh, tbl, ta2;
   r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, g.tap.nb, false);
+  const bool ph2 = g.tap.ny2 > 0;
+  if (r == DDRL_OK && ph2) r = tc_make_map_nhwc(&ta2, o, o.Xn, g.tap.ny2, g.tap.nb2, false);
   if (r == DDRL_OK) r = tc_make_map(&tbh, Whi, K, N, ldw, bns, false);
   if (r == DDRL_OK) r = tc_make_map(&tbl, Wlo, K, N, ldw, bns, false);
   if (r != DDRL_OK) return r;
   g.C = out; g.bias = bias; g.mask = mask; g.act = act;
   g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K; g.sCm = 0; g.sCn = 1;
   g.kb_total = g.tap.nslices; g.kb_per_split = g.kb_total;
-  g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi; g.n_tiles = ceil_div(N, bn);
+  g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi + (ph2 ? ceil_div(o.Bn, g.tap.nb2) : 0);
+  g.n_tiles = ceil_div(N, bn);
   g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && al16(out) && (!mask || al16(mask))) ? 1 : 0;
   dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
-  return launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s);
+  return launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s, ph2 ? &ta2 : nullptr);
 }
 
 // K splits of the weight gradient: one CTA per (tile, split) and one CTA per SM at a time, so the launch runs in

@@ -16,12 +16,22 @@ def forward_compute(net, batch_states: Sequence, play_mode: bool = False, draw: 
 
 
 class ForwardModule:
-    def __init__(self, net, play_mode: bool = False, nptype=np.float32, device="cuda"):
+    """chunk_bytes: batches whose observations exceed it are streamed in row chunks through a ring of pinned staging
+    buffers -- host copy of chunk c+1 (numpy releases the GIL: `copy_threads` workers fill disjoint row ranges), H2D
+    DMA of chunk c on a copy stream and the engine call of chunk c-1 all overlap."""
+
+    def __init__(self, net, play_mode: bool = False, nptype=np.float32, device="cuda", chunk_bytes: int = 96 << 20,
+                 copy_threads: int = 8):
         self.net = net
         self.play_mode = play_mode
         self.nptype = nptype
         self.device = torch.device(device)
+        self.chunk_bytes = int(chunk_bytes)
+        self.copy_threads = max(1, int(copy_threads))
         self._pinned = {}
+        self._ring = {}
+        self._pool = None
+        self._copy_stream = None
 
     def _stage(self, i: int, a) -> torch.Tensor:
         """np array (u8/f16/f32/f64, easybytes.py:21-26) -> fp32 device tensor through a reusable pinned buffer."""
@@ -37,11 +47,64 @@ class ForwardModule:
         buf.numpy()[...] = a
         return buf.to(self.device, non_blocking=True).to(torch.float32)
 
-    def step(self, batch_states: Sequence, draw: Optional[torch.Tensor] = None) -> List[np.ndarray]:
-        """Returns [actions, logps, values] as numpy (the list ``encode_forward_return_data`` consumes)."""
-        states = [self._stage(i, s) for i, s in enumerate(batch_states)]
-        actions, logps, values = self.net.act(states, draw=draw, play_mode=self.play_mode)
+    def _finish(self, actions, logps, values):
         out = torch.cat([actions.reshape(-1), logps, values.reshape(-1)]).cpu().numpy().astype(self.nptype, copy=False)
         B = logps.shape[0]
         na = actions.numel()
         return [out[:na].reshape(tuple(actions.shape)), out[na:na + B], out[na + B:].reshape(1, B, 1)]
+
+    def step(self, batch_states: Sequence, draw: Optional[torch.Tensor] = None) -> List[np.ndarray]:
+        """Returns [actions, logps, values] as numpy (the list ``encode_forward_return_data`` consumes)."""
+        host = all(not torch.is_tensor(s) for s in batch_states)
+        if host:
+            arrs = [np.asarray(s) for s in batch_states]
+            B = len(arrs[0])
+            row_bytes = sum(a.nbytes // max(B, 1) for a in arrs)
+            if B * row_bytes > self.chunk_bytes and B >= 512:
+                return self._step_streamed(arrs, B, row_bytes, draw)
+        states = [self._stage(i, s) for i, s in enumerate(batch_states)]
+        actions, logps, values = self.net.act(states, draw=draw, play_mode=self.play_mode)
+        return self._finish(actions, logps, values)
+
+    def _step_streamed(self, arrs, B, row_bytes, draw):
+        from concurrent.futures import ThreadPoolExecutor
+        rows = max(256, (self.chunk_bytes // max(row_bytes, 1)) // 128 * 128)
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(self.copy_threads)
+            self._copy_stream = torch.cuda.Stream(self.device)
+        key = (rows, tuple((a.shape[1:], a.dtype.str) for a in arrs))
+        if self._ring.get("key") != key:
+            self._ring = {"key": key, "slots": [
+                ([torch.empty((rows,) + a.shape[1:], dtype=torch.from_numpy(a[:0]).dtype).pin_memory() for a in arrs],
+                 torch.cuda.Event()) for _ in range(3)]}
+        main = torch.cuda.current_stream(self.device)
+        outs = []
+        for c, r0 in enumerate(range(0, B, rows)):
+            r1 = min(B, r0 + rows)
+            n = r1 - r0
+            bufs, ev = self._ring["slots"][c % 3]
+            ev.synchronize()                               # the DMA that last read this slot has finished
+            # host copy, split over worker threads by row range
+            per = -(-n // self.copy_threads)
+            jobs = [self._pool.submit(_copy_rows, a, b.numpy(), r0, q, min(n, q + per))
+                    for a, b in zip(arrs, bufs) for q in range(0, n, per)]
+            for j in jobs:
+                j.result()
+            with torch.cuda.stream(self._copy_stream):
+                dev = [b[:n].to(self.device, non_blocking=True) for b in bufs]
+                ev.record(self._copy_stream)
+            main.wait_event(ev)
+            dev32 = []
+            for d in dev:
+                d.record_stream(main)
+                dev32.append(d if d.dtype == torch.float32 else d.to(torch.float32))
+            dr = None if draw is None else draw[r0:r1]
+            outs.append(self.net.act(dev32, draw=dr, play_mode=self.play_mode))
+        actions = torch.cat([o[0] for o in outs], 0)
+        logps = torch.cat([o[1] for o in outs], 0)
+        values = torch.cat([o[2] for o in outs], 1)
+        return self._finish(actions, logps, values)
+
+
+def _copy_rows(src, dst, r0, q0, q1):
+    dst[q0:q1] = src[r0 + q0:r0 + q1]

@@ -216,6 +216,45 @@ def test_engine_layer_variants_agree(monkeypatch, env):
     assert rel_err(v2, v0) < 1e-5
 
 
+def test_forward_module_streamed_chunks_equal_one_shot():
+    """Batches larger than chunk_bytes go through the pinned ring / copy stream in row chunks; same draws -> same
+    actions, log-probs and values as the single-shot path (rows are independent)."""
+    from ddrl4nav_b200.server import ForwardModule
+    net, _, _ = make("pong")
+    B = 1100
+    states = [s.numpy() for s in R.synth_states("pong", B, seed=5)]
+    u = torch.rand(B, generator=torch.Generator().manual_seed(6))
+    one = ForwardModule(net, device=DEV, chunk_bytes=1 << 40).step(states, draw=u.to(DEV))
+    fm = ForwardModule(net, device=DEV, chunk_bytes=30 << 20, copy_threads=3)      # 256-row chunks, ragged tail
+    for _ in range(2):                                                              # second pass re-uses the ring slots
+        many = fm.step(states, draw=u.to(DEV))
+        assert np.array_equal(one[0], many[0])
+        assert np.allclose(one[1], many[1], rtol=1e-6, atol=1e-7) and np.allclose(one[2], many[2], rtol=1e-6, atol=1e-7)
+    f64 = fm.step([states[0].astype(np.float64)], draw=u.to(DEV))                   # Pong observations arrive as float64
+    assert np.array_equal(one[0], f64[0])
+
+
+def test_backward_module_prefetch_equals_plain():
+    from ddrl4nav_b200.data import Experience
+    from ddrl4nav_b200.server import BackwardModule
+    spec, params, states, a, old, adv, ret = _learn_case("pong", 24)
+
+    def fresh():
+        return Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                          values=ret.numpy()[None])
+    net1, _, _ = make("pong", TRAINING_ITER_TIME=2)
+    logs1 = BackwardModule(net1, device=DEV).train_on(fresh())
+    net2, _, _ = make("pong", TRAINING_ITER_TIME=2)
+    bm = BackwardModule(net2, device=DEV)
+    e = fresh()
+    bm.prefetch(e)
+    logs2 = bm.train_on(e)
+    for l1, l2 in zip(logs1, logs2):
+        for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss"):
+            assert l1[k] == l2[k]
+    assert torch.equal(net1.flat_params(), net2.flat_params()) if hasattr(net1, "flat_params") else True
+
+
 def test_shard_sum_equals_full_batch():
     """Data-parallel arithmetic on one GPU: two half-batches scaled by 1/B_global sum to the full-batch gradient."""
     spec, params, states, a, old, adv, ret = _learn_case("pong", 16)
