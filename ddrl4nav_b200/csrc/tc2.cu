@@ -98,6 +98,7 @@ struct T2Cfg {
   static_assert(NBARS * 8 + 16 <= 256, "barrier block");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
+  static_assert(STAGES > SA, "the stage barrier of K block it - SA releases TMEM slot it % SA");
 };
 
 // MODE 0: C[M,N] = epi(A[M,K] . B)   A K-major (plain 2-D or tap boxes), B = pre-split weights (K-major or MN-major)
@@ -282,8 +283,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               umma_tf32_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * kstep, Cfg::FOLD ? idesc2 : idesc,
                            (!first_in_chunk || k4 != 0) ? 1u : 0u);
             }
-            umma_commit(smem_u32(bar_empty + s));
-            umma_commit(smem_u32(bar_afree + a));
+            umma_commit(smem_u32(bar_empty + s));            // retires the stage AND the TMEM A slot of this K block
             if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
           } else {
             const uint64_t dbl0 = B_MN ? umma_desc(b_lo, 4096, 512, 1) : umma_desc(b_lo, 16, 1024, 2);
@@ -294,7 +294,6 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               if (!Cfg::FOLD) umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * kstep, idesc, 1u);
             }
             umma_commit(smem_u32(bar_empty + s));
-            umma_commit(smem_u32(bar_afree + a));
             if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
           }
         }
@@ -363,7 +362,12 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #ifdef TC2_TIMING
             w2 += clock64() - sp0;
 #endif
-            T2_WAIT(smem_u32(bar_afree + a), ((it / SA) & 1) ^ 1, w1);
+            // TMEM slot a was last read by K block it - SA: its stage barrier (both MMA streams commit to it) doubles as
+            // the slot's release -- S > SA, so that barrier cannot be a second phase ahead when we look at it
+            if (it >= (uint32_t)SA) {
+              const uint32_t j = it - SA;
+              T2_WAIT(smem_u32(bar_empty + (j % S)), (j / S) & 1, w1);
+            }
             tc_fence_after();
           }
           tmem_st16(ta + hf * 16, hi);
