@@ -266,6 +266,40 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   }
 }
 
+// float4 variant: thread = (row lane, 4 columns); 4 rows in flight per thread; N % 4 == 0, N <= 1024, 16-byte aligned rows
+__global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__ dy, int ld4, long long rows, int n4,
+                                                      float* __restrict__ db, long long rows_per_block) {
+  __shared__ float4 part[256];
+  const int ry = 256 / n4;                                // row lanes per block (n4 is a power-of-two divisor of 256 or < 256)
+  const int tx = threadIdx.x % n4, ty = threadIdx.x / n4;
+  const long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ty < ry) {
+    long long r = r0 + ty;
+    for (; r + 3LL * ry < r1; r += 4LL * ry) {
+      const float4 a = __ldg(dy + r * ld4 + tx), b = __ldg(dy + (r + ry) * ld4 + tx), c = __ldg(dy + (r + 2LL * ry) * ld4 + tx),
+                   d = __ldg(dy + (r + 3LL * ry) * ld4 + tx);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r1; r += ry) {
+      const float4 a = __ldg(dy + r * ld4 + tx);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    float4 sum = part[tx];
+    for (int k = 1; k < ry; ++k) {
+      const float4 v = part[k * n4 + tx];
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    atomicAdd(db + 4 * tx, sum.x); atomicAdd(db + 4 * tx + 1, sum.y);
+    atomicAdd(db + 4 * tx + 2, sum.z); atomicAdd(db + 4 * tx + 3, sum.w);
+  }
+}
+
 // ---------------------------------------------------------------- weight packing
 // packed[o*ld + i*J + j] = src[o*I*J + j*I + i]   (inner [J][I] -> [I][J] transpose; I = 1: row-stride change)
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int J,
@@ -464,8 +498,6 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restric
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int k = 0; k < K4 * 4; ++k) acc[j][k] = 0.f;
-  for (int i = threadIdx.x; i < NC4 * 4 * K4 * 4; i += 256) red[i] = 0.f;
-  __syncthreads();
   constexpr int UR = K4 <= 3 ? 4 : 2;
   const long long step = (long long)gridDim.x * RL;
   for (long long m0 = (long long)blockIdx.x * RL + rl; m0 < M; m0 += step * UR) {
@@ -490,12 +522,34 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restric
       }
     }
   }
+  // block reduction without shared-memory atomics: lanes l and l ^ 16 (NC4 = 16) / l ^ 8, l ^ 16 (NC4 = 8) hold the same
+  // channels -> shuffle; then one partial per warp in shared memory, summed by the first NC4*16*K4 threads
+  constexpr int NV = NC4 * 4 * K4 * 4;                  // outputs per block
+  constexpr int NW = 8;                                 // warps
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int k = 0; k < K4 * 4; ++k) atomicAdd(&red[(c4 * 4 + j) * (K4 * 4) + k], acc[j][k]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < NC4 * 4 * K4 * 4; i += 256) {
+    for (int k = 0; k < K4 * 4; ++k) {
+      float v = acc[j][k];
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (NC4 == 8) v += __shfl_xor_sync(0xffffffffu, v, 8);
+      acc[j][k] = v;
+    }
+  // the 8 warps add their partials into ONE [NV] buffer in turn (8 barriers, once per block)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int w = 0; w < NW; ++w) {
+    if (wid == w && lane < NC4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < K4 * 4; ++k) {
+          float* p = red + (lane * 4 + j) * (K4 * 4) + k;
+          *p = (w == 0 ? 0.f : *p) + acc[j][k];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NV; i += 256) {
     const int n = i / (K4 * 4), k = i % (K4 * 4);
     if (k < K) atomicAdd(dW + (size_t)n * ldw + k, red[i]);
   }
@@ -579,6 +633,19 @@ int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int 
 }
 int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s) {
   if (rows == 0 || N == 0) return DDRL_OK;
+  prof_work(4.0 * (double)rows * N);
+  if (N % 4 == 0 && ld % 4 == 0 && N <= 1024 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int n4 = N / 4;
+    const int ry = std::max(1, 256 / n4);
+    long long chunks = std::max<long long>(1, std::min<long long>((rows + 16LL * ry - 1) / (16LL * ry), 8LL * kNumSMs));
+    const long long rpb = (rows + chunks - 1) / chunks;
+    chunks = (rows + rpb - 1) / rpb;
+    if (n4 <= 256) {
+      colsum4_kernel<<<(unsigned)chunks, 256, 0, s>>>(reinterpret_cast<const float4*>(dy), ld / 4, rows, n4, db, rpb);
+      DDRL_LAUNCHED("colsum_kernel");
+      return DDRL_OK;
+    }
+  }
   const int nb = ceil_div(N, 32);
   long long chunks = std::max<long long>(1, std::min<long long>((rows + 255) / 256, (4LL * kNumSMs + nb - 1) / nb));
   const long long rpb = (rows + chunks - 1) / chunks;

@@ -54,7 +54,9 @@ __device__ unsigned long long g_tc2_wait[32];
 
 // Timing experiments (scratch/tc2_exp.py; WRONG RESULTS, never defined in the product build): -DT2_EXP=<bitmask>
 //   1 wgrad: skip the dy (B) tile split   2 wgrad: skip the A gather loads   4 fwd: skip the epilogue's global stores
-//   8 fwd: skip the splitter's smem loads   16 skip tcgen05.wait::st   32 fwd: skip the chunk drains' FADDs
+//   8 fwd: skip the splitter's smem loads   16 skip tcgen05.wait::st   64 issue no MMA at all (commits only)
+//   128 every MMA with N = 16 (same instruction count, ~no tensor-pipe time)   256 corr stream issues nothing
+//   512 fwd: no B (weight) TMA loads   1024 fwd: no A (activation) TMA load
 #ifndef T2_EXP
 #define T2_EXP 0
 #endif
@@ -77,12 +79,24 @@ struct T2Cfg {
   static constexpr int A_BYTES = T2_BM * T2_BK * 4;              // 16 KB raw activation tile (or 4 transposed slices)
   static constexpr int B_BYTES = BNS * T2_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;      // A raw | B hi | B lo
+#ifdef T2_NOFOLD
+  // Un-folded layout: accumulators [main0 | main1 | corr] = 3 BN TMEM columns leave room for more A slots.  The engine is
+  // bounded by the A-slot round trip (split -> tcgen05.st -> MMA -> commit -> slot free), not by MMA time
+  // (profiles/r1d_tc2_skeleton.md), so depth beats the saved MMA.
+  static constexpr int STAGES = BN <= 32 ? 7 : (BN <= 64 ? 6 : 4);
+#else
   static constexpr int STAGES = BN <= 32 ? 6 : (BN <= 64 ? 5 : 4);
+#endif
   // BN <= 64: hi*hi and hi*lo are ONE MMA of N' = 2 BN (B hi | B lo tiles are adjacent in shared memory) writing the
   // adjacent accumulators [main | corrB] of the current chunk buffer; lo*hi goes to corrA.  2 MMAs per k step instead
   // of 3 (every tf32 MMA with N <= 64 occupies the tensor pipe for ~45 cycles regardless of N, scratch/mma_bench.cu).
+#ifdef T2_NOFOLD
+  static constexpr bool FOLD = false;
+  static constexpr int SA = BN <= 32 ? 6 : (BN <= 64 ? 5 : 2);   // TMEM A slots (64 columns each: hi | lo)
+#else
   static constexpr bool FOLD = BN <= 64;
   static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
+#endif
   static constexpr int NEPI = BN <= 32 ? 4 : 8;                  // 32 accumulator columns per epilogue thread (64 for BN = 128)
   static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
   static constexpr int EPI0 = 4 + 4 * NSG;                       // first epilogue warp
@@ -92,7 +106,7 @@ struct T2Cfg {
   static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN,
                        TM_A = FOLD ? 5 * BN : 3 * BN;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
+  static constexpr int NBARS = 2 * STAGES + SA + 6;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES + 256;      // epilogue staging: one swizzled 32 x 32 fp32 panel per warp
   static constexpr int SMEM = 1024 + STG_OFF + NEPI * 4096;
   static_assert(NBARS * 8 + 16 <= 256, "barrier block");
@@ -115,8 +129,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint64_t* bar_full = bars;                  // [S]  TMA landed
   uint64_t* bar_empty = bars + S;             // [S]  MMAs that read the stage retired
   uint64_t* bar_aready = bars + 2 * S;        // [SA] TMEM A slot written
-  uint64_t* bar_afree = bars + 2 * S + SA;    // [SA] MMAs that read the slot retired
-  uint64_t* bar_mfull = bars + 2 * S + 2 * SA;      // [2] main accumulator chunk complete
+  uint64_t* bar_mfull = bars + 2 * S + SA;          // [2] main accumulator chunk complete
   uint64_t* bar_mfree = bar_mfull + 2;              // [2] drained
   uint64_t* bar_cfull = bar_mfull + 4;              // correction accumulator complete (tile end)
   uint64_t* bar_cfree = bar_mfull + 5;              // read by the epilogue
@@ -134,7 +147,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     // stages and A slots are released by BOTH MMA issuers' commits
     for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
-    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 2); }
+    for (int a = 0; a < SA; ++a) mbar_init(smem_u32(bar_aready + a), 4);
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
     mbar_init(smem_u32(bar_cfree), Cfg::NEPI);
@@ -205,14 +218,16 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                          bl_dst = bh_dst + Cfg::B_BYTES;
           const int k = (kb0 + i) * T2_BK;
           if (MODE == 0) {
+            const uint32_t bbytes = (T2_EXP & 512) ? 0u : 2u * Cfg::B_BYTES;
             if (!tapA) {
-              mbar_expect_tx(full, Cfg::A_BYTES + 2 * Cfg::B_BYTES);
-              tma_load_2d(&tmA, full, a_dst, k, m0);
+              mbar_expect_tx(full, ((T2_EXP & 1024) ? 0 : Cfg::A_BYTES) + bbytes);
+              if (!(T2_EXP & 1024)) tma_load_2d(&tmA, full, a_dst, k, m0);
             } else {
-              mbar_expect_tx(full, (ph2 ? tp.rows2 : tp.rows) * 128 + 2 * Cfg::B_BYTES);
-              tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
+              mbar_expect_tx(full, ((T2_EXP & 1024) ? 0 : (ph2 ? tp.rows2 : tp.rows) * 128) + bbytes);
+              if (!(T2_EXP & 1024)) tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
             }
-            if (!B_MN) {
+            if (T2_EXP & 512) {
+            } else if (!B_MN) {
               tma_load_2d(&tmBhi, full, bh_dst, k, n0);
               tma_load_2d(&tmBlo, full, bl_dst, k, n0);
             } else {
@@ -251,10 +266,10 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // warp 3: whole tile      corr  += A_lo . B_hi           [!FOLD: ... + A_hi . B_lo]
     // The two streams write disjoint accumulators, so they need no ordering between them.
     const bool chunk_role = warp == 1;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(T2_BM >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)((2 * BN) >> 3) << 17) |
-                            ((uint32_t)(T2_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(((T2_EXP & 128) ? 16 : BN) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                            ((uint32_t)(((T2_EXP & 128) ? 16 : 2 * BN) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
     constexpr uint32_t kstep = B_MN ? (1024 >> 4) : (32 >> 4);      // start-address field increment per k step
@@ -280,6 +295,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
               if (k4 >= ksteps) break;
+              if (!(T2_EXP & 64))
               umma_tf32_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * kstep, Cfg::FOLD ? idesc2 : idesc,
                            (!first_in_chunk || k4 != 0) ? 1u : 0u);
             }
@@ -290,6 +306,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
               if (k4 >= ksteps) break;
+              if (T2_EXP & (64 | 256)) continue;
               umma_tf32_ts(t_corr, a_lo + k4 * 8, dbh0 + k4 * kstep, idesc, (i | k4) != 0 ? 1u : 0u);
               if (!Cfg::FOLD) umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * kstep, idesc, 1u);
             }
@@ -618,6 +635,11 @@ static int launch2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tbh, con
 }
 
 static inline int pick_bn(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+// persistent grid of the forward / data-gradient launches (DDRL_TC2_GRID: experiments on L2 vs per-SM ingress limits)
+static inline int persistent_ctas() {
+  static const int n = [] { const char* e = getenv("DDRL_TC2_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v < kNumSMs ? v : kNumSMs; }();
+  return n;
+}
 // Implicit convolutions with a short K loop are bounded by the epilogue (one 64-column pass per warp and tile), not by
 // the MMA stream: DDRL_TC2_CONV_MAXBN=64 runs their N = 128 layers as two 64-wide tiles (twice the epilogue warps per
 // output column, FOLD MMAs) at the price of splitting the activation tile twice.
@@ -659,7 +681,7 @@ int tc2_gemm(int form, int M, int N, int K, const float* A, int lda, const float
   g.kb_total = ceil_div(K, T2_BK); g.kb_per_split = g.kb_total;
   g.m_tiles = ceil_div(M, T2_BM); g.n_tiles = ceil_div(N, bn);
   g.vec_store = (ldc % 4 == 0 && al16(C) && (!mask || al16(mask))) ? 1 : 0;
-  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, persistent_ctas()), 1, 1);
   return form == 0 ? launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s) : launch2_bn<0, true>(bn, ta, tbh, tbl, g, grid, s);
 }
 
@@ -700,7 +722,7 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi + (ph2 ? ceil_div(o.Bn, g.tap.nb2) : 0);
   g.n_tiles = ceil_div(N, bn);
   g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && al16(out) && (!mask || al16(mask))) ? 1 : 0;
-  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, persistent_ctas()), 1, 1);
   return launch2_bn<0, false>(bn, ta, tbh, tbl, g, grid, s, ph2 ? &ta2 : nullptr);
 }
 
