@@ -409,60 +409,6 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const int mt = MODE == 0 ? tile / g.n_tiles : (int)blockIdx.x;
       const int nt = MODE == 0 ? tile - mt * g.n_tiles : (int)blockIdx.y;
       const int m0 = mt * T2_BM, n0 = nt * BN;
-      const int r = q * 32 + lane;
-      bool rvalid;
-      long long roff;
-      if (MODE == 0 && tapA) {
-        const bool ph2 = mt >= tp.tiles1;
-        const int b0 = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb, y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
-        const int nyp = ph2 ? tp.ny2 : tp.ny;
-        const int x = r % tp.Xn, t2 = r / tp.Xn;
-        const int yy = t2 % nyp, bb = t2 / nyp;
-        rvalid = r < (ph2 ? tp.rows2 : tp.rows) && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
-        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
-      } else {
-        rvalid = (m0 + r) < g.M;
-        roff = (long long)(m0 + r) * g.sCm;
-      }
-      const float neg_slope = g.act == 3 ? 0.f : 0.01f;
-      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
-      const bool fused = MODE == 0 && tapA && tp.ncls > 1;
-      int py = 0, px = 0;
-      if (fused) {
-        const bool ph2 = mt >= tp.tiles1;
-        const int y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
-        px = (r % tp.Xn) * tp.out_s;
-        py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
-      }
-      // activation-derivative mask (= the layer's input, HBM-resident): start pulling this tile's lines into L2 now, so the
-      // loads in the store pass (one DRAM latency per 32-column panel, on the tile's critical path) become L2 hits
-      if (MODE == 0 && g.vec_store && g.act >= 3) {
-        const int cidx_p = lane & 7, rsub_p = lane >> 3;
-        const int pyx_p = (py << 16) | px;
-#pragma unroll
-        for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
-          const int colv = n0 + col0 + p0 + cidx_p * 4;
-          const bool cok = colv < g.N;
-          long long cadd = 0;
-          int ciy = 0, cix = 0;
-          if (fused && cok) {
-            const int qq = colv / tp.cls_cols;
-            ciy = tp.cls_iy[qq]; cix = tp.cls_ix[qq];
-            cadd = tp.cls_off[qq] - (long long)qq * tp.cls_cols;
-          }
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int rr = i8 * 4 + rsub_p;
-            const int ok = __shfl_sync(0xffffffffu, (int)rvalid, rr);
-            const long long ro = __shfl_sync(0xffffffffu, roff, rr);
-            const int ryx = __shfl_sync(0xffffffffu, pyx_p, rr);
-            bool live = ok && cok;
-            if (fused && ((ryx >> 16) + ciy >= tp.out_H || (ryx & 0xffff) + cix >= tp.out_W)) live = false;
-            if (live && (cidx_p & 7) == 0)       // one lane per 128-byte row segment
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(g.mask + ro + cadd + colv));
-          }
-        }
-      }
       float acc[Cfg::COLS];
 #pragma unroll
       for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
@@ -504,6 +450,31 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #ifdef TC2_TIMING
       const long long st0 = clock64();
 #endif
+      const int r = q * 32 + lane;
+      bool rvalid;
+      long long roff;
+      if (MODE == 0 && tapA) {
+        const bool ph2 = mt >= tp.tiles1;
+        const int b0 = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb, y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        const int nyp = ph2 ? tp.ny2 : tp.ny;
+        const int x = r % tp.Xn, t2 = r / tp.Xn;
+        const int yy = t2 % nyp, bb = t2 / nyp;
+        rvalid = r < (ph2 ? tp.rows2 : tp.rows) && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
+        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
+      } else {
+        rvalid = (m0 + r) < g.M;
+        roff = (long long)(m0 + r) * g.sCm;
+      }
+      const float neg_slope = g.act == 3 ? 0.f : 0.01f;
+      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
+      const bool fused = MODE == 0 && tapA && tp.ncls > 1;
+      int py = 0, px = 0;
+      if (fused) {
+        const bool ph2 = mt >= tp.tiles1;
+        const int y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        px = (r % tp.Xn) * tp.out_s;
+        py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
+      }
       if (T2_EXP & 4) {
         if (acc[0] == 123.456f) g.C[0] = acc[1];
       } else if (MODE == 0 && g.vec_store) {
