@@ -168,6 +168,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
