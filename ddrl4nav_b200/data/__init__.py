@@ -1,3 +1,4 @@
+from .easybytes import DeviceEasyBytes
 from .experience import Experience
 
-__all__ = ["Experience"]
+__all__ = ["Experience", "DeviceEasyBytes"]

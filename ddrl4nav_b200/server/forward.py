@@ -66,6 +66,18 @@ class ForwardModule:
         actions, logps, values = self.net.act(states, draw=draw, play_mode=self.play_mode)
         return self._finish(actions, logps, values)
 
+    def step_bytes(self, byte_states, draw: Optional[torch.Tensor] = None):
+        """One tick straight from the Redis payload (server/forward.py:117-146): the wire bytes cross PCIe once in their wire
+        dtypes and are sliced / concatenated / converted to fp32 by ONE kernel (data/easybytes.py), then the fused engine
+        call.  Returns (process_env_ids, [actions, logps, values]) -- the two things ``ForwardThread.run`` needs for
+        ``encode_forward_return_data`` and the reply keys."""
+        if getattr(self, "_eb", None) is None:
+            from ..data.easybytes import DeviceEasyBytes
+            self._eb = DeviceEasyBytes(self.device)
+        ids, states = self._eb.decode_forward_states(byte_states)
+        actions, logps, values = self.net.act(states, draw=draw, play_mode=self.play_mode)
+        return ids, self._finish(actions, logps, values)
+
     def _step_streamed(self, arrs, B, row_bytes, draw):
         from concurrent.futures import ThreadPoolExecutor
         rows = max(256, (self.chunk_bytes // max(row_bytes, 1)) // 128 * 128)

@@ -108,6 +108,17 @@ int ddrl_gae_tempo(const float* values, const float* rewards, const uint8_t* don
                    const double* table_host, int table_len, double lambda, int T, int V, int N,
                    void* ret, void* adv, int out_f64, void* stream);
 
+/* ---- EasyBytes payload decode ----------------------------------------
+ * replaces the decode half of EasyBytes.decode_forward_states / decode_data (USTC_lab/data/easybytes.py:47-61,114-139)
+ * plus the fp32 conversion of the Forward thread (server/forward.py:128-131): slice + concatenate + dtype conversion of
+ * the raw Redis payload in one kernel.  payload: the wire bytes on the DEVICE; segs: nseg DEVICE records
+ * { uint64 src_off (bytes into payload); uint64 dst_off (floats into dst); uint32 count; uint32 dtype } with dtype the
+ * wire code 1 = u8, 2 = f16, 3 = f32, 4 = f64 (easybytes.py:21-26); max_count = largest count (sizes the grid).
+ * The host parses only the headers (ddrl4nav_b200/data/easybytes.py).  Conversions are exact / round-to-nearest-even,
+ * i.e. bit-identical to numpy's astype(float32). */
+int ddrl_easybytes_decode(const uint8_t* payload, const void* segs, int nseg, unsigned int max_count, float* dst,
+                          void* stream);
+
 /* ---- K4: action sampling --------------------------------------------------------------
  * replaces random_choice_prob_index / select_action (USTC_lab/server/utils.py:20-47) and the
  * sample/log_prob lines of ForwardThread.run (server/forward.py:137-146).

@@ -491,3 +491,58 @@ def synth_learn_batch(spec: NetSpec, params: Dict[str, Tensor], states: Sequence
     adv = torch.randn(B, generator=g)
     ret = torch.randn(B, generator=g)
     return a, old, adv, ret
+
+
+# =========================================================================================
+# EasyBytes wire format -- USTC_lab/data/easybytes.py
+# =========================================================================================
+EASYBYTES_TYPES = {1: (1, np.uint8), 2: (2, np.float16), 3: (4, np.float32), 4: (8, np.float64)}   # easybytes.py:21-26
+
+
+def easybytes_decode_data(buf: bytes) -> List[np.ndarray]:
+    """easybytes.py:47-61: repeated blocks [type >h][count >I][ndim >I][shape >I x ndim][count*size raw bytes]."""
+    import struct
+    out, i = [], 0
+    while i < len(buf):
+        code = struct.unpack(">h", buf[i:i + 2])[0]
+        size, dt = EASYBYTES_TYPES[code]
+        count, ndim = struct.unpack(">II", buf[i + 2:i + 10])
+        shape = struct.unpack(">" + "I" * ndim, buf[i + 10:i + 10 + 4 * ndim])
+        i += 10 + 4 * ndim
+        out.append(np.frombuffer(buf[i:i + count * size], dtype=dt).reshape(*shape))
+        i += count * size
+    return out
+
+
+def easybytes_decode_forward_states(buf: bytes) -> Tuple[List[str], List[np.ndarray]]:
+    """easybytes.py:114-139: messages [length >Q][ip 4 x >H][process_env_id >I][decode_data payload of `length` bytes];
+    state slot i of the batch = concatenation over messages (axis 0) of their i-th array."""
+    import struct
+    ids, per_msg, i = [], [], 0
+    while i < len(buf):
+        length = struct.unpack(">Q", buf[i:i + 8])[0]
+        ip = struct.unpack(">HHHH", buf[i + 8:i + 16])
+        env_id = struct.unpack(">I", buf[i + 16:i + 20])[0]
+        per_msg.append(easybytes_decode_data(buf[i + 20:i + 20 + length]))
+        ids.append(".".join(str(x) for x in ip) + "_" + str(env_id))
+        i += 20 + length
+    slots = [np.concatenate([m[k] for m in per_msg], axis=0) for k in range(len(per_msg[0]))]
+    return ids, slots
+
+
+def easybytes_forward_states_fp32(buf: bytes) -> Tuple[List[str], List[np.ndarray]]:
+    """decode_forward_states followed by the fp32 conversion of the Forward thread (server/forward.py:128-131,
+    torch.tensor(state, dtype=float32)): what the device decoder must reproduce bit for bit."""
+    ids, slots = easybytes_decode_forward_states(buf)
+    return ids, [s.astype(np.float32) for s in slots]
+
+
+def easybytes_decode_backward_data(buf: bytes):
+    """easybytes.py:163-171: [len >Q][states blocks][len >Q][advs, actions, old_logps, values blocks][marshal dict]."""
+    import marshal
+    import struct
+    n0 = struct.unpack(">Q", buf[:8])[0]
+    states = easybytes_decode_data(buf[8:8 + n0])
+    n1 = struct.unpack(">Q", buf[8 + n0:16 + n0])[0]
+    other = easybytes_decode_data(buf[16 + n0:16 + n0 + n1])
+    return states, other, marshal.loads(buf[16 + n0 + n1:])

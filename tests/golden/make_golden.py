@@ -202,12 +202,49 @@ def golden_net(kind: str, B: int, iters: int = 4):
     np.savez_compressed(os.path.join(HERE, "net_%s.npz" % kind), **out)
 
 
+def golden_easybytes():
+    """Wire bytes produced by the reference's own encoder + what its decoder returns for them."""
+    ref_shim.import_reference()
+    from USTC_lab.data.easybytes import EasyBytes
+    eb = EasyBytes("10.0.3.17")
+    rng = np.random.default_rng(7)
+    out = {}
+    # forward states: 3 env processes with 2 / 1 / 3 envs; slots = u8 frames, f64 vector, f16 map, f32 scan
+    msgs = b""
+    for pid, n in [(0, 2), (5, 1), (131, 3)]:
+        frames = rng.integers(0, 256, size=(n, 2, 5, 7), dtype=np.uint8)
+        vec = rng.standard_normal((n, 5))                                   # float64, like Pong observations
+        half = (rng.random((n, 1, 6, 6)) * 255).astype(np.float16)
+        scan = rng.random((n, 1, 33)).astype(np.float32)
+        msgs += eb.encode_forward_states(pid, [frames, vec, half, scan])
+    ids, slots = eb.decode_forward_states(msgs)
+    out["fwd_bytes"] = np.frombuffer(msgs, dtype=np.uint8).copy()
+    out["fwd_ids"] = np.array(ids)
+    for i, s in enumerate(slots):
+        out["fwd_slot_%d" % i] = s
+        out["fwd_slot_%d_f32" % i] = torch.tensor(s, dtype=torch.float32).numpy()     # server/forward.py:128-131
+    # backward data: [[states...], advs, actions, old_logps, values] + logger dict
+    B = 6
+    data = [[rng.integers(0, 256, size=(B, 3, 4), dtype=np.uint8), rng.standard_normal((B, 4)).astype(np.float32)],
+            rng.standard_normal(B).astype(np.float32), rng.integers(0, 6, size=B).astype(np.float32),
+            rng.standard_normal(B).astype(np.float32), rng.standard_normal((1, B)).astype(np.float32)]
+    bb = eb.encode_backward_data(data, {"mean_reward": 1.5, "n": 3})
+    st, other, logd = eb.decode_backward_data(bb)
+    out["bwd_bytes"] = np.frombuffer(bb, dtype=np.uint8).copy()
+    for i, s in enumerate(st):
+        out["bwd_state_%d" % i] = s
+    for i, s in enumerate(other):
+        out["bwd_other_%d" % i] = s
+    out["bwd_logger_keys"] = np.array(sorted(logd))
+    np.savez_compressed(os.path.join(HERE, "easybytes.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `make_golden.py navped` regenerates one fixture
     todo = [("gae", golden_gae), ("gae_tempo", golden_gae_tempo), ("sampling", golden_sampling), ("pong", lambda: golden_net("pong", 8)),
             ("navimg", lambda: golden_net("navimg", 6)), ("navlaser", lambda: golden_net("navlaser", 4)),
-            ("navped", lambda: golden_net("navped", 5))]
+            ("navped", lambda: golden_net("navped", 5)), ("easybytes", golden_easybytes)]
     for name, fn in todo:
         if not only or name in only:
             fn()
