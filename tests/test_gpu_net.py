@@ -270,6 +270,35 @@ def test_shard_sum_equals_full_batch():
     assert torch.allclose(half[net._P:net._P + 3], full[net._P:net._P + 3], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("kind,B", [("pong", 8192), ("navimg", 2048), ("navlaser", 1024)])
+def test_full_size_row_independence_and_shard_linearity(kind, B):
+    """BASELINE rows per GPU (too large for the CPU oracle): size-independent properties instead.
+    (1) Samples are independent: permuting the rows permutes values / greedy actions BIT-exactly, although every row
+        then sits in a different tile, image group and tiling phase of the implicit-GEMM convolutions.
+    (2) The data-parallel arithmetic: two ragged shards scaled by 1/B_global sum to the full-batch gradient."""
+    net, _, _ = make(kind)
+    ds = [s.to(DEV) for s in R.synth_states(kind, B, seed=21)]
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    perm = torch.randperm(B, device=DEV, generator=gen)
+    a1, _, v1 = net.act(ds, play_mode=True)
+    a2, _, v2 = net.act([s[perm].contiguous() for s in ds], play_mode=True)
+    assert torch.equal(v2.reshape(-1), v1.reshape(-1)[perm])
+    assert torch.equal(a2, a1[perm])
+    acts, logp, _ = net.act(ds)
+    old = logp + 0.15 * torch.randn(B, device=DEV, generator=gen)
+    adv = torch.randn(B, device=DEV, generator=gen)
+    ret = torch.randn(B, device=DEV, generator=gen)
+    net.backward_only(ds, adv, acts, old, ret)
+    full = net._grads.clone()
+    k = B // 3 + 1                                                    # ragged split: neither shard is a multiple of a tile
+    parts = None
+    for sl in (slice(0, k), slice(k, B)):
+        net.backward_only([s[sl].contiguous() for s in ds], adv[sl], acts[sl].contiguous(), old[sl], ret[sl], b_global=B)
+        parts = net._grads.clone() if parts is None else parts + net._grads
+    assert rel_err(parts[:net._P], full[:net._P]) < 1e-5
+    assert torch.allclose(parts[net._P:net._P + 3], full[net._P:net._P + 3], rtol=1e-4, atol=1e-6)
+
+
 def test_state_dict_and_model_blob_roundtrip():
     net, spec, params = make("navlaser")
     net._ensure_engine()
