@@ -280,9 +280,13 @@ def run_ours(args):
     Bf = args.fwd_batch or wl["fwd_batch"]
     fstates_h, _, _ = synth_batch_host(args.workload, Bf, seed=200 + rank)
     fstates_d = [s.to(dev) for s in fstates_h]
-    sec_f = timed(lambda: net.act(fstates_d), 5, 3, dist)
+    # the Forward module is its own process with its own net object in the reference (predictor vs trainer managers): an
+    # inference-only engine instance (no training workspace) with the learner's current weights
+    fnet = make_net(args.workload, device=dev, gemm_mode=args.gemm_mode)
+    fnet.load_state_dict(net.state_dict())
+    sec_f = timed(lambda: fnet.act(fstates_d), 5, 3, dist)
     fwd_value = world * Bf * 5 / sec_f
-    fm = ForwardModule(net, device=dev)
+    fm = ForwardModule(fnet, device=dev)
     f_np = [s.numpy() for s in fstates_h]
     sec_fe = timed(lambda: fm.step(f_np), 3, 2, dist)
     fwd_e2e = world * Bf * 3 / sec_fe
@@ -300,7 +304,7 @@ def run_ours(args):
     # ---- the other named single-GPU configurations (BASELINE configs[1] / [4]), short runs, N=1 only
     others = {}
     if world == 1 and not args.no_others:
-        del net, exp_dev, states_d, fstates_d, bm, fm
+        del net, fnet, exp_dev, states_d, fstates_d, bm, fm
         torch.cuda.empty_cache()
         for other in [w for w in ("navlaser", "navimg", "pong") if w != args.workload]:
             others[other] = quick_workload(other, args.gemm_mode, dev, dist)
@@ -366,7 +370,11 @@ def quick_workload(kind, gemm_mode, dev, dist):
             pass
     sec = timed(step, 2, 3, dist)
     fstates_d = [s.to(dev) for s in synth_batch_host(kind, Bf, seed=200)[0]]
-    sec_f = timed(lambda: net.act(fstates_d), 5, 3, dist)
+    fnet = make_net(kind, device=dev, gemm_mode=gemm_mode)          # inference-only engine instance (predictor process)
+    fnet.load_state_dict(net.state_dict())
+    del net, exp
+    torch.cuda.empty_cache()
+    sec_f = timed(lambda: fnet.act(fstates_d), 5, 3, dist)
     return {"workload": wl["desc"], "rows_per_gpu": B, "value": round(B * ITERS * 2 / sec, 1), "unit": "learner sample-iterations/s",
             "ms_per_step": round(sec / 2 * 1e3, 3), "learner_tflops": round(B * ITERS * 2 / sec * wl["flops_learn"] / 1e12, 2),
             "forward_actions_per_s": round(Bf * 5 / sec_f, 1), "forward_rows": Bf}

@@ -418,6 +418,37 @@ __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, f
     __syncthreads();
   }
 }
+// C == 4, W % 4 == 0 (NatureCNN frames): 128-bit loads and stores, BANDS bands in flight per block iteration.  One output
+// float4 = the 4 channels of one (i, j) position.
+template <int BANDS>
+__global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int s,
+                                                     long long sb, long long bands) {
+  extern __shared__ float4 band4[];                     // [BANDS][4*s][W/4]
+  float* band = reinterpret_cast<float*>(band4);
+  const int H2 = H / s, W2 = W / s, W4 = W / 4, rows = 4 * s, C2 = s * s * 4;
+  const int n_in4 = rows * W4, n_out4 = W2 * s * s;
+  for (long long bd0 = (long long)blockIdx.x * BANDS; bd0 < bands; bd0 += (long long)gridDim.x * BANDS) {
+    const int nb = (int)min((long long)BANDS, bands - bd0);
+    for (int e = threadIdx.x; e < nb * n_in4; e += blockDim.x) {
+      const int k = e / n_in4, r4 = e - k * n_in4;
+      const int ci = r4 / W4, w4 = r4 - ci * W4;        // ci = c*s + i
+      const int c = ci / s, i = ci - c * s;
+      const long long bd = bd0 + k, b = bd / H2;
+      const int Y = (int)(bd - b * H2);
+      band4[e] = __ldg(reinterpret_cast<const float4*>(x + b * sb + (long long)c * H * W + (long long)(Y * s + i) * W) + w4);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * n_out4; e += blockDim.x) {
+      const int k = e / n_out4, r4 = e - k * n_out4;
+      const int X = r4 / (s * s), ij = r4 - X * (s * s);
+      const int i = ij / s, j = ij - i * s;
+      const float* bp = band + (size_t)k * rows * W + i * W + X * s + j;
+      const float4 v = make_float4(bp[0], bp[(size_t)s * W], bp[(size_t)2 * s * W], bp[(size_t)3 * s * W]);
+      reinterpret_cast<float4*>(out + (bd0 + k) * (long long)W2 * C2)[r4] = v;
+    }
+    __syncthreads();
+  }
+}
 // packed[o*ld + ((a*KW2 + b)*s*s + i*s + j)*C + c] = w[o, c, s*a + i, s*b + j]      (w: reference OIHW)
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ w, float* __restrict__ dst, int O, int C, int KH,
                                                        int KW, int s, int ld, int unpack) {
@@ -701,6 +732,14 @@ int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStr
   const size_t smem = sizeof(float) * (size_t)g.C * g.stride * g.W;
   if (smem > 48 * 1024) return DDRL_E_UNSUPPORTED;
   prof_work(8.0 * (double)B * g.C * g.H * g.W);
+  if (g.C == 4 && g.W % 4 == 0 && g.sb % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+      4 * smem <= 48 * 1024) {
+    constexpr int BANDS = 4;
+    const long long groups = (bands + BANDS - 1) / BANDS;
+    s2d_c4_kernel<BANDS><<<(int)std::min<long long>(groups, 8LL * kNumSMs), 256, BANDS * smem, s>>>(x, out, g.H, g.W, g.stride, g.sb, bands);
+    DDRL_LAUNCHED("s2d_kernel");
+    return DDRL_OK;
+  }
   s2d_kernel<<<(int)std::min<long long>(bands, 16LL * kNumSMs), 256, smem, s>>>(x, out, g.C, g.H, g.W, g.stride, g.sb, bands);
   DDRL_LAUNCHED("s2d_kernel");
   return DDRL_OK;

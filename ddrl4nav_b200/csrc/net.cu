@@ -43,6 +43,7 @@ struct Lin {
   float *wp_hi = nullptr, *wp_lo = nullptr;   // its tf32 hi / lo split (tc2 engine), refreshed with wp
   float* dwp = nullptr;          // packed weight gradient   (when packed and training)
   int s2d_s = 0, s2d_C = 0, s2d_KH = 0, s2d_KW = 0;   // space-to-depth first layer: packing follows pack_weight_s2d
+  bool s2d_fwd_only = false;     // ... for the forward weights only: the weight gradient runs on the im2col matrix (k = c,kh,kw)
 };
 
 struct Arena {
@@ -72,6 +73,7 @@ struct Tower {
   // im2col / a1 / da1 buffers (tower 0), 2 borrower.  conv slot 1 then reads channels [in1_coff, +C) of a in1_ctot-wide tensor.
   int fuse_role = 0, in1_ctot = 0, in1_coff = 0;
   bool s2d0 = false;                                        // conv slot 0 runs on the space-to-depth observation
+  bool s2d_infer = false;                                   // fused first conv: inference runs on the s2d observation
   ConvGeom gs = {};                                         // its stride-1 NHWC geometry (buf[0] holds the s2d tensor)
   // per-micro-batch buffers
   std::vector<float*> buf;
@@ -104,6 +106,13 @@ struct ddrl_net {
   int64_t seg_begin[3];
   int nseg = 1;
   bool fuse0 = false;            // both towers' first conv as ONE GEMM over the shared im2col matrix (N = 2 x Cout)
+  // ... and, in the Forward module (no training workspace), as an implicit stride-1 conv over the space-to-depth
+  // observation: no im2col matrix at all (3.4 GB per 8192 rows, 1.9 ms to build).  Measured (profiles/r1f_*): Forward
+  // 2.16 -> 2.38 M actions/s; in the learner the im2col matrix is cached across the 10 iterations and needed by the weight
+  // gradient anyway, and the im2col GEMM (842 us) beats the implicit kernel (944 us), so training keeps it.
+  bool fuse_s2d = false;
+  float* s2dbuf = nullptr;       // [MB, H/s, W/s, s*s*C] space-to-depth observation of the micro-batch
+  float* w0s2d = nullptr;        // [2 x Cout, K] both towers' conv1 weights in the space-to-depth K order (packed arena)
   float* bias0c = nullptr;       // its concatenated bias [2 x Cout]
   // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
   const float* cols_obs0 = nullptr;
@@ -363,7 +372,8 @@ static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std:
     case DDRL_ARCH_ATARI: {
       // 0 cols1, 1 a1, 2 cols2, 3 a2, 4 cols3, 5 a3 | train: 6 da3, 7 dcols, 8 da2, 9 da1
       // fused first conv: tower 0 owns cols1 and the 2x-wide a1 / da1, tower 1 borrows them
-      const size_t k0 = t.fuse_role == 2 ? 0 : 1, k1 = t.fuse_role == 2 ? 0 : (t.fuse_role == 1 ? 2 : 1);
+      const size_t k0 = (t.fuse_role == 2 || (t.fuse_role == 1 && t.s2d_infer && !train)) ? 0 : 1,
+                   k1 = t.fuse_role == 2 ? 0 : (t.fuse_role == 1 ? 2 : 1);
       f = {k0 * cols(t.g[0]), k1 * outp(t.g[0], 32), cols(t.g[1]), outp(t.g[1], 64), cols(t.g[2]), outp(t.g[2], 64)};
       if (train) { f.push_back(outp(t.g[2], 64)); f.push_back(std::max(cols(t.g[1]), cols(t.g[2])));
                    f.push_back(outp(t.g[1], 64)); f.push_back(k1 * outp(t.g[0], 32)); }
@@ -417,6 +427,8 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   size_t per = 0;
   for (auto& t : n->towers) per += tower_bytes_per_sample(t, train);
   per += (size_t)(n->ldA * 2 + 2 + 8) * 4;
+  const size_t s2d_floats = (n->fuse_s2d && !train) ? (size_t)n->towers[0].g[0].C * n->towers[0].g[0].H * n->towers[0].g[0].W : 0;
+  per += s2d_floats * 4;
   const char* env_gb = getenv("DDRL_WS_GB");
   const char* env_mb = getenv("DDRL_MICRO_BATCH");
   const double budget = (env_gb ? atof(env_gb) : 24.0) * (double)(1ull << 30);
@@ -439,6 +451,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     total += 2 * (((size_t)t.feat * mb * 4 + 255) & ~size_t(255));
   }
   total += 4 * (((size_t)n->ldA * mb * 4 + 255) & ~size_t(255)) + 4096;
+  total += (s2d_floats * mb * 4 + 255) & ~size_t(255);
   if (cudaMalloc(&n->ws.base, total) != cudaSuccess) {
     cudaGetLastError();
     n->ws.base = nullptr; n->MB = 0;
@@ -455,6 +468,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     t.h = n->ws.take((size_t)t.feat * mb);
     t.dh = train ? n->ws.take((size_t)t.feat * mb) : nullptr;
   }
+  n->s2dbuf = s2d_floats ? n->ws.take(s2d_floats * mb) : nullptr;
   if (n->fuse0) {
     Tower &t0 = n->towers[0], &t1 = n->towers[1];
     t1.buf[0] = t0.buf[0]; t1.buf[1] = t0.buf[1];
@@ -486,6 +500,8 @@ static int alloc_packed(ddrl_net* n) {
     if (((size_t)n->towers[0].L[0].N * n->towers[0].L[0].ldw * 4) % 256 != 0) return DDRL_E_STATE;   // rows must abut
     DDRL_CUDA(cudaMalloc(&n->bias0c, sizeof(float) * 2 * n->towers[0].L[0].N));
   }
+  const size_t w0s2d_off = bytes;                         // behind the layers' forward weights, inside the mirrored region
+  if (n->fuse_s2d) bytes += ((size_t)2 * n->towers[0].L[0].N * n->towers[0].L[0].ldw * 4 + 255) & ~size_t(255);
   n->packed_grad_off = bytes;
   n->packed_grad_bytes = bytes;
   // data-gradient weights of the implicit convs (one re-packed copy per parity class), after the two twin regions
@@ -526,6 +542,7 @@ static int alloc_packed(ddrl_net* n) {
           off += ((size_t)f.N * f.K * 4 + 255) & ~size_t(255);
         }
   }
+  if (n->fuse_s2d) n->w0s2d = reinterpret_cast<float*>(n->packed_base + w0s2d_off);
   size_t off = 0;
   for (Lin* lp : packed_order(n)) {
     Lin& l = *lp;
@@ -559,6 +576,13 @@ static int repack(ddrl_net* n, cudaStream_t s) {
         const Lin& l = t.L[t.conv_lin[i]];
         TRY(pack_dgrad_fused(n->params + n->T[l.w_t].offset, t.g[i], l.N, t.df[i], s));
       }
+  if (n->fuse_s2d) {
+    const ConvGeom& g = n->towers[0].g[0];
+    for (int k = 0; k < 2; ++k) {
+      const Lin& l = n->towers[k].L[0];
+      TRY(pack_weight_s2d(n->params + n->T[l.w_t].offset, n->w0s2d + (size_t)k * l.N * l.ldw, l.N, g.C, g.KH, g.KW, g.stride, l.ldw, s));
+    }
+  }
   if (n->fuse0) {
     const Lin &l0 = n->towers[0].L[0], &l1 = n->towers[1].L[0];
     DDRL_CUDA(cudaMemcpyAsync(n->bias0c, b_of(n, l0), sizeof(float) * l0.N, cudaMemcpyDeviceToDevice, s));
@@ -756,10 +780,19 @@ static int check_obs(const ddrl_net* n, const float* const* obs, int n_obs) {
 
 // First conv of both unshared towers in one pass over the shared im2col matrix: a1c[M, 2 Cout] = act(cols W01^T + b01)
 // (rows 0..Cout-1 of W01 = actor tower, the rest = critic tower; each tower's conv2 reads its channel half).
-static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0, int mb, cudaStream_t s, bool cols_cached) {
+static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s,
+                           bool cols_cached) {
   Tower& t0 = n->towers[0];
   const ConvGeom& g = t0.g[0];
   const Lin& l = t0.L[0];
+  if (n->fuse_s2d && !train && !n->ws_train) {
+    TRY(space_to_depth(g, obs[0] + row0 * g.sb, n->s2dbuf, mb, s));
+    const ConvGeom& gs = t0.gs;
+    const ConvOp o = conv_op_fwd(gs, n->s2dbuf, gs.C, 0, mb);
+    const int N2 = 2 * l.N;
+    return tc2_conv_fwd(o, hi_of(n, n->w0s2d), lo_of(n, n->w0s2d), l.ldw, N2, n->bias0c, l.act, nullptr, t0.buf[1], (long long)o.Yn * o.Xn * N2,
+                        (long long)o.Xn * N2, N2, s);
+  }
   if (!cols_cached) TRY(im2col(g, obs[0] + row0 * g.sb, t0.buf[0], mb, s));
   return gemm(n, 0, (int)((long long)mb * g.Ho * g.Wo), 2 * l.N, l.K, t0.buf[0], g.ldc, l.wp, l.ldw, t0.buf[1], 2 * l.N, n->bias0c,
               l.act, 0, 0, s);
@@ -779,7 +812,7 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
 // encoders + heads for rows [row0, row0+mb): fills n->logits [mb, ldA], n->vout [mb]
 static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, int mb, bool train, cudaStream_t s,
                          bool reuse_obs = false) {
-  if (n->fuse0) TRY(fused_conv0_fwd(n, obs, row0, mb, s, reuse_obs));
+  if (n->fuse0) TRY(fused_conv0_fwd(n, obs, row0, mb, train, s, reuse_obs));
   for (auto& t : n->towers) TRY(tower_forward(n, t, obs, row0, mb, train, s, reuse_obs));
   Tower& ta = n->towers[0];
   Tower& tc = n->towers[n->d.shared ? 0 : 1];
@@ -841,6 +874,19 @@ extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
       t0.fuse_role = 1; t1.fuse_role = 2;
       t0.in1_ctot = t1.in1_ctot = 2 * t0.L[0].N;
       t0.in1_coff = 0; t1.in1_coff = t0.L[0].N;
+      const ConvGeom& g = t0.g[0];
+      const int st = g.stride;
+      const char* ns = getenv("DDRL_NO_S2D_FWD");
+      if (!(ns && ns[0] == '1') && g.order == 1 && g.sw == 1 && g.pad == 0 && st > 1 && g.KH % st == 0 && g.KW % st == 0 &&
+          g.H % st == 0 && g.W % st == 0 && (st * st * g.C) % 32 == 0 && (size_t)g.C * st * g.W * 4 <= 48 * 1024) {
+        ConvGeom gs = conv_geom(g.H / st, g.W / st, st * st * g.C, false, g.KH / st, g.KW / st, 1, 0);
+        static const float* const kAligned = reinterpret_cast<const float*>(uintptr_t(256));
+        if (gs.Ho == g.Ho && gs.Wo == g.Wo && gs.K == g.K && conv_tc_supported(conv_op_fwd(gs, kAligned, gs.C, 0, 1), false)) {
+          n->fuse_s2d = true;
+          t0.gs = gs;
+          t0.s2d_infer = true;
+        }
+      }
     }
   }
   *out = n;
@@ -982,7 +1028,7 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   for (auto& t : n->towers)
     for (auto& l : t.L)
       if (l.packed) {
-        if (l.s2d_s) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
+        if (l.s2d_s && !l.s2d_fwd_only) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
         else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
       }
   return DDRL_OK;
