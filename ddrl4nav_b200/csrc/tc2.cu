@@ -95,7 +95,20 @@ struct T2Cfg {
   static constexpr int SA = BN <= 32 ? 6 : (BN <= 64 ? 5 : 2);   // TMEM A slots (64 columns each: hi | lo)
 #else
   static constexpr bool FOLD = BN <= 64;
+#ifdef T2_ONE_STREAM
+  // FOLD with ONE MMA stream: the lo*hi product accumulates into the corrB columns of the current chunk buffer (same
+  // issuing thread as the folded MMA that zero-initialises them, so program order = execution order).  No whole-tile
+  // correction accumulator: its single buffer serialised tile t+1's MMAs behind the epilogue's read of tile t, and its
+  // 64 columns now hold a 4th A slot.
+  static constexpr int SA = BN <= 32 ? 5 : (BN <= 64 ? 4 : 2);
+#else
   static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
+#endif
+#endif
+#if defined(T2_ONE_STREAM) && !defined(T2_NOFOLD)
+  static constexpr bool ONE = BN <= 64;
+#else
+  static constexpr bool ONE = false;
 #endif
   static constexpr int NEPI = BN <= 32 ? 4 : 8;                  // 32 accumulator columns per epilogue thread (64 for BN = 128)
   static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
@@ -104,7 +117,7 @@ struct T2Cfg {
   static constexpr int COLS = BN / (NEPI / 4);                   // accumulator columns per epilogue thread
   // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
   static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN,
-                       TM_A = FOLD ? 5 * BN : 3 * BN;
+                       TM_A = ONE ? 4 * BN : (FOLD ? 5 * BN : 3 * BN);
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBARS = 2 * STAGES + SA + 6;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES + 256;      // epilogue staging: one swizzled 32 x 32 fp32 panel per warp
@@ -146,7 +159,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   }
   if (warp == 0 && lane == 0) {
     // stages and A slots are released by BOTH MMA issuers' commits
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), Cfg::ONE ? 1 : 2); }
     for (int a = 0; a < SA; ++a) mbar_init(smem_u32(bar_aready + a), 4);
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
@@ -260,7 +273,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
     T2_ROLE_END(0, true);
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp == 1 || (warp == 3 && !Cfg::ONE)) {
     // ============================================================ MMA issuers (one elected thread each)
     // warp 1: chunk buffers   main (+)= A_hi . B_hi          [FOLD: [main | corrB] (+)= A_hi . [B_hi ; B_lo], N' = 2 BN]
     // warp 3: whole tile      corr  += A_lo . B_hi           [!FOLD: ... + A_hi . B_lo]
@@ -298,6 +311,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               if (!(T2_EXP & 64))
               umma_tf32_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * kstep, Cfg::FOLD ? idesc2 : idesc,
                            (!first_in_chunk || k4 != 0) ? 1u : 0u);
+              if (Cfg::ONE && !(T2_EXP & 64)) umma_tf32_ts(t_main + BN, a_lo + k4 * 8, dbh0 + k4 * kstep, idesc, 1u);
             }
             umma_commit(smem_u32(bar_empty + s));            // retires the stage AND the TMEM A slot of this K block
             if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
@@ -434,18 +448,20 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
       }
-      T2_WAIT(smem_u32(bar_cfull), tl & 1, w1);
-      tc_fence_after();
+      if (!Cfg::ONE) {
+        T2_WAIT(smem_u32(bar_cfull), tl & 1, w1);
+        tc_fence_after();
 #pragma unroll
-      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
+          for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
       // ---- stores
 #ifdef TC2_TIMING
       const long long st0 = clock64();
