@@ -65,17 +65,35 @@ def parse_forward_states(buf) -> Tuple[List[str], List[List[Tuple[int, Tuple[int
     return ids, msgs
 
 
-def concat_plan(msgs: Sequence[Sequence[Tuple[int, Tuple[int, ...], int, int]]]):
-    """np.concatenate(axis=0) of slot k over the messages, as a segment table:
+def concat_plan(msgs: Sequence[Sequence[Tuple[int, Tuple[int, ...], int, int]]], axis1_slots: Sequence[int] = ()):
+    """np.concatenate of slot k over the messages (axis 0; axis 1 for the 2-D slots listed in `axis1_slots`, i.e. the
+    [V, B] value rows of Experience.batch_data, data/experience.py:116-148), as a segment table:
     -> (slot shapes, slot float offsets into one flat fp32 buffer, total floats, segments structured array)."""
     n_slots = len(msgs[0])
     shapes, offs, segs, total = [], [], [], 0
     for k in range(n_slots):
+        if any(len(m) != n_slots for m in msgs):
+            raise ValueError("EasyBytes: messages carry different numbers of arrays")
+        offs.append(total)
+        if k in axis1_slots:
+            V = msgs[0][k][1][0]
+            if any(len(m[k][1]) != 2 or m[k][1][0] != V for m in msgs):
+                raise ValueError("EasyBytes: slot %d is not [V, B] with the same V in every message" % k)
+            cols = sum(m[k][1][1] for m in msgs)
+            col0 = 0
+            for m in msgs:
+                code, shape, off, count = m[k]
+                b = shape[1]
+                for v in range(V):                                   # row v of this message -> dst[v, col0 : col0 + b]
+                    segs.append((off + v * b * TYPE_SIZE[code], total + v * cols + col0, b, code))
+                col0 += b
+            shapes.append((V, cols))
+            total += V * cols
+            continue
         tail = msgs[0][k][1][1:]
         rows = 0
-        offs.append(total)
         for m in msgs:
-            if len(m) != n_slots or m[k][1][1:] != tail:
+            if m[k][1][1:] != tail:
                 raise ValueError("EasyBytes: state slot %d differs between env processes" % k)   # np.concatenate would raise
             code, shape, off, count = m[k]
             segs.append((off, total, count, code))
@@ -92,22 +110,26 @@ class DeviceEasyBytes:
         self.device = torch.device(device)
         self._pin = None
 
-    def _upload(self, buf, segs: np.ndarray):
-        n = len(buf)
+    def _upload(self, bufs, bases, segs: np.ndarray):
+        n = bases[-1]
         need = n + segs.nbytes + 64
         if self._pin is None or self._pin.numel() < need:
             self._pin = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
-        seg_off = (n + 31) // 32 * 32                              # 8-byte aligned records behind the payload
+        seg_off = (n + 31) // 32 * 32                              # 8-byte aligned records behind the payloads
         host = self._pin.numpy()
-        host[:n] = np.frombuffer(buf, dtype=np.uint8)
+        for b, o in zip(bufs, bases):
+            host[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
         host[seg_off:seg_off + segs.nbytes] = segs.view(np.uint8).reshape(-1)
         dev = self._pin[:seg_off + segs.nbytes].to(self.device, non_blocking=True)          # ONE H2D copy
         return dev, seg_off
 
-    def _decode(self, buf, msgs):
-        shapes, offs, total, segs = concat_plan(msgs)
+    def _decode(self, buf, msgs, axis1_slots=(), bases=None):
+        """buf: one payload, or a list of payloads with `bases` = their byte offsets in the staged buffer (+ total) --
+        the block offsets inside `msgs` are then already absolute."""
+        shapes, offs, total, segs = concat_plan(msgs, axis1_slots)
         lib = _lib.load()
-        dev, seg_off = self._upload(buf, segs)
+        bufs = [buf] if bases is None else buf
+        dev, seg_off = self._upload(bufs, [0, len(buf)] if bases is None else bases, segs)
         out = torch.empty(total, dtype=torch.float32, device=self.device)
         check(lib.ddrl_easybytes_decode(ptr(dev), dev.data_ptr() + seg_off, len(segs), int(segs["count"].max(initial=0)),
                                         ptr(out), current_stream()), "ddrl_easybytes_decode")
@@ -128,3 +150,28 @@ class DeviceEasyBytes:
         tensors = self._decode(bytes_data, [st + other])
         logger = marshal.loads(bytes(bytes_data[16 + n0 + n1:]))
         return tensors[:len(st)], tensors[len(st):], logger
+
+    def decode_backward_batch(self, payloads: Sequence[bytes]):
+        """BackwardQueue.get + Experience.batch_data on the device (server/backward.py:48-62, data/experience.py:116-148):
+        several training payloads -> ONE staged copy -> ONE kernel -> (Experience of concatenated fp32 device tensors,
+        [logger dicts]).  States / advs / actions / old_logps concatenate along axis 0, values [V, B] along axis 1."""
+        from .experience import Experience
+        msgs, loggers, bases, base = [], [], [], 0
+        n_states = None
+        for p in payloads:
+            n0 = struct.unpack_from(">Q", p, 0)[0]
+            st = parse_data(p, 8, 8 + n0)
+            n1 = struct.unpack_from(">Q", p, 8 + n0)[0]
+            other = parse_data(p, 16 + n0, 16 + n0 + n1)
+            if len(other) != 4 or (n_states is not None and len(st) != n_states):
+                raise ValueError("EasyBytes: training payload does not hold [states..., advs, actions, old_logps, values]")
+            n_states = len(st)
+            msgs.append([(c, sh, off + base, cnt) for c, sh, off, cnt in st + other])
+            loggers.append(marshal.loads(bytes(p[16 + n0 + n1:])))
+            bases.append(base)
+            base += (len(p) + 15) // 16 * 16
+        bases.append(base)
+        t = self._decode(list(payloads), msgs, axis1_slots=(n_states + 3,), bases=bases)
+        exp = Experience(states=t[:n_states], advs=t[n_states], actions=t[n_states + 1], old_logps=t[n_states + 2],
+                         values=t[n_states + 3])
+        return exp, loggers

@@ -132,3 +132,66 @@ def test_forward_module_step_bytes_equals_step_on_decoded_arrays():
     assert ids == ["127.0.0.1_%d" % i for i in range(5)]
     for a, b in zip(out_a, out_b):
         assert np.array_equal(a, b)
+
+
+def _enc(a):
+    code = {np.dtype(np.uint8): 1, np.dtype(np.float16): 2, np.dtype(np.float32): 3, np.dtype(np.float64): 4}[a.dtype]
+    return struct.pack(">h", code) + struct.pack(">II", a.size, a.ndim) + struct.pack(">" + "I" * a.ndim, *a.shape) + a.tobytes()
+
+
+def _train_payload(rng, B, V=1):
+    import marshal
+    states = [rng.integers(0, 256, size=(B, 3, 4), dtype=np.uint8), rng.standard_normal((B, 4)).astype(np.float32)]
+    other = [rng.standard_normal(B).astype(np.float32), rng.integers(0, 6, size=B).astype(np.float32),
+             rng.standard_normal(B).astype(np.float32), rng.standard_normal((V, B)).astype(np.float32)]
+    bs = b"".join(_enc(a) for a in states)
+    bo = b"".join(_enc(a) for a in other)
+    return struct.pack(">Q", len(bs)) + bs + struct.pack(">Q", len(bo)) + bo + marshal.dumps({"B": B}), states, other
+
+
+def test_backward_batch_plan_matches_batch_data(g):
+    """Segment plan of several training payloads (values concatenate along axis 1) replayed on the CPU =
+    Experience.batch_data of the oracle-decoded payloads; the reference-encoded golden payload is one of them."""
+    from ddrl4nav_b200.data import Experience
+    rng = np.random.default_rng(11)
+    pay = [g["bwd_bytes"].tobytes()] + [_train_payload(rng, B)[0] for B in (1, 9)]
+    exps = []
+    for p in pay:
+        st, other, _ = R.easybytes_decode_backward_data(p)
+        exps.append(Experience(states=st, advs=other[0], actions=other[1], old_logps=other[2], values=other[3]))
+    ref = Experience.batch_data(exps)
+    msgs, base = [], 0
+    raw = bytearray()
+    for p in pay:
+        n0 = struct.unpack_from(">Q", p, 0)[0]
+        n1 = struct.unpack_from(">Q", p, 8 + n0)[0]
+        blocks = E.parse_data(p, 8, 8 + n0) + E.parse_data(p, 16 + n0, 16 + n0 + n1)
+        msgs.append([(c, sh, off + base, cnt) for c, sh, off, cnt in blocks])
+        raw += p
+        base += len(p)
+    shapes, offs, total, segs = E.concat_plan(msgs, axis1_slots=(5,))
+    flat = np.empty(total, np.float32)
+    rawa = np.frombuffer(bytes(raw), np.uint8)
+    for s_ in segs:
+        dt = R.EASYBYTES_TYPES[int(s_["dtype"])][1]
+        n, off = int(s_["count"]), int(s_["src_off"])
+        flat[int(s_["dst_off"]):int(s_["dst_off"]) + n] = np.frombuffer(rawa[off:off + n * np.dtype(dt).itemsize].tobytes(), dt)
+    got = [flat[o:o + int(np.prod(sh))].reshape(sh) for o, sh in zip(offs, shapes)]
+    want = list(ref.states) + [ref.advs, ref.actions, ref.old_logps, ref.values]
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.array_equal(a, b.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V", [1, 2])
+def test_device_backward_batch_equals_batch_data(V):
+    from ddrl4nav_b200.data import Experience
+    rng = np.random.default_rng(12)
+    made = [_train_payload(rng, B, V) for B in (5, 1, 300)]
+    exp, loggers = E.DeviceEasyBytes("cuda:0").decode_backward_batch([m[0] for m in made])
+    ref = Experience.batch_data([Experience(states=m[1], advs=m[2][0], actions=m[2][1], old_logps=m[2][2], values=m[2][3])
+                                 for m in made])
+    assert [d["B"] for d in loggers] == [5, 1, 300] and len(exp) == 306
+    for a, b in zip(list(exp.states) + [exp.advs, exp.actions, exp.old_logps, exp.values],
+                    list(ref.states) + [ref.advs, ref.actions, ref.old_logps, ref.values]):
+        assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b.astype(np.float32))
