@@ -490,6 +490,22 @@ int tc_make_map_dy3(CUtensorMap* m, const float* dy, int ldy, int N, long long i
   return DDRL_OK;
 }
 
+// dy [image][y][x][N] (MN-major operand): boxes of xw x yh pixels x 32 columns; pixels outside the image read as zero
+int tc_make_map_dy4(CUtensorMap* m, const float* dy, int ldy, int N, int Xn, int Yn, int Bn, int xw, int yh) {
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)Xn, (cuuint64_t)Yn, (cuuint64_t)Bn};
+  cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)Xn * ldy * 4, (cuuint64_t)Yn * Xn * ldy * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)xw, (cuuint32_t)yh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(dy %d x %d box) failed (%d)", xw, yh, (int)cr);
+    return DDRL_E_CUDA;
+  }
+  return DDRL_OK;
+}
+
 bool conv_tc_supported(const ConvOp& o, bool wgrad) {
   if (o.Cin % 32 != 0 || o.Ctot % 4 != 0 || o.c_off % 4 != 0 || o.c_off + o.Cin > o.Ctot) return false;
   if ((reinterpret_cast<uintptr_t>(o.a) & 15) != 0) return false;

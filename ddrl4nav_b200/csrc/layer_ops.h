@@ -31,6 +31,10 @@ struct TcTap {
   // nb images per box); tiles >= tiles1 cover the remaining rows [y2, Yn) with nb2 images per box (their own tensor map).
   // 9x9 images: 7 rows x 2 images + 2 rows x 7 images = 126-row tiles instead of one 81-row image per 128-row tile.
   int tiles1, y2, ny2, nb2, rows2;
+  // weight gradient, two pixel-box classes per image (K blocks of exactly 32 pixels): columns [0, wxw0) in boxes of
+  // wxw0 x wyh0 pixels (wnb0 per image), columns [wxw0, Xn) in boxes of wxw1 x wyh1 (tpi - wnb0 per image).  A 20-pixel-wide
+  // map: 16x2 + 4x8 boxes = 13 full K blocks per image instead of 20 blocks of one 20-pixel row.
+  int w2on, wxw0, wyh0, wnb0, wxw1, wyh1;
   int kpad;                      // rows rounded up to 8 (wgrad: MMA K steps per block)
   int KW, cpb;                   // tap index = kh*KW + kw; 32-channel chunks per tap
   int nslices;                   // taps * cpb

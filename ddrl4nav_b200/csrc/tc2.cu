@@ -257,6 +257,16 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             for (int j = 0; j < 4; ++j) tma_load_2d(&tmA, full, a_dst + j * 4096, m0 + j * 32, k);
 #pragma unroll
             for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_2d(&tmBhi, full, bh_dst + j * 4096, n0 + j * 32, k);
+          } else if (tp.w2on) {
+            // two pixel-box classes (32 pixels each): class 1 covers the columns right of wxw0
+            const bool c1 = pj >= tp.wnb0;
+            const int x0 = c1 ? tp.wxw0 : 0, yy0 = c1 ? (pj - tp.wnb0) * tp.wyh1 : pj * tp.wyh0;
+            mbar_expect_tx(full, (na + Cfg::BNS / 32) * 32 * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < na) tma_load_4d(c1 ? &tmA2 : &tmA, full, a_dst + j * 4096, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+#pragma unroll
+            for (int j = 0; j < Cfg::BNS / 32; ++j) tma_load_4d(c1 ? &tmBlo : &tmBhi, full, bh_dst + j * 4096, n0 + j * 32, x0, yy0, pb);
           } else {
             const int yy0 = pj * tp.ny;
             mbar_expect_tx(full, (na + Cfg::BNS / 32) * tp.rows * 128);
@@ -791,15 +801,39 @@ int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp,
   tc_tap_common(g.tap, o, 32);
   if (g.tap.nb != 1) { g.tap.nb = 1; g.tap.rows = o.Xn * g.tap.ny; g.tap.kpad = (g.tap.rows + 7) & ~7; }
   const int K = o.KH * o.KW * o.Cin;
-  CUtensorMap ta, tb;
-  r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, false);
-  if (r == DDRL_OK) r = tc_make_map_dy3(&tb, dy, ldy, N, o.Yn * o.Xn, o.Bn, g.tap.rows);
+  CUtensorMap ta, tb, ta2, tb2;
+  // K blocks of exactly 32 pixels from two box classes when the map width is a sum of two powers of two and that packs
+  // the image into >= 10 % fewer K blocks than whole rows (the launch is bound by the per-K-block hand-off chain)
+  static const bool no_w2 = [] { const char* e = getenv("DDRL_TC2_NO_WGRAD_BOXES"); return e && e[0] == '1'; }();
+  if (!no_w2 && ldy == N) {
+    for (int xw0 = 32; xw0 >= 2; xw0 >>= 1) {
+      const int xw1 = o.Xn - xw0;
+      if (xw1 < 1 || xw1 > xw0 || (xw1 & (xw1 - 1)) != 0) continue;
+      const int yh0 = 32 / xw0, yh1 = 32 / xw1;
+      if ((yh0 - 1) * o.sy + 1 > 256 || (yh1 - 1) * o.sy + 1 > 256) continue;
+      const int nb0 = ceil_div(o.Yn, yh0), nb1 = ceil_div(o.Yn, yh1);
+      if ((nb0 + nb1) * 10 > g.tap.tpi * 9) continue;
+      g.tap.w2on = 1; g.tap.wxw0 = xw0; g.tap.wyh0 = yh0; g.tap.wnb0 = nb0; g.tap.wxw1 = xw1; g.tap.wyh1 = yh1;
+      g.tap.tpi = nb0 + nb1; g.tap.rows = 32; g.tap.kpad = 32;
+      break;
+    }
+  }
+  if (g.tap.w2on) {
+    r = tc_make_map_nhwc(&ta, o, g.tap.wxw0, g.tap.wyh0, 1, false);
+    if (r == DDRL_OK) r = tc_make_map_nhwc(&ta2, o, g.tap.wxw1, g.tap.wyh1, 1, false);
+    if (r == DDRL_OK) r = tc_make_map_dy4(&tb, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw0, g.tap.wyh0);
+    if (r == DDRL_OK) r = tc_make_map_dy4(&tb2, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw1, g.tap.wyh1);
+  } else {
+    r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, false);
+    if (r == DDRL_OK) r = tc_make_map_dy3(&tb, dy, ldy, N, o.Yn * o.Xn, o.Bn, g.tap.rows);
+  }
   if (r != DDRL_OK) return r;
   g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
   g.kb_total = o.Bn * g.tap.tpi;
   const int tiles = ceil_div(K, T2_BM) * ceil_div(N, bn);
   wgrad_splits(g, tiles);
   dim3 grid(ceil_div(K, T2_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  if (g.tap.w2on) return launch2_bn<1, true>(bn, ta, tb, tb2, g, grid, s, &ta2);
   return launch2_bn<1, true>(bn, ta, tb, tb, g, grid, s);
 }
 

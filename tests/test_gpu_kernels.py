@@ -430,6 +430,8 @@ CONV_CASES = [
     (6, 1, 478, 32, 32, 1, 3, 2, 0),      # laser conv1d2 (nn/nav_encoder.py:92)
     (1, 7, 5, 32, 32, 3, 3, 1, 1),        # single image, odd extents
     (130, 6, 6, 32, 96, 3, 3, 2, 1),      # stride 2 with padding, many images per tile, N not a multiple of 64
+    (3, 41, 41, 32, 64, 3, 3, 2, 0),      # 20x20 output at stride 2: two pixel-box classes (16x2 + 4x8) in the weight gradient
+    (2, 13, 25, 32, 32, 2, 2, 1, 0),      # 12 x 24 output (8x4 + 4x8 boxes would not apply: width 24 = 16 + 8), ragged last boxes
 ]
 
 
