@@ -255,6 +255,29 @@ def test_backward_module_prefetch_equals_plain():
             assert abs(l1[k] - l2[k]) <= 1e-5 * max(1.0, abs(l1[k]))     # split-K atomics: not bit-reproducible run to run
 
 
+@pytest.mark.parametrize("kind", ["pong", "navimg", "navlaser"])
+def test_inference_only_engine_micro_batches(monkeypatch, kind):
+    """A net that never trained (the predictor process) runs the inference-only lowering (Pong: space-to-depth conv1,
+    no im2col workspace); chunked over micro-batches it must reproduce the single-shot values and greedy actions, and
+    both must agree with a net whose workspace is the training one."""
+    B = 37
+    states = [s.to(DEV) for s in R.synth_states(kind, B, seed=8)]
+    net, _, _ = make(kind)
+    a0, _, v0 = net.act(states, play_mode=True)
+    monkeypatch.setenv("DDRL_MICRO_BATCH", "8")
+    net2, _, _ = make(kind)
+    a1, _, v1 = net2.act(states, play_mode=True)
+    assert torch.equal(a0, a1) and rel_err(v1, v0) < 1e-6
+    monkeypatch.delenv("DDRL_MICRO_BATCH")
+    net3, _, _ = make(kind)
+    acts, logp, _ = net3.act(states)
+    net3.backward_only(states, torch.randn(B, device=DEV), acts, logp, torch.randn(B, device=DEV))   # training workspace
+    a2, _, v2 = net3.act(states, play_mode=True)
+    assert rel_err(v2, v0) < 1e-5
+    if kind != "navlaser":
+        assert (a2 != a0).float().mean() <= 1.0 / B
+
+
 def test_shard_sum_equals_full_batch():
     """Data-parallel arithmetic on one GPU: two half-batches scaled by 1/B_global sum to the full-batch gradient."""
     spec, params, states, a, old, adv, ret = _learn_case("pong", 16)
