@@ -42,6 +42,40 @@ __global__ void __launch_bounds__(256) im2col_kernel(ConvGeom g, const float* __
   }
 }
 
+// Row-cooperative variant for the small-K first layers (K <= 1024, any order): a group of KT = 2^j >= min(ldc, 32) lanes owns
+// one output row -- the (image, ho, wo) decode happens once per row in 32-bit arithmetic, the per-k tap offsets come from a
+// table in shared memory, and the lanes' stores are consecutive floats of the row.
+__global__ void __launch_bounds__(256) im2col_rows_kernel(ConvGeom g, const float* __restrict__ x, float* __restrict__ cols,
+                                                          long long rows, int kt) {
+  extern __shared__ int tab[];                          // [ldc] input offset | [ldc] kh | [ldc] kw   (k >= K: kh = -2^20)
+  int* koff = tab; int* kkh = tab + g.ldc; int* kkw = tab + 2 * g.ldc;
+  for (int k = threadIdx.x; k < g.ldc; k += blockDim.x) {
+    int c = 0, kh = -(1 << 20), kw = 0;
+    if (k < g.K) {
+      if (g.order == 0) { c = k % g.C; const int t = k / g.C; kw = t % g.KW; kh = t / g.KW; }
+      else { kw = k % g.KW; const int t = k / g.KW; kh = t % g.KH; c = t / g.KH; }
+    }
+    koff[k] = (int)(c * g.sc + (long long)kh * g.sh + (long long)kw * g.sw);
+    kkh[k] = kh; kkw[k] = kw;
+  }
+  __syncthreads();
+  const int rpb = blockDim.x / kt;                      // rows per block iteration
+  const int kl = threadIdx.x % kt, rl = threadIdx.x / kt;
+  const int hw = g.Ho * g.Wo;
+  for (long long row = (long long)blockIdx.x * rpb + rl; row < rows; row += (long long)gridDim.x * rpb) {
+    const long long b = row / hw;
+    const int p = (int)(row - b * hw);
+    const int ho = p / g.Wo, wo = p - ho * g.Wo;
+    const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
+    const float* xb = x + b * g.sb + (long long)h0 * g.sh + (long long)w0 * g.sw;
+    float* cr = cols + row * g.ldc;
+    for (int k = kl; k < g.ldc; k += kt) {
+      const int h = h0 + kkh[k], w = w0 + kkw[k];
+      cr[k] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? __ldg(xb + koff[k]) : 0.f;
+    }
+  }
+}
+
 // float4 variant: 4 consecutive k of one row share their (kh,kw) tap [order 0, C % 4 == 0] or their (c,kh) and
 // cover 4 adjacent input pixels [order 1, KW % 4 == 0, sw == 1]: one 16 B load, one 16 B store, a quarter of the
 // index arithmetic.  Requires K % 4 == 0 (ldc == K) and 16 B aligned sources.
@@ -602,6 +636,16 @@ int im2col(const ConvGeom& g, const float* x, float* cols, int B, cudaStream_t s
   if (aligned && (v0 || v1)) {
     im2col_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(g, x, reinterpret_cast<float4*>(cols), total / 4);
     DDRL_LAUNCHED("im2col_vec4_kernel");
+    return DDRL_OK;
+  }
+  if (g.ldc <= 1024 && (long long)g.C * g.sc + (long long)g.KH * g.sh + (long long)g.KW * g.sw < (1LL << 30)) {
+    int kt = 1;
+    while (kt < g.ldc && kt < 32) kt <<= 1;
+    const long long rows = (long long)B * g.Ho * g.Wo;
+    const int rpb = 256 / kt;
+    im2col_rows_kernel<<<(int)std::min<long long>((rows + rpb - 1) / rpb, 16LL * kNumSMs), 256, 3 * g.ldc * sizeof(int), s>>>(
+        g, x, cols, rows, kt);
+    DDRL_LAUNCHED("im2col_kernel");
     return DDRL_OK;
   }
   im2col_kernel<<<grid_for(total), 256, 0, s>>>(g, x, cols, total);
