@@ -102,8 +102,18 @@ struct T2Cfg {
   // 64 columns now hold a 4th A slot.
   static constexpr int SA = BN <= 32 ? 5 : (BN <= 64 ? 4 : 2);
 #else
+#ifdef T2_SINGLE128
+  // BN = 128 experiment: ONE chunk accumulator (the MMA stream waits for the previous chunk's drain) buys a 3rd A slot
+  static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 3);   // 4 stages of 48 KB: S > SA
+#else
   static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
 #endif
+#endif
+#endif
+#ifdef T2_SINGLE128
+  static constexpr bool SINGLE = BN > 64;
+#else
+  static constexpr bool SINGLE = false;
 #endif
 #if defined(T2_ONE_STREAM) && !defined(T2_NOFOLD)
   static constexpr bool ONE = BN <= 64;
@@ -116,8 +126,8 @@ struct T2Cfg {
   static constexpr int THREADS = (EPI0 + NEPI) * 32;
   static constexpr int COLS = BN / (NEPI / 4);                   // accumulator columns per epilogue thread
   // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
-  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN,
-                       TM_A = ONE ? 4 * BN : (FOLD ? 5 * BN : 3 * BN);
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = SINGLE ? 0 : (FOLD ? 2 * BN : BN), TM_CORR = SINGLE ? BN : (FOLD ? 4 * BN : 2 * BN),
+                       TM_A = SINGLE ? 2 * BN : (ONE ? 4 * BN : (FOLD ? 5 * BN : 3 * BN));
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBARS = 2 * STAGES + SA + 6;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES + 256;      // epilogue staging: one swizzled 32 x 32 fp32 panel per warp
@@ -304,7 +314,13 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const uint32_t buf = ch & 1;
         const bool first_in_chunk = (i % T2_CHUNK) == 0;
         const bool last_in_chunk = (i % T2_CHUNK) == T2_CHUNK - 1 || i == nkb - 1;
-        if (chunk_role) { if (first_in_chunk) T2_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0); }
+        if (chunk_role) {
+          if (first_in_chunk) {
+            T2_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0);
+            // one physical accumulator: the previous chunk (other barrier of the pair) must be drained as well
+            if (Cfg::SINGLE && ch > 0) T2_WAIT(smem_u32(bar_mfree + ((ch - 1) & 1)), ((ch - 1) >> 1) & 1, w0);
+          }
+        }
         else if (i == 0) T2_WAIT(smem_u32(bar_cfree), (tl & 1) ^ 1, w0);
         T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w1);
         T2_WAIT(smem_u32(bar_aready + a), (it / SA) & 1, w2);
