@@ -74,6 +74,7 @@ struct Tower {
   int fuse_role = 0, in1_ctot = 0, in1_coff = 0;
   bool s2d0 = false;                                        // conv slot 0 runs on the space-to-depth observation
   bool s2d_infer = false;                                   // fused first conv: inference runs on the s2d observation
+  bool borrow_cols = false;                                 // second unshared tower: the observation-side im2col matrices are tower 0's
   ConvGeom gs = {};                                         // its stride-1 NHWC geometry (buf[0] holds the s2d tensor)
   // per-micro-batch buffers
   std::vector<float*> buf;
@@ -388,10 +389,11 @@ static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std:
                    p3 = (size_t)(g2->Ho / 2) * (g2->Wo / 2) * C3;
       const int ldcat = t.arch == DDRL_ARCH_NAV1D ? 776 : 524;
       // 0 cols1, 1 z1, 2 p1, 3 cols2, 4 z2, 5 p2, 6 cols3, 7 z3, 8 p3, 9 cat, 10 f1
-      f = {cols(*g0), outp(*g0, C1), p1, cols(*g1), outp(*g1, C2), p2, cols(*g2), outp(*g2, C3), p3, (size_t)ldcat, 512};
+      const size_t own = t.borrow_cols ? 0 : 1;           // the observation-side im2col matrices are shared between unshared towers
+      f = {own * cols(*g0), outp(*g0, C1), p1, cols(*g1), outp(*g1, C2), p2, cols(*g2), outp(*g2, C3), p3, (size_t)ldcat, 512};
       u8 = {p1, p2, p3};
       // 11 colsL1, 12 l1, 13 colsL2, 14 l2   (nav1d only; zero-sized otherwise)
-      if (t.arch == DDRL_ARCH_NAV1D) { f.push_back(cols(t.g[3])); f.push_back(outp(t.g[3], 32));
+      if (t.arch == DDRL_ARCH_NAV1D) { f.push_back(own * cols(t.g[3])); f.push_back(outp(t.g[3], 32));
                                        f.push_back(cols(t.g[4])); f.push_back(outp(t.g[4], 32)); }
       else { f.insert(f.end(), {0, 0, 0, 0}); }
       // 15 staging for NavPed channel concat (navped only)
@@ -469,6 +471,11 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     t.dh = train ? n->ws.take((size_t)t.feat * mb) : nullptr;
   }
   n->s2dbuf = s2d_floats ? n->ws.take(s2d_floats * mb) : nullptr;
+  if (n->towers.size() == 2 && n->towers[1].borrow_cols) {
+    Tower &t0 = n->towers[0], &t1 = n->towers[1];
+    t1.buf[0] = t0.buf[0];
+    if (t1.arch == DDRL_ARCH_NAV1D) t1.buf[11] = t0.buf[11];
+  }
   if (n->fuse0) {
     Tower &t0 = n->towers[0], &t1 = n->towers[1];
     t1.buf[0] = t0.buf[0]; t1.buf[1] = t0.buf[1];
@@ -652,7 +659,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
         img = b[15];
       }
       const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
-      TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s, reuse_obs));
+      TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s, reuse_obs || t.borrow_cols));    // tower 0 ran first: its cols are current
       TRY(pool_fwd(b[1], b[2], t.idx[0], mb, g0->Ho, g0->Wo, 64, s));
       TRY(conv_block(n, t, 1, 1, b[2], b[3], b[4], mb, s));
       TRY(pool_fwd(b[4], b[5], t.idx[1], mb, g1->Ho, g1->Wo, 128, s));
@@ -663,7 +670,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
       if (d1) {
         // laser branch: conv1d1 -> conv1d2 (no activation between, nav_encoder.py:109-110) -> fc_1d+relu -> cat[:, 0:256]
         const float* laser = obs[0] + row0 * 960;
-        TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s, reuse_obs));
+        TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s, reuse_obs || t.borrow_cols));
         TRY(conv_block(n, t, 4, 4, b[12], b[13], b[14], mb, s));
         TRY(lin_fwd(n, t.L[5], b[14], 7616, b[9], ldcat, mb, s));
         TRY(lin_fwd(n, t.L[6], b[8], flat, b[9] + 256, ldcat, mb, s));           // fc0 -> cat[:, 256:768]
@@ -867,6 +874,11 @@ extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
     build_tower(n, n->towers[1], "critic.pre.", n->d.arch, n->d.in_ch, F);
     // unshared towers read the same observation: run their first (explicit-im2col) conv as one N = 2 x Cout GEMM
     Tower &t0 = n->towers[0], &t1 = n->towers[1];
+    {
+      const char* nb = getenv("DDRL_NO_SHARED_COLS");
+      const bool nav = n->d.arch == DDRL_ARCH_NAV1D || n->d.arch == DDRL_ARCH_NAV;
+      if (nav && !(nb && nb[0] == '1') && !t0.implicit[0] && !t1.implicit[0] && !t0.s2d0) t1.borrow_cols = true;
+    }
     const char* nf = getenv("DDRL_NO_FUSE0");
     if (n->d.arch == DDRL_ARCH_ATARI && tc2_mode(n) && !(nf && nf[0] == '1') && !t0.s2d0 && !t0.implicit[0] && t0.implicit[1] &&
         t0.df[1].on && t1.df[1].on && t0.L[0].N % 32 == 0 && 2 * t0.L[0].N <= 128 && t0.g[0].ldc % 4 == 0) {
