@@ -106,21 +106,36 @@ def concat_plan(msgs: Sequence[Sequence[Tuple[int, Tuple[int, ...], int, int]]],
 class DeviceEasyBytes:
     """decode_forward_states / decode_backward_data with fp32 DEVICE tensors as the result."""
 
+    N_SLOTS = 3                                                    # pinned staging ring (one event per slot)
+
     def __init__(self, device="cuda"):
         self.device = torch.device(device)
-        self._pin = None
+        self._pin = [None] * self.N_SLOTS
+        self._evt = [None] * self.N_SLOTS
+        self._slot = 0
 
     def _upload(self, bufs, bases, segs: np.ndarray):
+        """Stage payloads + segment table in the next pinned slot and queue ONE H2D copy.  The copy is asynchronous (it may
+        sit behind training kernels when the learner prefetches batch k+1): the slot's event is recorded behind it and
+        waited on before the host writes that slot again, so a queued copy never reads bytes of a later call."""
         n = bases[-1]
         need = n + segs.nbytes + 64
-        if self._pin is None or self._pin.numel() < need:
-            self._pin = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
+        k = self._slot
+        self._slot = (k + 1) % self.N_SLOTS
+        if self._evt[k] is not None:
+            self._evt[k].synchronize()
+        if self._pin[k] is None or self._pin[k].numel() < need:
+            self._pin[k] = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
         seg_off = (n + 31) // 32 * 32                              # 8-byte aligned records behind the payloads
-        host = self._pin.numpy()
+        host = self._pin[k].numpy()
         for b, o in zip(bufs, bases):
             host[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
         host[seg_off:seg_off + segs.nbytes] = segs.view(np.uint8).reshape(-1)
-        dev = self._pin[:seg_off + segs.nbytes].to(self.device, non_blocking=True)          # ONE H2D copy
+        dev = self._pin[k][:seg_off + segs.nbytes].to(self.device, non_blocking=True)       # ONE H2D copy
+        if self.device.type == "cuda":
+            if self._evt[k] is None:
+                self._evt[k] = torch.cuda.Event()
+            self._evt[k].record(torch.cuda.current_stream(self.device))
         return dev, seg_off
 
     def _decode(self, buf, msgs, axis1_slots=(), bases=None):

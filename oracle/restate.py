@@ -546,3 +546,41 @@ def easybytes_decode_backward_data(buf: bytes):
     n1 = struct.unpack(">Q", buf[8 + n0:16 + n0])[0]
     other = easybytes_decode_data(buf[16 + n0:16 + n0 + n1])
     return states, other, marshal.loads(buf[16 + n0 + n1:])
+
+
+_EASYBYTES_CODE = {np.dtype(np.uint8): 1, np.dtype(np.float16): 2, np.dtype(np.float32): 3, np.dtype(np.float64): 4}
+
+
+def easybytes_encode_data(arrays: Sequence[np.ndarray]) -> bytes:
+    """easybytes.py:62-75: per array [type >h][count >I][ndim >I][shape >I x ndim][raw bytes]."""
+    import struct
+    out = b""
+    for a in arrays:
+        a = np.asarray(a)
+        out += struct.pack(">h", _EASYBYTES_CODE[a.dtype]) + struct.pack(">II", int(a.size), a.ndim)
+        out += struct.pack(">" + "I" * a.ndim, *a.shape) + a.tobytes()
+    return out
+
+
+def easybytes_encode_forward_states(ip: str, process_env_id: int, arrays: Sequence[np.ndarray]) -> bytes:
+    """easybytes.py:28-33,141-148: [length >Q][ip 4 x >H][process_env_id >I][blocks]; length counts the blocks only."""
+    import struct
+    body = easybytes_encode_data(arrays)
+    return struct.pack(">Q", len(body)) + struct.pack(">HHHH", *[int(x) for x in ip.split(".")]) + struct.pack(">I", process_env_id) + body
+
+
+def easybytes_encode_backward_data(states: Sequence[np.ndarray], other4: Sequence[np.ndarray], logger: dict) -> bytes:
+    """easybytes.py:150-161."""
+    import marshal
+    import struct
+    s, o = easybytes_encode_data(states), easybytes_encode_data(other4)
+    return struct.pack(">Q", len(s)) + s + struct.pack(">Q", len(o)) + o + marshal.dumps(logger)
+
+
+def easybytes_encode_forward_return_data(arrays: Sequence[np.ndarray], env_batch_nums: Sequence[int]) -> List[bytes]:
+    """easybytes.py:77-109: env process j gets rows [i0, i1) of every array -- columns [i0, i1) of array 2 (values [V, B, 1])."""
+    out, i0 = [], 0
+    for nb in env_batch_nums:
+        out.append(easybytes_encode_data([a[:, i0:i0 + nb] if k == 2 else a[i0:i0 + nb] for k, a in enumerate(arrays)]))
+        i0 += nb
+    return out

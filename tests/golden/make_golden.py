@@ -236,6 +236,14 @@ def golden_easybytes():
     for i, s in enumerate(other):
         out["bwd_other_%d" % i] = s
     out["bwd_logger_keys"] = np.array(sorted(logd))
+    # replies of the Forward thread: [actions, logps, values [V,B,1]] cut per env process (2 / 1 / 3 rows); discrete and
+    # 2-d Gaussian actions, float32 (MODULE_NUMPY_DTYPE)
+    for tag, act in (("cat", rng.integers(0, 6, size=6).astype(np.float32)), ("gauss", rng.standard_normal((6, 2)).astype(np.float32))):
+        arrs = [act, rng.standard_normal(6).astype(np.float32), rng.standard_normal((1, 6, 1)).astype(np.float32)]
+        for k, a in enumerate(arrs):
+            out["reply_%s_in_%d" % (tag, k)] = a
+        for j, b in enumerate(eb.encode_forward_return_data([a.copy() for a in arrs], [2, 1, 3])):
+            out["reply_%s_bytes_%d" % (tag, j)] = np.frombuffer(b, dtype=np.uint8).copy()
     np.savez_compressed(os.path.join(HERE, "easybytes.npz"), **out)
 
 
