@@ -33,7 +33,7 @@ class ConvDesc(C.Structure):
 
 ARCH = {"atari": 0, "nav": 1, "navped": 2, "nav1d": 3, "mlp": 4}
 DIST = {"categorical": 0, "gaussian": 1}
-GEMM_MODE = {"simt": 0, "tc": 1, "tc2": 2}
+GEMM_MODE = {"simt": 0, "tc": 1, "tc2": 2, "tc3": 3}
 
 _P = C.c_void_p
 _I = C.c_int
@@ -70,6 +70,7 @@ SIGNATURES = {
     "ddrl_net_num_obs": (_I, [_P]),
     "ddrl_net_obs_elems": (_L, [_P, _I]),
     "ddrl_net_forward": (_I, [_P, C.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ddrl_net_encode": (_I, [_P, C.POINTER(_P), _I, _I, _I, _P, _P]),
     "ddrl_net_backward": (_I, [_P, C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, C.POINTER(PPOHparams), _I, _P]),
     "ddrl_net_clip_adam": (_I, [_P, _I, C.POINTER(PPOHparams), _P, _P]),
     "ddrl_net_workspace_bytes": (_L, [_P]),

@@ -128,6 +128,50 @@ extern "C" int ddrl_gemm_f32(int mode, int form, int M, int N, int K, const floa
     cudaFree(tmp);
     return r;
   }
+  if (mode == DDRL_GEMM_TC3_F16) {
+    if (form == 2) {
+      // C[m,n] (+)= sum_k A[k,m] B[k,n]: the engine's weight-gradient form with dy := A, x := B (output row = dy column)
+      if (bias || act) return DDRL_E_UNSUPPORTED;
+      if (!beta) DDRL_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
+      float* slots = nullptr;
+      DDRL_CUDA(cudaMalloc(&slots, 256));
+      int r = DDRL_OK;
+      if (cudaMemsetAsync(slots, 0, 256, s) != cudaSuccess) r = DDRL_E_CUDA;
+      if (r == DDRL_OK) r = amax_f32(B, K, N, ldb, slots, false, s);
+      if (r == DDRL_OK) r = amax_f32(A, K, M, lda, slots + 1, false, s);
+      if (r == DDRL_OK) r = tc3_wgrad(N, M, K, B, ldb, A, lda, slots, slots + 1, C, ldc, s);
+      cudaStreamSynchronize(s);
+      cudaFree(slots);
+      return r;
+    }
+    if (beta) return DDRL_E_UNSUPPORTED;
+    // split B on the fly: K-major hi / lo' [N, ld16] (form 1: through the transposing output of the split)
+    const int ld16 = (K + 7) & ~7, ldN16 = (N + 7) & ~7;
+    const size_t halfs = (size_t)N * ld16 + (form == 1 ? (size_t)K * ldN16 : 0);
+    char* tmp = nullptr;
+    DDRL_CUDA(cudaMalloc(&tmp, 256 + 4 * halfs));
+    float* slots = reinterpret_cast<float*>(tmp);
+    char* h0 = tmp + 256;
+    int r = DDRL_OK;
+    if (cudaMemsetAsync(tmp, 0, 256 + 4 * halfs, s) != cudaSuccess) r = DDRL_E_CUDA;
+    if (r == DDRL_OK) r = amax_f32(A, M, K, lda, slots, false, s);
+    if (form == 0) {
+      char *hi = h0, *lo = h0 + 2 * halfs;
+      if (r == DDRL_OK) r = amax_f32(B, N, K, ldb, slots + 1, false, s);
+      if (r == DDRL_OK) r = split_f16(B, N, K, ldb, slots + 1, hi, lo, ld16, nullptr, nullptr, 0, s);
+      if (r == DDRL_OK) r = tc3_gemm(M, N, K, A, lda, hi, lo, ld16, slots, slots + 1, C, ldc, bias, act, nullptr, slots + 2, s);
+    } else {
+      // B is [K, N]: split it as a [K rows, N cols] matrix and use the transposed pair [N, ld16]
+      char *hiT = h0, *loT = h0 + 2 * (size_t)N * ld16;
+      char *hi = h0 + 4 * (size_t)N * ld16, *lo = hi + 2 * (size_t)K * ldN16;
+      if (r == DDRL_OK) r = amax_f32(B, K, N, ldb, slots + 1, false, s);
+      if (r == DDRL_OK) r = split_f16(B, K, N, ldb, slots + 1, hi, lo, ldN16, hiT, loT, ld16, s);
+      if (r == DDRL_OK) r = tc3_gemm(M, N, K, A, lda, hiT, loT, ld16, slots, slots + 1, C, ldc, bias, act, nullptr, slots + 2, s);
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    return r;
+  }
   if (mode != DDRL_GEMM_SIMT_F32) return DDRL_E_ARG;
   return gemm_simt(form, M, N, K, A, lda, B, ldb, C, ldc, bias, act, beta, 0, s);
 }

@@ -89,7 +89,7 @@ int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClas
 
 // dx (dense NHWC [B, H, W, C]) = sum over classes; every input pixel belongs to exactly one class
 int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
-                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine) {
+                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine, const Tc3Ctx* t3) {
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const int sy = g.stride, sx = W == 1 ? 1 : g.stride;
@@ -100,7 +100,10 @@ int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cl
     o.Yn = c.Yn; o.Xn = c.Xn; o.Bn = B;
     const long long off = ((long long)c.iy0 * W + c.ix0) * g.C;
     int r;
-    if (tmem_engine)
+    if (t3)
+      r = tc3_conv_fwd(o, c.w16.hi, c.w16.lo, c.w16.ld, g.C, t3->amax_a, c.w16.amax, nullptr, act, mask ? mask + off : nullptr,
+                       dx + off, (long long)H * W * g.C, (long long)sy * W * g.C, (long long)sx * g.C, t3->amax_out, s);
+    else if (tmem_engine)
       r = tc2_conv_fwd(o, c.wd_hi, c.wd_lo, c.K, g.C, nullptr, act, mask ? mask + off : nullptr, dx + off,
                        (long long)H * W * g.C, (long long)sy * W * g.C, (long long)sx * g.C, s);
     else
@@ -186,7 +189,7 @@ int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const Dgr
 // out_ctot / out_coff: dx (and the mask, addressed like dx) are channels [out_coff, out_coff + C) of an out_ctot-wide
 // NHWC tensor (0 = dense [B, H, W, C])
 int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
-                         const float* mask, int B, cudaStream_t s, int out_ctot, int out_coff) {
+                         const float* mask, int B, cudaStream_t s, int out_ctot, int out_coff, const Tc3Ctx* t3) {
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const int sx = W == 1 ? 1 : f.s;
@@ -206,6 +209,9 @@ int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const
       cls.cls_off[q] = ((long long)f.iy0[cy] * W + f.ix0[cx]) * ct;
     }
   // tile pixel (jy, jx) -> base input pixel (s*jy, sx*jx); out_s scales both axes, so a 1-D layer (W == 1) keeps x = 0
+  if (t3)
+    return tc3_conv_fwd(o, f.w16.hi, f.w16.lo, f.w16.ld, f.N, t3->amax_a, f.w16.amax, nullptr, act, mask, dx, (long long)H * W * ct,
+                        (long long)f.s * W * ct, (long long)sx * ct, t3->amax_out, s, &cls);
   return tc2_conv_fwd(o, f.wd_hi, f.wd_lo, f.K, f.N, nullptr, act, mask, dx, (long long)H * W * ct, (long long)f.s * W * ct,
                       (long long)sx * ct, s, &cls);
 }
@@ -235,7 +241,8 @@ using namespace ddrl;
 extern "C" int ddrl_conv_nhwc_f32(int mode, int op, const ddrl_conv_desc* d, const float* x, const float* w, const float* bias,
                                   const float* dy, int act, const float* mask, float* out, void* stream) {
   if (!d || !out || !w || op < 0 || op > 2) return DDRL_E_ARG;
-  if (mode != DDRL_GEMM_TC_3XTF32 && mode != DDRL_GEMM_TC2_TMEM) return DDRL_E_ARG;
+  if (mode != DDRL_GEMM_TC_3XTF32 && mode != DDRL_GEMM_TC2_TMEM && mode != DDRL_GEMM_TC3_F16) return DDRL_E_ARG;
+  const bool v3 = mode == DDRL_GEMM_TC3_F16;
   const bool v2 = mode == DDRL_GEMM_TC2_TMEM;
   if (d->B < 1 || d->H < 1 || d->W < 1 || d->Cin < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1 || d->stride < 1 || d->pad < 0)
     return DDRL_E_ARG;
@@ -252,6 +259,73 @@ extern "C" int ddrl_conv_nhwc_f32(int mode, int op, const ddrl_conv_desc* d, con
   const int taps = d->KH * d->KW;
   int rc = DDRL_OK;
   float* tmp = nullptr;
+  if (v3 && op != 2) {
+    // tc3: pack the weights (forward layout, or the fused / per-class data-gradient layouts), split them to scaled fp16,
+    // take amax of the activation operand, run
+    char* raw = nullptr;
+    auto finish = [&](int r) { cudaStreamSynchronize(s); if (raw) cudaFree(raw); return r; };
+    auto split_into = [&](const float* wp, int rows, int K, W16& w16, char* h16, float* slot) {
+      const int ld16 = (K + 7) & ~7;
+      w16.hi = h16; w16.lo = h16 + (size_t)rows * ld16 * 2; w16.ld = ld16; w16.amax = slot;
+      int r = amax_f32(wp, rows, K, K, slot, true, s);
+      if (r == DDRL_OK) r = split_f16(wp, rows, K, K, slot, const_cast<void*>(w16.hi), const_cast<void*>(w16.lo), ld16, nullptr, nullptr, 0, s);
+      return r;
+    };
+    if (op == 0) {
+      if (!x) return DDRL_E_ARG;
+      const size_t nw = (size_t)d->Cout * g.K, n16 = (size_t)d->Cout * ((g.K + 7) & ~7);
+      DDRL_CUDA(cudaMalloc(&raw, 256 + 4 * nw + 4 * n16 + 256));
+      float* slots = reinterpret_cast<float*>(raw);
+      float* wp = reinterpret_cast<float*>(raw + 256);
+      DDRL_CUDA(cudaMemsetAsync(raw, 0, 256, s));
+      rc = pack_weight(w, wp, d->Cout, taps, d->Cin, g.K, s);
+      ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
+      if (rc == DDRL_OK && !conv_tc_supported(o, false)) rc = DDRL_E_UNSUPPORTED;
+      W16 w16;
+      if (rc == DDRL_OK) rc = split_into(wp, d->Cout, g.K, w16, raw + 256 + 4 * nw, slots + 1);
+      if (rc == DDRL_OK) rc = amax_f32(x, (long long)d->B * d->H * d->W, d->Cin, d->Cin, slots, false, s);
+      if (rc == DDRL_OK)
+        rc = tc3_conv_fwd(o, w16.hi, w16.lo, w16.ld, d->Cout, slots, slots + 1, bias, act, mask, out, (long long)o.Yn * o.Xn * d->Cout,
+                          (long long)o.Xn * d->Cout, d->Cout, slots + 2, s);
+      return finish(rc);
+    }
+    if (!dy) return DDRL_E_ARG;
+    DgradFused fz;
+    std::vector<DgradClass> cls;
+    const bool fused = conv_dgrad_fused_plan(g, d->Cout, fz) == DDRL_OK;
+    size_t tot = 0, tot16 = 0;
+    if (fused) { tot = (size_t)fz.N * fz.K; tot16 = (size_t)fz.N * ((fz.K + 7) & ~7); }
+    else {
+      rc = conv_dgrad_plan(g, d->Cout, cls);
+      if (rc != DDRL_OK) return rc;
+      for (auto& c : cls) { tot += (size_t)g.C * c.K; tot16 += (size_t)g.C * ((c.K + 7) & ~7); }
+    }
+    DDRL_CUDA(cudaMalloc(&raw, 1024 + 4 * tot + 4 * tot16 + 256));
+    DDRL_CUDA(cudaMemsetAsync(raw, 0, 1024, s));
+    float* slots = reinterpret_cast<float*>(raw);
+    float* wp = reinterpret_cast<float*>(raw + 1024);
+    char* h16 = raw + 1024 + 4 * tot;
+    rc = amax_f32(dy, (long long)d->B * g.Ho * g.Wo, d->Cout, d->Cout, slots, false, s);
+    Tc3Ctx ctx{slots, slots + 1};
+    if (fused) {
+      fz.wd = wp;
+      if (rc == DDRL_OK) rc = pack_dgrad_fused(w, g, d->Cout, fz, s);
+      if (rc == DDRL_OK) rc = split_into(wp, fz.N, fz.K, fz.w16, h16, slots + 2);
+      if (rc == DDRL_OK) rc = conv_dgrad_fused_tc2(g, d->Cout, fz, dy, out, act, mask, d->B, s, 0, 0, &ctx);
+      return finish(rc);
+    }
+    size_t off = 0, off16 = 0;
+    int si = 2;
+    for (auto& c : cls) {
+      c.wd = wp + off;
+      if (rc == DDRL_OK) rc = pack_dgrad(w, g, d->Cout, c, s);
+      if (rc == DDRL_OK) rc = split_into(c.wd, g.C, c.K, c.w16, h16 + 4 * off16, slots + si++);
+      off += (size_t)g.C * c.K; off16 += (size_t)g.C * ((c.K + 7) & ~7);
+    }
+    if (rc == DDRL_OK && !conv_dgrad_supported(g, d->Cout, cls, dy, d->Cout, 0, d->B)) rc = DDRL_E_UNSUPPORTED;
+    if (rc == DDRL_OK) rc = conv_dgrad_tc(g, d->Cout, cls, dy, d->Cout, 0, out, act, mask, d->B, s, true, &ctx);
+    return finish(rc);
+  }
   if (op == 0) {
     if (!x) return DDRL_E_ARG;
     const size_t nw = ((size_t)d->Cout * g.K + 3) & ~size_t(3);
@@ -299,6 +373,20 @@ extern "C" int ddrl_conv_nhwc_f32(int mode, int op, const ddrl_conv_desc* d, con
     DDRL_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)d->Cout * g.K));
     DDRL_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (size_t)d->Cout * g.K, s));
     ConvOp o = conv_op_fwd(g, x, d->Cin, 0, d->B);
+    if (v3) {
+      float* slots = nullptr;
+      if (!tc3_conv_wgrad_supported(o)) rc = DDRL_E_UNSUPPORTED;
+      if (rc == DDRL_OK && cudaMalloc(&slots, 256) != cudaSuccess) rc = DDRL_E_CUDA;
+      if (rc == DDRL_OK && cudaMemsetAsync(slots, 0, 256, s) != cudaSuccess) rc = DDRL_E_CUDA;
+      if (rc == DDRL_OK) rc = amax_f32(x, (long long)d->B * d->H * d->W, d->Cin, d->Cin, slots, false, s);
+      if (rc == DDRL_OK) rc = amax_f32(dy, (long long)d->B * g.Ho * g.Wo, d->Cout, d->Cout, slots + 1, false, s);
+      if (rc == DDRL_OK) rc = tc3_conv_wgrad(o, dy, d->Cout, d->Cout, slots, slots + 1, tmp, g.K, s);
+      if (rc == DDRL_OK) rc = unpack_grad(tmp, out, d->Cout, taps, d->Cin, g.K, s);
+      cudaStreamSynchronize(s);
+      if (slots) cudaFree(slots);
+      if (tmp) cudaFree(tmp);
+      return rc;
+    }
     if (!conv_tc_supported(o, true)) rc = DDRL_E_UNSUPPORTED;
     if (rc == DDRL_OK) rc = v2 ? tc2_conv_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s) : conv_tc_wgrad(o, dy, d->Cout, d->Cout, tmp, g.K, s);
     if (rc == DDRL_OK) rc = unpack_grad(tmp, out, d->Cout, taps, d->Cin, g.K, s);

@@ -48,6 +48,21 @@ struct TcTap {
   long long cls_off[4];
 };
 
+// tc3 engine: one weight operand as scaled fp16 hi / lo' rows (split_f16), its transposed twin (linear layers: the K-major
+// operand of the data gradient) and the device scalar holding amax|w|
+struct W16 {
+  const void *hi = nullptr, *lo = nullptr;
+  int ld = 0;
+  const void *hiT = nullptr, *loT = nullptr;
+  int ldT = 0;
+  const float* amax = nullptr;
+};
+// per-launch operand scalars of the tc3 engine: amax of the activation operand (device), optional amax accumulator of the output
+struct Tc3Ctx {
+  const float* amax_a;
+  float* amax_out;
+};
+
 // One implicit-GEMM convolution launch over an NHWC tensor a[Bn, Hin, Win, Ctot] (channels [c_off, c_off+Cin)).
 struct ConvOp {
   const float* a;
@@ -75,6 +90,23 @@ int tc2_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const floa
 int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp, int ldw, cudaStream_t s);
 int split_hi_lo(const float* w, float* hi, float* lo, long long n, cudaStream_t s);
 
+// tc3.cu: scaled-fp16 3-product engine (kind::f16, 64-wide K blocks); weights pre-split by split_f16, operand amax scalars
+bool tc3_gemm_supported(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16);
+int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16, const float* amax_a,
+             const float* amax_b, float* C, int ldc, const float* bias, int act, const float* mask, float* amax_out,
+             cudaStream_t s);
+int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, int N, const float* amax_a, const float* amax_b,
+                 const float* bias, int act, const float* mask, float* out, long long osb, long long osy, long long osx,
+                 float* amax_out, cudaStream_t s, const TcTap* cls = nullptr);
+int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s);
+bool tc3_conv_wgrad_supported(const ConvOp& o);
+int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
+                   cudaStream_t s);
+int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s);
+int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT,
+              int ldT16, cudaStream_t s);
+
 // conv_ops.cu: convolution layers on the implicit-GEMM path
 struct DgradClass {              // one parity class (pix + pad) mod stride of the data gradient
   int ry, rx;                    // class residues
@@ -85,6 +117,7 @@ struct DgradClass {              // one parity class (pix + pad) mod stride of t
   int K;                         // nty*ntx*Cout
   float* wd;                     // packed weights [Cin, K]
   float *wd_hi, *wd_lo;          // their tf32 hi / lo split (tc2 engine)
+  W16 w16;                       // scaled fp16 split (tc3 engine)
 };
 struct DgradFused {              // all parity classes of a strided data gradient as ONE GEMM (tc2 engine)
   bool on;
@@ -94,16 +127,19 @@ struct DgradFused {              // all parity classes of a strided data gradien
   int K, N;                      // nty*ntx*Cout, ncy*ncx*Cin
   int iy0[2], ix0[2], q0y[2], q0x[2];
   float *wd, *wd_hi, *wd_lo;     // [N, K] (class-major rows), zero where a class has no tap
+  W16 w16;                       // scaled fp16 split (tc3 engine)
 };
 int conv_dgrad_fused_plan(const ConvGeom& g, int Cout, DgradFused& f);
 int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const DgradFused& f, cudaStream_t s);
 int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const float* dy, float* dx, int act,
-                         const float* mask, int B, cudaStream_t s, int out_ctot = 0, int out_coff = 0);
+                         const float* mask, int B, cudaStream_t s, int out_ctot = 0, int out_coff = 0,
+                         const Tc3Ctx* t3 = nullptr);          // t3 != nullptr: the tc3 engine (f.w16)
 ConvOp conv_op_fwd(const ConvGeom& g, const float* x, int Ctot, int c_off, int B);
 int conv_dgrad_plan(const ConvGeom& g, int Cout, std::vector<DgradClass>& out);
 int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClass& c, cudaStream_t s);
 int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot, int dy_coff,
-                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine = false);
+                  float* dx, int act, const float* mask, int B, cudaStream_t s, bool tmem_engine = false,
+                  const Tc3Ctx* t3 = nullptr);                  // t3 != nullptr: the tc3 engine (c.w16)
 bool conv_dgrad_supported(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cls, const float* dy, int dy_ctot,
                           int dy_coff, int B);
 

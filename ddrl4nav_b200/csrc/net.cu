@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -41,6 +42,7 @@ struct Lin {
   int act = 0;
   float* wp = nullptr;           // packed weight [N, ldw]   (when packed)
   float *wp_hi = nullptr, *wp_lo = nullptr;   // its tf32 hi / lo split (tc2 engine), refreshed with wp
+  W16 w16;                       // scaled fp16 split (+ transposed twin) of wp (tc3 engine), refreshed with wp
   float* dwp = nullptr;          // packed weight gradient   (when packed and training)
   int s2d_s = 0, s2d_C = 0, s2d_KH = 0, s2d_KW = 0;   // space-to-depth first layer: packing follows pack_weight_s2d
   bool s2d_fwd_only = false;     // ... for the forward weights only: the weight gradient runs on the im2col matrix (k = c,kh,kw)
@@ -74,6 +76,7 @@ struct Tower {
   int fuse_role = 0, in1_ctot = 0, in1_coff = 0;
   bool s2d0 = false;                                        // conv slot 0 runs on the space-to-depth observation
   bool s2d_infer = false;                                   // fused first conv: inference runs on the s2d observation
+  bool s2d_train = false;                                   // ... and so does training (tc3 engine): no im2col matrix at all
   bool borrow_cols = false;                                 // second unshared tower: the observation-side im2col matrices are tower 0's
   ConvGeom gs = {};                                         // its stride-1 NHWC geometry (buf[0] holds the s2d tensor)
   // per-micro-batch buffers
@@ -112,18 +115,96 @@ struct ddrl_net {
   // 2.16 -> 2.38 M actions/s; in the learner the im2col matrix is cached across the 10 iterations and needed by the weight
   // gradient anyway, and the im2col GEMM (842 us) beats the implicit kernel (944 us), so training keeps it.
   bool fuse_s2d = false;
+  // tc3 engine: the learner runs the fused first conv (forward AND weight gradient) on the space-to-depth observation too --
+  // the 3.4 GB im2col matrix and its two HBM-bound passes per iteration are gone (DDRL_NO_S2D_TRAIN=1 keeps the im2col GEMM)
+  bool s2d_train = false;
   float* s2dbuf = nullptr;       // [MB, H/s, W/s, s*s*C] space-to-depth observation of the micro-batch
   float* w0s2d = nullptr;        // [2 x Cout, K] both towers' conv1 weights in the space-to-depth K order (packed arena)
   float* bias0c = nullptr;       // its concatenated bias [2 x Cout]
   // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
   const float* cols_obs0 = nullptr;
   int cols_rows = -1;
+  // ---- tc3 engine: scaled fp16 weight operands and the amax scalars of every GEMM operand
+  char* h16_base = nullptr;      // fp16 arena of the split weights
+  size_t h16_bytes = 0;
+  float* amax_dev = nullptr;     // [kAmaxSlots] device scalars: [0, kAmaxWeights) weights (persistent), the rest activations
+  int amax_w_used = 0, amax_a_used = 0;
+  struct SplitJob { const float* w; int rows, K, ldw; W16* dst; bool transposed; };
+  std::vector<SplitJob> split_jobs;                 // every weight operand, in repack order
+  std::vector<W16> w16_extra;                       // operands that are not a Lin / dgrad class (fused first conv, s2d weights)
+  std::unordered_map<const float*, const W16*> w16_of;   // packed fp32 operand -> its split
+  struct AmaxEntry { int slot; unsigned long long epoch; bool persistent; };
+  std::unordered_map<std::string, AmaxEntry> amax_keys;  // activation view -> slot (valid while epoch == amax_epoch)
+  unsigned long long amax_epoch = 1;
+  W16 w16_fuse0, w16_s2d;
+  bool amax_persist_next = false;  // the next gemm()'s activation operand is observation-side staging (persistent amax entry)
 };
 
 namespace ddrl {
 
-static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM; }
-static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC2_TMEM; }
+constexpr int kAmaxSlots = 1024, kAmaxWeights = 256;
+// mode 3 (tc3) is a superset of mode 2: same lowering decisions; the tc2 kernels keep the launches tc3 does not take
+static inline bool tc3_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC3_F16; }
+static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
+static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
+
+// ---- amax registry of the tc3 engine -------------------------------------------------------------------------------
+// A view is (pointer, rows, cols, row stride); contiguous views are keyed by (pointer, element count) so that a conv
+// output [B*Ho*Wo, C] and the next layer's [B, Ho*Wo*C] read of it are the same key.  Only EXACT matches are trusted:
+// any other view of a buffer gets its own standalone reduction.  Slots of the activation region are zeroed at the start
+// of every engine pass; producers atomicMax into them, so a slot written several times in one pass (micro-batches,
+// shared scratch buffers) holds an upper bound -- which is all the scale needs.
+static std::string amax_key(const float* p, long long rows, long long cols, long long ld) {
+  char b[96];
+  if (ld == cols) snprintf(b, sizeof(b), "%p:%lld", (const void*)p, rows * cols);
+  else snprintf(b, sizeof(b), "%p:%lld:%lld:%lld", (const void*)p, rows, cols, ld);
+  return b;
+}
+static void amax_new_pass(ddrl_net* n, cudaStream_t s, bool keep_persistent) {
+  if (!n->amax_dev) return;
+  ++n->amax_epoch;
+  if (!keep_persistent)
+    for (auto& kv : n->amax_keys) if (kv.second.persistent) kv.second.epoch = 0;
+  cudaMemsetAsync(n->amax_dev + kAmaxWeights, 0, sizeof(float) * (kAmaxSlots - kAmaxWeights), s);
+}
+// persistent entries (observation-side staging that survives the iterations of one learn call) live in the weight region,
+// which the per-pass memset does not touch
+static int amax_slot_index(ddrl_net* n, const std::string& key, bool persistent = false) {
+  auto it = n->amax_keys.find(key);
+  if (it != n->amax_keys.end()) return it->second.slot;
+  int slot;
+  if (persistent) {
+    if (n->amax_w_used >= kAmaxWeights) return -1;
+    slot = n->amax_w_used++;
+  } else {
+    if (n->amax_a_used >= kAmaxSlots - kAmaxWeights) return -1;
+    slot = kAmaxWeights + n->amax_a_used++;
+  }
+  n->amax_keys[key] = {slot, 0, persistent};
+  return slot;
+}
+// slot a tc3 epilogue accumulates the amax of its output into (nullptr: not tracked)
+static float* amax_out_slot(ddrl_net* n, const float* p, long long rows, long long cols, long long ld) {
+  if (!tc3_mode(n) || !n->amax_dev) return nullptr;
+  const std::string key = amax_key(p, rows, cols, ld);
+  const int slot = amax_slot_index(n, key);
+  if (slot < 0) return nullptr;
+  n->amax_keys[key].epoch = n->amax_epoch;
+  return n->amax_dev + slot;
+}
+// amax of an operand view: the producer's slot when this exact view was written by a tracked producer in this pass,
+// otherwise a standalone reduction (result cached for the rest of the pass)
+static int amax_in_slot(ddrl_net* n, const float* p, long long rows, long long cols, long long ld, cudaStream_t s, const float** out,
+                        bool persistent = false) {
+  const std::string key = amax_key(p, rows, cols, ld);
+  const int slot = amax_slot_index(n, key, persistent);
+  if (slot < 0) return DDRL_E_STATE;
+  ddrl_net::AmaxEntry& e = n->amax_keys[key];
+  *out = n->amax_dev + slot;
+  if (e.persistent ? e.epoch != 0 : e.epoch == n->amax_epoch) return DDRL_OK;
+  e.epoch = n->amax_epoch;
+  return amax_f32(p, rows, (int)cols, ld, n->amax_dev + slot, e.persistent, s);
+}
 // hi / lo mirrors of a pointer into the packed arena
 static inline const float* hi_of(const ddrl_net* n, const float* p) {
   return reinterpret_cast<const float*>(n->split_base + (reinterpret_cast<const char*>(p) - n->packed_base));
@@ -306,6 +387,25 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
 static int gemm(const ddrl_net* n, int form, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const float* bias, int act, int beta, int trans_c, cudaStream_t s,
                 const float* mask = nullptr) {
+  // tc3: forward / dgrad GEMMs whose B operand is a packed weight with a scaled-fp16 split (form 1 reads the transposed twin)
+  if (tc3_mode(n) && form != 2 && !beta && !trans_c) {
+    auto it = n->w16_of.find(B);
+    if (it != n->w16_of.end()) {
+      const W16& w = *it->second;
+      const void *hi = form == 0 ? w.hi : w.hiT, *lo = form == 0 ? w.lo : w.loT;
+      const int ld16 = form == 0 ? w.ld : w.ldT;
+      if (hi && tc3_gemm_supported(M, N, K, A, lda, hi, lo, ld16)) {
+        ddrl_net* nn = const_cast<ddrl_net*>(n);
+        const float* ama = nullptr;
+        const bool persist = nn->amax_persist_next;
+        nn->amax_persist_next = false;
+        int r = amax_in_slot(nn, A, M, K, lda, s, &ama, persist);
+        if (r != DDRL_OK) return r;
+        return tc3_gemm(M, N, K, A, lda, hi, lo, ld16, ama, w.amax, C, ldc, bias, act, mask, amax_out_slot(nn, C, M, N, ldc), s);
+      }
+    }
+  }
+  const_cast<ddrl_net*>(n)->amax_persist_next = false;
   // tc2: forward / dgrad GEMMs whose B operand is a packed weight (pre-split mirrors exist)
   if (tc2_mode(n) && form != 2 && !beta && !trans_c && in_packed(n, B) &&
       tc2_gemm_supported(form, M, N, K, A, lda, hi_of(n, B), lo_of(n, B), ldb))
@@ -333,8 +433,12 @@ static float* db_of(const ddrl_net* n, const Lin& l) { return n->grads + n->T[l.
 
 // y = act(x W^T + b)
 static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* y, int ldy, long long M, cudaStream_t s) {
+  ddrl_net* nn = const_cast<ddrl_net*>(n);
+  const bool persist = nn->amax_persist_next;          // set by the caller when x is observation-side staging
+  nn->amax_persist_next = false;
   if (l.K <= 36 && l.act <= 2 && thin_supported(M, l.N, l.K, x, ldx, y, ldy))
     return thin_fwd(x, ldx, W_of(n, l), l.ldw, b_of(n, l), y, M, l.N, l.K, l.act, s);
+  nn->amax_persist_next = persist;
   return gemm(n, 0, (int)M, l.N, l.K, x, ldx, W_of(n, l), l.ldw, y, ldy, b_of(n, l), l.act, 0, 0, s);
 }
 // dy holds dL/d(pre-activation) of this layer (the activation derivative was applied by whoever produced dy).
@@ -342,11 +446,20 @@ static int lin_fwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
 // mask_act: 0 none, 1 relu, 2 leaky -- the activation that produced x, i.e. of the layer BELOW; mask = that x)
 static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, float* dy, int ldy, float* dx, int lddx,
                    int ncols_dx, int mask_act, const float* mask, long long M, cudaStream_t s) {
+  ddrl_net* nn = const_cast<ddrl_net*>(n);
+  const bool persist = nn->amax_persist_next;          // set by the caller when x is observation-side staging
+  nn->amax_persist_next = false;
   TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
   // dW[N, K] += dy[M,N]^T x[M,K]
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 && ldx % 4 == 0 && ldy % 4 == 0;
   if (l.K <= 36 && thin_supported(M, l.N, l.K, x, ldx, dy, ldy))
     TRY(thin_wgrad(x, ldx, dy, dW_of(n, l), l.ldw, M, l.N, l.K, s));
+  else if (tc3_mode(n) && al && l.K >= 32 && !getenv("DDRL_TC3_NO_WGRAD")) {
+    const float *amx = nullptr, *amy = nullptr;
+    TRY(amax_in_slot(nn, x, M, l.K, ldx, s, &amx, persist));
+    TRY(amax_in_slot(nn, dy, M, l.N, ldy, s, &amy));
+    TRY(tc3_wgrad(l.K, l.N, M, x, ldx, dy, ldy, amx, amy, dW_of(n, l), l.ldw, s));
+  }
   else if (tc2_mode(n) && al && l.K >= 32)
     TRY(tc2_wgrad(l.K, l.N, M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, s));
   // older engines: run with the larger of (N, K) on the 128-row side
@@ -373,7 +486,7 @@ static void tower_sizes(const Tower& t, bool train, std::vector<size_t>& f, std:
     case DDRL_ARCH_ATARI: {
       // 0 cols1, 1 a1, 2 cols2, 3 a2, 4 cols3, 5 a3 | train: 6 da3, 7 dcols, 8 da2, 9 da1
       // fused first conv: tower 0 owns cols1 and the 2x-wide a1 / da1, tower 1 borrows them
-      const size_t k0 = (t.fuse_role == 2 || (t.fuse_role == 1 && t.s2d_infer && !train)) ? 0 : 1,
+      const size_t k0 = (t.fuse_role == 2 || (t.fuse_role == 1 && t.s2d_infer && (!train || t.s2d_train))) ? 0 : 1,
                    k1 = t.fuse_role == 2 ? 0 : (t.fuse_role == 1 ? 2 : 1);
       f = {k0 * cols(t.g[0]), k1 * outp(t.g[0], 32), cols(t.g[1]), outp(t.g[1], 64), cols(t.g[2]), outp(t.g[2], 64)};
       if (train) { f.push_back(outp(t.g[2], 64)); f.push_back(std::max(cols(t.g[1]), cols(t.g[2])));
@@ -429,7 +542,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   size_t per = 0;
   for (auto& t : n->towers) per += tower_bytes_per_sample(t, train);
   per += (size_t)(n->ldA * 2 + 2 + 8) * 4;
-  const size_t s2d_floats = (n->fuse_s2d && !train) ? (size_t)n->towers[0].g[0].C * n->towers[0].g[0].H * n->towers[0].g[0].W : 0;
+  const size_t s2d_floats = (n->fuse_s2d && (!train || n->s2d_train)) ? (size_t)n->towers[0].g[0].C * n->towers[0].g[0].H * n->towers[0].g[0].W : 0;
   per += s2d_floats * 4;
   const char* env_gb = getenv("DDRL_WS_GB");
   const char* env_mb = getenv("DDRL_MICRO_BATCH");
@@ -441,6 +554,10 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   mb = std::min(mb, std::max(B, 1));
   if (n->ws.base && n->MB >= mb && (n->ws_train || !train)) return DDRL_OK;
   if (n->ws.base) { cudaDeviceSynchronize(); cudaFree(n->ws.base); n->ws.base = nullptr; }
+  // the amax registry is keyed by workspace pointers: start over (persistent entries are re-created on demand)
+  for (auto it = n->amax_keys.begin(); it != n->amax_keys.end();) it = it->second.persistent ? std::next(it) : n->amax_keys.erase(it);
+  for (auto& kv : n->amax_keys) kv.second.epoch = 0;
+  n->amax_a_used = 0;
   n->MB = mb;
   n->ws_train = train;
   // total with per-buffer 256 B alignment slack
@@ -561,6 +678,54 @@ static int alloc_packed(ddrl_net* n) {
     }
     off += ((size_t)l.N * l.ldw * 4 + 255) & ~size_t(255);
   }
+  if (tc3_mode(n)) {
+    // every weight operand of a tcgen05 GEMM: layers (linear layers with their transposed twin for the data gradient),
+    // data-gradient repacks of the implicit convs, the fused first conv's [2 Cout, K] operand and its s2d variant
+    n->split_jobs.clear();
+    auto add = [&](const float* w, int rows, int K, int ldw, W16* dst, bool tr) { n->split_jobs.push_back({w, rows, K, ldw, dst, tr}); };
+    for (auto& t : n->towers)
+      for (size_t i = 0; i < t.L.size(); ++i) {
+        Lin& l = t.L[i];
+        if (!l.packed || l.K < 32) continue;                      // thin first layers never reach the tensor-core engines
+        if (n->fuse0 && i == 0) continue;                         // covered by the fused [2 Cout, K] operand
+        const bool conv = i < 5 && t.conv_lin[i] == (int)i;
+        add(l.wp, l.N, l.K, l.ldw, &l.w16, !conv);
+      }
+    if (n->fuse0) add(n->towers[0].L[0].wp, 2 * n->towers[0].L[0].N, n->towers[0].L[0].K, n->towers[0].L[0].ldw, &n->w16_fuse0, false);
+    if (n->fuse_s2d) add(n->w0s2d, 2 * n->towers[0].L[0].N, n->towers[0].L[0].K, n->towers[0].L[0].ldw, &n->w16_s2d, false);
+    for (auto& t : n->towers)
+      for (int i = 0; i < 5; ++i) {
+        for (auto& c : t.dg[i]) add(c.wd, t.g[i].C, c.K, c.K, &c.w16, false);
+        if (t.df[i].on) add(t.df[i].wd, t.df[i].N, t.df[i].K, t.df[i].K, &t.df[i].w16, false);
+      }
+    if ((int)n->split_jobs.size() > kAmaxWeights / 2) return DDRL_E_UNSUPPORTED;
+    size_t bytes16 = 0;
+    auto r256 = [](size_t b) { return (b + 255) & ~size_t(255); };
+    for (auto& j : n->split_jobs) {
+      bytes16 += 2 * r256((size_t)j.rows * ((j.K + 7) & ~7) * 2);
+      if (j.transposed) bytes16 += 2 * r256((size_t)j.K * ((j.rows + 7) & ~7) * 2);
+    }
+    n->h16_bytes = bytes16;
+    DDRL_CUDA(cudaMalloc(&n->h16_base, bytes16));
+    DDRL_CUDA(cudaMemset(n->h16_base, 0, bytes16));
+    DDRL_CUDA(cudaMalloc(&n->amax_dev, sizeof(float) * kAmaxSlots));
+    DDRL_CUDA(cudaMemset(n->amax_dev, 0, sizeof(float) * kAmaxSlots));
+    size_t o16 = 0;
+    n->w16_of.clear();
+    for (auto& j : n->split_jobs) {
+      W16& w = *j.dst;
+      w.ld = (j.K + 7) & ~7;
+      w.hi = n->h16_base + o16; o16 += r256((size_t)j.rows * w.ld * 2);
+      w.lo = n->h16_base + o16; o16 += r256((size_t)j.rows * w.ld * 2);
+      if (j.transposed) {
+        w.ldT = (j.rows + 7) & ~7;
+        w.hiT = n->h16_base + o16; o16 += r256((size_t)j.K * w.ldT * 2);
+        w.loT = n->h16_base + o16; o16 += r256((size_t)j.K * w.ldT * 2);
+      }
+      w.amax = n->amax_dev + n->amax_w_used++;
+      n->w16_of[j.w] = &w;
+    }
+  }
   return DDRL_OK;
 }
 
@@ -605,6 +770,13 @@ static int repack(ddrl_net* n, cudaStream_t s) {
     if (dgn) TRY(split_hi_lo(reinterpret_cast<float*>(n->packed_base + dg0), reinterpret_cast<float*>(hi + dg0),
                              reinterpret_cast<float*>(lo + dg0), (long long)(dgn / 4), s));
   }
+  for (auto& j : n->split_jobs) {
+    W16& w = *j.dst;
+    float* slot = const_cast<float*>(w.amax);
+    TRY(amax_f32(j.w, j.rows, j.K, j.ldw, slot, true, s));
+    TRY(split_f16(j.w, j.rows, j.K, j.ldw, slot, const_cast<void*>(w.hi), const_cast<void*>(w.lo), w.ld, const_cast<void*>(w.hiT),
+                  const_cast<void*>(w.loT), w.ldT, s));
+  }
   n->dirty = false;
   return DDRL_OK;
 }
@@ -619,6 +791,14 @@ static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const f
     const Lin& l = t.L[li];
     const bool sub = gi == 1 && t.in1_ctot;
     const ConvOp o = conv_op_fwd(g, s2d ? cols : x, sub ? t.in1_ctot : g.C, sub ? t.in1_coff : 0, mb);
+    if (tc3_mode(n) && l.w16.hi) {
+      ddrl_net* nn = const_cast<ddrl_net*>(n);
+      const float* ama = nullptr;
+      TRY(amax_in_slot(nn, o.a, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &ama, s2d));
+      return tc3_conv_fwd(o, l.w16.hi, l.w16.lo, l.w16.ld, l.N, ama, l.w16.amax, b_of(n, l), l.act, nullptr, y,
+                          (long long)o.Yn * o.Xn * l.N, (long long)o.Xn * l.N, l.N,
+                          amax_out_slot(nn, y, (long long)mb * o.Yn * o.Xn, l.N, l.N), s);
+    }
     if (tc2_mode(n))
       return tc2_conv_fwd(o, l.wp_hi, l.wp_lo, l.ldw, l.N, b_of(n, l), l.act, nullptr, y, (long long)o.Yn * o.Xn * l.N,
                           (long long)o.Xn * l.N, l.N, s);
@@ -626,6 +806,7 @@ static int conv_block(const ddrl_net* n, const Tower& t, int gi, int li, const f
                        (long long)o.Xn * l.N, l.N, s);
   }
   if (!cols_cached) TRY(im2col(g, x, cols, mb, s));
+  if (gi == 0) const_cast<ddrl_net*>(n)->amax_persist_next = true;     // observation-side im2col matrix
   return lin_fwd(n, t.L[li], cols, g.ldc, y, t.L[li].N, (long long)mb * g.Ho * g.Wo, s);
 }
 
@@ -702,6 +883,13 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
   const long long M = (long long)mb * g.Ho * g.Wo;
   if (s2d) {                                       // first layer: no data gradient; x2 = the cached space-to-depth tensor
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
+    if (tc3_mode(n) && tc3_conv_wgrad_supported(conv_op_fwd(g, cols, g.C, 0, mb)) && !getenv("DDRL_TC3_NO_WGRAD")) {
+      ddrl_net* nn = const_cast<ddrl_net*>(n);
+      const float *amx = nullptr, *amy = nullptr;
+      TRY(amax_in_slot(nn, cols, (long long)mb * g.H * g.W, g.C, g.C, s, &amx, true));
+      TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
+      return tc3_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s);
+    }
     if (tc2_mode(n)) return tc2_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
     return conv_tc_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
   }
@@ -709,16 +897,33 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
     const bool sub = gi == 1 && t.in1_ctot;
     const int ctot = sub ? t.in1_ctot : g.C, coff = sub ? t.in1_coff : 0;
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
-    if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    if (tc3_mode(n) && tc3_conv_wgrad_supported(conv_op_fwd(g, x, ctot, coff, mb)) && !getenv("DDRL_TC3_NO_WGRAD")) {
+      ddrl_net* nn = const_cast<ddrl_net*>(n);
+      const float *amx = nullptr, *amy = nullptr;
+      TRY(amax_in_slot(nn, x, (long long)mb * g.H * g.W, ctot, ctot, s, &amx));
+      TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
+      TRY(tc3_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s));
+    }
+    else if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
     else TRY(conv_tc_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+    Tc3Ctx ctx{nullptr, nullptr};
+    const bool t3 = tc3_mode(n) && dx && (t.df[gi].on ? t.df[gi].w16.hi != nullptr : (!t.dg[gi].empty() && t.dg[gi][0].w16.hi != nullptr));
+    if (t3) {
+      ddrl_net* nn = const_cast<ddrl_net*>(n);
+      TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &ctx.amax_a));
+      // a data gradient that fills only a channel slice of a wider tensor does not describe that tensor's amax
+      if (!sub) ctx.amax_out = amax_out_slot(nn, dx, (long long)mb * g.H * g.W, g.C, g.C);
+    }
     if (dx && t.df[gi].on)
-      TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s, ctot, coff));
+      TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s, ctot, coff,
+                               t3 ? &ctx : nullptr));
     else if (dx && sub) return DDRL_E_STATE;
     else if (dx)
       TRY(conv_dgrad_tc(g, l.N, t.dg[gi], dy, l.N, 0, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s,
-                        tc2_mode(n)));
+                        tc2_mode(n), t3 ? &ctx : nullptr));
     return DDRL_OK;
   }
+  if (gi == 0) const_cast<ddrl_net*>(n)->amax_persist_next = true;     // observation-side im2col matrix
   TRY(lin_bwd(n, l, cols, g.ldc, dy, l.N, dx ? dcols : nullptr, g.ldc, g.ldc, 0, nullptr, M, s));
   if (dx) {
     TRY(col2im(g, dcols, dx, mb, s));
@@ -792,15 +997,23 @@ static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0,
   Tower& t0 = n->towers[0];
   const ConvGeom& g = t0.g[0];
   const Lin& l = t0.L[0];
-  if (n->fuse_s2d && !train && !n->ws_train) {
-    TRY(space_to_depth(g, obs[0] + row0 * g.sb, n->s2dbuf, mb, s));
+  if (n->fuse_s2d && (n->s2d_train || (!train && !n->ws_train))) {
+    if (!cols_cached) TRY(space_to_depth(g, obs[0] + row0 * g.sb, n->s2dbuf, mb, s));
     const ConvGeom& gs = t0.gs;
     const ConvOp o = conv_op_fwd(gs, n->s2dbuf, gs.C, 0, mb);
     const int N2 = 2 * l.N;
+    if (tc3_mode(n) && n->w16_s2d.hi) {
+      const float* ama = nullptr;
+      TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &ama, true));
+      return tc3_conv_fwd(o, n->w16_s2d.hi, n->w16_s2d.lo, n->w16_s2d.ld, N2, ama, n->w16_s2d.amax, n->bias0c, l.act, nullptr, t0.buf[1],
+                          (long long)o.Yn * o.Xn * N2, (long long)o.Xn * N2, N2,
+                          amax_out_slot(n, t0.buf[1], (long long)mb * o.Yn * o.Xn, N2, N2), s);
+    }
     return tc2_conv_fwd(o, hi_of(n, n->w0s2d), lo_of(n, n->w0s2d), l.ldw, N2, n->bias0c, l.act, nullptr, t0.buf[1], (long long)o.Yn * o.Xn * N2,
                         (long long)o.Xn * N2, N2, s);
   }
   if (!cols_cached) TRY(im2col(g, obs[0] + row0 * g.sb, t0.buf[0], mb, s));
+  n->amax_persist_next = true;                       // the im2col matrix of the observations survives the learn call's iterations
   return gemm(n, 0, (int)((long long)mb * g.Ho * g.Wo), 2 * l.N, l.K, t0.buf[0], g.ldc, l.wp, l.ldw, t0.buf[1], 2 * l.N, n->bias0c,
               l.act, 0, 0, s);
 }
@@ -813,6 +1026,22 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
   float* dy = t0.buf[9];
   TRY(colsum_add(dy, 2 * l0.N, M, l0.N, db_of(n, l0), s));
   TRY(colsum_add(dy + l0.N, 2 * l0.N, M, l1.N, db_of(n, l1), s));
+  if (n->s2d_train) {
+    // weight gradient of both towers in the space-to-depth K order: dW0s2d [2 Cout, K] (the twin of w0s2d in the gradient
+    // half of the packed arena), un-permuted per tower after the micro-batch loop
+    const ConvOp o = conv_op_fwd(t0.gs, n->s2dbuf, t0.gs.C, 0, mb);
+    const float *amx = nullptr, *amy = nullptr;
+    TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &amx, true));
+    TRY(amax_in_slot(n, dy, M, 2 * l0.N, 2 * l0.N, s, &amy));
+    float* dw = reinterpret_cast<float*>(reinterpret_cast<char*>(n->w0s2d) + n->packed_grad_off);
+    return tc3_conv_wgrad(o, dy, 2 * l0.N, 2 * l0.N, amx, amy, dw, l0.ldw, s);
+  }
+  if (tc3_mode(n) && !getenv("DDRL_TC3_NO_WGRAD")) {
+    const float *amx = nullptr, *amy = nullptr;
+    TRY(amax_in_slot(n, t0.buf[0], M, l0.K, g.ldc, s, &amx, true));
+    TRY(amax_in_slot(n, dy, M, 2 * l0.N, 2 * l0.N, s, &amy));
+    return tc3_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, amx, amy, l0.dwp, l0.ldw, s);
+  }
   return tc2_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, l0.dwp, l0.ldw, s);
 }
 
@@ -897,6 +1126,11 @@ extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
           n->fuse_s2d = true;
           t0.gs = gs;
           t0.s2d_infer = true;
+          const char* nst = getenv("DDRL_NO_S2D_TRAIN");
+          if (tc3_mode(n) && !(nst && nst[0] == '1') && tc3_conv_wgrad_supported(conv_op_fwd(gs, kAligned, gs.C, 0, 1))) {
+            n->s2d_train = true;
+            t0.s2d_train = true;
+          }
         }
       }
     }
@@ -910,6 +1144,8 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
   if (n->split_base) cudaFree(n->split_base);
+  if (n->h16_base) cudaFree(n->h16_base);
+  if (n->amax_dev) cudaFree(n->amax_dev);
   if (n->bias0c) cudaFree(n->bias0c);
   delete n;
   return DDRL_OK;
@@ -977,6 +1213,7 @@ extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs,
   const int A = n->d.act_dim;
   for (long long r0 = 0; r0 < B; r0 += n->MB) {
     const int mb = (int)std::min<long long>(n->MB, B - r0);
+    amax_new_pass(n, s, false);      // every micro-batch rewrites the workspace: amax entries live for one chunk
     TRY(forward_chunk(n, obs, r0, mb, false, s));
     if (n->d.dist == DDRL_DIST_CATEGORICAL) {
       TRY(ddrl_categorical_head(n->logits, n->ldA, draw ? draw + r0 : nullptr, mb, A, actions + r0, logp + r0,
@@ -987,6 +1224,28 @@ extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs,
       if (pi_out) TRY(copy2d(n->logits, n->ldA, pi_out + r0 * A, A, mb, A, s));
     }
     DDRL_CUDA(cudaMemcpyAsync(values + r0, n->vout, sizeof(float) * mb, cudaMemcpyDeviceToDevice, s));
+  }
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_net_encode(ddrl_net* n, const float* const* obs, int n_obs, int B, int tower, float* out, void* stream) {
+  if (!n || B < 0 || tower < 0 || tower >= (int)n->towers.size()) return DDRL_E_ARG;
+  if (!n->params) return DDRL_E_STATE;
+  if (B == 0) return DDRL_OK;
+  TRY(check_obs(n, obs, n_obs));
+  if (!out) return DDRL_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(ensure_workspace(n, B, n->ws_train));
+  if (n->dirty) TRY(repack(n, s));
+  n->cols_obs0 = nullptr;            // the workspace is about to be overwritten
+  const int F = n->towers[tower].feat;
+  for (long long r0 = 0; r0 < B; r0 += n->MB) {
+    const int mb = (int)std::min<long long>(n->MB, B - r0);
+    amax_new_pass(n, s, false);      // every micro-batch rewrites the workspace: amax entries live for one chunk
+    if (n->fuse0) TRY(fused_conv0_fwd(n, obs, r0, mb, false, s, false));
+    // towers that borrow tower 0's observation-side im2col matrices need it to have run on this micro-batch
+    for (int t = n->towers[tower].borrow_cols ? 0 : tower; t <= tower; ++t) TRY(tower_forward(n, n->towers[t], obs, r0, mb, false, s));
+    DDRL_CUDA(cudaMemcpyAsync(out + r0 * F, n->towers[tower].h, sizeof(float) * (size_t)mb * F, cudaMemcpyDeviceToDevice, s));
   }
   return DDRL_OK;
 }
@@ -1019,6 +1278,8 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   float* cw = n->params + n->T[n->t_cw].offset;
   for (long long r0 = 0; r0 < B_local; r0 += n->MB) {
     const int mb = (int)std::min<long long>(n->MB, B_local - r0);
+    // amax entries live for one micro-batch; the observation-side ones survive while the staged observations do
+    amax_new_pass(n, s, reuse_obs);
     TRY(forward_chunk(n, obs, r0, mb, true, s, reuse_obs));
     if (n->d.dist == DDRL_DIST_CATEGORICAL) {
       TRY(ddrl_ppo_loss_categorical(n->logits, n->ldA, actions + r0, old_logp + r0, adv + r0, returns + r0, n->vout, mb, A,
@@ -1037,9 +1298,18 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
     if (n->fuse0) TRY(fused_conv0_bwd(n, mb, s));
   }
   // packed weight grads -> reference layout
+  if (n->s2d_train) {
+    const ConvGeom& g = n->towers[0].g[0];
+    const float* dw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(n->w0s2d) + n->packed_grad_off);
+    for (int k = 0; k < 2; ++k) {
+      const Lin& l = n->towers[k].L[0];
+      TRY(unpack_grad_s2d(dw + (size_t)k * l.N * l.ldw, n->grads + n->T[l.w_t].offset, l.N, g.C, g.KH, g.KW, g.stride, l.ldw, s));
+    }
+  }
   for (auto& t : n->towers)
     for (auto& l : t.L)
       if (l.packed) {
+        if (n->s2d_train && &l == &t.L[0]) continue;         // done above from the fused space-to-depth gradient
         if (l.s2d_s && !l.s2d_fwd_only) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
         else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
       }

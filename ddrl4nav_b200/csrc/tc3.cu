@@ -1,0 +1,1274 @@
+// Third-generation tcgen05 engine: fp32 in / fp32 out through THREE kind::f16 products of scaled fp16 splits.
+//
+// What the round-1 engine (tc2.cu, 3xTF32) was bound by, measured on B200 (profiles/tf32_peak.json, r1d_tc2_skeleton.md):
+//   * every M = 128 MMA with N <= 64 holds the tensor pipe for 45 clk and kind::tf32 covers only K = 8 per instruction;
+//   * the single issuing thread paid two mbarrier round trips per 32-wide K block;
+//   * the tf32 weight tiles are 4 bytes per element of shared-memory traffic on every MMA pass.
+// This engine keeps tc2's structure (persistent CTAs, activation operand split by dedicated warps into TENSOR MEMORY,
+// implicit-GEMM tap boxes, fused parity-class data gradient, swizzled staging epilogue) and changes the arithmetic and
+// the hand-off granularity:
+//   * operands are split as  x*s = hi + lo * 2^-11,  hi = rn_f16(x*s), lo = rn_f16((x*s - hi) * 2^11)  with a per-tensor
+//     power-of-two scale s = 2^(13 - floor(log2 amax|x|)) (the fp16 exponent range is the only thing lost against tf32:
+//     the 22 significant bits are the same, and elements below amax * 2^-27 only lose RELATIVE precision).  Products
+//     hi*hi -> main accumulator, hi*lo' + lo'*hi -> correction accumulators, result = (main + corr * 2^-11) / (sA sB).
+//     kind::f16 is K = 16 per MMA in the clocks kind::tf32 needs for K = 8: half the tensor time, half the weight bytes.
+//   * K blocks are 64 wide (two 32-float TMA boxes of the raw activation tile; one 128-byte swizzle row of fp16 weights):
+//     half the barrier round trips per FLOP; the MMA issuers wait on ONE barrier per K block (the splitter's "A slot
+//     ready" arrival happens after the stage's TMA barrier, so it covers the weight tile as well).
+//   * amax|x| of every GEMM operand is a device scalar maintained by its producer (this engine's epilogue tracks the
+//     running max of what it stores: one atomicMax per epilogue warp per launch) or by `amax_f32` for foreign tensors.
+//   * weights are split, scaled and -- for the data gradient of linear layers -- transposed once per optimiser step, so
+//     the weight operand is always K-major.
+// Accumulation: the tensor core adds into fp32 with truncation (scratch/tc_acc.py), so `main` lives in TMEM only for 16
+// MMAs (4 K blocks) and is then added round-to-nearest into fp32 registers, exactly as in tc2.
+// Warp roles: 0 TMA producer | 1 MMA issuer (chunk accumulators) | 3 MMA issuer (whole-tile correction accumulator) |
+// 2 TMEM allocator | splitter groups of 4 warps | epilogue warps.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "layer_ops.h"
+#include "tc_ptx.cuh"
+
+namespace ddrl {
+
+constexpr int T3_BM = 128;
+constexpr int T3_BK = 64;                     // k per K block (two 32-float boxes of A; 64 halfs = one swizzle row of B)
+constexpr int T3_CHUNK = 4;                   // K blocks per TMEM main-accumulator chunk (16 accumulating MMAs)
+constexpr float T3_LO = 2048.f, T3_LO_INV = 1.f / 2048.f;
+
+// Optional role-level accounting (build with -DTC3_TIMING, scratch/tc3_roles.py): cycles each warp role of the forward
+// kernel spends in each of its phases, accumulated over every launch.  [role*8 + k]; k = 7 is the role's lifetime.
+// roles: 0 producer {empty} | 1 chunk MMA {mfree, aready, issue+commit} | 2 corr MMA {cfree, aready, issue+commit} |
+//        3 splitter warp 4 {full, afree, lds+split, st+wait::st} | 4 epilogue warp 0 {mfull, cfull, stores, drain}
+__device__ unsigned long long g_tc3_wait[64];
+#ifdef TC3_TIMING
+#define T3_T0 const long long _t0 = clock64()
+#define T3_ACC(acc) acc += clock64() - _t0
+#define T3_WAIT(bar, par, acc) do { T3_T0; mbar_wait(bar, par); T3_ACC(acc); } while (0)
+#define T3_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0, w3 = 0; const long long role_t0 = clock64();
+#define T3_ROLE_END(role, cond) do { if ((cond) && lane == 0) { \
+    atomicAdd(&g_tc3_wait[(role) * 8 + 0], (unsigned long long)w0); atomicAdd(&g_tc3_wait[(role) * 8 + 1], (unsigned long long)w1); \
+    atomicAdd(&g_tc3_wait[(role) * 8 + 2], (unsigned long long)w2); atomicAdd(&g_tc3_wait[(role) * 8 + 3], (unsigned long long)w3); \
+    atomicAdd(&g_tc3_wait[(role) * 8 + 7], (unsigned long long)(clock64() - role_t0)); } } while (0)
+#define T3_SECTION_BEGIN const long long _s0 = clock64()
+#define T3_SECTION_END(acc) acc += clock64() - _s0
+#else
+#define T3_WAIT(bar, par, acc) mbar_wait(bar, par)
+#define T3_ROLE_BEGIN
+#define T3_ROLE_END(role, cond)
+#define T3_SECTION_BEGIN
+#define T3_SECTION_END(acc)
+#endif
+
+struct Tc3Args {
+  float* C;
+  const float* bias;
+  const float* mask;
+  long long sCm, sCn;
+  int M, N, K;
+  int kb_total, kb_per_split;                 // K blocks of 64 (tap mode: pairs of 32-channel slices)
+  int act, atomic, vec_store;
+  int tma_store;                              // outputs leave through TMA tile stores of the staged panels (tmC / tmC2)
+  int m_tiles, n_tiles;
+  const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
+  const float* amax_b;
+  float* amax_out;                            // optional: running amax of the stored output (atomicMax on the bits)
+  TcTap tap;
+};
+
+// power-of-two scale that maps amax into [2^13, 2^14) and its inverse, from the exponent bits (amax = 0 or denormal: the
+// clamp keeps both finite; inf / nan inputs poison the result either way)
+__host__ __device__ __forceinline__ void t3_scale(float amax, float& s, float& inv) {
+#ifdef __CUDA_ARCH__
+  int e = (__float_as_int(amax) >> 23) & 0xff;
+#else
+  uint32_t bits; memcpy(&bits, &amax, 4);
+  int e = (int)((bits >> 23) & 0xff);
+#endif
+  if (amax == 0.f) e = 127 + 13;
+  e = e < 14 ? 14 : (e > 253 ? 253 : e);
+  const uint32_t sb = (uint32_t)(267 - e) << 23, ib = (uint32_t)(e - 13) << 23;
+#ifdef __CUDA_ARCH__
+  s = __uint_as_float(sb); inv = __uint_as_float(ib);
+#else
+  memcpy(&s, &sb, 4); memcpy(&inv, &ib, 4);
+#endif
+}
+
+// (x0, x1) * s -> packed fp16 hi pair and packed fp16 lo' pair (saturating: a stale amax gives a wrong, finite result)
+__device__ __forceinline__ void t3_split2(float x0, float x1, float s, uint32_t& hi, uint32_t& lo) {
+  const float y0 = x0 * s, y1 = x1 * s;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y1), "f"(y0));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float r0 = (y0 - f.x) * T3_LO, r1 = (y1 - f.y) * T3_LO;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int BN>
+struct T3Cfg {
+  static constexpr int A_SUB = T3_BM * 128;                      // one 32-float box of the raw activation tile: 16 KB
+  static constexpr int A_BYTES = 2 * A_SUB;
+  static constexpr int B_BYTES = BN * 128;                       // BN rows x 64 halfs
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;      // A raw (2 boxes) | B hi | B lo
+  static constexpr int STAGES = BN <= 32 ? 5 : (BN <= 64 ? 4 : 3);
+  // BN <= 64: hi*hi and hi*lo are ONE MMA of N' = 2 BN over the adjacent [B_hi ; B_lo] tiles (N' = 128 runs at the full
+  // N/2-clk rate, two N = 64 MMAs would cost 45 clk each); lo*hi goes to the whole-tile correction accumulator.
+  static constexpr bool FOLD = BN <= 64;
+  static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots: 64 columns each = [hi 32 | lo 32] for 64 k
+  static constexpr int NEPI = BN <= 32 ? 4 : 8;
+  static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
+  static constexpr int EPI0 = 4 + 4 * NSG;
+  static constexpr int THREADS = (EPI0 + NEPI) * 32;
+  static constexpr int COLS = BN / (NEPI / 4);
+  // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN, TM_A = FOLD ? 5 * BN : 3 * BN;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NBARS = 2 * STAGES + SA + 6;
+  // epilogue staging: NEPI/4 panels of 128 rows x 32 fp32 columns (128-byte rows, 128B swizzle = the box layout of a TMA
+  // tile store; warp e owns rows [32 (e & 3), +32) of panel e >> 2), 1024-byte aligned
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + NEPI * 4096;
+  static constexpr int SMEM = 1024 + BAR_OFF + 256;
+  static_assert(NBARS * 8 + 16 <= 256, "barrier block");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
+  static_assert(STAGES > SA, "the stage barrier of K block it - SA releases TMEM slot it % SA");
+};
+
+// C[M,N] = epi( (A[M,K] . B[N,K]^T) )   A: fp32, plain 2-D or tap boxes; B: pre-split fp16 hi / lo', K-major
+template <int BN>
+__global__ void __launch_bounds__(T3Cfg<BN>::THREADS, 1)
+tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+           const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmA2,
+           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, Tc3Args g) {
+  using Cfg = T3Cfg<BN>;
+  constexpr int S = Cfg::STAGES, SA = Cfg::SA;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* bar_full = bars;                  // [S]  TMA landed
+  uint64_t* bar_empty = bars + S;             // [S]  MMAs that read the stage (and its TMEM slot) retired
+  uint64_t* bar_aready = bars + 2 * S;        // [SA] TMEM A slot written
+  uint64_t* bar_mfull = bars + 2 * S + SA;    // [2] main accumulator chunk complete
+  uint64_t* bar_mfree = bar_mfull + 2;        // [2] drained
+  uint64_t* bar_cfull = bar_mfull + 4;        // correction accumulator complete (tile end)
+  uint64_t* bar_cfree = bar_mfull + 5;        // read by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcTap& tp = g.tap;
+  const bool tapA = tp.mode != 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
+    for (int a = 0; a < SA; ++a) mbar_init(smem_u32(bar_aready + a), 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
+    mbar_init(smem_u32(bar_cfull), 1);
+    mbar_init(smem_u32(bar_cfree), Cfg::NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work enumeration, identical in every role: tiles blockIdx.x, +gridDim.x, ... of the (m_tiles x n_tiles) space
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int tile_step = (int)gridDim.x, tile_first = (int)blockIdx.x;
+  const int nkb = g.kb_total;
+  // tap mode with an odd slice count: the last K block holds ONE 32-channel slice (2 k steps)
+  const bool odd_tail = tapA && (tp.nslices & 1);
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    uint32_t it = 0;
+    T3_ROLE_BEGIN
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+      const int m0 = mt * T3_BM, n0 = nt * BN;
+      int b0 = 0, y0 = 0;
+      const bool ph2 = tapA && mt >= tp.tiles1;       // second tiling phase: the images' remaining rows
+      if (tapA) {
+        if (!ph2) { b0 = (mt / tp.tpi) * tp.nb; y0 = (mt % tp.tpi) * tp.ny * tp.sy - tp.py; }
+        else { b0 = (mt - tp.tiles1) * tp.nb2; y0 = tp.y2 * tp.sy - tp.py; }
+      }
+      int cc = 0, kw = 0, kh = 0;                     // tap slices advance (chunk fastest, then kw, then kh)
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S;
+        T3_WAIT(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1, w0);
+        if (elect_one()) {
+          const uint32_t full = smem_u32(bar_full + s);
+          const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
+          const int k = i * T3_BK;
+          if (!tapA) {
+            mbar_expect_tx(full, Cfg::A_BYTES + 2u * Cfg::B_BYTES);
+            tma_load_2d(&tmA, full, a_dst, k, m0);
+            tma_load_2d(&tmA, full, a_dst + Cfg::A_SUB, k + 32, m0);
+          } else {
+            const bool two = !(odd_tail && i == nkb - 1);
+            const uint32_t box = (uint32_t)(ph2 ? tp.rows2 : tp.rows) * 128u;
+            mbar_expect_tx(full, (two ? 2u : 1u) * box + 2u * Cfg::B_BYTES);
+            tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
+            if (two) {
+              int cc2 = cc + 1, kw2 = kw, kh2 = kh;
+              if (cc2 == tp.cpb) { cc2 = 0; if (++kw2 == tp.KW) { kw2 = 0; ++kh2; } }
+              tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst + Cfg::A_SUB, tp.c_off + cc2 * 32, kw2 - tp.px, y0 + kh2, b0);
+            }
+          }
+          tma_load_2d(&tmBhi, full, bh_dst, k, n0);
+          tma_load_2d(&tmBlo, full, bl_dst, k, n0);
+        }
+        __syncwarp();
+        if (tapA) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (++cc == tp.cpb) { cc = 0; if (++kw == tp.KW) { kw = 0; ++kh; } }
+        }
+      }
+    }
+    T3_ROLE_END(0, true);
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers (one elected thread each)
+    // warp 1: chunk buffers   main (+)= A_hi . B_hi          [FOLD: [main | corrB] (+)= A_hi . [B_hi ; B_lo], N' = 2 BN]
+    // warp 3: whole tile      corr  += A_lo . B_hi           [!FOLD: ... + A_hi . B_lo]
+    const bool chunk_role = warp == 1;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);        // f16 x f16 -> f32
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
+    uint32_t it = 0, ch = 0, tl = 0;
+    T3_ROLE_BEGIN
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S, a = it % SA;
+        const uint32_t buf = ch & 1;
+        const bool first_in_chunk = (i % T3_CHUNK) == 0;
+        const bool last_in_chunk = (i % T3_CHUNK) == T3_CHUNK - 1 || i == nkb - 1;
+        const int ksteps = (odd_tail && i == nkb - 1) ? 2 : 4;
+        if (chunk_role) { if (first_in_chunk) T3_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0); }
+        else if (i == 0) T3_WAIT(smem_u32(bar_cfree), (tl & 1) ^ 1, w0);
+        // ONE wait per K block: the splitters arrive on `aready` after they have seen the stage's TMA barrier, so the
+        // weight tile of the stage is complete (and visible through the same release / acquire chain) as well
+        T3_WAIT(smem_u32(bar_aready + a), (it / SA) & 1, w1);
+        tc_fence_after();
+        T3_SECTION_BEGIN;
+        if (elect_one()) {
+          const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
+          const uint64_t dbh0 = umma_desc(b_hi, 16, 1024, 2);
+          if (chunk_role) {
+            const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_f16_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * 2, Cfg::FOLD ? idesc2 : idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(bar_empty + s));            // retires the stage AND the TMEM A slot of this K block
+            if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+          } else {
+            const uint64_t dbl0 = umma_desc(b_lo, 16, 1024, 2);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_f16_ts(t_corr, a_lo + k4 * 8, dbh0 + k4 * 2, idesc, (i | k4) != 0 ? 1u : 0u);
+              if (!Cfg::FOLD) umma_f16_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * 2, idesc, 1u);
+            }
+            umma_commit(smem_u32(bar_empty + s));
+            if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
+          }
+        }
+        __syncwarp();
+        T3_SECTION_END(w2);
+        if (last_in_chunk) ++ch;
+      }
+    }
+    T3_ROLE_END(chunk_role ? 1 : 2, true);
+  } else if (warp >= 4 && warp < Cfg::EPI0) {
+    // ============================================================ splitters: smem A (fp32) -> scaled fp16 hi / lo' -> TMEM
+    const int q = (warp - 4) & 3, grp = (warp - 4) >> 2;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    float sA, sA_inv;
+    t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    T3_ROLE_BEGIN
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
+        const int s = it % S, a = it % SA;
+        T3_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
+        T3_SECTION_BEGIN;
+        const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
+        const int nsub = (odd_tail && i == nkb - 1) ? 1 : 2;
+        // thread = tile row; sub-tile j holds k [32 j, 32 j + 32) of the row as eight 16-byte chunks (128B swizzle)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j >= nsub) break;
+          uint32_t hi[16], lo[16];
+          const uint8_t* rp = st + j * Cfg::A_SUB + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+            t3_split2(v.x, v.y, sA, hi[2 * c], lo[2 * c]);
+            t3_split2(v.z, v.w, sA, hi[2 * c + 1], lo[2 * c + 1]);
+          }
+          if (j == 0) {
+            // TMEM slot a was last read by K block it - SA: its stage barrier (both MMA streams commit to it) doubles as
+            // the slot's release -- S > SA, so that barrier cannot be a second phase ahead when we look at it
+            if (it >= (uint32_t)SA) {
+              const uint32_t jj = it - SA;
+              T3_WAIT(smem_u32(bar_empty + (jj % S)), (jj / S) & 1, w1);
+            }
+            tc_fence_after();
+          }
+          tmem_st16(ta + j * 16, hi);
+          tmem_st16(ta + 32 + j * 16, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
+        T3_SECTION_END(w2);                                        // includes the afree wait (subtract w1)
+      }
+    }
+    T3_ROLE_END(3, warp == 4);
+  } else if (warp >= Cfg::EPI0) {
+    // ============================================================ drain + epilogue
+    const int e = warp - Cfg::EPI0;
+    const int q = e & 3, half = e >> 2;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const uint32_t col0 = half * Cfg::COLS;
+    float sA, sA_inv, sB, sB_inv;
+    t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    t3_scale(__ldg(g.amax_b), sB, sB_inv);
+    float run_max = 0.f;
+    uint32_t ch = 0, tl = 0;
+    T3_ROLE_BEGIN
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
+      const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+      const int m0 = mt * T3_BM, n0 = nt * BN;
+      float acc[Cfg::COLS];
+#pragma unroll
+      for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
+      const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
+      for (int c = 0; c < nch; ++c, ++ch) {
+        const int buf = ch & 1;
+        T3_WAIT(smem_u32(bar_mfull + buf), (ch >> 1) & 1, w0);
+        tc_fence_after();
+#pragma unroll
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
+          if (Cfg::FOLD) {
+            // the hi*lo' term of this chunk sits BN columns further (second half of the folded N' = 2 BN MMA)
+            tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
+      }
+      T3_WAIT(smem_u32(bar_cfull), tl & 1, w1);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
+#pragma unroll
+      for (int j = 0; j < Cfg::COLS; ++j) acc[j] = (acc[j] * sA_inv) * sB_inv;
+      // ---- stores
+      T3_SECTION_BEGIN;
+      const int r = q * 32 + lane;
+      bool rvalid;
+      long long roff;
+      if (tapA) {
+        const bool ph2 = mt >= tp.tiles1;
+        const int b0 = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb, y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        const int nyp = ph2 ? tp.ny2 : tp.ny;
+        const int x = r % tp.Xn, t2 = r / tp.Xn;
+        const int yy = t2 % nyp, bb = t2 / nyp;
+        rvalid = r < (ph2 ? tp.rows2 : tp.rows) && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
+        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
+      } else {
+        rvalid = (m0 + r) < g.M;
+        roff = (long long)(m0 + r) * g.sCm;
+      }
+      const float neg_slope = g.act == 3 ? 0.f : 0.01f;
+      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
+      const bool fused = tapA && tp.ncls > 1;
+      int py = 0, px = 0;
+      if (fused) {
+        const bool ph2 = mt >= tp.tiles1;
+        const int y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        px = (r % tp.Xn) * tp.out_s;
+        py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
+      }
+      if (g.tma_store) {
+        // TMA path: bias + activation in registers, the warp's 32 rows x 32 columns into its slice of the swizzled panel,
+        // then ONE elected thread stores the whole tile panel(s) with a tensor-map box that mirrors the load-side box
+        // (rows past the tensor's extents are clipped by the TMA unit: no per-row addressing, no per-element stores)
+        float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
+        int cy = 0, cb = 0;
+        if (tapA) {
+          const bool ph2 = mt >= tp.tiles1;
+          cb = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb;
+          cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        }
+#pragma unroll
+        for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
+          const int colb = n0 + col0 + p0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = colb + 4 * c + k;
+              float x = acc[p0 + 4 * c + k];
+              if (col < g.N) {
+                if (g.bias != nullptr) x += __ldg(g.bias + col);
+                if (g.act == 1) x = fmaxf(x, 0.f);
+                else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+                if (rvalid) run_max = fmaxf(run_max, fabsf(x));
+              }
+              o[k] = x;
+            }
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
+          if (e == 0 && elect_one()) {
+#pragma unroll
+            for (int h = 0; h < Cfg::NEPI / 4; ++h) {
+              const int col = n0 + h * Cfg::COLS + p0;
+              if (col >= g.N) continue;
+              const uint32_t src = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
+              if (!tapA)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(src), "r"(col), "r"(m0) : "memory");
+              else
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(mt >= tp.tiles1 ? &tmC2 : &tmC)), "r"(src), "r"(col), "r"(0), "r"(cy), "r"(cb)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");     // staging reusable
+        }
+      } else if (g.vec_store) {
+        // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
+        // (and activation-mask load) instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+        float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
+        const int cidx = lane & 7, rsub = lane >> 3;
+        const int pyx = (py << 16) | px;
+#pragma unroll
+        for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                make_float4(acc[p0 + 4 * c], acc[p0 + 4 * c + 1], acc[p0 + 4 * c + 2], acc[p0 + 4 * c + 3]);
+          __syncwarp();
+          const int colv = n0 + col0 + p0 + cidx * 4;
+          const bool cok = colv < g.N;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (colv + k < g.N) bv[k] = g.bias[colv + k];
+          }
+          long long cadd = 0;
+          int ciy = 0, cix = 0;
+          if (fused && cok) {
+            const int qq = colv / tp.cls_cols;
+            ciy = tp.cls_iy[qq]; cix = tp.cls_ix[qq];
+            cadd = tp.cls_off[qq] - (long long)qq * tp.cls_cols;     // column colv of group qq lands at channel colv - qq*cls_cols
+          }
+          // pass 1: addresses + all activation-mask loads of the panel in flight together
+          long long off[8];
+          float4 mk[8];
+          uint32_t okm = 0;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rr = i8 * 4 + rsub;
+            const int ok = __shfl_sync(0xffffffffu, (int)rvalid, rr);
+            const long long ro = __shfl_sync(0xffffffffu, roff, rr);
+            const int ryx = __shfl_sync(0xffffffffu, pyx, rr);
+            bool live = ok && cok;
+            if (fused && ((ryx >> 16) + ciy >= tp.out_H || (ryx & 0xffff) + cix >= tp.out_W)) live = false;
+            off[i8] = ro + cadd + colv;
+            mk[i8] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (live) {
+              okm |= 1u << i8;
+              if (g.act >= 3) {
+                if (colv + 4 <= g.N) mk[i8] = __ldg(reinterpret_cast<const float4*>(g.mask + off[i8]));
+                else {
+                  float* mv = reinterpret_cast<float*>(&mk[i8]);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) if (colv + k < g.N) mv[k] = __ldg(g.mask + off[i8] + k);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            if (!((okm >> i8) & 1u)) continue;
+            const int rr = i8 * 4 + rsub;
+            const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cidx ^ (rr & 7)) << 2));
+            const float xv[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float* mv = reinterpret_cast<const float*>(&mk[i8]);
+            float4 o;
+            float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float x = xv[k] + bv[k];
+              if (g.act == 1) x = fmaxf(x, 0.f);
+              else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+              else if (g.act >= 3) x = mv[k] > 0.f ? x : neg_slope * x;
+              ov[k] = x;
+            }
+            if (colv + 4 <= g.N) {
+              *reinterpret_cast<float4*>(g.C + off[i8]) = o;
+              run_max = fmaxf(run_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) if (colv + k < g.N) { g.C[off[i8] + k] = ov[k]; run_max = fmaxf(run_max, fabsf(ov[k])); }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (rvalid) {
+#pragma unroll
+        for (int j0 = 0; j0 < Cfg::COLS; j0 += 4) {
+          const int colv = n0 + col0 + j0;
+          long long coff = roff;
+          if (fused) {
+            if (colv >= g.N) continue;
+            const int qq = colv / tp.cls_cols;
+            if (py + tp.cls_iy[qq] >= tp.out_H || px + tp.cls_ix[qq] >= tp.out_W) continue;
+            coff += tp.cls_off[qq] - (long long)qq * tp.cls_cols;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int col = colv + k;
+            if (col < g.N) {
+              float x = acc[j0 + k];
+              float* p = g.C + coff + col * g.sCn;
+              if (g.atomic) {
+                atomicAdd(p, x);
+              } else {
+                if (g.bias != nullptr) x += g.bias[col];
+                if (g.act == 1) x = fmaxf(x, 0.f);
+                else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
+                else if (g.act >= 3) x = g.mask[coff + col * g.sCn] > 0.f ? x : neg_slope * x;
+                *p = x;
+                run_max = fmaxf(run_max, fabsf(x));
+              }
+            }
+          }
+        }
+      }
+      T3_SECTION_END(w2);
+    }
+    T3_ROLE_END(4, warp == Cfg::EPI0);
+    if (g.amax_out != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+      if (lane == 0 && run_max > 0.f) atomicMax(reinterpret_cast<unsigned int*>(g.amax_out), __float_as_uint(run_max));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct Tc3Maps { CUtensorMap a, bhi, blo, a2, c, c2; };
+
+template <int BN>
+static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s) {
+  using Cfg = T3Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DDRL_CUDA(cudaFuncSetAttribute(tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, g);
+  prof_work(2.0 * g.M * (double)g.N * g.K);
+  if (g_prof_on && g_prof_shapes) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "%s3[fwd,M=%d,N=%d,K=%d,g=%d]", g.tap.mode ? "conv_tc" : "gemm_tc", g.M, g.N, g.K,
+             (int)(grid.x * grid.y * grid.z));
+    DDRL_LAUNCHED(prof_intern(nm));
+    return DDRL_OK;
+  }
+  DDRL_LAUNCHED("tc3_kernel");
+  return DDRL_OK;
+}
+
+static int launch3_bn(int bn, const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s) {
+  switch (bn) {
+    case 128: return launch3<128>(m, g, grid, s);
+    case 64: return launch3<64>(m, g, grid, s);
+    default: return launch3<32>(m, g, grid, s);
+  }
+}
+static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
+
+static inline int pick_bn3(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// pre-split weight operand [N, ldb16 halfs] (K-major): box = 64 halfs x bn rows, 128B swizzle
+static int make_map_b16(CUtensorMap* m, const void* base, int K, int N, int ldb16, int bn) {
+  const unsigned long long dims[2] = {(unsigned long long)K, (unsigned long long)N};
+  const unsigned long long strides[1] = {(unsigned long long)ldb16 * 2};
+  const unsigned box[2] = {64u, (unsigned)bn}, estr[2] = {1u, 1u};
+  return tc_encode_tiled(m, true, 2, base, dims, strides, box, estr, true);
+}
+
+bool tc3_gemm_supported(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16) {
+  if (M < 1 || N < 1 || K < 1) return false;
+  if (!al16(A) || !al16(Bhi) || !al16(Blo) || lda % 4 != 0 || ldb16 % 8 != 0) return false;
+  return true;
+}
+
+// C[M,N] = epi(A[M,K] . B[N,K]^T)   B = pre-split fp16 hi / lo' rows of ldb16 halfs (t3 split of the fp32 weights)
+int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16, const float* amax_a,
+             const float* amax_b, float* C, int ldc, const float* bias, int act, const float* mask, float* amax_out,
+             cudaStream_t s) {
+  if (!tc3_gemm_supported(M, N, K, A, lda, Bhi, Blo, ldb16)) return DDRL_E_UNSUPPORTED;
+  if ((act >= 3 && !mask) || !amax_a || !amax_b) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn3(N);
+  Tc3Maps mp;
+  r = tc_make_map(&mp.a, A, K, M, lda, T3_BM, false);
+  if (r == DDRL_OK) r = make_map_b16(&mp.bhi, Bhi, K, N, ldb16, bn);
+  if (r == DDRL_OK) r = make_map_b16(&mp.blo, Blo, K, N, ldb16, bn);
+  if (r != DDRL_OK) return r;
+  mp.a2 = mp.a;
+  Tc3Args g;
+  memset(&g, 0, sizeof(g));
+  g.C = C; g.bias = bias; g.mask = mask; g.act = act;
+  g.M = M; g.N = N; g.K = K; g.sCm = ldc; g.sCn = 1;
+  g.kb_total = ceil_div(K, T3_BK); g.kb_per_split = g.kb_total;
+  g.m_tiles = ceil_div(M, T3_BM); g.n_tiles = ceil_div(N, bn);
+  g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
+  g.vec_store = (ldc % 4 == 0 && al16(C) && (!mask || al16(mask))) ? 1 : 0;
+  if (g.vec_store && act < 3 && g_t3_tma_store) {
+    // output tiles leave through TMA: boxes of 128 rows x 32 columns of C [M, N]
+    const unsigned long long dims[2] = {(unsigned long long)N, (unsigned long long)M};
+    const unsigned long long strides[1] = {(unsigned long long)ldc * 4};
+    const unsigned box[2] = {32u, (unsigned)T3_BM}, estr[2] = {1u, 1u};
+    if (tc_encode_tiled(&mp.c, false, 2, C, dims, strides, box, estr, true) == DDRL_OK) g.tma_store = 1;
+  }
+  if (!g.tma_store) mp.c = mp.a;
+  mp.c2 = mp.c;
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  return launch3_bn(bn, mp, g, grid, s);
+}
+
+int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, int N, const float* amax_a, const float* amax_b,
+                 const float* bias, int act, const float* mask, float* out, long long osb, long long osy, long long osx,
+                 float* amax_out, cudaStream_t s, const TcTap* cls) {
+  if (!conv_tc_supported(o, false) || N < 1 || ldw16 % 8 != 0 || !al16(Whi) || !al16(Wlo)) return DDRL_E_UNSUPPORTED;
+  if ((act >= 3 && !mask) || !amax_a || !amax_b) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = pick_bn3(N);
+  Tc3Args g;
+  memset(&g, 0, sizeof(g));
+  tc_tap_common(g.tap, o, T3_BM, true);
+  g.tap.osb = osb; g.tap.osy = osy; g.tap.osx = osx;
+  if (cls && cls->ncls > 1) {
+    if (cls->ncls > 4 || N != cls->ncls * cls->cls_cols || cls->cls_cols % 4 != 0) return DDRL_E_ARG;
+    g.tap.ncls = cls->ncls; g.tap.cls_cols = cls->cls_cols; g.tap.out_s = cls->out_s; g.tap.out_H = cls->out_H;
+    g.tap.out_W = cls->out_W;
+    for (int q = 0; q < cls->ncls; ++q) {
+      g.tap.cls_iy[q] = cls->cls_iy[q]; g.tap.cls_ix[q] = cls->cls_ix[q]; g.tap.cls_off[q] = cls->cls_off[q];
+      if (cls->cls_off[q] % 4 != 0) return DDRL_E_ARG;
+    }
+  }
+  const int K = o.KH * o.KW * o.Cin;
+  Tc3Maps mp;
+  r = tc_make_map_nhwc(&mp.a, o, o.Xn, g.tap.ny, g.tap.nb, false);
+  const bool ph2 = g.tap.ny2 > 0;
+  if (r == DDRL_OK && ph2) r = tc_make_map_nhwc(&mp.a2, o, o.Xn, g.tap.ny2, g.tap.nb2, false);
+  if (r == DDRL_OK) r = make_map_b16(&mp.bhi, Whi, K, N, ldw16, bn);
+  if (r == DDRL_OK) r = make_map_b16(&mp.blo, Wlo, K, N, ldw16, bn);
+  if (r != DDRL_OK) return r;
+  if (!ph2) mp.a2 = mp.a;
+  g.C = out; g.bias = bias; g.mask = mask; g.act = act;
+  g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K; g.sCm = 0; g.sCn = 1;
+  g.kb_total = (g.tap.nslices + 1) / 2; g.kb_per_split = g.kb_total;
+  g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi + (ph2 ? ceil_div(o.Bn, g.tap.nb2) : 0);
+  g.n_tiles = ceil_div(N, bn);
+  g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
+  g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && al16(out) && (!mask || al16(mask))) ? 1 : 0;
+  if (g.vec_store && act < 3 && g.tap.ncls <= 1 && g_t3_tma_store) {
+    // output tiles leave through TMA: the store box (32 columns x Xn pixels x ny rows x nb images of out[b, y, x, n])
+    // mirrors the load-side pixel box, one map per tiling phase
+    const unsigned long long dims[4] = {(unsigned long long)N, (unsigned long long)o.Xn, (unsigned long long)o.Yn, (unsigned long long)o.Bn};
+    const unsigned long long strides[3] = {(unsigned long long)osx * 4, (unsigned long long)osy * 4, (unsigned long long)osb * 4};
+    const unsigned estr[4] = {1u, 1u, 1u, 1u};
+    const unsigned box1[4] = {32u, (unsigned)o.Xn, (unsigned)g.tap.ny, (unsigned)g.tap.nb};
+    int rs = tc_encode_tiled(&mp.c, false, 4, out, dims, strides, box1, estr, true);
+    if (rs == DDRL_OK && ph2) {
+      const unsigned box2[4] = {32u, (unsigned)o.Xn, (unsigned)g.tap.ny2, (unsigned)g.tap.nb2};
+      rs = tc_encode_tiled(&mp.c2, false, 4, out, dims, strides, box2, estr, true);
+    }
+    if (rs == DDRL_OK) g.tma_store = 1;
+  }
+  if (!g.tma_store) mp.c = mp.a;
+  if (!g.tma_store || !ph2) mp.c2 = mp.c;
+  dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
+  return launch3_bn(bn, mp, g, grid, s);
+}
+
+// ================================================================ weight gradient
+// C[m, n] += sum_r A[r, m] * B[r, n]     A = activations [rows, k] (plain 2-D or tap boxes), B = dy [rows, n], both raw fp32.
+// The GEMM's M axis is the im2col K axis, so A must be transposed: free, because each splitter thread gathers one k
+// column of the landed [64 rows x 32 k] slice into its TMEM lane (pairs of rows packed as fp16x2).  The dy tile is
+// converted by the same warps into MN-major fp16 hi / lo' tiles (64 rows x 128 B, 128B swizzle) that belong to the TMEM
+// slot, so the raw TMA stage is released as soon as it has been read (before the MMAs run).
+//   barriers: full[S] TMA landed | empty[S] splitter warps done with the raw stage | aready[SA] slot + B tiles written |
+//             afree[SA] both MMA streams retired the slot | mfull/mfree[2], cfull as in the forward kernel
+template <int BN>
+struct T3WCfg {
+  static_assert(BN == 64 || BN == 128, "weight-gradient tiles are 64 or 128 columns");
+  static constexpr int A_SUB = T3_BK * 128;                      // one slice: 64 rows x 32 k fp32 = 8 KB
+  static constexpr int A_BYTES = 4 * A_SUB;
+  static constexpr int BRAW_BYTES = (BN / 32) * A_SUB;           // dy tile raw: slabs of 64 rows x 32 n
+  static constexpr int STAGE_BYTES = A_BYTES + BRAW_BYTES;
+  static constexpr int B16_TILE = T3_BK * 128;                   // 64 rows x 64 n halfs = 8 KB
+  static constexpr int B16_BYTES = 2 * (BN / 64) * B16_TILE;     // [hi groups | lo groups]
+  static constexpr bool FOLD = BN <= 64;
+  static constexpr int SA = BN <= 64 ? 3 : 2;
+  static constexpr int STAGES = BN <= 64 ? 3 : 2;
+  static constexpr int NEPI = 8;
+  static constexpr int NSG = 2;
+  static constexpr int EPI0 = 4 + 4 * NSG;
+  static constexpr int THREADS = (EPI0 + NEPI) * 32;
+  static constexpr int COLS = BN / 2;
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN, TM_A = FOLD ? 5 * BN : 3 * BN;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
+  static constexpr int B16_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = B16_OFF + SA * B16_BYTES;
+  static constexpr int SMEM = 1024 + BAR_OFF + 256;
+  static_assert(NBARS * 8 + 16 <= 256, "barrier block");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(T3WCfg<BN>::THREADS, 1)
+tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, Tc3Args g) {
+  using Cfg = T3WCfg<BN>;
+  constexpr int S = Cfg::STAGES, SA = Cfg::SA;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + S;
+  uint64_t* bar_aready = bars + 2 * S;
+  uint64_t* bar_afree = bars + 2 * S + SA;
+  uint64_t* bar_mfull = bars + 2 * S + 2 * SA;
+  uint64_t* bar_mfree = bar_mfull + 2;
+  uint64_t* bar_cfull = bar_mfull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcTap& tp = g.tap;
+  const bool tapA = tp.mode != 0;
+
+  if (tapA) {
+    // pixel-box K blocks shorter than 64 rows: the rows no box covers must read as zero
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < S * Cfg::STAGE_BYTES / 16; i += Cfg::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 4); }
+    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
+    mbar_init(smem_u32(bar_cfull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // one unit per CTA: (blockIdx.x = M block, blockIdx.y = N tile, blockIdx.z = K split)
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int nkb = min(g.kb_total, kb0 + g.kb_per_split) - kb0;
+  const int ksteps = tapA ? tp.kpad / 16 : 4;
+  const int m0 = (int)blockIdx.x * T3_BM, n0 = (int)blockIdx.y * BN;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    int sl_c[4] = {0, 0, 0, 0}, sl_x[4] = {0, 0, 0, 0}, sl_y[4] = {0, 0, 0, 0}, na = 0;
+    if (tapA) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sl = (int)blockIdx.x * 4 + j;
+        if (sl < tp.nslices) {
+          const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
+          const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
+          sl_c[j] = tp.c_off + cc * 32; sl_x[j] = kw - tp.px; sl_y[j] = kh - tp.py;
+          na = j + 1;
+        }
+      }
+    }
+    int pb = 0, pj = 0;
+    if (tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
+    for (int i = 0; i < nkb; ++i) {
+      const uint32_t s = i % S;
+      mbar_wait(smem_u32(bar_empty + s), ((i / S) & 1) ^ 1);
+      if (elect_one()) {
+        const uint32_t full = smem_u32(bar_full + s);
+        const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, b_dst = a_dst + Cfg::A_BYTES;
+        const int k = (kb0 + i) * T3_BK;
+        if (!tapA) {
+          mbar_expect_tx(full, Cfg::A_BYTES + Cfg::BRAW_BYTES);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(&tmA, full, a_dst + j * Cfg::A_SUB, m0 + j * 32, k);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, k);
+        } else if (tp.w2on) {
+          // two pixel-box classes (64 pixels each): class 1 covers the columns right of wxw0
+          const bool c1 = pj >= tp.wnb0;
+          const int x0 = c1 ? tp.wxw0 : 0, yy0 = c1 ? (pj - tp.wnb0) * tp.wyh1 : pj * tp.wyh0;
+          mbar_expect_tx(full, (na + BN / 32) * 64 * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < na) tma_load_4d(c1 ? &tmA2 : &tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_4d(c1 ? &tmB2 : &tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, x0, yy0, pb);
+        } else {
+          const int yy0 = pj * tp.ny;
+          mbar_expect_tx(full, (na + BN / 32) * tp.rows * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < na) tma_load_4d(&tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, yy0 * tp.Xn, pb);
+        }
+      }
+      __syncwarp();
+      if (tapA && ++pj == tp.tpi) { pj = 0; ++pb; }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers
+    const bool chunk_role = warp == 1;
+    // f16 x f16 -> f32, B MN-major (bit 16)
+    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+    const uint32_t b16_base = smem_u32(smem) + Cfg::B16_OFF;
+    const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
+    uint32_t ch = 0;
+    for (int i = 0; i < nkb; ++i) {
+      const uint32_t a = i % SA;
+      const uint32_t buf = ch & 1;
+      const bool first_in_chunk = (i % T3_CHUNK) == 0;
+      const bool last_in_chunk = (i % T3_CHUNK) == T3_CHUNK - 1 || i == nkb - 1;
+      if (chunk_role && first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1);
+      mbar_wait(smem_u32(bar_aready + a), (i / SA) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        // MN-major 128B-swizzled fp16 tiles: 64-column groups 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO);
+        // one k step = 16 rows = 2 KB
+        const uint32_t b_hi = b16_base + a * Cfg::B16_BYTES, b_lo = b_hi + (BN / 64) * Cfg::B16_TILE;
+        const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
+        const uint64_t dbh0 = umma_desc(b_hi, Cfg::B16_TILE, 1024, 2);
+        if (chunk_role) {
+          const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            if (k4 >= ksteps) break;
+            umma_f16_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * (2048 >> 4), Cfg::FOLD ? idesc2 : idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(bar_afree + a));
+          if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+        } else {
+          const uint64_t dbl0 = umma_desc(b_lo, Cfg::B16_TILE, 1024, 2);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            if (k4 >= ksteps) break;
+            umma_f16_ts(t_corr, a_lo + k4 * 8, dbh0 + k4 * (2048 >> 4), idesc, (i | k4) != 0 ? 1u : 0u);
+            if (!Cfg::FOLD) umma_f16_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * (2048 >> 4), idesc, 1u);
+          }
+          umma_commit(smem_u32(bar_afree + a));
+          if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
+        }
+      }
+      __syncwarp();
+      if (last_in_chunk) ++ch;
+    }
+  } else if (warp >= 4 && warp < Cfg::EPI0) {
+    // ============================================================ splitters: dy tile -> fp16 tiles, A columns -> TMEM
+    const int q = (warp - 4) & 3, grp = (warp - 4) >> 2;
+    const int st_tid = (threadIdx.x - 128) & 127;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    float sA, sA_inv, sB, sB_inv;
+    t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    t3_scale(__ldg(g.amax_b), sB, sB_inv);
+    for (int i = 0; i < nkb; ++i) {
+      if ((i % Cfg::NSG) != grp) continue;
+      const int s = i % S, a = i % SA;
+      mbar_wait(smem_u32(bar_full + s), (i / S) & 1);
+      // the slot (TMEM columns + fp16 dy tiles) was last read by K block i - SA
+      if (i >= SA) mbar_wait(smem_u32(bar_afree + a), ((i / SA) - 1) & 1);
+      tc_fence_after();
+      const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      uint8_t* b16 = smem + Cfg::B16_OFF + a * Cfg::B16_BYTES;
+      // dy tile: task = (row r, 8 consecutive columns): 2 swizzled 16-byte fp32 chunks -> 1 chunk of hi + 1 chunk of lo'
+      for (int v = st_tid; v < T3_BK * (BN / 8); v += 128) {
+        const int r = v / (BN / 8), c8 = v - r * (BN / 8);
+        const uint8_t* src = st + Cfg::A_BYTES + (c8 >> 2) * Cfg::A_SUB + r * 128;
+        const float4 x0 = *reinterpret_cast<const float4*>(src + ((((c8 & 3) * 2) ^ (r & 7)) << 4));
+        const float4 x1 = *reinterpret_cast<const float4*>(src + ((((c8 & 3) * 2 + 1) ^ (r & 7)) << 4));
+        uint4 h, l;
+        t3_split2(x0.x, x0.y, sB, h.x, l.x); t3_split2(x0.z, x0.w, sB, h.y, l.y);
+        t3_split2(x1.x, x1.y, sB, h.z, l.z); t3_split2(x1.z, x1.w, sB, h.w, l.w);
+        uint8_t* dst = b16 + (c8 >> 3) * Cfg::B16_TILE + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = h;
+        *reinterpret_cast<uint4*>(dst + (BN / 64) * Cfg::B16_TILE) = l;
+      }
+      fence_async_smem();
+      // A: thread = k column `lane` of slice q; gathers it over the 64 rows of the box, pairs of rows -> fp16x2
+      const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
+      const uint8_t* sp = st + q * Cfg::A_SUB + (lane & 3) * 4;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int pp = hf * 32 + 2 * p;
+          const float x0 = *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
+          const float x1 = *reinterpret_cast<const float*>(sp + (pp + 1) * 128 + (((lane >> 2) ^ ((pp + 1) & 7)) << 4));
+          t3_split2(x0, x1, sA, hi[p], lo[p]);
+        }
+        tmem_st16(ta + hf * 16, hi);
+        tmem_st16(ta + 32 + hf * 16, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(smem_u32(bar_empty + s)); mbar_arrive(smem_u32(bar_aready + a)); }
+    }
+  } else if (warp >= Cfg::EPI0) {
+    // ============================================================ drain + atomic accumulate
+    const int e = warp - Cfg::EPI0;
+    const int q = e & 3, half = e >> 2;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const uint32_t col0 = half * Cfg::COLS;
+    float sA, sA_inv, sB, sB_inv;
+    t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    t3_scale(__ldg(g.amax_b), sB, sB_inv);
+    float acc[Cfg::COLS];
+#pragma unroll
+    for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
+    const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
+    for (int c = 0; c < nch; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(bar_mfull + buf), (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
+        if (Cfg::FOLD) {
+          tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
+    }
+    if (nkb > 0) {
+      mbar_wait(smem_u32(bar_cfull), 0);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+      }
+      const int r = q * 32 + lane;
+      if (m0 + r < g.M) {
+        float* crow = g.C + (long long)(m0 + r) * g.sCm;
+#pragma unroll
+        for (int j = 0; j < Cfg::COLS; ++j) {
+          const int col = n0 + col0 + j;
+          if (col < g.N) atomicAdd(crow + (long long)col * g.sCn, (acc[j] * sA_inv) * sB_inv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int BN>
+static int launch3w(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2, const Tc3Args& g,
+                    dim3 grid, cudaStream_t s) {
+  using Cfg = T3WCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DDRL_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  tc3_wgrad_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, ta2, tb2, g);
+  prof_work(2.0 * g.M * (double)g.N * g.K);
+  if (g_prof_on && g_prof_shapes) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "%s3[wgrad,M=%d,N=%d,K=%d,g=%d]", g.tap.mode ? "conv_tc" : "gemm_tc", g.M, g.N, g.K,
+             (int)(grid.x * grid.y * grid.z));
+    DDRL_LAUNCHED(prof_intern(nm));
+    return DDRL_OK;
+  }
+  DDRL_LAUNCHED("tc3_wgrad_kernel");
+  return DDRL_OK;
+}
+
+// K splits: one CTA per (tile, split), one CTA per SM at a time -> waves of equal-length CTAs; pick the split count whose
+// last wave is fullest, preferring fewer splits among near-equals; every split keeps >= 4 K blocks
+static void wgrad3_splits(Tc3Args& g, int tiles) {
+  const int max_splits = std::max(1, std::min(g.kb_total / 4, 1024));
+  int best = 1;
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= max_splits && (long long)tiles * sp <= 4LL * kNumSMs; ++sp) {
+    const int kbps = ceil_div(g.kb_total, sp);
+    const int waves = ceil_div(tiles * ceil_div(g.kb_total, kbps), kNumSMs);
+    const double cost = (double)waves * (kbps + 4);
+    if (cost < best_cost * 0.98) { best_cost = cost; best = sp; }
+  }
+  g.kb_per_split = ceil_div(g.kb_total, best);
+}
+
+// dW[n*ldw + k] += sum_r dy[r, n] * x[r, k]     (x [rows, Kx], dy [rows, N]; accumulates atomically)
+int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s) {
+  if (Kx < 1 || N < 1 || rows < 1 || !al16(x) || !al16(dy) || ldx % 4 != 0 || ldy % 4 != 0 || rows > 0x7fffffffLL)
+    return DDRL_E_UNSUPPORTED;
+  if (!amax_x || !amax_dy) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = N > 64 ? 128 : 64;
+  CUtensorMap ta, tb;
+  r = tc_make_map(&ta, x, Kx, rows, ldx, T3_BK, false);           // [64 rows x 32 k] boxes, plain 128B swizzle
+  if (r == DDRL_OK) r = tc_make_map(&tb, dy, N, rows, ldy, T3_BK, false);
+  if (r != DDRL_OK) return r;
+  Tc3Args g;
+  memset(&g, 0, sizeof(g));
+  g.C = dW; g.M = Kx; g.N = N; g.K = (int)rows; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
+  g.kb_total = (int)ceil_div64(rows, T3_BK);
+  g.amax_a = amax_x; g.amax_b = amax_dy;
+  const int tiles = ceil_div(Kx, T3_BM) * ceil_div(N, bn);
+  wgrad3_splits(g, tiles);
+  dim3 grid(ceil_div(Kx, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  return bn == 128 ? launch3w<128>(ta, tb, ta, tb, g, grid, s) : launch3w<64>(ta, tb, ta, tb, g, grid, s);
+}
+
+bool tc3_conv_wgrad_supported(const ConvOp& o) {
+  if (o.Cin % 32 != 0 || o.Ctot % 4 != 0 || o.c_off % 4 != 0 || o.c_off + o.Cin > o.Ctot || !al16(o.a)) return false;
+  if (o.sx < 1 || o.sx > 8 || o.sy < 1 || o.sy > 8 || o.Xn < 1 || o.Yn < 1 || o.Bn < 1) return false;
+  if (o.Xn > T3_BK || (o.Xn - 1) * o.sx + 1 > 256) return false;
+  const int ny = std::min(o.Yn, std::max(1, T3_BK / o.Xn));
+  return (ny - 1) * o.sy + 1 <= 256;
+}
+
+// dy boxes of the tap weight gradient: swizzle 128B (the tile is converted in shared memory, not fed to the MMA)
+static int make_map_dy3w(CUtensorMap* m, const float* dy, int ldy, int N, long long ipix, int Bn, int rows) {
+  const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)ipix, (unsigned long long)Bn};
+  const unsigned long long strides[2] = {(unsigned long long)ldy * 4, (unsigned long long)ipix * ldy * 4};
+  const unsigned box[3] = {32u, (unsigned)rows, 1u}, estr[3] = {1u, 1u, 1u};
+  return tc_encode_tiled(m, false, 3, dy, dims, strides, box, estr, true);
+}
+static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn, int Yn, int Bn, int xw, int yh) {
+  const unsigned long long dims[4] = {(unsigned long long)N, (unsigned long long)Xn, (unsigned long long)Yn, (unsigned long long)Bn};
+  const unsigned long long strides[3] = {(unsigned long long)ldy * 4, (unsigned long long)Xn * ldy * 4, (unsigned long long)Yn * Xn * ldy * 4};
+  const unsigned box[4] = {32u, (unsigned)xw, (unsigned)yh, 1u}, estr[4] = {1u, 1u, 1u, 1u};
+  return tc_encode_tiled(m, false, 4, dy, dims, strides, box, estr, true);
+}
+
+int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
+                   cudaStream_t s) {
+  if (!tc3_conv_wgrad_supported(o) || N < 1 || ldy % 4 != 0 || !al16(dy)) return DDRL_E_UNSUPPORTED;
+  if (!amax_x || !amax_dy) return DDRL_E_ARG;
+  int r = tc_get_encode();
+  if (r != DDRL_OK) return r;
+  const int bn = N > 64 ? 128 : 64;
+  Tc3Args g;
+  memset(&g, 0, sizeof(g));
+  tc_tap_common(g.tap, o, T3_BK);
+  if (g.tap.nb != 1) { g.tap.nb = 1; g.tap.ny = std::min(o.Yn, std::max(1, T3_BK / o.Xn)); g.tap.tpi = ceil_div(o.Yn, g.tap.ny); }
+  g.tap.rows = o.Xn * g.tap.ny;
+  g.tap.kpad = (g.tap.rows + 15) & ~15;
+  const int K = o.KH * o.KW * o.Cin;
+  CUtensorMap ta, tb, ta2, tb2;
+  // K blocks of exactly 64 pixels from two box classes when the map width is a sum of two powers of two and that packs
+  // the image into >= 10 % fewer K blocks than whole rows
+  static const bool no_w2 = [] { const char* e = getenv("DDRL_TC2_NO_WGRAD_BOXES"); return e && e[0] == '1'; }();
+  if (!no_w2 && ldy == N) {
+    for (int xw0 = 64; xw0 >= 2; xw0 >>= 1) {
+      const int xw1 = o.Xn - xw0;
+      if (xw1 < 1 || xw1 > xw0 || (xw1 & (xw1 - 1)) != 0) continue;
+      const int yh0 = 64 / xw0, yh1 = 64 / xw1;
+      if ((yh0 - 1) * o.sy + 1 > 256 || (yh1 - 1) * o.sy + 1 > 256 || yh1 > 256) continue;
+      const int nb0 = ceil_div(o.Yn, yh0), nb1 = ceil_div(o.Yn, yh1);
+      if ((nb0 + nb1) * 10 > g.tap.tpi * 9) continue;
+      g.tap.w2on = 1; g.tap.wxw0 = xw0; g.tap.wyh0 = yh0; g.tap.wnb0 = nb0; g.tap.wxw1 = xw1; g.tap.wyh1 = yh1;
+      g.tap.tpi = nb0 + nb1; g.tap.rows = 64; g.tap.kpad = 64;
+      break;
+    }
+  }
+  if (g.tap.w2on) {
+    r = tc_make_map_nhwc(&ta, o, g.tap.wxw0, g.tap.wyh0, 1, false);
+    if (r == DDRL_OK) r = tc_make_map_nhwc(&ta2, o, g.tap.wxw1, g.tap.wyh1, 1, false);
+    if (r == DDRL_OK) r = make_map_dy4w(&tb, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw0, g.tap.wyh0);
+    if (r == DDRL_OK) r = make_map_dy4w(&tb2, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw1, g.tap.wyh1);
+  } else {
+    r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, false);
+    if (r == DDRL_OK) r = make_map_dy3w(&tb, dy, ldy, N, (long long)o.Yn * o.Xn, o.Bn, g.tap.rows);
+    ta2 = ta; tb2 = tb;
+  }
+  if (r != DDRL_OK) return r;
+  g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
+  g.kb_total = o.Bn * g.tap.tpi;
+  g.amax_a = amax_x; g.amax_b = amax_dy;
+  const int tiles = ceil_div(K, T3_BM) * ceil_div(N, bn);
+  wgrad3_splits(g, tiles);
+  dim3 grid(ceil_div(K, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  return bn == 128 ? launch3w<128>(ta, tb, ta2, tb2, g, grid, s) : launch3w<64>(ta, tb, ta2, tb2, g, grid, s);
+}
+
+// ---------------------------------------------------------------- operand preparation
+// amax|x| over a [rows, cols] view (row stride ld) -> atomicMax on the bits of *slot (the caller zeroes the slot)
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
+                                                   unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  if (cols == ld && (cols & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long n4 = rows * cols / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = x4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    const long long n = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / cols;
+      m = fmaxf(m, fabsf(x[r * ld + (i - r * cols)]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    if (m > 0.f) atomicMax(slot, __float_as_uint(m));
+  }
+}
+int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s) {
+  if (!slot || rows < 0 || cols < 0) return DDRL_E_ARG;
+  if (zero_first) DDRL_CUDA(cudaMemsetAsync(slot, 0, sizeof(float), s));
+  if (rows == 0 || cols == 0) return DDRL_OK;
+  if (!x) return DDRL_E_ARG;
+  const long long work = (rows * cols + 1023) / 1024;
+  const int blocks = (int)std::min<long long>(std::max<long long>(work, 1), 8LL * kNumSMs);
+  amax_kernel<<<blocks, 256, 0, s>>>(x, rows, cols, ld, reinterpret_cast<unsigned int*>(slot));
+  DDRL_LAUNCHED("amax_kernel");
+  return DDRL_OK;
+}
+
+// weights w [N, ldw] fp32 (K valid columns) -> hi / lo' [N, ld16] fp16 with the scale of *amax; optionally the transposed
+// pair hiT / loT [K, ldT16] (the K-major weight operand of a linear layer's data gradient).  Padding columns are zero.
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, int N, int K, int ldw, const float* __restrict__ amax,
+                                                        __half* __restrict__ hi, __half* __restrict__ lo, int ld16,
+                                                        __half* __restrict__ hiT, __half* __restrict__ loT, int ldT16) {
+  float s, inv;
+  t3_scale(*amax, s, inv);
+  const long long n = (long long)N * ld16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld16), k = (int)(i - (long long)r * ld16);
+    __half h = __float2half_rn(0.f), l = h;
+    if (k < K) {
+      const float y = w[(long long)r * ldw + k] * s;
+      h = __float2half_rn(y);
+      l = __float2half_rn((y - __half2float(h)) * T3_LO);
+      if (hiT) { hiT[(long long)k * ldT16 + r] = h; loT[(long long)k * ldT16 + r] = l; }
+    }
+    hi[i] = h; lo[i] = l;
+  }
+}
+int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT, int ldT16,
+              cudaStream_t s) {
+  if (!w || !amax || !hi || !lo || N < 1 || K < 1 || ld16 < K) return DDRL_E_ARG;
+  const long long n = (long long)N * ld16;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * kNumSMs);
+  split_f16_kernel<<<blocks, 256, 0, s>>>(w, N, K, ldw, amax, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ld16,
+                                          reinterpret_cast<__half*>(hiT), reinterpret_cast<__half*>(loT), ldT16);
+  DDRL_LAUNCHED("split_f16_kernel");
+  return DDRL_OK;
+}
+
+}  // namespace ddrl
+
+// debugging aid (not part of the public header): role counters of the tc3 forward kernel (all zero unless built -DTC3_TIMING)
+extern "C" int ddrl_tc3_timing_read(unsigned long long* out64, int reset) {
+  if (out64) DDRL_CUDA(cudaMemcpyFromSymbol(out64, ddrl::g_tc3_wait, sizeof(unsigned long long) * 64));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    DDRL_CUDA(cudaMemcpyToSymbol(ddrl::g_tc3_wait, z, sizeof(z)));
+  }
+  return DDRL_OK;
+}

@@ -27,13 +27,13 @@ class Actor(nn.Module):
 
     def _head(self, x):
         from .. import kernels
-        from .._lib import DDRLError
         if self.pre is not None:
-            raise DDRLError("Actor with its own encoder runs inside PPO's fused CUDA engine")
+            x = self.pre(x)                    # nn/actor.py:28-31: states -> features through the actor's own encoder
         return kernels.gemm(0, x, self.actor_linear.weight.detach(), self.actor_linear.bias.detach())
 
     def forward(self, x, act=None, play_mode=False):
-        """Stand-alone use on FEATURES x [B, last_input_dim]; PPO.forward is the fused path."""
+        """Stand-alone call (nn/actor.py:26-40): x = states when the actor owns an encoder, features [B, last_input_dim]
+        otherwise; PPO.forward is the fused path."""
         pi = self._distribution(self._head(x), play_mode)
         log_p = self._log_prob_from_distribution(pi, act) if act is not None else None
         return pi, log_p

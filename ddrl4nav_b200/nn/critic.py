@@ -12,9 +12,8 @@ class Critic(nn.Module):
         self.pre = pre
 
     def forward(self, x):
-        """Stand-alone use on FEATURES x [B, last_input_dim] (shared-encoder mode); returns [B,1]."""
+        """Stand-alone call (nn/critic.py:14-21): x = states when the critic owns an encoder, features otherwise; [B,1]."""
         from .. import kernels
-        from .._lib import DDRLError
         if self.pre is not None:
-            raise DDRLError("Critic with its own encoder runs inside PPO's fused CUDA engine")
+            x = self.pre(x)
         return kernels.gemm(0, x, self.critic_linear.weight.detach(), self.critic_linear.bias.detach())

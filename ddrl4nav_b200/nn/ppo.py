@@ -154,6 +154,12 @@ class PPO(Basenn):
         self._flat, self._offsets = flat, offsets
         self._P = P
         check(lib.ddrl_net_bind(h, ptr(flat), ptr(self._grads), ptr(self._m), ptr(self._v)), "ddrl_net_bind")
+        # stand-alone encoder calls (enc(states) -> [B, 512]) run on this engine's towers
+        if self.prenet is not None:
+            self.prenet._attach(self, 0)
+        else:
+            self.actor.pre._attach(self, 0)
+            self.critic.pre._attach(self, 1)
         self._versions = sum(p._version for _, p in plist)
         if self.prenet is None:
             self._seg = ([0, offsets[[n for n, _ in plist].index("critic.critic_linear.weight")], P],
@@ -225,6 +231,15 @@ class PPO(Basenn):
                                    current_stream()), "ddrl_net_forward")
         out = (actions, logps, values.view(1, B, 1))
         return out + (pi,) if want_pi else out
+
+    def encode(self, states, tower=0):
+        """Features [B, feat] of one encoder tower (0 = prenet / actor.pre, 1 = critic.pre): the stand-alone encoder
+        forward of the reference (nn/atari_encoder.py:25-32, nn/nav_encoder.py:35-43,115-128)."""
+        self._ensure_engine()
+        keep, arr, n_obs, B = self._obs_ptrs(states)
+        out = torch.empty(B, self.actor.actor_linear.in_features, dtype=torch.float32, device=self._flat.device)
+        check(_lib.load().ddrl_net_encode(self._h, arr, n_obs, B, int(tower), ptr(out), current_stream()), "ddrl_net_encode")
+        return out
 
     def forward(self, states, act=None, play_mode=False):
         """Reference-shaped output: ((pi, log_p), [values [B,1]]) with pi = Categorical / Normal, or the raw

@@ -40,8 +40,11 @@ enum ddrl_dist { DDRL_DIST_CATEGORICAL = 0, DDRL_DIST_GAUSSIAN = 1 };   /* nn/ac
 enum ddrl_gemm_mode {
   DDRL_GEMM_SIMT_F32 = 0,      /* CUDA-core fp32 FMA (reference / fallback-free baseline) */
   DDRL_GEMM_TC_3XTF32 = 1,     /* tcgen05 kind::tf32, hi/lo split in shared memory, one tile per CTA (gemm_tc.cu) */
-  DDRL_GEMM_TC2_TMEM = 2       /* same arithmetic; persistent CTAs, activation operand split into TMEM, weights
+  DDRL_GEMM_TC2_TMEM = 2,      /* same arithmetic; persistent CTAs, activation operand split into TMEM, weights
                                   pre-split per optimiser step (tc2.cu).  Shapes it does not take run on mode 1. */
+  DDRL_GEMM_TC3_F16 = 3        /* tcgen05 kind::f16 on scaled fp16 hi / lo splits (22 significant bits, per-tensor power-of-two
+                                  scale from a device-resident amax), 64-wide K blocks (tc3.cu).  Shapes it does not take
+                                  run on mode 2. */
 };
 
 typedef struct ddrl_net ddrl_net;
@@ -118,6 +121,16 @@ int ddrl_gae_tempo(const float* values, const float* rewards, const uint8_t* don
  * i.e. bit-identical to numpy's astype(float32). */
 int ddrl_easybytes_decode(const uint8_t* payload, const void* segs, int nseg, unsigned int max_count, float* dst,
                           void* stream);
+
+/* Replies of one Forward tick, encoded on the device -- replaces EasyBytes.encode_forward_return_data
+ * (USTC_lab/data/easybytes.py:77-109) for [actions, logps, values]: env process j gets the data blocks
+ * actions[j*nb:(j+1)*nb] (fp32 [nb] when act_cols == 0, else [nb, act_cols]), logps[...] ([nb]) and
+ * values[:, j*nb:(j+1)*nb] ([V, nb, 1]; values is [V, B] row-major).  out = n_env replies of
+ * ddrl_easybytes_reply_bytes(nb, act_cols, V) bytes each, back to back (device buffer): one device->host copy, the host
+ * cuts it per env process. */
+int64_t ddrl_easybytes_reply_bytes(int nb, int act_cols, int V);
+int ddrl_easybytes_encode_replies(const float* actions, int act_cols, const float* logps, const float* values, int V, int B,
+                                  int n_env, int nb, uint8_t* out, void* stream);
 
 /* ---- K4: action sampling --------------------------------------------------------------
  * replaces random_choice_prob_index / select_action (USTC_lab/server/utils.py:20-47) and the
@@ -214,6 +227,12 @@ int64_t ddrl_net_obs_elems(const ddrl_net* net, int slot);
  * caller views it as [V=1,B,1]); pi_out (optional) probs [B,A] or mu [B,A]. */
 int ddrl_net_forward(ddrl_net* net, const float* const* obs, int n_obs, int B, const float* draw,
                      float* actions, float* logp, float* values, float* pi_out, void* stream);
+
+/* Stand-alone encoder forward: features [B, feat] of tower `tower` (0 = prenet / actor.pre, 1 = critic.pre) for the
+ * observations obs[] -- replaces AtariPreNet.forward (nn/atari_encoder.py:25-32), NavPreNet / NavPedPreNet.forward
+ * (nn/nav_encoder.py:35-43,66-79), NavPreNet1D.forward (nav_encoder.py:115-128), MLPPreNet.forward
+ * (nn/mlp_encoder.py:24-29).  out: fp32 device [B, feat]. */
+int ddrl_net_encode(ddrl_net* net, const float* const* obs, int n_obs, int B, int tower, float* out, void* stream);
 
 /* One learn iteration, first half (nn/ppo.py:82-123): forward with act=data.actions, fused loss,
  * backward through heads and encoders.  Leaves d(loss)/d(params) for the LOCAL B rows, scaled

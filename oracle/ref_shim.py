@@ -34,7 +34,7 @@ class _FakePipeline:
         self._ops.append(("incr", k)); return self
 
     def lpush(self, k, *v):
-        self._ops.append(("lpush", k, v)); return self
+        self._ops.append(("lpush", k) + tuple(v)); return self
 
     def get(self, k):
         self._ops.append(("get", k)); return self

@@ -356,13 +356,13 @@ def test_clip_adam_vs_torch(n, nseg):
 
 
 # ------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("mode", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("mode", ["simt", "tc", "tc2", "tc3"])
 @pytest.mark.parametrize("form", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 33, 100), (1000, 512, 3136), (64, 6, 512), (4096, 32, 256), (37, 200, 9),
                                    (128, 32, 32), (300, 64, 1152), (2048, 256, 1600)])
 def test_gemm_forms(mode, form, M, N, K):
     from ddrl4nav_b200 import kernels
-    if mode in ("tc", "tc2"):
+    if mode in ("tc", "tc2", "tc3"):
         # the tcgen05 paths need 16-byte row strides (TMA) and N >= 16; other shapes stay on the SIMT engine
         lds = {0: (K, K), 1: (K, N), 2: (M, N)}[form]
         if N < 16 or lds[0] % 4 or lds[1] % 4:
@@ -379,7 +379,7 @@ def test_gemm_forms(mode, form, M, N, K):
         ref = A.double().T @ B.double()
     bias = torch.randn(N, generator=g)
     prod = ref
-    if mode == "tc2" and form == 2:
+    if mode in ("tc2", "tc3") and form == 2:
         # the TMEM engine's transposed-operand form is the weight gradient: no bias / activation, accumulates
         out = kernels.gemm(form, A.to(DEV), B.to(DEV), None, act=0, mode=mode)
         assert close(out, prod, rtol=1e-5, atol_scale=2e-6)
@@ -389,13 +389,13 @@ def test_gemm_forms(mode, form, M, N, K):
     out = kernels.gemm(form, A.to(DEV), B.to(DEV), bias.to(DEV), act=2, mode=mode)
     ref = torch.nn.functional.leaky_relu(prod + bias.double(), 0.01)
     assert close(out, ref, rtol=1e-5, atol_scale=2e-6)
-    if mode == "tc2":
+    if mode in ("tc2", "tc3"):
         return                       # accumulate-into-C exists only for the weight-gradient form on this engine
     out2 = kernels.gemm(form, A.to(DEV), B.to(DEV), None, act=0, mode=mode, out=out.clone(), beta=1)   # C += A op B
     assert close(out2, ref + prod, rtol=1e-5, atol_scale=2e-6)
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc", "tc2"])
+@pytest.mark.parametrize("mode", ["simt", "tc", "tc2", "tc3"])
 def test_gemm_split_k_wgrad_shape(mode):
     from ddrl4nav_b200 import kernels
     g = torch.Generator().manual_seed(5)
@@ -413,9 +413,26 @@ def test_gemm_tc_is_3xtf32_accurate():
     ref = A.double() @ B.double().T
     e_tc = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc").cpu().double() - ref).abs().max() / ref.abs().max())
     e_tc2 = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc2").cpu().double() - ref).abs().max() / ref.abs().max())
+    e_tc3 = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc3").cpu().double() - ref).abs().max() / ref.abs().max())
     e_simt = float((kernels.gemm(0, A.to(DEV), B.to(DEV), mode="simt").cpu().double() - ref).abs().max() / ref.abs().max())
-    print("max err / max|ref|: tc %.2e  tc2 %.2e  simt %.2e" % (e_tc, e_tc2, e_simt))
-    assert e_tc < 2e-6 and e_tc2 < 2e-6 and e_simt < 2e-6
+    print("max err / max|ref|: tc %.2e  tc2 %.2e  tc3 %.2e  simt %.2e" % (e_tc, e_tc2, e_tc3, e_simt))
+    assert e_tc < 2e-6 and e_tc2 < 2e-6 and e_tc3 < 2e-6 and e_simt < 2e-6
+
+
+@pytest.mark.parametrize("scale_a,scale_b", [(1.0, 1.0), (1e-7, 3.0), (4e4, 1e-6), (1e-20, 1e-12)])
+def test_gemm_tc3_scaled_fp16_split_keeps_fp32_range(scale_a, scale_b):
+    """tc3 splits operands into scaled fp16 pairs: tensors far outside the fp16 exponent range, and rows whose magnitudes
+    differ by 2^20 inside one tensor, must come out as accurate as the fp32 FFMA engine."""
+    from ddrl4nav_b200 import kernels
+    g = torch.Generator().manual_seed(13)
+    A, B = torch.randn(384, 1024, generator=g) * scale_a, torch.randn(96, 1024, generator=g) * scale_b
+    A[::7] *= 2.0 ** -20                                       # small rows next to large ones
+    ref = A.double() @ B.double().T
+    out = kernels.gemm(0, A.to(DEV), B.to(DEV), mode="tc3").cpu().double()
+    assert torch.isfinite(out).all()
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-6
+    small = ref[::7]
+    assert float((out[::7] - small).abs().max() / small.abs().max()) < 1e-4      # relative to THEIR scale: 2^-20 * 2e-6 would be 0
 
 
 # ------------------------------------------------------------------ implicit-GEMM convolutions (tap-TMA path)
@@ -442,7 +459,7 @@ def _conv_ref(x_nhwc, w, stride, pad, conv1d):
     return torch.nn.functional.conv2d(x, w.double(), None, stride=stride, padding=pad)
 
 
-@pytest.mark.parametrize("mode", ["tc", "tc2"])
+@pytest.mark.parametrize("mode", ["tc", "tc2", "tc3"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_implicit_forward_dgrad_wgrad(case, mode):
     """ddrl_conv_nhwc_f32 (4-D TMA tap boxes, no im2col) == torch conv2d forward / autograd, fp32 tolerance 1e-5."""

@@ -15,7 +15,7 @@ from oracle import restate as R
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 # every engine is checked against the same oracle: CUDA-core fp32, tcgen05 (smem split), tcgen05 (TMEM operand)
-GEMM_MODES = os.environ.get("DDRL_TEST_GEMM_MODE", "simt,tc,tc2").split(",")
+GEMM_MODES = os.environ.get("DDRL_TEST_GEMM_MODE", "simt,tc,tc2,tc3").split(",")
 GEMM_MODE = GEMM_MODES[0]
 
 

@@ -87,7 +87,7 @@ def test_forward_thread_one_tick(kind):
     net, spec, params = _make(kind)
     cfgs = _configs(kind, B_env, "fwd-" + kind)
     mid = _FakeRedis("fwd-" + kind, 2)
-    net.conn = mid                                                  # Basenn.conn (nn/base.py:28)
+    net.conn, net.model_key = mid, "tMODEL"                         # Basenn.conn / model_key (nn/base.py:28-33)
     net.nn2redis(mid.pipeline(), "tupd")                            # trainer published weights once
     flag = types.SimpleNamespace(value=b"0")
     th = ForwardThread(net, 0, _Logger(), None, flag, cfgs)
@@ -124,6 +124,7 @@ def test_backward_threads_one_batch():
     kind, B_env = "pong", 4
     net, spec, params = _make(kind)
     net.training_iter_time = 2
+    net.model_key = "tMODEL"
     cfgs = _configs(kind, B_env, "bwd")
     flag = types.SimpleNamespace(value=b"0")
     q = BackwardQueue("cuda")
@@ -148,6 +149,9 @@ def test_backward_threads_one_batch():
     # the first logged loss = the oracle's first iteration on the same batch
     st = R.LearnState(spec, params)
     want, _, _ = R.learn_iteration(st, [states[0]], advs, actions, old_logps, returns, R.PPOHyper())
-    got = dict((k, v[0]) for k, v in trainer.logger_f.rows if k in ("ActorLoss", "VLoss", "EntLoss"))
+    got = {}
+    for k, v in trainer.logger_f.rows:                        # first logged value of every key = iteration 1
+        if k in ("ActorLoss", "VLoss", "EntLoss"):
+            got.setdefault(k, v[0])
     for k in ("ActorLoss", "VLoss"):
         assert abs(got[k] - want[k]) <= 1e-4 * max(1.0, abs(want[k]))
