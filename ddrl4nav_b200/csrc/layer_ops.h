@@ -98,11 +98,12 @@ int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, cons
 int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, int N, const float* amax_a, const float* amax_b,
                  const float* bias, int act, const float* mask, float* out, long long osb, long long osy, long long osx,
                  float* amax_out, cudaStream_t s, const TcTap* cls = nullptr);
+// db (optional): bias gradient db[n] += sum_r dy[r, n], fused into the kernel's dy conversion (no separate column-sum pass)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
-              const float* amax_dy, float* dW, int ldw, cudaStream_t s);
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db = nullptr);
 bool tc3_conv_wgrad_supported(const ConvOp& o);
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s);
+                   cudaStream_t s, float* db = nullptr);
 int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s);
 int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT,
               int ldT16, cudaStream_t s);

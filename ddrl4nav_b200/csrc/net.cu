@@ -137,6 +137,11 @@ struct ddrl_net {
   std::unordered_map<std::string, AmaxEntry> amax_keys;  // activation view -> slot (valid while epoch == amax_epoch)
   unsigned long long amax_epoch = 1;
   W16 w16_fuse0, w16_s2d;
+  // the weight preparation after every optimiser step is ~90 tiny independent launches: they are spread round-robin over
+  // side streams (fork / join with events) so their launch latencies overlap instead of adding up
+  static constexpr int kSide = 8;
+  cudaStream_t side[kSide] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
   bool amax_persist_next = false;  // the next gemm()'s activation operand is observation-side staging (persistent amax entry)
 };
 
@@ -357,6 +362,7 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
     t.implicit[i] = true;
     t.dg[i] = cls;
     if (tc2_mode(n) && g.stride > 1) conv_dgrad_fused_plan(g, Cout, t.df[i]);    // leaves df.on = false if unsupported
+    if (t.df[i].on) t.dg[i].clear();                 // the per-class repacks would never be read
   }
   // first layer on the raw NCHW observation: a strided valid conv whose extents divide by the stride becomes a stride-1
   // implicit conv over the space-to-depth tensor (same size as the observation; no im2col matrix)
@@ -449,16 +455,22 @@ static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
   ddrl_net* nn = const_cast<ddrl_net*>(n);
   const bool persist = nn->amax_persist_next;          // set by the caller when x is observation-side staging
   nn->amax_persist_next = false;
-  TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
   // dW[N, K] += dy[M,N]^T x[M,K]
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 && ldx % 4 == 0 && ldy % 4 == 0;
-  if (l.K <= 36 && thin_supported(M, l.N, l.K, x, ldx, dy, ldy))
+  const bool thin = l.K <= 36 && thin_supported(M, l.N, l.K, x, ldx, dy, ldy);
+  const bool w3 = !thin && tc3_mode(n) && al && l.K >= 32 && !getenv("DDRL_TC3_NO_WGRAD");
+  // DDRL_TC3_FUSE_COLSUM=1: the tc3 weight gradient sums the dy columns while it converts the dy tiles.  Measured
+  // (profiles/r2h_*): the splitter warps are that kernel's critical role, so the fused sums cost what the separate pass
+  // saves (weight gradients +2.0 ms, column sums -2.1 ms per Pong step): off by default
+  static const bool fuse_cs = [] { const char* e = getenv("DDRL_TC3_FUSE_COLSUM"); return e && e[0] == '1'; }();
+  if (!(w3 && fuse_cs)) TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
+  if (thin)
     TRY(thin_wgrad(x, ldx, dy, dW_of(n, l), l.ldw, M, l.N, l.K, s));
-  else if (tc3_mode(n) && al && l.K >= 32 && !getenv("DDRL_TC3_NO_WGRAD")) {
+  else if (w3) {
     const float *amx = nullptr, *amy = nullptr;
     TRY(amax_in_slot(nn, x, M, l.K, ldx, s, &amx, persist));
     TRY(amax_in_slot(nn, dy, M, l.N, ldy, s, &amy));
-    TRY(tc3_wgrad(l.K, l.N, M, x, ldx, dy, ldy, amx, amy, dW_of(n, l), l.ldw, s));
+    TRY(tc3_wgrad(l.K, l.N, M, x, ldx, dy, ldy, amx, amy, dW_of(n, l), l.ldw, s, fuse_cs ? db_of(n, l) : nullptr));
   }
   else if (tc2_mode(n) && al && l.K >= 32)
     TRY(tc2_wgrad(l.K, l.N, M, x, ldx, dy, ldy, dW_of(n, l), l.ldw, s));
@@ -729,10 +741,40 @@ static int alloc_packed(ddrl_net* n) {
   return DDRL_OK;
 }
 
-static int repack(ddrl_net* n, cudaStream_t s) {
+static int side_init(ddrl_net* n) {
+  if (n->ev_fork) return DDRL_OK;
+  for (int k = 0; k < ddrl_net::kSide; ++k) {
+    DDRL_CUDA(cudaStreamCreateWithFlags(&n->side[k], cudaStreamNonBlocking));
+    DDRL_CUDA(cudaEventCreateWithFlags(&n->ev_join[k], cudaEventDisableTiming));
+  }
+  DDRL_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+  return DDRL_OK;
+}
+static int side_fork(ddrl_net* n, cudaStream_t s) {
+  DDRL_CUDA(cudaEventRecord(n->ev_fork, s));
+  for (int k = 0; k < ddrl_net::kSide; ++k) DDRL_CUDA(cudaStreamWaitEvent(n->side[k], n->ev_fork, 0));
+  return DDRL_OK;
+}
+static int side_join(ddrl_net* n, cudaStream_t s) {
+  for (int k = 0; k < ddrl_net::kSide; ++k) {
+    DDRL_CUDA(cudaEventRecord(n->ev_join[k], n->side[k]));
+    DDRL_CUDA(cudaStreamWaitEvent(s, n->ev_join[k], 0));
+  }
+  return DDRL_OK;
+}
+
+static int repack(ddrl_net* n, cudaStream_t s0) {
+  // phase 1: every fp32 repack on a side stream; phase 2 (after a join): per weight operand amax -> fp16 split.  With the
+  // profiler hooks on (per-launch events on ONE stream) everything stays on the caller's stream.
+  const bool par = !g_prof_on && !getenv("DDRL_REPACK_SERIAL");
+  if (par) { TRY(side_init(n)); TRY(side_fork(n, s0)); }
+  int rr = 0;
+  cudaStream_t s = s0;
+#define NEXT_STREAM() do { if (par) s = n->side[rr++ % ddrl_net::kSide]; } while (0)
   for (auto& t : n->towers)
     for (auto& l : t.L)
       if (l.packed) {
+        NEXT_STREAM();
         if (l.s2d_s) TRY(pack_weight_s2d(n->params + n->T[l.w_t].offset, l.wp, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
         else TRY(pack_weight(n->params + n->T[l.w_t].offset, l.wp, l.N, l.I, l.J, l.ldw, s));
       }
@@ -740,27 +782,33 @@ static int repack(ddrl_net* n, cudaStream_t s) {
     for (int i = 0; i < 5; ++i)
       for (auto& c : t.dg[i]) {
         const Lin& l = t.L[t.conv_lin[i]];
+        NEXT_STREAM();
         TRY(pack_dgrad(n->params + n->T[l.w_t].offset, t.g[i], l.N, c, s));
       }
   for (auto& t : n->towers)
     for (int i = 0; i < 5; ++i)
       if (t.df[i].on) {
         const Lin& l = t.L[t.conv_lin[i]];
+        NEXT_STREAM();
         TRY(pack_dgrad_fused(n->params + n->T[l.w_t].offset, t.g[i], l.N, t.df[i], s));
       }
   if (n->fuse_s2d) {
     const ConvGeom& g = n->towers[0].g[0];
     for (int k = 0; k < 2; ++k) {
       const Lin& l = n->towers[k].L[0];
+      NEXT_STREAM();
       TRY(pack_weight_s2d(n->params + n->T[l.w_t].offset, n->w0s2d + (size_t)k * l.N * l.ldw, l.N, g.C, g.KH, g.KW, g.stride, l.ldw, s));
     }
   }
   if (n->fuse0) {
     const Lin &l0 = n->towers[0].L[0], &l1 = n->towers[1].L[0];
+    NEXT_STREAM();
     DDRL_CUDA(cudaMemcpyAsync(n->bias0c, b_of(n, l0), sizeof(float) * l0.N, cudaMemcpyDeviceToDevice, s));
     DDRL_CUDA(cudaMemcpyAsync(n->bias0c + l0.N, b_of(n, l1), sizeof(float) * l1.N, cudaMemcpyDeviceToDevice, s));
   }
+  if (par) { TRY(side_join(n, s0)); TRY(side_fork(n, s0)); }
   if (n->split_base) {
+    NEXT_STREAM();
     // tf32 hi / lo mirrors of the forward weights [0, grad_off) and of the data-gradient weights [2*grad_off, end)
     const size_t fwd = n->packed_grad_off, dg0 = 2 * n->packed_grad_off, dgn = n->packed_bytes - dg0;
     char* hi = n->split_base;
@@ -773,10 +821,13 @@ static int repack(ddrl_net* n, cudaStream_t s) {
   for (auto& j : n->split_jobs) {
     W16& w = *j.dst;
     float* slot = const_cast<float*>(w.amax);
+    NEXT_STREAM();
     TRY(amax_f32(j.w, j.rows, j.K, j.ldw, slot, true, s));
     TRY(split_f16(j.w, j.rows, j.K, j.ldw, slot, const_cast<void*>(w.hi), const_cast<void*>(w.lo), w.ld, const_cast<void*>(w.hiT),
                   const_cast<void*>(w.loT), w.ldT, s));
   }
+  if (par) TRY(side_join(n, s0));
+#undef NEXT_STREAM
   n->dirty = false;
   return DDRL_OK;
 }
@@ -882,14 +933,15 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
   const Lin& l = t.L[li];
   const long long M = (long long)mb * g.Ho * g.Wo;
   if (s2d) {                                       // first layer: no data gradient; x2 = the cached space-to-depth tensor
-    TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
     if (tc3_mode(n) && tc3_conv_wgrad_supported(conv_op_fwd(g, cols, g.C, 0, mb)) && !getenv("DDRL_TC3_NO_WGRAD")) {
       ddrl_net* nn = const_cast<ddrl_net*>(n);
       const float *amx = nullptr, *amy = nullptr;
       TRY(amax_in_slot(nn, cols, (long long)mb * g.H * g.W, g.C, g.C, s, &amx, true));
       TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
+      TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
       return tc3_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s);
     }
+    TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
     if (tc2_mode(n)) return tc2_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
     return conv_tc_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
   }
@@ -903,9 +955,10 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
       TRY(amax_in_slot(nn, x, (long long)mb * g.H * g.W, ctot, ctot, s, &amx));
       TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
       TRY(tc3_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s));
+    } else {
+      if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
+      else TRY(conv_tc_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
     }
-    else if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
-    else TRY(conv_tc_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
     Tc3Ctx ctx{nullptr, nullptr};
     const bool t3 = tc3_mode(n) && dx && (t.df[gi].on ? t.df[gi].w16.hi != nullptr : (!t.dg[gi].empty() && t.dg[gi][0].w16.hi != nullptr));
     if (t3) {
@@ -1144,6 +1197,10 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
   if (n->split_base) cudaFree(n->split_base);
+  if (n->ev_fork) {
+    for (int k = 0; k < ddrl_net::kSide; ++k) { cudaStreamDestroy(n->side[k]); cudaEventDestroy(n->ev_join[k]); }
+    cudaEventDestroy(n->ev_fork);
+  }
   if (n->h16_base) cudaFree(n->h16_base);
   if (n->amax_dev) cudaFree(n->amax_dev);
   if (n->bias0c) cudaFree(n->bias0c);

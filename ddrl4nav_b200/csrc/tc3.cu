@@ -39,6 +39,11 @@ namespace ddrl {
 constexpr int T3_BM = 128;
 constexpr int T3_BK = 64;                     // k per K block (two 32-float boxes of A; 64 halfs = one swizzle row of B)
 constexpr int T3_CHUNK = 4;                   // K blocks per TMEM main-accumulator chunk (16 accumulating MMAs)
+// lo' = lo * 2^11 keeps the residual in the fp16 normal range down to |x s| = 2^-14, i.e. 2^-27 of the tensor's amax.
+// Measured alternative (profiles/r2h_*): an unscaled residual and s = 1 for tensors already inside the fp16 range save
+// two of ten splitter instructions per element pair (forward convs 5 % faster), but rows 2^-20 below the tensor's amax
+// drop from 22 to ~10 significant bits and micro-batched runs stop being bit-identical to single-shot ones (the power-of-two
+// scale is otherwise exact, so the split mantissas do not depend on it): not adopted.
 constexpr float T3_LO = 2048.f, T3_LO_INV = 1.f / 2048.f;
 
 // Optional role-level accounting (build with -DTC3_TIMING, scratch/tc3_roles.py): cycles each warp role of the forward
@@ -50,6 +55,7 @@ __device__ unsigned long long g_tc3_wait[64];
 #define T3_T0 const long long _t0 = clock64()
 #define T3_ACC(acc) acc += clock64() - _t0
 #define T3_WAIT(bar, par, acc) do { T3_T0; mbar_wait(bar, par); T3_ACC(acc); } while (0)
+#define T3_WAITL(bar, par, acc) do { T3_T0; mbar_wait_long(bar, par); T3_ACC(acc); } while (0)
 #define T3_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0, w3 = 0; const long long role_t0 = clock64();
 #define T3_ROLE_END(role, cond) do { if ((cond) && lane == 0) { \
     atomicAdd(&g_tc3_wait[(role) * 8 + 0], (unsigned long long)w0); atomicAdd(&g_tc3_wait[(role) * 8 + 1], (unsigned long long)w1); \
@@ -59,6 +65,7 @@ __device__ unsigned long long g_tc3_wait[64];
 #define T3_SECTION_END(acc) acc += clock64() - _s0
 #else
 #define T3_WAIT(bar, par, acc) mbar_wait(bar, par)
+#define T3_WAITL(bar, par, acc) mbar_wait_long(bar, par)
 #define T3_ROLE_BEGIN
 #define T3_ROLE_END(role, cond)
 #define T3_SECTION_BEGIN
@@ -78,6 +85,7 @@ struct Tc3Args {
   const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
   const float* amax_b;
   float* amax_out;                            // optional: running amax of the stored output (atomicMax on the bits)
+  float* colsum;                              // weight gradient: optional db[n] += sum_r dy[r, n] (bias gradient), fused into the dy conversion
   TcTap tap;
 };
 
@@ -101,8 +109,9 @@ __host__ __device__ __forceinline__ void t3_scale(float amax, float& s, float& i
 }
 
 // (x0, x1) * s -> packed fp16 hi pair and packed fp16 lo' pair (saturating: a stale amax gives a wrong, finite result)
+template <bool SCALED = true>
 __device__ __forceinline__ void t3_split2(float x0, float x1, float s, uint32_t& hi, uint32_t& lo) {
-  const float y0 = x0 * s, y1 = x1 * s;
+  const float y0 = SCALED ? x0 * s : x0, y1 = SCALED ? x1 * s : x1;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y1), "f"(y0));
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   const float r0 = (y0 - f.x) * T3_LO, r1 = (y1 - f.y) * T3_LO;
@@ -213,7 +222,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int cc = 0, kw = 0, kh = 0;                     // tap slices advance (chunk fastest, then kw, then kh)
       for (int i = 0; i < nkb; ++i, ++it) {
         const uint32_t s = it % S;
-        T3_WAIT(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1, w0);
+        T3_WAITL(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1, w0);
         if (elect_one()) {
           const uint32_t full = smem_u32(bar_full + s);
           const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
@@ -307,6 +316,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     float sA, sA_inv;
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    const bool unit_scale = sA == 1.f;
     const int row = q * 32 + lane;
     uint32_t it = 0;
     T3_ROLE_BEGIN
@@ -314,7 +324,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       for (int i = 0; i < nkb; ++i, ++it) {
         if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
         const int s = it % S, a = it % SA;
-        T3_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
+        T3_WAITL(smem_u32(bar_full + s), (it / S) & 1, w0);
         T3_SECTION_BEGIN;
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
@@ -325,11 +335,20 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           if (j >= nsub) break;
           uint32_t hi[16], lo[16];
           const uint8_t* rp = st + j * Cfg::A_SUB + row * 128;
+          if (unit_scale) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
-            t3_split2(v.x, v.y, sA, hi[2 * c], lo[2 * c]);
-            t3_split2(v.z, v.w, sA, hi[2 * c + 1], lo[2 * c + 1]);
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+              t3_split2<false>(v.x, v.y, 1.f, hi[2 * c], lo[2 * c]);
+              t3_split2<false>(v.z, v.w, 1.f, hi[2 * c + 1], lo[2 * c + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+              t3_split2<true>(v.x, v.y, sA, hi[2 * c], lo[2 * c]);
+              t3_split2<true>(v.z, v.w, sA, hi[2 * c + 1], lo[2 * c + 1]);
+            }
           }
           if (j == 0) {
             // TMEM slot a was last read by K block it - SA: its stage barrier (both MMA streams commit to it) doubles as
@@ -372,7 +391,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
       for (int c = 0; c < nch; ++c, ++ch) {
         const int buf = ch & 1;
-        T3_WAIT(smem_u32(bar_mfull + buf), (ch >> 1) & 1, w0);
+        T3_WAITL(smem_u32(bar_mfull + buf), (ch >> 1) & 1, w0);
         tc_fence_after();
 #pragma unroll
         for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
@@ -391,7 +410,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
       }
-      T3_WAIT(smem_u32(bar_cfull), tl & 1, w1);
+      T3_WAITL(smem_u32(bar_cfull), tl & 1, w1);
       tc_fence_after();
 #pragma unroll
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
@@ -643,7 +662,9 @@ static int launch3_bn(int bn, const Tc3Maps& m, const Tc3Args& g, dim3 grid, cud
     default: return launch3<32>(m, g, grid, s);
   }
 }
-static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
+// measured (profiles/r2f_*): the tile stores through TMA are correct but 10-15 % slower than the per-warp coalesced stores
+// (two CTA-wide epilogue barriers per tile), so they are opt-in
+static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_TMA_STORE"); return e && e[0] == '1'; }();
 
 static inline int pick_bn3(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -860,7 +881,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
     for (int i = 0; i < nkb; ++i) {
       const uint32_t s = i % S;
-      mbar_wait(smem_u32(bar_empty + s), ((i / S) & 1) ^ 1);
+      mbar_wait_long(smem_u32(bar_empty + s), ((i / S) & 1) ^ 1);
       if (elect_one()) {
         const uint32_t full = smem_u32(bar_full + s);
         const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, b_dst = a_dst + Cfg::A_BYTES;
@@ -949,6 +970,11 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float sA, sA_inv, sB, sB_inv;
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
     t3_scale(__ldg(g.amax_b), sB, sB_inv);
+    // bias gradient: every conversion task of this thread covers the same 8 columns (128 threads, BN / 8 tasks per row),
+    // so the column sums of the dy tiles ride along in 8 registers (only the CTAs of the first M block contribute)
+    const bool unit_a = sA == 1.f;
+    const bool do_colsum = g.colsum != nullptr && blockIdx.x == 0;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < nkb; ++i) {
       if ((i % Cfg::NSG) != grp) continue;
       const int s = i % S, a = i % SA;
@@ -967,6 +993,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint4 h, l;
         t3_split2(x0.x, x0.y, sB, h.x, l.x); t3_split2(x0.z, x0.w, sB, h.y, l.y);
         t3_split2(x1.x, x1.y, sB, h.z, l.z); t3_split2(x1.z, x1.w, sB, h.w, l.w);
+        if (do_colsum) {
+          cs[0] += x0.x; cs[1] += x0.y; cs[2] += x0.z; cs[3] += x0.w; cs[4] += x1.x; cs[5] += x1.y; cs[6] += x1.z; cs[7] += x1.w;
+        }
         uint8_t* dst = b16 + (c8 >> 3) * Cfg::B16_TILE + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(dst) = h;
         *reinterpret_cast<uint4*>(dst + (BN / 64) * Cfg::B16_TILE) = l;
@@ -983,7 +1012,8 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int pp = hf * 32 + 2 * p;
           const float x0 = *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
           const float x1 = *reinterpret_cast<const float*>(sp + (pp + 1) * 128 + (((lane >> 2) ^ ((pp + 1) & 7)) << 4));
-          t3_split2(x0, x1, sA, hi[p], lo[p]);
+          if (unit_a) t3_split2<false>(x0, x1, 1.f, hi[p], lo[p]);
+          else t3_split2<true>(x0, x1, sA, hi[p], lo[p]);
         }
         tmem_st16(ta + hf * 16, hi);
         tmem_st16(ta + 32 + hf * 16, lo);
@@ -992,6 +1022,21 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(smem_u32(bar_empty + s)); mbar_arrive(smem_u32(bar_aready + a)); }
+    }
+    if (do_colsum) {
+      // threads with equal (st_tid mod BN/8) hold partial sums of the same 8 columns: lanes l, l + BN/8, ... of a warp
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = cs[k];
+#pragma unroll
+        for (int o = 16; o >= BN / 8; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        cs[k] = v;
+      }
+      if (lane < BN / 8) {
+        const int col = n0 + lane * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (col + k < g.N) atomicAdd(g.colsum + col + k, cs[k]);
+      }
     }
   } else if (warp >= Cfg::EPI0) {
     // ============================================================ drain + atomic accumulate
@@ -1008,7 +1053,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
     for (int c = 0; c < nch; ++c) {
       const int buf = c & 1;
-      mbar_wait(smem_u32(bar_mfull + buf), (c >> 1) & 1);
+      mbar_wait_long(smem_u32(bar_mfull + buf), (c >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
@@ -1094,7 +1139,7 @@ static void wgrad3_splits(Tc3Args& g, int tiles) {
 
 // dW[n*ldw + k] += sum_r dy[r, n] * x[r, k]     (x [rows, Kx], dy [rows, N]; accumulates atomically)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
-              const float* amax_dy, float* dW, int ldw, cudaStream_t s) {
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db) {
   if (Kx < 1 || N < 1 || rows < 1 || !al16(x) || !al16(dy) || ldx % 4 != 0 || ldy % 4 != 0 || rows > 0x7fffffffLL)
     return DDRL_E_UNSUPPORTED;
   if (!amax_x || !amax_dy) return DDRL_E_ARG;
@@ -1109,7 +1154,7 @@ int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const floa
   memset(&g, 0, sizeof(g));
   g.C = dW; g.M = Kx; g.N = N; g.K = (int)rows; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
   g.kb_total = (int)ceil_div64(rows, T3_BK);
-  g.amax_a = amax_x; g.amax_b = amax_dy;
+  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db;
   const int tiles = ceil_div(Kx, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(Kx, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
@@ -1139,7 +1184,7 @@ static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn
 }
 
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s) {
+                   cudaStream_t s, float* db) {
   if (!tc3_conv_wgrad_supported(o) || N < 1 || ldy % 4 != 0 || !al16(dy)) return DDRL_E_UNSUPPORTED;
   if (!amax_x || !amax_dy) return DDRL_E_ARG;
   int r = tc_get_encode();
@@ -1182,7 +1227,7 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   if (r != DDRL_OK) return r;
   g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
   g.kb_total = o.Bn * g.tap.tpi;
-  g.amax_a = amax_x; g.amax_b = amax_dy;
+  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db;
   const int tiles = ceil_div(K, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(K, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));

@@ -31,6 +31,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// same, for waits that are expected to be long (epilogue waiting for a chunk, producer waiting for a free stage): the
+// suspend-time hint lets the hardware park the warp longer per probe, so the spin loop issues fewer instructions
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
