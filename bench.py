@@ -52,8 +52,19 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+        pk = dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    else:
+        pk = dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+    # tcgen05 issue-rate ceilings measured by this repo (scratch/mma_bench.cu -> profiles/tf32_peak.json): what a 3-product
+    # split engine can reach at best is a third of the kind::tf32 / kind::f16 rate
+    pk["tf32_issue"], pk["f16_issue"] = 1116.4, 2232.7
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "tf32_peak.json")))
+        rates = {(m["kind"], m["N"], m["a"]): m["chip_tflops_sustained"] for m in t["tcgen05"]["mma"]}
+        pk["tf32_issue"], pk["f16_issue"] = rates[("tf32", 128, "tmem")], rates[("f16", 128, "tmem")]
+    except Exception:  # noqa: BLE001
+        pass
+    return pk
 
 
 class ClockSampler:
@@ -279,14 +290,26 @@ def run_ours(args):
         name, ms, n, work = line.split()
         prof[name] = dict(ms=float(ms), launches=int(n), work=float(work))
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    gemm_names = [k for k in prof if "gemm" in k or "tc2" in k or "conv_tc" in k]
+    gemm_names = [k for k in prof if "gemm" in k or "tc2" in k or "tc3" in k or "conv_tc" in k]
     dom = max(prof, key=lambda k: prof[k]["ms"])
     if dom in gemm_names:
+        # achieved = ALGORITHMIC flops of the launches of the dominant kernel (the launchers declare 2*M*N*K of the
+        # convolution / GEMM they implement, not of the zero-padded tiles they issue) / their CUDA-event time
         ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e12
+        split = {"tc3": ("f16", peaks["f16_issue"]), "tc2": ("tf32", peaks["tf32_issue"]), "tc": ("tf32", peaks["tf32_issue"])}.get(args.gemm_mode)
         roof = dict(bound="tensor", kernel=dom, achieved=round(ach, 2), peak=peaks["tensor_sustained"], unit="TFLOP/s",
                     frac=round(ach / peaks["tensor_sustained"], 4), traffic=ncu_traffic(args.workload, dom),
-                    peak_note="bf16 cuBLAS sustained, of %s (no TF32/FP32 peak is in MEASURED_PEAKS.json)" % peaks["src"],
+                    peak_note="frac: of the bf16 cuBLAS sustained rate (%s, MEASURED_PEAKS.json).  The engine computes fp32 results "
+                              "as THREE kind::%s products: its ceiling is a third of the tcgen05 kind::%s issue rate measured by "
+                              "scratch/mma_bench.cu (profiles/tf32_peak.json), reported as frac_split3" % (
+                                  peaks["src"], split[0] if split else "-", split[0] if split else "-"),
                     share_of_step=round(prof[dom]["ms"] / tot_ms, 3), avg_launch_ms=round(prof[dom]["ms"] / prof[dom]["launches"], 4))
+        if split:
+            roof["split3_peak"] = round(split[1] / 3.0, 1)
+            roof["frac_split3"] = round(ach / (split[1] / 3.0), 4)
+        all_tc_ms = sum(prof[k]["ms"] for k in gemm_names)
+        roof["all_gemm_kernels"] = dict(share_of_step=round(all_tc_ms / tot_ms, 3),
+                                        achieved=round(sum(prof[k]["work"] for k in gemm_names) / (all_tc_ms / 1e3) / 1e12, 2))
     else:
         ach = prof[dom]["work"] / (prof[dom]["ms"] / 1e3) / 1e9
         roof = dict(bound="hbm", kernel=dom, achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s",
@@ -321,11 +344,13 @@ def run_ours(args):
 
     # ---- the other named single-GPU configurations (BASELINE configs[1] / [4]), short runs, N=1 only
     others = {}
-    if world == 1 and not args.no_others:
+    if not args.no_others:
+        # every rank runs its shard of the other named configurations too (BASELINE configs[1] and [4]: the nav learner /
+        # "inference sharded over 8 GPUs"), so the scaling runs carry them
         del net, fnet, exp_dev, states_d, fstates_d, bm, fm
         torch.cuda.empty_cache()
         for other in [w for w in ("navlaser", "navimg", "pong") if w != args.workload]:
-            others[other] = quick_workload(other, args.gemm_mode, dev, dist)
+            others[other] = quick_workload(other, args.gemm_mode, dev, dist, world, rank)
             torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0 only, N=1 only): the oracle port on the host cores, bounded sample
@@ -340,7 +365,8 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": "learner sample-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.gemm_mode == "simt" else "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulate)",
+            "dtype": {"simt": "f32", "tc3": "f32 (three tcgen05 kind::f16 products of scaled fp16 hi/lo splits, fp32 accumulate)"}.get(
+                args.gemm_mode, "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B * world, "iters_per_step": ITERS,
                        "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode,
@@ -368,15 +394,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def quick_workload(kind, gemm_mode, dev, dist):
+def quick_workload(kind, gemm_mode, dev, dist, world=1, rank=0):
     """Learner sample-iterations/s (3 warm-up + 2 timed learn calls, inputs resident) and Forward actions/s of another
-    named configuration, same definitions as the headline numbers."""
+    named configuration, same definitions as the headline numbers (whole-job aggregates over `world` ranks: rows
+    sharded, one gradient all-reduce per iteration; inference shards env rows with no collective)."""
     from ddrl4nav_b200.data import Experience
     from ddrl4nav_b200.runner import make_net
     wl = WORKLOADS[kind]
     B, Bf = wl["batch"], wl["fwd_batch"]
     net = make_net(kind, device=dev, gemm_mode=gemm_mode, TRAINING_ITER_TIME=ITERS)
-    states_h, adv_h, ret_h = synth_batch_host(kind, B, seed=100)
+    if dist is not None:
+        net.enable_data_parallel()
+        net.broadcast_parameters(0)
+    states_h, adv_h, ret_h = synth_batch_host(kind, B, seed=100 + rank)
     states_d = [s.to(dev) for s in states_h]
     with torch.no_grad():
         acts_d, logp_d, _ = net.act(states_d)
@@ -387,15 +417,16 @@ def quick_workload(kind, gemm_mode, dev, dist):
         for _ in net.learn(exp):
             pass
     sec = timed(step, 2, 3, dist)
-    fstates_d = [s.to(dev) for s in synth_batch_host(kind, Bf, seed=200)[0]]
+    fstates_d = [s.to(dev) for s in synth_batch_host(kind, Bf, seed=200 + rank)[0]]
     fnet = make_net(kind, device=dev, gemm_mode=gemm_mode)          # inference-only engine instance (predictor process)
     fnet.load_state_dict(net.state_dict())
     del net, exp
     torch.cuda.empty_cache()
     sec_f = timed(lambda: fnet.act(fstates_d), 5, 3, dist)
-    return {"workload": wl["desc"], "rows_per_gpu": B, "value": round(B * ITERS * 2 / sec, 1), "unit": "learner sample-iterations/s",
-            "ms_per_step": round(sec / 2 * 1e3, 3), "learner_tflops": round(B * ITERS * 2 / sec * wl["flops_learn"] / 1e12, 2),
-            "forward_actions_per_s": round(Bf * 5 / sec_f, 1), "forward_rows": Bf}
+    return {"workload": wl["desc"], "rows_per_gpu": B, "n_gpus": world, "value": round(world * B * ITERS * 2 / sec, 1),
+            "unit": "learner sample-iterations/s", "ms_per_step": round(sec / 2 * 1e3, 3),
+            "learner_tflops": round(world * B * ITERS * 2 / sec * wl["flops_learn"] / 1e12, 2),
+            "forward_actions_per_s": round(world * Bf * 5 / sec_f, 1), "forward_rows_per_gpu": Bf}
 
 
 def cpu_reference(kind, B, iters, warm):
@@ -462,7 +493,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("DDRL_BENCH_WORKLOAD", "pong"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "tc2"), choices=["simt", "tc", "tc2"])
+    ap.add_argument("--gemm-mode", dest="gemm_mode", default=os.environ.get("DDRL_GEMM_MODE", "tc3"),
+                    choices=["simt", "tc", "tc2", "tc3"])
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--fwd-batch", dest="fwd_batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ddrl_gae_f32": (_I, [_P, _P, _P, C.POINTER(_F), _F, _I, _I, _I, _P, _P, _I, _P]),
     "ddrl_gae_tempo": (_I, [_P, _P, _P, _P, C.POINTER(C.c_double), _I, C.c_double, _I, _I, _I, _P, _P, _I, _P]),
     "ddrl_easybytes_decode": (_I, [_P, _P, _I, C.c_uint, _P, _P]),
+    "ddrl_easybytes_reply_bytes": (_L, [_I, _I, _I]),
+    "ddrl_easybytes_encode_replies": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ddrl_sample_categorical_probs": (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     "ddrl_categorical_head": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
     "ddrl_gaussian_head": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P]),

@@ -202,6 +202,7 @@ int conv_dgrad_fused_tc2(const ConvGeom& g, int Cout, const DgradFused& f, const
   TcTap cls;
   memset(&cls, 0, sizeof(cls));
   cls.ncls = f.ncy * f.ncx; cls.cls_cols = g.C; cls.out_s = f.s; cls.out_H = H; cls.out_W = W;
+  cls.work_scale = (float)(KH * KW) / (float)(f.ncy * f.ncx * f.nty * f.ntx);
   for (int cy = 0; cy < f.ncy; ++cy)
     for (int cx = 0; cx < f.ncx; ++cx) {
       const int q = cy * f.ncx + cx;

@@ -46,6 +46,7 @@ struct TcTap {
   int ncls, cls_cols, out_s, out_H, out_W;
   int cls_iy[4], cls_ix[4];
   long long cls_off[4];
+  float work_scale;              // algorithmic / issued flops of the launch (fused classes pad missing taps with zeros); 0 = 1
 };
 
 // tc3 engine: one weight operand as scaled fp16 hi / lo' rows (split_f16), its transposed twin (linear layers: the K-major

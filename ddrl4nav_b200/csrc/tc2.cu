@@ -654,7 +654,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensor
     attr_done = true;
   }
   tc2_kernel<BN, MODE, B_MN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tbh, tbl, ta2 ? *ta2 : ta, g);
-  prof_work(2.0 * g.M * (double)g.N * g.K);
+  prof_work(2.0 * g.M * (double)g.N * g.K * (g.tap.work_scale > 0.f ? g.tap.work_scale : 1.f));   // algorithmic flops
   if (g_prof_on && g_prof_shapes) {
     char nm[96];
     snprintf(nm, sizeof(nm), "%s2[%s,M=%d,N=%d,K=%d,g=%d]", g.tap.mode ? "conv_tc" : "gemm_tc",
@@ -744,7 +744,7 @@ int tc2_conv_fwd(const ConvOp& o, const float* Whi, const float* Wlo, int ldw, i
   if (cls && cls->ncls > 1) {
     if (cls->ncls > 4 || N != cls->ncls * cls->cls_cols || cls->cls_cols % 4 != 0) return DDRL_E_ARG;
     g.tap.ncls = cls->ncls; g.tap.cls_cols = cls->cls_cols; g.tap.out_s = cls->out_s; g.tap.out_H = cls->out_H;
-    g.tap.out_W = cls->out_W;
+    g.tap.out_W = cls->out_W; g.tap.work_scale = cls->work_scale;
     for (int q = 0; q < cls->ncls; ++q) {
       g.tap.cls_iy[q] = cls->cls_iy[q]; g.tap.cls_ix[q] = cls->cls_ix[q]; g.tap.cls_off[q] = cls->cls_off[q];
       if (cls->cls_off[q] % 4 != 0) return DDRL_E_ARG;

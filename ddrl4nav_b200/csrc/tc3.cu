@@ -643,7 +643,7 @@ static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s
     attr_done = true;
   }
   tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, g);
-  prof_work(2.0 * g.M * (double)g.N * g.K);
+  prof_work(2.0 * g.M * (double)g.N * g.K * (g.tap.work_scale > 0.f ? g.tap.work_scale : 1.f));   // algorithmic flops
   if (g_prof_on && g_prof_shapes) {
     char nm[96];
     snprintf(nm, sizeof(nm), "%s3[fwd,M=%d,N=%d,K=%d,g=%d]", g.tap.mode ? "conv_tc" : "gemm_tc", g.M, g.N, g.K,
@@ -734,7 +734,7 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
   if (cls && cls->ncls > 1) {
     if (cls->ncls > 4 || N != cls->ncls * cls->cls_cols || cls->cls_cols % 4 != 0) return DDRL_E_ARG;
     g.tap.ncls = cls->ncls; g.tap.cls_cols = cls->cls_cols; g.tap.out_s = cls->out_s; g.tap.out_H = cls->out_H;
-    g.tap.out_W = cls->out_W;
+    g.tap.out_W = cls->out_W; g.tap.work_scale = cls->work_scale;
     for (int q = 0; q < cls->ncls; ++q) {
       g.tap.cls_iy[q] = cls->cls_iy[q]; g.tap.cls_ix[q] = cls->cls_ix[q]; g.tap.cls_off[q] = cls->cls_off[q];
       if (cls->cls_off[q] % 4 != 0) return DDRL_E_ARG;

@@ -127,7 +127,7 @@ class PreNet(torch.nn.Module):
         if self._solo is not None:
             lib.ddrl_net_destroy(self._solo[0])
         import os
-        mode = _lib.GEMM_MODE[os.environ.get("DDRL_GEMM_MODE", "tc2")]
+        mode = _lib.GEMM_MODE[os.environ.get("DDRL_GEMM_MODE", "tc3")]
         desc = NetDesc(_lib.ARCH[self.ARCH], self.engine_in_ch(), 1, _lib.DIST["categorical"], 1, self._feat(), mode, 0)
         h = C.c_void_p()
         check(lib.ddrl_net_create(C.byref(desc), C.byref(h)), "ddrl_net_create")

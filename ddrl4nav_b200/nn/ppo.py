@@ -58,7 +58,7 @@ class PPO(Basenn):
         self.v_loss_theta, self.ent_loss_theta = self.hp.v_coef, self.hp.ent_coef
         self.ppo_clip, self.duel_ppo_clip = self.hp.ppo_clip, self.hp.dual_clip
         self.training_iter_time = _cfg(config_nn, "TRAINING_ITER_TIME", 10)
-        self.gemm_mode = os.environ.get("DDRL_GEMM_MODE", _cfg(config_nn, "GEMM_MODE", "tc2"))
+        self.gemm_mode = os.environ.get("DDRL_GEMM_MODE", _cfg(config_nn, "GEMM_MODE", "tc3"))
         self.update_time = 0
         self._adam_step = 0
         self._h = None                  # ddrl_net*

@@ -19,7 +19,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "pong"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else bench.WORKLOADS[kind]["batch"]
 dev = torch.device("cuda", 0)
 lib = _lib.load()
-net = make_net(kind, device=dev, gemm_mode=os.environ.get("DDRL_GEMM_MODE", "tc2"), TRAINING_ITER_TIME=10)
+net = make_net(kind, device=dev, gemm_mode=os.environ.get("DDRL_GEMM_MODE", "tc3"), TRAINING_ITER_TIME=10)
 states_h, adv_h, ret_h = bench.synth_batch_host(kind, B, seed=100)
 states_d = [s.to(dev) for s in states_h]
 acts, logp, _ = net.act(states_d)
