@@ -158,6 +158,27 @@ def synth_batch_host(kind, B, seed):
     return states, adv, ret
 
 
+def wl_dist(kind):
+    """True for the categorical (1-D action) workloads."""
+    return kind != "navlaser"
+
+
+def encode_forward_payload(arrays, per_env):
+    """Forward payload in the reference's wire format (data/easybytes.py:62-75,141-148): one message per env process of
+    `per_env` rows: [length >Q][ip 4 x >H][process_env_id >I][blocks: type >h | count >I | ndim >I | shape >I.. | raw]."""
+    import struct
+    code = {np.dtype(np.uint8): 1, np.dtype(np.float16): 2, np.dtype(np.float32): 3, np.dtype(np.float64): 4}
+    B = len(arrays[0])
+    out = []
+    for j, r0 in enumerate(range(0, B, per_env)):
+        body = b""
+        for a in arrays:
+            sl = np.ascontiguousarray(a[r0:r0 + per_env])
+            body += struct.pack(">hII", code[sl.dtype], sl.size, sl.ndim) + struct.pack(">" + "I" * sl.ndim, *sl.shape) + sl.tobytes()
+        out.append(struct.pack(">Q", len(body)) + struct.pack(">HHHH", 10, 0, 0, 1) + struct.pack(">I", j) + body)
+    return b"".join(out)
+
+
 def timed(fn, steps, warmup, dist=None):
     """W warm-up + K timed calls bracketed by barrier + synchronize; device time by CUDA events on the current
     stream; returns max-over-ranks seconds."""
@@ -331,6 +352,36 @@ def run_ours(args):
     f_np = [s.numpy() for s in fstates_h]
     sec_fe = timed(lambda: fm.step(f_np), 3, 2, dist)
     fwd_e2e = world * Bf * 3 / sec_fe
+    # ... the Forward tick as the reference runs it (server/forward.py:117-181): a Redis payload of env-process messages in,
+    # reply bytes out -- ForwardModule.step_bytes_replies from a PINNED payload: H2D of the wire bytes (streamed in chunks),
+    # decode + net + sampling + reply encode on the device, D2H of the replies, all inside the timed region.  Wire dtypes:
+    # the reference's Pong wrapper emits float64 frames (warputils.py:300); uint8 frames are what the emulator produces.
+    fwd_wire = {}
+    per_env = 64
+    wires = (("u8", np.uint8), ("f64", np.float64), ("f32", np.float32)) if args.workload == "pong" else (("f32", np.float32),)
+    for tag, dt in wires:
+        rows_w = Bf // 4 if dt is np.float64 else Bf          # float64 frames are 8 bytes per pixel: a quarter batch bounds the payload
+        arrs = [(a[:rows_w] * 255).astype(np.uint8) if (i == 0 and dt is np.uint8) else (a[:rows_w].astype(dt) if i == 0 else a[:rows_w])
+                for i, a in enumerate(f_np)]
+        payload = torch.frombuffer(bytearray(encode_forward_payload(arrs, per_env)), dtype=torch.uint8).pin_memory()
+        sec_w = timed(lambda: fm.step_bytes_replies(payload, per_env), 3, 2, dist)
+        fwd_wire[tag] = {"value": round(world * rows_w * 3 / sec_w, 1), "rows_per_gpu": rows_w, "h2d_bytes_per_step": int(payload.numel()),
+                         "d2h_bytes_per_step": int(lib.ddrl_easybytes_reply_bytes(per_env, 0 if wl_dist(args.workload) else 2, 1)) * (rows_w // per_env)}
+        del payload, arrs
+    # ... and the batch grid of SURVEY 8(d): resident actions/s and per-call latency at B = 256 / 4096 / Bf (the live
+    # predictor runs at a few hundred rows per tick, server/forward.py:117-131)
+    fwd_grid = {}
+    for bq in (256, 4096):
+        if bq >= Bf:
+            continue
+        sq = [s[:bq].contiguous() for s in fstates_d]
+        sec_q = timed(lambda: fnet.act(sq), 20, 5, dist)
+        arrs_q = [(a[:bq] * 255).astype(np.uint8) if (i == 0 and args.workload == "pong") else a[:bq] for i, a in enumerate(f_np)]
+        pay_q = torch.frombuffer(bytearray(encode_forward_payload(arrs_q, per_env)), dtype=torch.uint8).pin_memory()
+        sec_qe = timed(lambda: fm.step_bytes_replies(pay_q, per_env), 10, 3, dist)
+        fwd_grid[str(bq)] = {"actions_per_s": round(world * bq * 20 / sec_q, 1), "latency_ms": round(sec_q / 20 * 1e3, 4),
+                             "e2e_actions_per_s": round(world * bq * 10 / sec_qe, 1), "e2e_latency_ms": round(sec_qe / 10 * 1e3, 4),
+                             "e2e_wire": "u8" if args.workload == "pong" else "f32", "e2e_h2d_bytes": int(pay_q.numel())}
 
     # ---- GAE: BASELINE C3 corner 64k envs x T=2048 (2.28 GB algorithmic traffic), columns sharded over ranks
     T, N = 2048, 65536
@@ -352,6 +403,11 @@ def run_ours(args):
         for other in [w for w in ("navlaser", "navimg", "pong") if w != args.workload]:
             others[other] = quick_workload(other, args.gemm_mode, dev, dist, world, rank)
             torch.cuda.empty_cache()
+        # BASELINE configs[3] as a STRONG-scaling point: the 64k-row Pong batch split over the ranks (N = 1 runs all 65536
+        # rows, micro-batched through the 8192-row workspace)
+        others["pong_64k_strong"] = dict(quick_workload("pong", args.gemm_mode, dev, dist, world, rank, rows=65536 // world, forward=False),
+                                         scaling="strong")
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0 only, N=1 only): the oracle port on the host cores, bounded sample
     cpu = None
@@ -379,7 +435,9 @@ def run_ours(args):
             "kernel_time_shares": kernel_shares,
             "learner_tflops": round(value * wl["flops_learn"] / 1e12, 2),
             "forward": {"value": round(fwd_value, 1), "unit": "actions/s", "rows_per_gpu": Bf,
-                        "e2e": round(fwd_e2e, 1), "tflops": round(fwd_value * wl["flops_fwd"] / 1e12, 2)},
+                        "e2e": round(fwd_e2e, 1), "e2e_note": "ForwardModule.step from pageable fp32 numpy arrays",
+                        "e2e_wire": fwd_wire, "batch_grid": fwd_grid,
+                        "tflops": round(fwd_value * wl["flops_fwd"] / 1e12, 2)},
             "gae": {"value": round(gae_elems, 1), "unit": "(t*env) elements/s", "shape": "T=2048 x N=65536 per GPU",
                     "roofline": {"bound": "hbm", "achieved": round(gae_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                  "frac": round(gae_gbs / peaks["hbm"], 4)}},
@@ -394,14 +452,14 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def quick_workload(kind, gemm_mode, dev, dist, world=1, rank=0):
+def quick_workload(kind, gemm_mode, dev, dist, world=1, rank=0, rows=None, forward=True):
     """Learner sample-iterations/s (3 warm-up + 2 timed learn calls, inputs resident) and Forward actions/s of another
     named configuration, same definitions as the headline numbers (whole-job aggregates over `world` ranks: rows
     sharded, one gradient all-reduce per iteration; inference shards env rows with no collective)."""
     from ddrl4nav_b200.data import Experience
     from ddrl4nav_b200.runner import make_net
     wl = WORKLOADS[kind]
-    B, Bf = wl["batch"], wl["fwd_batch"]
+    B, Bf = rows or wl["batch"], wl["fwd_batch"]
     net = make_net(kind, device=dev, gemm_mode=gemm_mode, TRAINING_ITER_TIME=ITERS)
     if dist is not None:
         net.enable_data_parallel()
@@ -416,7 +474,11 @@ def quick_workload(kind, gemm_mode, dev, dist, world=1, rank=0):
     def step():
         for _ in net.learn(exp):
             pass
-    sec = timed(step, 2, 3, dist)
+    sec = timed(step, 2, 3 if rows is None else 1, dist)
+    if not forward:
+        return {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B * world, "n_gpus": world,
+                "value": round(world * B * ITERS * 2 / sec, 1), "unit": "learner sample-iterations/s",
+                "ms_per_step": round(sec / 2 * 1e3, 3)}
     fstates_d = [s.to(dev) for s in synth_batch_host(kind, Bf, seed=200 + rank)[0]]
     fnet = make_net(kind, device=dev, gemm_mode=gemm_mode)          # inference-only engine instance (predictor process)
     fnet.load_state_dict(net.state_dict())

@@ -103,6 +103,10 @@ def concat_plan(msgs: Sequence[Sequence[Tuple[int, Tuple[int, ...], int, int]]],
     return shapes, offs, total, np.array(segs, dtype=SEG_DTYPE)
 
 
+def _copy_bytes(dst, src, b0, q0, q1):
+    dst[q0:q1] = src[b0 + q0:b0 + q1]
+
+
 class DeviceEasyBytes:
     """decode_forward_states / decode_backward_data with fp32 DEVICE tensors as the result."""
 
@@ -154,6 +158,77 @@ class DeviceEasyBytes:
         """easybytes.py:114-139 + server/forward.py:128-131: (process_env_ids, fp32 device state slots)."""
         ids, msgs = parse_forward_states(byte_states)
         return ids, self._decode(byte_states, msgs)
+
+    # ---- large payloads: chunks of whole messages, staged copy / H2D / decode of consecutive chunks overlapped ---------
+    def forward_chunks(self, byte_states, chunk_bytes: int = 64 << 20):
+        """Splits a Forward payload into runs of whole env-process messages of <= chunk_bytes each.
+        -> (process_env_ids, [(byte0, byte1, msgs with offsets relative to byte0)])."""
+        ids, msgs, bounds, i, n = [], [], [], 0, len(byte_states)
+        view = byte_states if isinstance(byte_states, (bytes, bytearray, memoryview)) else memoryview(byte_states.numpy())
+        while i < n:
+            if i + 20 > n:
+                raise ValueError("EasyBytes: truncated message header at byte %d" % i)
+            length = struct.unpack_from(">Q", view, i)[0]
+            if i + 20 + length > n:
+                raise ValueError("EasyBytes: message at byte %d claims %d payload bytes, %d left" % (i, length, n - i - 20))
+            ip = struct.unpack_from(">HHHH", view, i + 8)
+            env_id = struct.unpack_from(">I", view, i + 16)[0]
+            msgs.append(parse_data(view, i + 20, i + 20 + length))
+            ids.append(".".join(str(x) for x in ip) + "_" + str(env_id))
+            bounds.append((i, i + 20 + length))
+            i += 20 + length
+        chunks, k = [], 0
+        while k < len(msgs):
+            b0, j = bounds[k][0], k
+            while j < len(msgs) and (j == k or bounds[j][1] - b0 <= chunk_bytes):
+                j += 1
+            b1 = bounds[j - 1][1]
+            chunks.append((b0, b1, [[(c, sh, off - b0, cnt) for c, sh, off, cnt in m] for m in msgs[k:j]]))
+            k = j
+        return ids, chunks
+
+    def upload_chunk(self, src, b0: int, b1: int, segs: np.ndarray, stream, pool=None, threads: int = 8):
+        """Queues the H2D copy of src[b0:b1] (+ the segment table) on `stream`.  src: a PINNED uint8 tensor (copied straight
+        from where it lies) or a bytes-like object (staged through the pinned ring; `pool` splits the host copy over
+        `threads` workers -- numpy releases the GIL).  -> (device payload, device segment table)."""
+        n = b1 - b0
+        if torch.is_tensor(src) and src.is_pinned():
+            with torch.cuda.stream(stream):
+                dev = src[b0:b1].to(self.device, non_blocking=True)
+                seg_dev = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(self.device, non_blocking=True)
+            return dev, seg_dev
+        k = self._slot
+        self._slot = (k + 1) % self.N_SLOTS
+        if self._evt[k] is not None:
+            self._evt[k].synchronize()
+        need = n + segs.nbytes + 64
+        if self._pin[k] is None or self._pin[k].numel() < need:
+            self._pin[k] = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
+        host = self._pin[k].numpy()
+        raw = np.frombuffer(src, dtype=np.uint8) if not torch.is_tensor(src) else src.numpy()
+        if pool is not None and n > (8 << 20):
+            per = -(-n // threads)
+            jobs = [pool.submit(_copy_bytes, host, raw, b0, q, min(n, q + per)) for q in range(0, n, per)]
+            for j in jobs:
+                j.result()
+        else:
+            host[:n] = raw[b0:b1]
+        seg_off = (n + 31) // 32 * 32
+        host[seg_off:seg_off + segs.nbytes] = segs.view(np.uint8).reshape(-1)
+        with torch.cuda.stream(stream):
+            dev_all = self._pin[k][:seg_off + segs.nbytes].to(self.device, non_blocking=True)
+            if self._evt[k] is None:
+                self._evt[k] = torch.cuda.Event()
+            self._evt[k].record(stream)
+        return dev_all[:n], dev_all[seg_off:]
+
+    def decode_uploaded(self, dev, seg_dev, msgs):
+        """Runs the decode kernel on an uploaded chunk (current stream).  -> fp32 device state slots of the chunk."""
+        shapes, offs, total, segs = concat_plan(msgs)
+        out = torch.empty(total, dtype=torch.float32, device=self.device)
+        check(_lib.load().ddrl_easybytes_decode(ptr(dev), ptr(seg_dev), len(segs), int(segs["count"].max(initial=0)), ptr(out),
+                                                current_stream()), "ddrl_easybytes_decode")
+        return [out[o:o + int(np.prod(s, dtype=np.int64))].view(*s) for o, s in zip(offs, shapes)]
 
     def decode_backward_data(self, bytes_data) -> Tuple[List[torch.Tensor], List[torch.Tensor], Dict]:
         """easybytes.py:163-171: (states, [advs, actions, old_logps, values], logger dict), tensors fp32 on the device."""

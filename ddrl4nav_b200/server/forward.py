@@ -71,12 +71,82 @@ class ForwardModule:
         dtypes and are sliced / concatenated / converted to fp32 by ONE kernel (data/easybytes.py), then the fused engine
         call.  Returns (process_env_ids, [actions, logps, values]) -- the two things ``ForwardThread.run`` needs for
         ``encode_forward_return_data`` and the reply keys."""
+        ids, (actions, logps, values) = self._run_bytes(byte_states, draw)
+        return ids, self._finish(actions, logps, values)
+
+    def step_bytes_replies(self, byte_states, per_env: int, draw: Optional[torch.Tensor] = None):
+        """``step_bytes`` + ``encode_forward_return_data`` (data/easybytes.py:77-109) with the replies cut on the DEVICE:
+        one kernel writes every env process's reply (headers + fp32 payloads) into one byte buffer, ONE device->host copy
+        brings them back, the host slices it.  -> (process_env_ids, [reply bytes per env process])."""
+        import ctypes as C
+        from .. import _lib
+        from .._lib import check, current_stream, ptr
+        ids, (actions, logps, values) = self._run_bytes(byte_states, draw)
+        lib = _lib.load()
+        n_env, B = len(ids), logps.shape[0]
+        if n_env * per_env != B:
+            raise ValueError("%d env processes x %d rows != batch of %d rows" % (n_env, per_env, B))
+        A = actions.shape[1] if actions.dim() == 2 else 0
+        rb = int(lib.ddrl_easybytes_reply_bytes(per_env, A, 1))
+        out = torch.empty(n_env * rb, dtype=torch.uint8, device=self.device)
+        check(lib.ddrl_easybytes_encode_replies(ptr(actions), A, ptr(logps), ptr(values), 1, B, n_env, per_env, ptr(out),
+                                                current_stream()), "ddrl_easybytes_encode_replies")
+        key = ("replies", out.numel())
+        host = self._pinned.get(key)
+        if host is None:
+            host = torch.empty(out.numel(), dtype=torch.uint8).pin_memory()
+            self._pinned[key] = host
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        raw = host.numpy().tobytes()
+        return ids, [raw[j * rb:(j + 1) * rb] for j in range(n_env)]
+
+    def _run_bytes(self, byte_states, draw):
+        """decode + engine call for a payload; payloads above `chunk_bytes` stream through in chunks of whole messages:
+        host staging (threaded) / H2D on the copy stream of chunk c+1 overlap decode + engine call of chunk c."""
         if getattr(self, "_eb", None) is None:
             from ..data.easybytes import DeviceEasyBytes
             self._eb = DeviceEasyBytes(self.device)
-        ids, states = self._eb.decode_forward_states(byte_states)
-        actions, logps, values = self.net.act(states, draw=draw, play_mode=self.play_mode)
-        return ids, self._finish(actions, logps, values)
+        n = byte_states.numel() if torch.is_tensor(byte_states) else len(byte_states)
+        if n <= self.chunk_bytes:
+            if torch.is_tensor(byte_states):
+                byte_states = byte_states.numpy().tobytes()
+            ids, states = self._eb.decode_forward_states(byte_states)
+            return ids, self.net.act(states, draw=draw, play_mode=self.play_mode)
+        from concurrent.futures import ThreadPoolExecutor
+        from ..data.easybytes import concat_plan
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(self.copy_threads)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        ids, chunks = self._eb.forward_chunks(byte_states, self.chunk_bytes)
+        outs, row0 = [], 0
+        nxt = None
+        for c, (b0, b1, msgs) in enumerate(chunks):
+            if nxt is None:
+                segs = concat_plan(msgs)[3]
+                nxt = self._eb.upload_chunk(byte_states, b0, b1, segs, self._copy_stream, self._pool, self.copy_threads)
+                ev = torch.cuda.Event(); ev.record(self._copy_stream)
+                nxt = nxt + (ev,)
+            dev, seg_dev, ev = nxt
+            nxt = None
+            if c + 1 < len(chunks):                      # start the next chunk's staging + H2D before this chunk computes
+                nb0, nb1, nmsgs = chunks[c + 1]
+                up = self._eb.upload_chunk(byte_states, nb0, nb1, concat_plan(nmsgs)[3], self._copy_stream, self._pool, self.copy_threads)
+                nev = torch.cuda.Event(); nev.record(self._copy_stream)
+                nxt = up + (nev,)
+            main.wait_event(ev)
+            dev.record_stream(main); seg_dev.record_stream(main)
+            states = self._eb.decode_uploaded(dev, seg_dev, msgs)
+            rows = states[0].shape[0]
+            dr = None if draw is None else draw[row0:row0 + rows]
+            outs.append(self.net.act(states, draw=dr, play_mode=self.play_mode))
+            row0 += rows
+        actions = torch.cat([o[0] for o in outs], 0)
+        logps = torch.cat([o[1] for o in outs], 0)
+        values = torch.cat([o[2] for o in outs], 1)
+        return ids, (actions, logps, values)
 
     def _step_streamed(self, arrs, B, row_bytes, draw):
         from concurrent.futures import ThreadPoolExecutor

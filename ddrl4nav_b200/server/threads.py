@@ -8,9 +8,10 @@
 Same constructor contracts, same Redis keys / ordering of Redis operations, same logger calls as the reference threads;
 what runs between the Redis pop and the Redis push is the device path of this package:
 
-  * Forward tick: the popped payload goes through ``ForwardModule.step_bytes`` (header parse on the host, ONE H2D copy in
-    wire dtypes, decode + encoders + heads + sampling + log-prob + value on the device, ONE D2H copy) and the replies are
-    cut by ``encode_forward_replies`` (one header template per layout instead of a struct.pack per array).
+  * Forward tick: the popped payload goes through ``ForwardModule.step_bytes_replies`` (header parse on the host, ONE H2D
+    copy in wire dtypes -- streamed in chunks of whole messages when large --, decode + encoders + heads + sampling +
+    log-prob + value + reply encode on the device, ONE D2H copy of the reply bytes).  ``encode_forward_replies`` is the
+    host-side equivalent of the reply encoder (``encode_forward_return_data``), kept for arrays that are already on the host.
   * Trainer: ``BackwardGetDataThread`` queues the RAW payload (decoding it on the host is exactly the work the device
     decoder removes); ``BackwardQueue.get`` hands the payloads of one batch to ``DeviceEasyBytes.decode_backward_batch``
     (one staged copy + one kernel = decode + ``Experience.batch_data``), so ``train_data.to_tensor`` has nothing left to do.
@@ -125,9 +126,9 @@ class ForwardThread(Thread):
             if train_update > self._pre_update:
                 self.net.updatenn_by_redis(self.conn_middle)
                 self._pre_update = train_update
-        env_ids, out = self.module.step_bytes(byte_states, draw=draw)        # [actions, logps, values [1,B,1]] numpy
         per_env = self.batch_num_per_env * self.agent_num_per_env
-        replies = encode_forward_replies(out, [per_env] * len(env_ids))
+        # decode + encoders + heads + sampling + reply encode on the device; one H2D of the wire bytes, one D2H of the replies
+        env_ids, replies = self.module.step_bytes_replies(byte_states, per_env, draw=draw)
         for env_id, payload in zip(env_ids, replies):
             self.pipe_pre.lpush(self.pre_actionkey.format(env_id), payload)
         self.pipe_pre.execute()

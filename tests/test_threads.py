@@ -155,3 +155,38 @@ def test_backward_threads_one_batch():
             got.setdefault(k, v[0])
     for k in ("ActorLoss", "VLoss"):
         assert abs(got[k] - want[k]) <= 1e-4 * max(1.0, abs(want[k]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["pong", "navlaser"])
+def test_device_reply_encode_and_chunked_payload(kind):
+    """step_bytes_replies (decode, engine, reply encode on the device) == host encoder over step_bytes' arrays, and a payload
+    streamed in chunks of whole messages gives the same replies as the single-shot path."""
+    from ddrl4nav_b200.server import ForwardModule, encode_forward_replies
+    B_env, n_env = 5, 7
+    net, spec, params = _make(kind)
+    states = [s.numpy() for s in R.synth_states(kind, B_env * n_env, seed=4)]
+    wire = [(s * 255).astype(np.uint8) if (i == 0 and kind == "pong") else s for i, s in enumerate(states)]
+    payload = b"".join(R.easybytes_encode_forward_states("10.1.2.3", 100 + j, [w[j * B_env:(j + 1) * B_env] for w in wire])
+                       for j in range(n_env))
+    gen = torch.Generator().manual_seed(6)
+    draw = (torch.randn(B_env * n_env, spec.act_dim, generator=gen) if spec.dist == "gaussian"
+            else torch.rand(B_env * n_env, generator=gen)).cuda()
+    fm = ForwardModule(net, device="cuda")
+    ids, arrs = fm.step_bytes(payload, draw=draw)
+    want = encode_forward_replies(arrs, [B_env] * n_env)
+    ids2, got = fm.step_bytes_replies(payload, B_env, draw=draw)
+    assert ids2 == ids and got == want
+    # chunked: at most two messages per chunk; also from a pinned uint8 tensor (copied to the device from where it lies)
+    fm_c = ForwardModule(net, device="cuda", chunk_bytes=2 * (len(payload) // n_env) + 8)
+    ids3, got3 = fm_c.step_bytes_replies(payload, B_env, draw=draw)
+    assert ids3 == ids
+    pinned = torch.frombuffer(bytearray(payload), dtype=torch.uint8).pin_memory()
+    ids4, got4 = fm_c.step_bytes_replies(pinned, B_env, draw=draw)
+    assert ids4 == ids
+    for a, b, c in zip(want, got3, got4):
+        da, db, dc = (R.easybytes_decode_data(x) for x in (a, b, c))
+        for u, v, w in zip(da, db, dc):
+            assert u.shape == v.shape == w.shape
+            np.testing.assert_allclose(v, u, rtol=1e-5, atol=1e-6)       # chunk amax differs: scaled-fp16 rounding, not bit-equal
+            np.testing.assert_array_equal(v, w)
