@@ -217,10 +217,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    saved_stdout = None
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner to fd 1 from C (at NCCL_DEBUG=VERSION and
+        # above), so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
@@ -447,6 +450,9 @@ def run_ours(args):
             line["other_workloads"] = others
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
