@@ -361,16 +361,16 @@ int tc_get_encode() {
   return DDRL_OK;
 }
 
-// generic tiled map (tc3.cu builds its fp16 weight maps with it); swizzle128 = false: SWIZZLE_128B_ATOM_32B
+// generic tiled map (tc3.cu / tc4.cu build their fp16 maps with it); swizzle: 0 SWIZZLE_128B_ATOM_32B, 1 SWIZZLE_128B, 2 SWIZZLE_64B
 int tc_encode_tiled(CUtensorMap* m, bool f16, int rank, const void* base, const unsigned long long* dims,
-                    const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr, bool swizzle128) {
+                    const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr, int swizzle) {
   cuuint64_t d[5], st[4];
   cuuint32_t b[5], e[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
   CUresult r = g_encode(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                         const_cast<void*>(base), d, st, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled(rank %d%s) failed (%d)", rank, f16 ? ", f16" : "", (int)r);

@@ -177,7 +177,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 int tc_get_encode();
 int tc_make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_outer, bool mn_major);
 int tc_encode_tiled(CUtensorMap* m, bool f16, int rank, const void* base, const unsigned long long* dims,
-                    const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr, bool swizzle128);
+                    const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estr, int swizzle);
 int tc_make_map_nhwc(CUtensorMap* m, const ConvOp& o, int nx, int ny, int nb, bool mn_major);
 int tc_make_map_dy4(CUtensorMap* m, const float* dy, int ldy, int N, int Xn, int Yn, int Bn, int xw, int yh);
 int tc_make_map_dy3(CUtensorMap* m, const float* dy, int ldy, int N, long long ipix, int Bn, int rows);
