@@ -33,15 +33,15 @@ METRIC = "PPO learner samples/s & batched policy actions/s at 1/2/4/8 B200"
 # per-GPU batch of the named BASELINE.json configs (weak scaling: fixed per GPU)
 WORKLOADS = {
     # C4 = "8xB200 data-parallel learner: Pong PPO batch 64k, minibatch sharded" -> 8192 rows per GPU
-    "pong": dict(batch=8192, fwd_batch=32768, cpu_batch=1024, desc="Pong PPO learner, NatureCNN 4x84x84, unshared towers, "
+    "pong": dict(batch=8192, fwd_batch=32768, cpu_batch=1024, ref_batch=8192, desc="Pong PPO learner, NatureCNN 4x84x84, unshared towers, "
                  "6-way categorical (BASELINE C1/C4: 64k batch at 8 GPUs = 8192 rows/GPU)",
                  flops_fwd=37.37e6, flops_learn=99.0e6, obs_bytes=112896),
     # C2 = "robot-nav PPO: laser-scan + goal/vel vector, Gaussian policy" (reference shapes: 1x960 + 5 + 3x48x48)
-    "navlaser": dict(batch=1024, fwd_batch=4096, cpu_batch=128, desc="robot-nav PPO learner, NavPreNet1D laser 1x960 + vec5 + "
+    "navlaser": dict(batch=1024, fwd_batch=4096, cpu_batch=128, ref_batch=256, desc="robot-nav PPO learner, NavPreNet1D laser 1x960 + vec5 + "
                      "ped-map 3x48x48, unshared towers, 2-d Gaussian (BASELINE C2)",
                      flops_fwd=545.3e6, flops_learn=1562.6e6, obs_bytes=31508),
     # C5 = "nav image-env PPO (1x48x48 egocentric map), shared encoder, 28-way categorical"
-    "navimg": dict(batch=2048, fwd_batch=8192, cpu_batch=256, desc="nav image-env PPO learner, NavPreNet 1x48x48 + vec9, shared "
+    "navimg": dict(batch=2048, fwd_batch=8192, cpu_batch=256, ref_batch=1024, desc="nav image-env PPO learner, NavPreNet 1x48x48 + vec9, shared "
                    "encoder, 28-way categorical (BASELINE C5)",
                    flops_fwd=183.0e6, flops_learn=546.4e6, obs_bytes=9252),
 }
@@ -497,58 +497,80 @@ def quick_workload(kind, gemm_mode, dev, dist, world=1, rank=0, rows=None, forwa
             "forward_actions_per_s": round(world * Bf * 5 / sec_f, 1), "forward_rows_per_gpu": Bf}
 
 
-def cpu_reference(kind, B, iters, warm):
-    """The reference's CPU path for the learner step (oracle port: same torch ops as nn/ppo.py:79-129) on all host
-    cores.  Returns the cpu_baseline object."""
+def _reference_learner(kind, B):
+    """One full-batch PPO iteration on the host cores as a callable, plus what ran it.
+    kind "reference": the UNMODIFIED reference (`USTC_lab.nn.PPO.learn`, nn/ppo.py:77-142, one iteration per call) imported
+    from /root/reference or from the snapshot build() leaves in oracle/_ref/ (oracle/snapshot_ref.py);
+    kind "port": the oracle restatement of the same torch op sequence, when neither exists."""
     from oracle import restate as R
     torch.set_num_threads(os.cpu_count() or 1)
     spec = R.SPECS[kind]
     params = R.init_params(spec, seed=1)
     states = R.synth_states(kind, B, seed=2)
     a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=3)
+    try:
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            raise RuntimeError("no reference tree")
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):            # the reference's config prints the env name on import
+            net, _, _ = ref_shim.make_ref_net(kind)
+        from USTC_lab.data import Experience as RefExperience
+        net.load_state_dict({k: params[k] for k in net.state_dict()})
+        net.training_iter_time = 1
+        exp = RefExperience(states=states, advs=adv, actions=a, old_logps=old, values=ret.unsqueeze(0))
+
+        def step():
+            for _ in net.learn(exp):
+                pass
+        return step, "reference", "USTC_lab.nn.PPO.learn (unmodified reference, %s)" % (
+            "mounted tree" if ref_shim.REFERENCE_ROOT != ref_shim.SNAPSHOT_ROOT else "oracle/_ref snapshot")
+    except Exception as e:                      # noqa: BLE001 -- any import problem falls back to the port, and says so
+        why = "%s: %s" % (type(e).__name__, e)
     st = R.LearnState(spec, params)
     hp = R.PPOHyper()
+    return (lambda: R.learn_iteration(st, states, adv, a, old, ret, hp)), "port", "oracle/restate.py port (reference not importable: %s)" % why[:120]
+
+
+def cpu_reference(kind, B, iters, warm):
+    """The reference's CPU path for the learner step on all host cores (the real `PPO.learn` when the reference or its
+    snapshot is importable, else the oracle port).  Returns the cpu_baseline object."""
+    step, how, what = _reference_learner(kind, B)
     for _ in range(warm):
-        R.learn_iteration(st, states, adv, a, old, ret, hp)
+        step()
     t0 = time.perf_counter()
     for _ in range(iters):
-        R.learn_iteration(st, states, adv, a, old, ret, hp)
+        step()
     dt = time.perf_counter() - t0
     return {"value": round(B * iters / dt, 1), "unit": "learner sample-iterations/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "%d full-batch iterations of B=%d (%s), torch %s CPU" % (iters, B, kind, torch.__version__)}
+            "kind": how, "sample": "%d full-batch iterations of B=%d (%s), %s, torch %s CPU" % (iters, B, kind, what, torch.__version__)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the learner step (oracle port), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the learner step, rank 0 only.  Each step is ONE
+    full-batch iteration (a tenth of the 10-iteration learn call) at the product arm's rows per GPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import restate as R
     wl = WORKLOADS[args.workload]
-    B = wl["cpu_batch"]
-    torch.set_num_threads(os.cpu_count() or 1)
-    spec = R.SPECS[args.workload]
-    params = R.init_params(spec, seed=1)
-    states = R.synth_states(args.workload, B, seed=2)
-    a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=3)
-    st = R.LearnState(spec, params)
-    hp = R.PPOHyper()
+    B = args.batch or wl["ref_batch"]
+    step, how, what = _reference_learner(args.workload, B)
     for _ in range(args.warmup):
-        R.learn_iteration(st, states, adv, a, old, ret, hp)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        R.learn_iteration(st, states, adv, a, old, ret, hp)
+        step()
     dt = time.perf_counter() - t0
     value = B * args.steps / dt
-    sample = "each step = ONE full-batch iteration of B=%d rows (bounded sample of the %d-row x %d-iteration step)" % (
-        B, wl["batch"], ITERS)
+    sample = "each step = ONE full-batch iteration of B=%d rows (a tenth of the %d-row x %d-iteration learn call); %s" % (
+        B, wl["batch"], ITERS, what)
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "learner sample-iterations/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "rows_per_step": B, "device": "cpu"},
+            "config": {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B, "iters_per_step": 1, "device": "cpu"},
             "cpu_baseline": {"value": round(value, 1), "unit": "learner sample-iterations/s", "cores": torch.get_num_threads(),
-                             "kind": "port", "sample": sample},
+                             "kind": how, "sample": sample},
             "e2e": {"value": round(value, 1), "unit": "learner sample-iterations/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

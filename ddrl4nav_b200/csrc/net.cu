@@ -104,6 +104,11 @@ struct ddrl_net {
   int MB = 0;                    // micro-batch rows the workspace is sized for
   bool ws_train = false;
   float *logits = nullptr, *vout = nullptr, *dlogits = nullptr, *dv = nullptr, *stage = nullptr;
+  // extra value heads on the critic-side feature (nn/ppo.py:63-64 add_critic; share-CNN mode): parameters and gradients
+  // live OUTSIDE the flat buffers (the reference's optimisers are built before add_critic and never see them)
+  struct ExtraCritic { const float *w, *b; float *dw, *db; int in_loss; };
+  std::vector<ExtraCritic> extra;
+  float *vout_x = nullptr, *dv_x = nullptr;    // [kMaxExtra, MB]
   char* packed_base = nullptr;   // packed weights + packed grads arena
   char* split_base = nullptr;    // tc2 engine: [hi mirror of the packed arena | lo mirror]
   size_t packed_bytes = 0, packed_grad_off = 0, packed_grad_bytes = 0;
@@ -148,6 +153,7 @@ struct ddrl_net {
 namespace ddrl {
 
 constexpr int kAmaxSlots = 1024, kAmaxWeights = 256;
+constexpr int kMaxExtra = 2;      // extra critic heads ("suppose 3 critic net at most", nn/ppo.py:93)
 // mode 3 (tc3) is a superset of mode 2: same lowering decisions; the tc2 kernels keep the launches tc3 does not take
 static inline bool tc3_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC3_F16; }
 static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
@@ -582,6 +588,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     total += 2 * (((size_t)t.feat * mb * 4 + 255) & ~size_t(255));
   }
   total += 4 * (((size_t)n->ldA * mb * 4 + 255) & ~size_t(255)) + 4096;
+  total += 2 * (((size_t)kMaxExtra * mb * 4 + 255) & ~size_t(255));
   total += (s2d_floats * mb * 4 + 255) & ~size_t(255);
   if (cudaMalloc(&n->ws.base, total) != cudaSuccess) {
     cudaGetLastError();
@@ -614,6 +621,8 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   n->dlogits = n->ws.take((size_t)n->ldA * mb);
   n->vout = n->ws.take(mb);
   n->dv = n->ws.take(mb);
+  n->vout_x = n->ws.take((size_t)kMaxExtra * mb);
+  n->dv_x = n->ws.take((size_t)kMaxExtra * mb);
   return DDRL_OK;
 }
 
@@ -1108,6 +1117,8 @@ static int forward_chunk(ddrl_net* n, const float* const* obs, long long row0, i
   const int A = n->d.act_dim, F = n->d.feat;
   TRY(skinny_fwd(ta.h, F, n->params + n->T[n->t_aw].offset, n->params + n->T[n->t_ab].offset, mb, A, F, n->logits, n->ldA, s));
   TRY(skinny_fwd(tc.h, F, n->params + n->T[n->t_cw].offset, n->params + n->T[n->t_cb].offset, mb, 1, F, n->vout, 1, s));
+  for (size_t k = 0; k < n->extra.size(); ++k)       // [critic(states) for critic in self._critics], nn/ppo.py:75
+    TRY(skinny_fwd(tc.h, F, n->extra[k].w, n->extra[k].b, mb, 1, F, n->vout_x + k * (size_t)n->MB, 1, s));
   return DDRL_OK;
 }
 
@@ -1229,6 +1240,21 @@ extern "C" int ddrl_net_bind(ddrl_net* n, float* params, float* grads, float* ad
   return DDRL_OK;
 }
 
+extern "C" int ddrl_net_set_extra_critics(ddrl_net* n, int count, const float* const* w, const float* const* b,
+                                          float* const* dw, float* const* db, const int* in_loss) {
+  if (!n || count < 0 || count > kMaxExtra) return DDRL_E_ARG;
+  if (count > 0 && !n->d.shared) return DDRL_E_UNSUPPORTED;     // an unshared extra critic owns an encoder: a net of its own
+  if (count > 0 && (!w || !b)) return DDRL_E_ARG;
+  n->extra.clear();
+  for (int k = 0; k < count; ++k) {
+    if (!w[k] || !b[k]) return DDRL_E_ARG;
+    const int on = in_loss ? in_loss[k] : 0;
+    if (on && (!dw || !db || !dw[k] || !db[k])) return DDRL_E_ARG;
+    n->extra.push_back({w[k], b[k], dw ? dw[k] : nullptr, db ? db[k] : nullptr, on});
+  }
+  return DDRL_OK;
+}
+
 extern "C" int ddrl_net_params_changed(ddrl_net* n) {
   if (!n) return DDRL_E_ARG;
   n->dirty = true;
@@ -1281,6 +1307,9 @@ extern "C" int ddrl_net_forward(ddrl_net* n, const float* const* obs, int n_obs,
       if (pi_out) TRY(copy2d(n->logits, n->ldA, pi_out + r0 * A, A, mb, A, s));
     }
     DDRL_CUDA(cudaMemcpyAsync(values + r0, n->vout, sizeof(float) * mb, cudaMemcpyDeviceToDevice, s));
+    for (size_t k = 0; k < n->extra.size(); ++k)     // values is [1 + extras, B]
+      DDRL_CUDA(cudaMemcpyAsync(values + (k + 1) * (size_t)B + r0, n->vout_x + k * (size_t)n->MB, sizeof(float) * mb,
+                                cudaMemcpyDeviceToDevice, s));
   }
   return DDRL_OK;
 }
@@ -1351,6 +1380,16 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
     TRY(skinny_wgrad(n->dv, 1, tc.h, F, mb, 1, F, n->grads + n->T[n->t_cw].offset, n->grads + n->T[n->t_cb].offset, s));
     TRY(skinny_dgrad(n->dlogits, n->ldA, aw, mb, A, F, ta.dh, F, 0, s));
     TRY(skinny_dgrad(n->dv, 1, cw, mb, 1, F, tc.dh, F, n->d.shared ? 1 : 0, s));
+    // extra value heads (nn/ppo.py:99-107): returns row k+1, loss added to the value-loss sum, gradient into the shared feature
+    for (size_t k = 0; k < n->extra.size(); ++k) {
+      const ddrl_net::ExtraCritic& x = n->extra[k];
+      if (!x.in_loss) continue;
+      float* dvx = n->dv_x + k * (size_t)n->MB;
+      TRY(ddrl_value_loss(returns + (k + 1) * (size_t)B_local + r0, n->vout_x + k * (size_t)n->MB, mb, invB, hp, n->d.shared, dvx,
+                          loss_sums, s));
+      TRY(skinny_wgrad(dvx, 1, tc.h, F, mb, 1, F, x.dw, x.db, s));
+      TRY(skinny_dgrad(dvx, 1, x.w, mb, 1, F, tc.dh, F, 1, s));
+    }
     for (auto& t : n->towers) TRY(tower_backward(n, t, obs, r0, mb, s));
     if (n->fuse0) TRY(fused_conv0_bwd(n, mb, s));
   }

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(128) ppo_loss_categorical_kernel(
     for (int j = 0; j < A; ++j) { p[j] = expf(x[j] - m); s += p[j]; }
     float s2 = 0.f;
     for (int j = 0; j < A; ++j) { p[j] = p[j] / s; s2 += p[j]; }
-    const int a = (int)actions[b];            // Categorical.log_prob: value.long()
+    int a = (int)actions[b];                  // Categorical.log_prob: value.long()
+    a = a < 0 ? 0 : (a >= A ? A - 1 : a);     // the reference raises on an action outside [0, A); never read out of bounds
     const float Ai = adv[b];
     // log-prob of the taken action
     const float qa = p[a] / s2;
@@ -172,6 +173,21 @@ __global__ void __launch_bounds__(128) ppo_loss_gaussian_kernel(
   }
 }
 
+// value loss of one extra critic head (nn/ppo.py:97-104)
+__global__ void __launch_bounds__(128) value_loss_kernel(const float* __restrict__ returns, const float* __restrict__ v, int B,
+                                                         LossParams hp, float* __restrict__ dv, float* __restrict__ loss_sums) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l_v = 0.f;
+  if (b < B) {
+    float dl;
+    l_v = value_loss(returns[b], v[b], hp.smooth_l1, &dl) * hp.inv_B;
+    dv[b] = dl * hp.inv_B * (hp.shared ? hp.v_coef : 1.f);
+  }
+  l_v = block_sum(l_v, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss_sums + 1, l_v);
+}
+
 static LossParams make_params(const ddrl_ppo_hparams* hp, float inv_B, int shared) {
   LossParams p;
   p.ppo_clip = hp->ppo_clip; p.dual_clip = hp->dual_clip; p.v_coef = hp->v_coef; p.ent_coef = hp->ent_coef;
@@ -195,6 +211,18 @@ extern "C" int ddrl_ppo_loss_categorical(const float* logits, int ld, const floa
       loss_sums);
   prof_work((8.0 * A + 24.0) * B);
   DDRL_LAUNCHED("ppo_loss_categorical_kernel");
+  return DDRL_OK;
+}
+
+extern "C" int ddrl_value_loss(const float* returns, const float* v, int B, float inv_B_global, const ddrl_ppo_hparams* hp,
+                               int shared, float* dv, float* loss_sums, void* stream) {
+  if (B < 0 || !hp) return DDRL_E_ARG;
+  if (B == 0) return DDRL_OK;
+  if (!returns || !v || !dv || !loss_sums) return DDRL_E_ARG;
+  value_loss_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(returns, v, B, make_params(hp, inv_B_global, shared), dv,
+                                                                         loss_sums);
+  prof_work(12.0 * B);
+  DDRL_LAUNCHED("value_loss_kernel");
   return DDRL_OK;
 }
 

@@ -69,6 +69,9 @@ class PPO(Basenn):
         self._dp_group = None
         self._dp_world = 1
         self._loss4 = None
+        self._extra_key = None          # pointers the engine holds for the extra value heads (shared mode)
+        self._extra_scratch = None      # per extra head: this iteration's (dw, db), written by the engine
+        self._aux = []                  # one value-only engine per extra critic that owns an encoder (unshared mode)
 
     # ------------------------------------------------------------------ engine plumbing
     def _encoder(self):
@@ -109,6 +112,74 @@ class PPO(Basenn):
         if ver != self._versions:
             check(_lib.load().ddrl_net_params_changed(self._h), "ddrl_net_params_changed")
             self._versions = ver
+        if len(self._critics) > 1 or self._extra_key is not None:
+            self._sync_extra_critics(dev)
+
+    # ------------------------------------------------------------------ extra critics (nn/ppo.py:63-64,75,95-105)
+    def _extra_in_loss(self, k):
+        """Only the LAST critic's loss is added, and only under gail_critic (ppo.py:101-104); RND (ppo.py:97-100) is out
+        of scope and rejected by the constructor."""
+        return bool(self.gail_critic) and k == len(self._critics) - 2
+
+    def _sync_extra_critics(self, dev):
+        extras = self._critics[1:]
+        if self.prenet is None:
+            return                      # unshared: every extra critic runs on a value-only engine of its own (self._aux)
+        lib = _lib.load()
+        key = []
+        if self._extra_scratch is None or len(self._extra_scratch) != len(extras):
+            self._extra_scratch = [(torch.zeros_like(c.critic_linear.weight, device=dev), torch.zeros_like(c.critic_linear.bias, device=dev))
+                                   for c in extras]
+        for k, c in enumerate(extras):
+            w, b = c.critic_linear.weight, c.critic_linear.bias
+            if w.device != dev or not w.is_contiguous() or w.dtype != torch.float32:
+                raise DDRLError("extra critic %d must hold contiguous fp32 parameters on %s (call .to(device))" % (k, dev))
+            gw, gb = self._extra_scratch[k]
+            key.append((w.data_ptr(), b.data_ptr(), gw.data_ptr(), gb.data_ptr(), int(self._extra_in_loss(k))))
+        key = tuple(key)
+        if key == self._extra_key:
+            return
+        n = len(key)
+        arr = lambda col: (C.c_void_p * max(n, 1))(*[e[col] or None for e in key])
+        flags = (C.c_int * max(n, 1))(*[e[4] for e in key])
+        check(lib.ddrl_net_set_extra_critics(self._h, n, arr(0), arr(1), arr(2), arr(3), flags), "ddrl_net_set_extra_critics")
+        self._extra_key = key if n else None
+
+    def _extra_grads_to_params(self):
+        """Adds this iteration's gradients of the extra heads (engine scratch, all-reduced in a data-parallel learner) to
+        their `.grad`, which nobody in PPO zeroes -- as with the reference's autograd accumulation."""
+        for k, c in enumerate(self._critics[1:]):
+            if not self._extra_in_loss(k):
+                continue
+            for p, g in zip((c.critic_linear.weight, c.critic_linear.bias), self._extra_scratch[k]):
+                if self._dp_world > 1:
+                    import torch.distributed as tdist
+                    tdist.all_reduce(g, group=self._dp_group)
+                p.grad = g.clone() if p.grad is None else p.grad.add_(g)
+                g.zero_()
+
+    def _aux_net(self, k):
+        """Value-only engine of extra critic k in unshared mode: its own encoder + its critic_linear, built as a share-CNN
+        net with a throw-away 1-way actor (zero advantage => the actor path contributes exactly nothing)."""
+        while len(self._aux) <= k:
+            self._aux.append(None)
+        c = self._critics[1 + k]
+        if self._aux[k] is None or self._aux[k][0] is not c:
+            from .actor import CategoricalActor
+            from .critic import Critic
+            feat = c.critic_linear.in_features
+            holder = Critic(last_input_dim=feat, pre=None)
+            holder.critic_linear = c.critic_linear               # the SAME parameters: p.data re-points into aux's flat buffer
+            actor = CategoricalActor(1, last_input_dim=feat, pre=None)
+            aux = PPO(actor, holder, c.pre, None, self.config, None)
+            aux.gemm_mode = self.gemm_mode
+            aux.hp = kernels.make_hparams(
+                ppo_clip=self.hp.ppo_clip, dual_clip=self.hp.dual_clip, v_coef=1.0, ent_coef=0.0,
+                max_grad_norm=self.hp.max_grad_norm, clip_grad=self.hp.clip_grad, smooth_l1=self.hp.smooth_l1, lr=0.0,
+                lr_actor=0.0, lr_critic=0.0)
+            aux.to(self._flat.device)
+            self._aux[k] = (c, aux)
+        return self._aux[k][1]
 
     def _build(self, plist, dev):
         lib = _lib.load()
@@ -210,7 +281,8 @@ class PPO(Basenn):
         """Fused compute body of ForwardThread.run (server/forward.py:128-146).
 
         draw: uniforms [B] (categorical) or standard normals [B,A] (gaussian); generated on the device
-        when None and not play_mode.  Returns (actions [B] | [B,A], logps [B], values [V=1,B,1][, pi])."""
+        when None and not play_mode.  Returns (actions [B] | [B,A], logps [B], values [V,B,1][, pi]); V = number of
+        critics (1 unless add_critic was called)."""
         self._ensure_engine()
         lib = _lib.load()
         keep, arr, n_obs, B = self._obs_ptrs(states)
@@ -225,11 +297,15 @@ class PPO(Basenn):
             draw = draw.to(device=dev, dtype=torch.float32).contiguous()
         actions = torch.empty((B, A) if gauss else (B,), dtype=torch.float32, device=dev)
         logps = torch.empty(B, dtype=torch.float32, device=dev)
-        values = torch.empty(B, dtype=torch.float32, device=dev)
+        V = len(self._critics)
+        values = torch.empty(V, B, dtype=torch.float32, device=dev)       # shared mode: the engine fills all V rows
         pi = torch.empty((B, A), dtype=torch.float32, device=dev) if want_pi else None
         check(lib.ddrl_net_forward(self._h, arr, n_obs, B, ptr(draw), ptr(actions), ptr(logps), ptr(values), ptr(pi),
                                    current_stream()), "ddrl_net_forward")
-        out = (actions, logps, values.view(1, B, 1))
+        if V > 1 and self.prenet is None:                                  # unshared: each extra critic on its own engine
+            for k in range(V - 1):
+                values[1 + k] = self._aux_net(k).act(keep, play_mode=True)[2].view(B)
+        out = (actions, logps, values.view(V, B, 1))
         return out + (pi,) if want_pi else out
 
     def encode(self, states, tower=0):
@@ -254,7 +330,7 @@ class PPO(Basenn):
             if play_mode:
                 raise DDRLError("log-prob of given actions needs play_mode=False (as in the reference)")
             log_p = self.actor.log_prob_from_distribution(pi, act.to(pi_raw.device))
-        return (pi, log_p), [values.view(-1, 1)]
+        return (pi, log_p), [values[k].view(-1, 1) for k in range(values.shape[0])]
 
     # ------------------------------------------------------------------ Backward module
     def enable_data_parallel(self, group=None):
@@ -278,10 +354,34 @@ class PPO(Basenn):
         dev = self._flat.device
         f = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         advs, actions, old_logps, returns = f(advs), f(actions), f(old_logps), f(returns)
-        if returns.dim() == 2:             # data.values is [V,B]; the PPO critic uses row 0 (ppo.py:95)
-            returns = returns[0].contiguous()
+        V = len(self._critics)
+        rows = returns if returns.dim() == 2 else returns.view(1, -1)
+        if V > 1 and self.prenet is not None:
+            # the engine reads returns [V, B]: row 0 = data.values[0] (ppo.py:95), last row = data.values[-1] (ppo.py:102)
+            ret = torch.empty(V, B, dtype=torch.float32, device=dev)
+            ret[:] = rows[0]
+            ret[V - 1] = rows[-1]
+            returns = ret
+        else:
+            returns = rows[0].contiguous()     # data.values is [V,B]; the PPO critic uses row 0 (ppo.py:95)
         check(lib.ddrl_net_backward(self._h, arr, n_obs, B, int(b_global or B), ptr(actions), ptr(old_logps), ptr(advs),
                                     ptr(returns), C.byref(self.hp), int(bool(obs_unchanged)), current_stream()), "ddrl_net_backward")
+        if V > 1 and self.prenet is not None:
+            self._extra_grads_to_params()
+        if V > 1 and self.prenet is None and self.gail_critic:
+            # unshared: gailv_loss.backward() only reaches the extra critic's own tower (ppo.py:101-104,122-123)
+            k = V - 2
+            aux = self._aux_net(k)
+            zeros = torch.zeros(B, dtype=torch.float32, device=dev)
+            aux.backward_only(keep, zeros, zeros, zeros, rows[-1].contiguous(), b_global, obs_unchanged)
+            if self._dp_world > 1:
+                dist.allreduce_grads(aux._grads, aux._P, self._dp_group)      # its loss sum rides in the tail, as ours does
+            for n, g in aux.named_grads().items():
+                if n.startswith("actor."):
+                    continue
+                p = dict(aux.named_parameters())[n]
+                p.grad = g.clone() if p.grad is None else p.grad.add_(g)
+            self._grads[self._P + 1] += aux._grads[aux._P + 1] / (self._dp_world if self._dp_world > 1 else 1)
         return B
 
     def optimizer_step(self):
@@ -313,4 +413,13 @@ class PPO(Basenn):
             yield loss_log, self.update_time, True
 
     def add_critic(self, critic):
-        raise DDRLError("extra critics (RND/GAIL value heads) are outside the B200 hot path")
+        """nn/ppo.py:63-64.  The extra critic's values come back from forward()/act() as further rows; its value loss joins
+        VLoss when `gail_critic` is set (ppo.py:101-104), with the gradient flowing where the reference's autograd sends it:
+        through the shared encoder in share-CNN mode, into the critic's own encoder otherwise.  As in the reference, none of
+        PPO's optimisers steps the extra critic (they are built before add_critic, ppo.py:40-42): its gradients accumulate
+        in `.grad` for whoever owns it (nn/GAIL.py)."""
+        if len(self._critics) >= 3:
+            raise DDRLError("at most 3 critics (nn/ppo.py:93)")
+        if (self.prenet is not None) != (critic.pre is None):
+            raise DDRLError("an extra critic carries its own encoder exactly when SHARE_CNN_NET is off (runner/utils.py:162)")
+        self._critics.append(critic)

@@ -165,6 +165,11 @@ int ddrl_ppo_loss_gaussian(const float* mu, int ld, const float* log_std, const 
                            int B, int A, float inv_B_global, const ddrl_ppo_hparams* hp, int shared,
                            float* dmu, int ld_d, float* dv, float* dlog_std, float* loss_sums, void* stream);
 
+/* Value loss of ONE extra critic head (nn/ppo.py:97-104: rndv_loss / gailv_loss = vlossf(data.values[k], values[k])):
+ * dv[b] = d(loss)/d(v[b]) (times v_coef when shared, ppo.py:108), loss_sums[1] += contribution scaled by inv_B_global. */
+int ddrl_value_loss(const float* returns, const float* v, int B, float inv_B_global, const ddrl_ppo_hparams* hp,
+                    int shared, float* dv, float* loss_sums, void* stream);
+
 /* ---- K7: fused global-norm clip + Adam ------------------------------------------------
  * replaces torch.nn.utils.clip_grad_norm_ (nn/ppo.py:115,126) and torch.optim.Adam.step
  * (ppo.py:117,128-129).  Flat buffers of n floats; segment s covers [seg_begin[s], seg_begin[s+1])
@@ -215,6 +220,17 @@ int ddrl_net_tensor_info(const ddrl_net* net, int i, char* name, int name_cap,
  * [P .. P+3] carries {actor, v, entropy, unused} loss sums so one all-reduce covers both.
  * grads/m/v may be NULL for an inference-only net. */
 int ddrl_net_bind(ddrl_net* net, float* params, float* grads, float* adam_m, float* adam_v);
+/* Extra value heads (nn/ppo.py:63-64 `add_critic`, :75 `[critic(states) for critic in self._critics]`, :95-105 the V > 1
+ * value losses; agent/agent.py:96-108 value_dim_num): `count` (<= 2, "suppose 3 critic net at most", ppo.py:93) Critic
+ * heads WITHOUT an encoder of their own (share-CNN mode: runner/utils.py:162 deepcopy(critic)) reading the shared feature.
+ * w[k] [feat] and b[k] [1] are device pointers OUTSIDE the flat parameter buffer -- the reference's optimisers are built
+ * before add_critic (ppo.py:40-42) and never step them; dw[k] / db[k] receive their gradients (+=, the caller zeroes).
+ * While extras are set, ddrl_net_forward writes `values` as [1+count, B] (row stride B) and ddrl_net_backward reads
+ * `returns` as [1+count, B_local] (row k = data.values[k]); in_loss[k] != 0 adds vlossf(values[k+1]) to the value loss
+ * (gail_critic, ppo.py:101-104) and its gradient to the shared encoder.  Unshared nets: DDRL_E_UNSUPPORTED (an extra critic
+ * with its own encoder is a net of its own -- ddrl4nav_b200/nn/ppo.py builds one).  count = 0 clears. */
+int ddrl_net_set_extra_critics(ddrl_net* net, int count, const float* const* w, const float* const* b,
+                               float* const* dw, float* const* db, const int* in_loss);
 /* tell the net the flat params were changed behind its back (load_state_dict, updatenn_by_redis) */
 int ddrl_net_params_changed(ddrl_net* net);
 /* number of observation slots and per-sample element count of each (for argument checking) */

@@ -15,7 +15,22 @@ import sys
 import types
 from types import SimpleNamespace
 
-REFERENCE_ROOT = os.environ.get("DDRL_REFERENCE_ROOT", "/root/reference")
+# Where the unmodified reference lives: the mounted tree in the build container, else the snapshot `build()` drops into
+# the git-ignored oracle/_ref/ (python sources only; it travels to the GPU box like a built .so, oracle/snapshot_ref.py).
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SNAPSHOT_ROOT = os.path.join(_HERE, "_ref")
+
+
+def _default_root():
+    env = os.environ.get("DDRL_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/USTC_lab"):
+        return "/root/reference"
+    return SNAPSHOT_ROOT
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available() -> bool:

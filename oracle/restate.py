@@ -493,6 +493,19 @@ def synth_learn_batch(spec: NetSpec, params: Dict[str, Tensor], states: Sequence
     return a, old, adv, ret
 
 
+def synth_extra_critic(params: Dict[str, Tensor], ret: Tensor, seed: int = 77):
+    """Second critic the way runner/utils.py:162 makes it (copy.deepcopy(critic)) with re-seeded weights so that its values
+    differ, and the [V=2, B] returns matrix a V > 1 learner reads (nn/ppo.py:95-104).  Returns (ret2, extra) with `extra`
+    keyed by the critic's own parameter names (critic_linear.*, pre.*) in registration order."""
+    g = torch.Generator().manual_seed(seed)
+    ret2 = torch.stack([ret, ret * 0.5 + 0.25 * torch.randn(ret.shape[0], generator=g)])
+    extra = {}
+    for n, p in params.items():
+        if n.startswith("critic."):
+            extra[n[len("critic."):]] = p.detach().clone() + 0.05 * torch.randn(p.shape, generator=g)
+    return ret2, extra
+
+
 # =========================================================================================
 # EasyBytes wire format (SURVEY 8f row f2) -- USTC_lab/data/easybytes.py
 # =========================================================================================

@@ -247,12 +247,58 @@ def golden_easybytes():
     np.savez_compressed(os.path.join(HERE, "easybytes.npz"), **out)
 
 
+def golden_multicritic():
+    """add_critic / gail_critic (nn/ppo.py:63-64,75,95-105) on the unmodified reference: a second critic the way
+    runner/utils.py:162 makes it (copy.deepcopy(critic), here with re-seeded head weights so its values differ), forward
+    values of both critics and ONE learn iteration with gail_critic = True -- shared encoder (navimg: the extra head's
+    gradient reaches the shared encoder) and unshared towers (pong: it only reaches the extra critic's own tower)."""
+    import copy
+    ref_shim.import_reference()
+    from USTC_lab.data import Experience
+    out = {}
+    for kind, B in (("navimg", 6), ("pong", 5)):
+        spec = R.SPECS[kind]
+        params = R.init_params(spec, seed=11)
+        states = R.synth_states(kind, B, seed=5)
+        a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=9)
+        ret2, extra_params = R.synth_extra_critic(params, ret)                                # data.values [V=2, B]
+        net, cfg, cnn = ref_shim.make_ref_net(kind)
+        load_into_reference(net, params)
+        extra = copy.deepcopy(net.critic)
+        assert [n for n, _ in extra.named_parameters()] == list(extra_params)
+        extra.load_state_dict(extra_params, strict=True)
+        net.add_critic(extra)
+        net.gail_critic = True
+        net.training_iter_time = 1
+        with torch.no_grad():
+            (_, _), values = net([s.clone() for s in states], a.clone())
+        exp = Experience(states=[s.clone() for s in states], advs=adv.clone(), actions=a.clone(), old_logps=old.clone(),
+                         values=ret2.clone())
+        (loss, upd, last), = list(net.learn(exp))
+        out[kind + "_ret2"] = ret2.numpy()
+        out[kind + "_values"] = torch.stack(values, 0).numpy()                              # [2, B, 1]
+        out[kind + "_losses"] = np.array([loss["PpoTotalLoss"], loss["ActorLoss"], loss["VLoss"], loss["EntLoss"]], np.float64)
+        names = [n for n, _ in net.named_parameters()]
+        after = dict(net.named_parameters())
+        out[kind + "_names"] = np.array(names)
+        for i, n in enumerate(names):
+            gr = after[n].grad if after[n].grad is not None else torch.zeros_like(after[n])
+            out[kind + "_grad_sample_%d" % i] = sample_of(gr)                                # CLIPPED grads of PPO's own params
+            out[kind + "_grad_digest_%d" % i] = tensor_digest(gr)
+        out[kind + "_extra_names"] = np.array(list(extra_params))
+        for i, (n, p) in enumerate(extra.named_parameters()):
+            out[kind + "_extra_param_digest_%d" % i] = tensor_digest(extra_params[n])
+            out[kind + "_extra_grad_sample_%d" % i] = sample_of(p.grad)                      # never clipped (not in PPO.parameters())
+            out[kind + "_extra_grad_digest_%d" % i] = tensor_digest(p.grad)
+    np.savez_compressed(os.path.join(HERE, "multicritic.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `make_golden.py navped` regenerates one fixture
     todo = [("gae", golden_gae), ("gae_tempo", golden_gae_tempo), ("sampling", golden_sampling), ("pong", lambda: golden_net("pong", 8)),
             ("navimg", lambda: golden_net("navimg", 6)), ("navlaser", lambda: golden_net("navlaser", 4)),
-            ("navped", lambda: golden_net("navped", 5)), ("easybytes", golden_easybytes)]
+            ("navped", lambda: golden_net("navped", 5)), ("easybytes", golden_easybytes), ("multicritic", golden_multicritic)]
     for name, fn in todo:
         if not only or name in only:
             fn()

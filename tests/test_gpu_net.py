@@ -182,6 +182,66 @@ def test_learn_matches_golden(golden_dir, kind, B):
     assert net2.update_time == g["losses_traj"].shape[0]
 
 
+@pytest.mark.parametrize("kind,B", [("navimg", 6), ("pong", 5)])
+def test_add_critic_gail_matches_reference_golden(golden_dir, kind, B):
+    """V > 1 (nn/ppo.py:63-64,75,95-105): a second critic added the way nn/GAIL.py:116-118 does.  Forward returns both value
+    rows; with gail_critic the last critic's loss joins VLoss and its gradient goes where the reference's autograd sends it
+    (shared encoder: navimg; the extra critic's own tower: pong).  Golden = the unmodified reference (make_golden.py)."""
+    from ddrl4nav_b200.data import Experience
+    from ddrl4nav_b200.runner import make_net
+    g = np.load(os.path.join(golden_dir, "multicritic.npz"))
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    ret2, extra_params = R.synth_extra_critic(params, ret)
+    assert np.array_equal(ret2.numpy(), g[kind + "_ret2"])
+    net, _, _ = make(kind, TRAINING_ITER_TIME=1)
+    extra = make_net(kind, device=None, gemm_mode=GEMM_MODE).critic          # same class / encoder family as net.critic
+    assert [n for n, _ in extra.named_parameters()] == list(g[kind + "_extra_names"]) == list(extra_params)
+    extra.load_state_dict(extra_params, strict=True)
+    extra = extra.to(DEV)
+    net.add_critic(extra)
+    net.gail_critic = True
+    ds = [s.to(DEV) for s in states]
+    (pi, logp), values = net(ds, a.to(DEV))
+    assert len(values) == 2 and values[1].shape == (B, 1)
+    assert rel_err(torch.stack(values, 0), g[kind + "_values"]) < 1e-5
+    _, _, v3 = net.act(ds, play_mode=True)
+    assert v3.shape == (2, B, 1) and rel_err(v3, g[kind + "_values"]) < 1e-5
+    exp = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                     values=ret2.numpy())
+    exp.to_tensor(device=DEV)
+    (l, upd, last), = list(net.learn(exp))
+    assert np.allclose([l["PpoTotalLoss"], l["ActorLoss"], l["VLoss"], l["EntLoss"]], g[kind + "_losses"], rtol=1e-5, atol=1e-6)
+    # PPO's own parameters: the golden holds the CLIPPED gradients (clip_grad_norm_ is in place): scale ours by the same coefficient
+    raw = net.named_grads()
+    norm = float(torch.sqrt(sum((x.double() ** 2).sum() for x in raw.values())))
+    coef = min(1.0, 0.5 / (norm + 1e-6))
+    for i, n in enumerate(g[kind + "_names"]):
+        ours = (raw[n].flatten() * coef).cpu()
+        ours = (ours if ours.numel() <= 4096 else ours[::997]).numpy()
+        ref = g[kind + "_grad_sample_%d" % i]
+        scale = max(np.sqrt(g[kind + "_grad_digest_%d" % i][2] / max(raw[n].numel(), 1)), 1e-12)     # rms of the tensor
+        assert np.abs(ours - ref).max() <= 2e-4 * scale + 2e-5 * np.abs(ref).max(), (n, np.abs(ours - ref).max(), scale)
+    # the extra critic's gradients (never clipped: it is not in PPO.parameters())
+    for i, (n, p) in enumerate(extra.named_parameters()):
+        assert p.grad is not None, n
+        ours = p.grad.flatten().cpu()
+        ours = (ours if ours.numel() <= 4096 else ours[::997]).numpy()
+        ref = g[kind + "_extra_grad_sample_%d" % i]
+        scale = max(np.sqrt(g[kind + "_extra_grad_digest_%d" % i][2] / max(p.numel(), 1)), 1e-12)
+        assert np.abs(ours - ref).max() <= 2e-4 * scale + 2e-5 * np.abs(ref).max(), (n, np.abs(ours - ref).max(), scale)
+    # without gail_critic the extra critic only adds a value row (ppo.py:101-106)
+    net2, _, _ = make(kind, TRAINING_ITER_TIME=1)
+    net2.add_critic(extra)
+    (l2, _, _), = list(net2.learn(exp))
+    net3, _, _ = make(kind, TRAINING_ITER_TIME=1)
+    exp1 = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                      values=ret.numpy()[None])
+    exp1.to_tensor(device=DEV)
+    (l3, _, _), = list(net3.learn(exp1))
+    assert np.allclose([l2[k] for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss")],
+                       [l3[k] for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss")], rtol=1e-6, atol=1e-7)
+
+
 def test_micro_batching_equals_single_shot(monkeypatch):
     spec, params, states, a, old, adv, ret = _learn_case("pong", 21)
     net, _, _ = make("pong")
