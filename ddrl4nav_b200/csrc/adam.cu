@@ -98,14 +98,11 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
   }
 }
 
-// scratch double for the norm: one per stream would be cleaner; the learner uses one stream.
-static double* g_sumsq = nullptr;
+// scratch double for the norm of callers that bring none (the stand-alone ddrl_clip_adam entry point): one per device
+static double* g_sumsq[64] = {};
 
-int clip_adam_launch(float* params, const float* grads, float* m, float* v, long long n, const long long* seg_begin,
-                     const float* seg_lr, int nseg, int step, const ddrl_ppo_hparams* hp, float* norm_out,
-                     cudaStream_t s) {
-  if (!g_sumsq) DDRL_CUDA(cudaMalloc(&g_sumsq, sizeof(double)));
-  AdamSegs segs;
+static void adam_host_scalars(const long long* seg_begin, const float* seg_lr, int nseg, int step, const ddrl_ppo_hparams* hp,
+                              AdamSegs& segs, AdamScalars& sc) {
   segs.n = nseg;
   const double bc1 = 1.0 - pow((double)hp->beta1, (double)step);
   const double bc2 = 1.0 - pow((double)hp->beta2, (double)step);
@@ -114,7 +111,6 @@ int clip_adam_launch(float* params, const float* grads, float* m, float* v, long
     segs.step_size[i] = (float)((double)seg_lr[i] / bc1);
   }
   segs.begin[nseg] = seg_begin[nseg];
-  AdamScalars sc;
   sc.beta1_w = (float)(1.0 - (double)hp->beta1);
   sc.beta2 = hp->beta2;
   sc.one_m_beta2 = (float)(1.0 - (double)hp->beta2);
@@ -122,15 +118,52 @@ int clip_adam_launch(float* params, const float* grads, float* m, float* v, long
   sc.eps = hp->adam_eps;
   sc.max_norm = hp->max_grad_norm;
   sc.clip = hp->clip_grad;
-  DDRL_CUDA(cudaMemsetAsync(g_sumsq, 0, sizeof(double), s));
+}
+
+// sumsq_scratch: a device double owned by the caller (per net, so two nets / devices / streams never share it); nullptr
+// falls back to a lazily allocated per-device scalar
+int clip_adam_launch(float* params, const float* grads, float* m, float* v, long long n, const long long* seg_begin,
+                     const float* seg_lr, int nseg, int step, const ddrl_ppo_hparams* hp, float* norm_out,
+                     cudaStream_t s, double* sumsq_scratch) {
+  if (!sumsq_scratch) {
+    int dev = 0;
+    DDRL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DDRL_E_ARG;
+    if (!g_sumsq[dev]) DDRL_CUDA(cudaMalloc(&g_sumsq[dev], sizeof(double)));
+    sumsq_scratch = g_sumsq[dev];
+  }
+  AdamSegs segs;
+  AdamScalars sc;
+  adam_host_scalars(seg_begin, seg_lr, nseg, step, hp, segs, sc);
+  DDRL_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), s));
   const int blocks = (int)std::min<long long>(ceil_div64(n, 256 * 4), 4 * kNumSMs);
-  sumsq_kernel<<<blocks, 256, 0, s>>>(grads, n, g_sumsq);
+  sumsq_kernel<<<blocks, 256, 0, s>>>(grads, n, sumsq_scratch);
   prof_work(4.0 * n);
   DDRL_LAUNCHED("sumsq_kernel");
   const int blocks2 = (int)std::min<long long>(ceil_div64(n, 256 * 4), 8 * kNumSMs);
-  clip_adam_kernel<<<blocks2, 256, 0, s>>>(params, grads, m, v, n, segs, sc, g_sumsq, norm_out);
+  clip_adam_kernel<<<blocks2, 256, 0, s>>>(params, grads, m, v, n, segs, sc, sumsq_scratch, norm_out);
   prof_work(28.0 * n);
   DDRL_LAUNCHED("clip_adam_kernel");
+  return DDRL_OK;
+}
+
+// ---- CUDA-graph support: the clip+Adam kernel node of a captured optimiser step carries the step-dependent scalars
+// (lr / (1 - beta1^t), sqrt(1 - beta2^t)) BY VALUE; a replay for another step rewrites exactly those two arguments.
+const void* clip_adam_kernel_func() { return reinterpret_cast<const void*>(&clip_adam_kernel); }
+
+int clip_adam_update_node(cudaGraphExec_t exec, cudaGraphNode_t node, const long long* seg_begin, const float* seg_lr, int nseg,
+                          int step, const ddrl_ppo_hparams* hp) {
+  cudaKernelNodeParams np;
+  DDRL_CUDA(cudaGraphKernelNodeGetParams(node, &np));
+  AdamSegs segs;
+  AdamScalars sc;
+  adam_host_scalars(seg_begin, seg_lr, nseg, step, hp, segs, sc);
+  void* args[9];
+  for (int i = 0; i < 9; ++i) args[i] = np.kernelParams[i];
+  args[5] = &segs;
+  args[6] = &sc;
+  np.kernelParams = args;
+  DDRL_CUDA(cudaGraphExecKernelNodeSetParams(exec, node, &np));
   return DDRL_OK;
 }
 
@@ -145,5 +178,5 @@ extern "C" int ddrl_clip_adam(float* params, float* grads, float* m, float* v, i
   if (!params || !grads || !m || !v) return DDRL_E_ARG;
   long long sb[kMaxSeg + 1];
   for (int i = 0; i <= nseg; ++i) sb[i] = seg_begin_host[i];
-  return clip_adam_launch(params, grads, m, v, n, sb, seg_lr_host, nseg, step, hp, norm_out, (cudaStream_t)stream);
+  return clip_adam_launch(params, grads, m, v, n, sb, seg_lr_host, nseg, step, hp, norm_out, (cudaStream_t)stream, nullptr);
 }

@@ -15,22 +15,14 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "prep_kernels.cuh"
 
 namespace ddrl {
 
-// Wd[c, (th*ntx + tw)*Cout + o] = w[o, c, kh, kw]  with kh = ry + s*(nty-1-th), kw = rx + s*(ntx-1-tw)   (w: reference OIHW)
+// body: prep_kernels.cuh
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin,
                                                          int KH, int KW, int s, int ry, int rx, int nty, int ntx) {
-  const long long total = (long long)Cin * nty * ntx * Cout;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(t % Cout);
-    long long r = t / Cout;
-    const int tw = (int)(r % ntx); r /= ntx;
-    const int th = (int)(r % nty);
-    const int c = (int)(r / nty);
-    const int kh = ry + s * (nty - 1 - th), kw = rx + s * (ntx - 1 - tw);
-    wd[t] = w[(((long long)o * Cin + c) * KH + kh) * KW + kw];
-  }
+  pack_dgrad_body(w, wd, Cout, Cin, KH, KW, s, ry, rx, nty, ntx, blockIdx.x, gridDim.x);
 }
 
 // 1-D convolutions (H == 1) are run with the pixel axis on the box's row dimension
@@ -80,6 +72,12 @@ int pack_dgrad(const float* w_oihw, const ConvGeom& g, int Cout, const DgradClas
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const long long total = (long long)g.C * c.K;
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_PACK_DGRAD; j.a = w_oihw; j.b = c.wd; j.total = total; j.vblocks = prep_blocks(total);
+    const int v[9] = {Cout, g.C, KH, KW, g.stride, c.ry, c.rx, c.nty, c.ntx};
+    for (int k = 0; k < 9; ++k) j.i[k] = v[k];
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);
   // the reference weight is [Cout, Cin, g.KH, g.KW]; in the transposed (1-D) orientation KH/KW swap with it
   pack_dgrad_kernel<<<blocks, 256, 0, s>>>(w_oihw, c.wd, Cout, g.C, KH, KW, g.stride, c.ry, c.rx, c.nty, c.ntx);
@@ -115,24 +113,13 @@ int conv_dgrad_tc(const ConvGeom& g, int Cout, const std::vector<DgradClass>& cl
 }
 
 // ---- fused parity classes (tc2 engine) ----------------------------------------------------------------------------
-// Wd[(cy*ncx + cx)*Cin + c, (th*ntx + tw)*Cout + o] = w[o, c, kh, kw],  kh = cy + s*(q0y[cy] + pady - th) (0 if no such tap)
+// body: prep_kernels.cuh
 __global__ void __launch_bounds__(256) pack_dgrad_fused_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout,
                                                                int Cin, int KH, int KW, int s, int sx, int ncx, int nty, int ntx,
                                                                int pady, int padx, int q0y0, int q0y1, int q0x0, int q0x1,
                                                                long long total) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(t % Cout);
-    long long r = t / Cout;
-    const int tw = (int)(r % ntx); r /= ntx;
-    const int th = (int)(r % nty); r /= nty;
-    const int c = (int)(r % Cin); r /= Cin;
-    const int cx = (int)(r % ncx), cy = (int)(r / ncx);
-    const int uy = (cy ? q0y1 : q0y0) + pady - th, ux = (cx ? q0x1 : q0x0) + padx - tw;
-    const int kh = cy + s * uy, kw = cx + sx * ux;
-    float v = 0.f;
-    if (uy >= 0 && ux >= 0 && kh < KH && kw < KW) v = w[(((long long)o * Cin + c) * KH + kh) * KW + kw];
-    wd[t] = v;
-  }
+  pack_dgrad_fused_body(w, wd, Cout, Cin, KH, KW, s, sx, ncx, nty, ntx, pady, padx, q0y0, q0y1, q0x0, q0x1, total, blockIdx.x,
+                        gridDim.x);
 }
 
 int conv_dgrad_fused_plan(const ConvGeom& g, int Cout, DgradFused& f) {
@@ -179,6 +166,12 @@ int pack_dgrad_fused(const float* w_oihw, const ConvGeom& g, int Cout, const Dgr
   int H, W, KH, KW, Ho, Wo;
   oriented(g, H, W, KH, KW, Ho, Wo);
   const long long total = (long long)f.N * f.K;
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_PACK_DGRAD_FUSED; j.a = w_oihw; j.b = f.wd; j.total = total; j.vblocks = prep_blocks(total);
+    const int v[15] = {Cout, g.C, KH, KW, f.s, W == 1 ? 1 : f.s, f.ncx, f.nty, f.ntx, f.pady, f.padx, f.q0y[0], f.q0y[1], f.q0x[0], f.q0x[1]};
+    for (int k = 0; k < 15; ++k) j.i[k] = v[k];
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);
   pack_dgrad_fused_kernel<<<blocks, 256, 0, s>>>(w_oihw, f.wd, Cout, g.C, KH, KW, f.s, W == 1 ? 1 : f.s, f.ncx, f.nty, f.ntx,
                                                  f.pady, f.padx, f.q0y[0], f.q0y[1], f.q0x[0], f.q0x[1], total);

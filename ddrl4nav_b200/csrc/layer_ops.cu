@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "prep_kernels.cuh"
 
 namespace ddrl {
 
@@ -302,7 +303,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 
 // float4 variant: thread = (row lane, 4 columns); 4 rows in flight per thread; N % 4 == 0, N <= 1024, 16-byte aligned rows
 __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__ dy, int ld4, long long rows, int n4,
-                                                      float* __restrict__ db, long long rows_per_block) {
+                                                      float* __restrict__ db, long long rows_per_block,
+                                                      float* __restrict__ db2, int split4) {
   __shared__ float4 part[256];
   const int ry = 256 / n4;                                // row lanes per block (n4 is a power-of-two divisor of 256 or < 256)
   const int tx = threadIdx.x % n4, ty = threadIdx.x / n4;
@@ -329,35 +331,22 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__
       const float4 v = part[k * n4 + tx];
       sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
     }
-    atomicAdd(db + 4 * tx, sum.x); atomicAdd(db + 4 * tx + 1, sum.y);
-    atomicAdd(db + 4 * tx + 2, sum.z); atomicAdd(db + 4 * tx + 3, sum.w);
+    // columns [0, 4 split4) -> db, the rest -> db2 (two layers' biases behind ONE pass over a fused [rows, N0 + N1] gradient)
+    float* out = (db2 != nullptr && tx >= split4) ? db2 + 4 * (tx - split4) : db + 4 * tx;
+    atomicAdd(out, sum.x); atomicAdd(out + 1, sum.y);
+    atomicAdd(out + 2, sum.z); atomicAdd(out + 3, sum.w);
   }
 }
 
 // ---------------------------------------------------------------- weight packing
-// packed[o*ld + i*J + j] = src[o*I*J + j*I + i]   (inner [J][I] -> [I][J] transpose; I = 1: row-stride change)
+// bodies: prep_kernels.cuh (shared with the multi-job kernel of prep.cu)
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int J,
                                                    int ld) {
-  const long long total = (long long)O * I * J;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(t % J);
-    const long long r = t / J;
-    const int i = (int)(r % I);
-    const long long o = r / I;
-    dst[o * ld + (long long)i * J + j] = src[o * I * J + (long long)j * I + i];
-  }
+  pack_body(src, dst, O, I, J, ld, blockIdx.x, gridDim.x);
 }
-// grad[o*I*J + j*I + i] (+)= packed_grad[o*ld + i*J + j]
 __global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I,
                                                      int J, int ld) {
-  const long long total = (long long)O * I * J;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(t % I);
-    const long long r = t / I;
-    const int j = (int)(r % J);
-    const long long o = r / J;
-    dst[t] = src[o * ld + (long long)i * J + j];
-  }
+  unpack_body(src, dst, O, I, J, ld, blockIdx.x, gridDim.x);
 }
 
 // dst[r*ld_d + c] = src[r*ld_s + c]
@@ -483,21 +472,9 @@ __global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x
     __syncthreads();
   }
 }
-// packed[o*ld + ((a*KW2 + b)*s*s + i*s + j)*C + c] = w[o, c, s*a + i, s*b + j]      (w: reference OIHW)
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ w, float* __restrict__ dst, int O, int C, int KH,
                                                        int KW, int s, int ld, int unpack) {
-  const long long total = (long long)O * C * KH * KW;
-  const int KW2 = KW / s;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int kw = (int)(t % KW);
-    long long r = t / KW;
-    const int kh = (int)(r % KH); r /= KH;
-    const int c = (int)(r % C);
-    const long long o = r / C;
-    const int a = kh / s, i = kh - a * s, b = kw / s, j = kw - b * s;
-    const long long pk = o * ld + ((long long)(a * KW2 + b) * s * s + i * s + j) * C + c;
-    if (unpack) dst[t] = w[pk]; else dst[pk] = w[t];
-  }
+  pack_s2d_body(w, dst, O, C, KH, KW, s, ld, unpack, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------- thin-K layers (first convs on 1..4-channel maps)
@@ -706,8 +683,12 @@ int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int 
   DDRL_LAUNCHED("act_bwd_kernel");
   return DDRL_OK;
 }
-int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s) {
+int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s, float* db2, int split) {
   if (rows == 0 || N == 0) return DDRL_OK;
+  if (db2 && !(N % 4 == 0 && split % 4 == 0 && ld % 4 == 0 && N <= 1024 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)) {
+    { const int rc = colsum_add(dy, ld, rows, split, db, s, nullptr, 0); if (rc != DDRL_OK) return rc; }
+    return colsum_add(dy + split, ld, rows, N - split, db2, s, nullptr, 0);
+  }
   prof_work(4.0 * (double)rows * N);
   if (N % 4 == 0 && ld % 4 == 0 && N <= 1024 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
     const int n4 = N / 4;
@@ -716,7 +697,7 @@ int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaSt
     const long long rpb = (rows + chunks - 1) / chunks;
     chunks = (rows + rpb - 1) / rpb;
     if (n4 <= 256) {
-      colsum4_kernel<<<(unsigned)chunks, 256, 0, s>>>(reinterpret_cast<const float4*>(dy), ld / 4, rows, n4, db, rpb);
+      colsum4_kernel<<<(unsigned)chunks, 256, 0, s>>>(reinterpret_cast<const float4*>(dy), ld / 4, rows, n4, db, rpb, db2, split / 4);
       DDRL_LAUNCHED("colsum_kernel");
       return DDRL_OK;
     }
@@ -730,11 +711,21 @@ int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaSt
   return DDRL_OK;
 }
 int pack_weight(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s) {
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_PACK; j.a = src; j.b = dst; j.total = (long long)O * I * J; j.vblocks = prep_blocks(j.total);
+    j.i[0] = O; j.i[1] = I; j.i[2] = J; j.i[3] = ld;
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   pack_kernel<<<grid_for((long long)O * I * J), 256, 0, s>>>(src, dst, O, I, J, ld);
   DDRL_LAUNCHED("pack_kernel");
   return DDRL_OK;
 }
 int unpack_grad(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s) {
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_UNPACK; j.a = src; j.b = dst; j.total = (long long)O * I * J; j.vblocks = prep_blocks(j.total);
+    j.i[0] = O; j.i[1] = I; j.i[2] = J; j.i[3] = ld;
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   unpack_kernel<<<grid_for((long long)O * I * J), 256, 0, s>>>(src, dst, O, I, J, ld);
   DDRL_LAUNCHED("unpack_kernel");
   return DDRL_OK;
@@ -788,12 +779,19 @@ int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStr
   DDRL_LAUNCHED("s2d_kernel");
   return DDRL_OK;
 }
+static int record_s2d(const float* src, float* dst, int O, int C, int KH, int KW, int stride, int ld, int unpack) {
+  PrepJob j{}; j.type = PREP_PACK_S2D; j.a = src; j.b = dst; j.total = (long long)O * C * KH * KW; j.vblocks = prep_blocks(j.total);
+  j.i[0] = O; j.i[1] = C; j.i[2] = KH; j.i[3] = KW; j.i[4] = stride; j.i[5] = ld; j.i[6] = unpack;
+  return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+}
 int pack_weight_s2d(const float* w_oihw, float* dst, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s) {
+  if (g_prep_rec) return record_s2d(w_oihw, dst, O, C, KH, KW, stride, ld, 0);
   pack_s2d_kernel<<<grid_for((long long)O * C * KH * KW), 256, 0, s>>>(w_oihw, dst, O, C, KH, KW, stride, ld, 0);
   DDRL_LAUNCHED("pack_kernel");
   return DDRL_OK;
 }
 int unpack_grad_s2d(const float* src, float* dst_oihw, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s) {
+  if (g_prep_rec) return record_s2d(src, dst_oihw, O, C, KH, KW, stride, ld, 1);
   pack_s2d_kernel<<<grid_for((long long)O * C * KH * KW), 256, 0, s>>>(src, dst_oihw, O, C, KH, KW, stride, ld, 1);
   DDRL_LAUNCHED("unpack_kernel");
   return DDRL_OK;

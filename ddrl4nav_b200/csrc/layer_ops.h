@@ -159,7 +159,8 @@ int col2im(const ConvGeom& g, const float* dcols, float* dx, int B, cudaStream_t
 int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s);
 int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s);
 int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int colsN, int act, cudaStream_t s);
-int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s);
+// db2 != nullptr: columns [0, split) accumulate into db, [split, N) into db2 (one pass over a fused two-layer gradient)
+int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s, float* db2 = nullptr, int split = 0);
 int pack_weight(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s);
 int unpack_grad(const float* src, float* dst, int O, int I, int J, int ld, cudaStream_t s);
 // thin-K layers (K <= 36, N <= 64): register-resident weights / partial sums, HBM-streaming (layer_ops.cu)
@@ -179,9 +180,24 @@ int skinny_dgrad(const float* dy, int ldy, const float* W, int B, int N, int K, 
 int skinny_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int N, int K, float* dW, float* db,
                  cudaStream_t s);
 
+// device-resident job table of one weight-preparation phase (prep.cu)
+struct PrepJob;
+struct PrepTable {
+  void* dev_jobs = nullptr;
+  int* dev_starts = nullptr;
+  int njobs = 0, total_blocks = 0;
+  int upload(const std::vector<PrepJob>& jobs);       // synchronous (cudaMalloc + cudaMemcpy): never inside a capture
+  int launch(const char* name, cudaStream_t s) const;
+  void clear();
+};
+
 // K7 (adam.cu)
 int clip_adam_launch(float* params, const float* grads, float* m, float* v, long long n, const long long* seg_begin,
                      const float* seg_lr, int nseg, int step, const ddrl_ppo_hparams* hp, float* norm_out,
-                     cudaStream_t s);
+                     cudaStream_t s, double* sumsq_scratch);
+// graph replay of an optimiser step: rewrites the step-dependent arguments of the captured clip_adam_kernel node
+const void* clip_adam_kernel_func();
+int clip_adam_update_node(cudaGraphExec_t exec, cudaGraphNode_t node, const long long* seg_begin, const float* seg_lr, int nseg,
+                          int step, const ddrl_ppo_hparams* hp);
 
 }  // namespace ddrl

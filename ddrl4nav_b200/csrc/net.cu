@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "prep_kernels.cuh"
 
 namespace ddrl {
 
@@ -144,6 +145,26 @@ struct ddrl_net {
   W16 w16_fuse0, w16_s2d;
   // the weight preparation after every optimiser step is ~90 tiny independent launches: they are spread round-robin over
   // side streams (fork / join with events) so their launch latencies overlap instead of adding up
+  // ---- CUDA graphs of the steady-state learn iteration (iterations 2..10 of PPO.learn run the SAME launches on the SAME
+  // pointers): the backward pass and the optimiser step + weight re-preparation are captured once per argument set and
+  // replayed with one cudaGraphLaunch each (DDRL_NO_GRAPH=1: every launch goes to the stream, as the profiler hooks need)
+  struct GraphEntry {
+    std::string key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t adam_node = nullptr;
+    long long launches = 0;
+    unsigned long long used = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  unsigned long long graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  bool graphs_off = false;
+  double* sumsq_dev = nullptr;     // clip+Adam norm scratch of THIS net
+  // weight preparation as three dependent multi-job launches (prep.cu): [re-packs + amax-slot zeroing] -> [amax + tf32
+  // mirrors] -> [fp16 splits]; and the gradient un-permutation that ends a backward pass as one more
+  PrepTable prep[3], unprep;
+  bool prep_ready = false;
   static constexpr int kSide = 8;
   cudaStream_t side[kSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
@@ -158,6 +179,8 @@ constexpr int kMaxExtra = 2;      // extra critic heads ("suppose 3 critic net a
 static inline bool tc3_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC3_F16; }
 static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
 static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
+
+static void graphs_clear(ddrl_net* n);
 
 // ---- amax registry of the tc3 engine -------------------------------------------------------------------------------
 // A view is (pointer, rows, cols, row stride); contiguous views are keyed by (pointer, element count) so that a conv
@@ -571,6 +594,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   if (mb >= 128) mb &= ~127;
   mb = std::min(mb, std::max(B, 1));
   if (n->ws.base && n->MB >= mb && (n->ws_train || !train)) return DDRL_OK;
+  graphs_clear(n);                  // captured launches point into the old workspace
   if (n->ws.base) { cudaDeviceSynchronize(); cudaFree(n->ws.base); n->ws.base = nullptr; }
   // the amax registry is keyed by workspace pointers: start over (persistent entries are re-created on demand)
   for (auto it = n->amax_keys.begin(); it != n->amax_keys.end();) it = it->second.persistent ? std::next(it) : n->amax_keys.erase(it);
@@ -772,14 +796,14 @@ static int side_join(ddrl_net* n, cudaStream_t s) {
   return DDRL_OK;
 }
 
-static int repack(ddrl_net* n, cudaStream_t s0) {
-  // phase 1: every fp32 repack on a side stream; phase 2 (after a join): per weight operand amax -> fp16 split.  With the
-  // profiler hooks on (per-launch events on ONE stream) everything stays on the caller's stream.
-  const bool par = !g_prof_on && !getenv("DDRL_REPACK_SERIAL");
-  if (par) { TRY(side_init(n)); TRY(side_fork(n, s0)); }
+// Emits the weight preparation.  phase_begin(k) is called before the launches of dependent phase k = 0, 1, 2 (the stream
+// version joins / re-forks its side streams there; the recording version switches the job list).
+template <class PhaseFn>
+static int repack_emit(ddrl_net* n, cudaStream_t s0, bool par, PhaseFn&& phase_begin) {
   int rr = 0;
   cudaStream_t s = s0;
 #define NEXT_STREAM() do { if (par) s = n->side[rr++ % ddrl_net::kSide]; } while (0)
+  TRY(phase_begin(0));
   for (auto& t : n->towers)
     for (auto& l : t.L)
       if (l.packed) {
@@ -812,10 +836,20 @@ static int repack(ddrl_net* n, cudaStream_t s0) {
   if (n->fuse0) {
     const Lin &l0 = n->towers[0].L[0], &l1 = n->towers[1].L[0];
     NEXT_STREAM();
-    DDRL_CUDA(cudaMemcpyAsync(n->bias0c, b_of(n, l0), sizeof(float) * l0.N, cudaMemcpyDeviceToDevice, s));
-    DDRL_CUDA(cudaMemcpyAsync(n->bias0c + l0.N, b_of(n, l1), sizeof(float) * l1.N, cudaMemcpyDeviceToDevice, s));
+    if (g_prep_rec) {
+      PrepJob j{}; j.type = PREP_COPY; j.vblocks = 1;
+      j.a = b_of(n, l0); j.b = n->bias0c; j.total = l0.N; prep_record(j);
+      j.a = b_of(n, l1); j.b = n->bias0c + l0.N; j.total = l1.N; prep_record(j);
+    } else {
+      DDRL_CUDA(cudaMemcpyAsync(n->bias0c, b_of(n, l0), sizeof(float) * l0.N, cudaMemcpyDeviceToDevice, s));
+      DDRL_CUDA(cudaMemcpyAsync(n->bias0c + l0.N, b_of(n, l1), sizeof(float) * l1.N, cudaMemcpyDeviceToDevice, s));
+    }
   }
-  if (par) { TRY(side_join(n, s0)); TRY(side_fork(n, s0)); }
+  if (g_prep_rec)                 // the stream version zeroes each amax slot right before its reduction (amax_f32)
+    for (auto& j : n->split_jobs) {
+      PrepJob z{}; z.type = PREP_ZERO; z.vblocks = 1; z.b = const_cast<float*>(j.dst->amax); z.total = 1; prep_record(z);
+    }
+  TRY(phase_begin(1));
   if (n->split_base) {
     NEXT_STREAM();
     // tf32 hi / lo mirrors of the forward weights [0, grad_off) and of the data-gradient weights [2*grad_off, end)
@@ -827,17 +861,158 @@ static int repack(ddrl_net* n, cudaStream_t s0) {
     if (dgn) TRY(split_hi_lo(reinterpret_cast<float*>(n->packed_base + dg0), reinterpret_cast<float*>(hi + dg0),
                              reinterpret_cast<float*>(lo + dg0), (long long)(dgn / 4), s));
   }
-  for (auto& j : n->split_jobs) {
-    W16& w = *j.dst;
-    float* slot = const_cast<float*>(w.amax);
-    NEXT_STREAM();
-    TRY(amax_f32(j.w, j.rows, j.K, j.ldw, slot, true, s));
-    TRY(split_f16(j.w, j.rows, j.K, j.ldw, slot, const_cast<void*>(w.hi), const_cast<void*>(w.lo), w.ld, const_cast<void*>(w.hiT),
-                  const_cast<void*>(w.loT), w.ldT, s));
+  if (g_prep_rec) {
+    for (auto& j : n->split_jobs) TRY(amax_f32(j.w, j.rows, j.K, j.ldw, const_cast<float*>(j.dst->amax), true, s));
+    TRY(phase_begin(2));
+    for (auto& j : n->split_jobs) {
+      W16& w = *j.dst;
+      TRY(split_f16(j.w, j.rows, j.K, j.ldw, w.amax, const_cast<void*>(w.hi), const_cast<void*>(w.lo), w.ld, const_cast<void*>(w.hiT),
+                    const_cast<void*>(w.loT), w.ldT, s));
+    }
+  } else {
+    for (auto& j : n->split_jobs) {           // amax -> split of one operand stay on one stream
+      W16& w = *j.dst;
+      float* slot = const_cast<float*>(w.amax);
+      NEXT_STREAM();
+      TRY(amax_f32(j.w, j.rows, j.K, j.ldw, slot, true, s));
+      TRY(split_f16(j.w, j.rows, j.K, j.ldw, slot, const_cast<void*>(w.hi), const_cast<void*>(w.lo), w.ld, const_cast<void*>(w.hiT),
+                    const_cast<void*>(w.loT), w.ldT, s));
+    }
+    TRY(phase_begin(2));
   }
-  if (par) TRY(side_join(n, s0));
 #undef NEXT_STREAM
+  return DDRL_OK;
+}
+
+// gradient un-permutation (packed layout -> reference OIHW / [out, in]) of every packed layer
+static int unpack_emit(ddrl_net* n, cudaStream_t s) {
+  if (n->s2d_train) {
+    const ConvGeom& g = n->towers[0].g[0];
+    const float* dw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(n->w0s2d) + n->packed_grad_off);
+    for (int k = 0; k < 2; ++k) {
+      const Lin& l = n->towers[k].L[0];
+      TRY(unpack_grad_s2d(dw + (size_t)k * l.N * l.ldw, n->grads + n->T[l.w_t].offset, l.N, g.C, g.KH, g.KW, g.stride, l.ldw, s));
+    }
+  }
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.packed) {
+        if (n->s2d_train && &l == &t.L[0]) continue;         // done above from the fused space-to-depth gradient
+        if (l.s2d_s && !l.s2d_fwd_only) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
+        else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
+      }
+  return DDRL_OK;
+}
+
+static bool prep_fused(const ddrl_net* n) {
+  const char* e = getenv("DDRL_PREP_LAUNCHES");          // 1: one launch per layer and step (the round-1 behaviour)
+  return !(e && e[0] == '1');
+}
+
+// builds the device job tables (synchronous allocations + copies: runs on the first preparation after bind, never inside a
+// graph capture -- the first optimiser step and every `dirty` re-preparation go straight to the stream)
+static int prep_build(ddrl_net* n) {
+  PrepRecorder rec[3], unrec;
+  struct Guard { ~Guard() { g_prep_rec = nullptr; } } guard;
+  int rc = repack_emit(n, nullptr, false, [&](int k) { g_prep_rec = &rec[k]; return DDRL_OK; });
+  if (rc == DDRL_OK && n->grads) { g_prep_rec = &unrec; rc = unpack_emit(n, nullptr); }
+  g_prep_rec = nullptr;
+  if (rc != DDRL_OK) return rc;
+  for (int k = 0; k < 3; ++k) TRY(n->prep[k].upload(rec[k].jobs));
+  TRY(n->unprep.upload(unrec.jobs));
+  n->prep_ready = true;
+  return DDRL_OK;
+}
+
+static int repack(ddrl_net* n, cudaStream_t s0) {
+  if (prep_fused(n)) {
+    if (!n->prep_ready) TRY(prep_build(n));
+    TRY(n->prep[0].launch("prep_pack_kernel", s0));
+    TRY(n->prep[1].launch("prep_amax_kernel", s0));
+    TRY(n->prep[2].launch("prep_split_kernel", s0));
+    n->dirty = false;
+    return DDRL_OK;
+  }
+  // one launch per operand: fp32 re-packs on side streams; after a join, per weight operand amax -> fp16 split.  With the
+  // profiler hooks on (per-launch events on ONE stream) everything stays on the caller's stream.
+  const bool par = !g_prof_on && !getenv("DDRL_REPACK_SERIAL");
+  if (par) TRY(side_init(n));
+  TRY(repack_emit(n, s0, par, [&](int k) {
+    if (!par) return DDRL_OK;
+    if (k > 0) TRY(side_join(n, s0));
+    if (k < 2) TRY(side_fork(n, s0));
+    return DDRL_OK;
+  }));
   n->dirty = false;
+  return DDRL_OK;
+}
+
+// ---- CUDA-graph cache ------------------------------------------------------------------
+static void graphs_clear(ddrl_net* n) {
+  for (auto& e : n->graphs) {
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (e.graph) cudaGraphDestroy(e.graph);
+  }
+  n->graphs.clear();
+}
+static bool graphs_enabled(ddrl_net* n) {
+  const char* e = getenv("DDRL_NO_GRAPH");
+  return !(e && e[0] == '1') && !n->graphs_off && !g_prof_on;
+}
+static std::string graph_key(const char* tag, std::initializer_list<const void*> ptrs, std::initializer_list<long long> ints,
+                             const void* blob, size_t blob_bytes) {
+  std::string k(tag);
+  char b[40];
+  for (const void* p : ptrs) { snprintf(b, sizeof(b), "|%p", p); k += b; }
+  for (long long v : ints) { snprintf(b, sizeof(b), "|%lld", v); k += b; }
+  k += '|';
+  k.append(reinterpret_cast<const char*>(blob), blob_bytes);
+  return k;
+}
+// Runs `body(stream)` through a cached graph: the first call with this key captures it on the net's private capture stream
+// (nothing executes during capture; side-stream forks inside `body` become parallel branches), later calls replay.  A
+// failed capture switches graphs off for this net and runs the body on the caller's stream.
+template <class F>
+static int run_graphed(ddrl_net* n, const std::string& key, cudaStream_t s, F&& body, ddrl_net::GraphEntry** out = nullptr) {
+  ddrl_net::GraphEntry* e = nullptr;
+  for (auto& g : n->graphs) if (g.key == key) { e = &g; break; }
+  if (!e) {
+    if (!n->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
+    TRY(side_init(n));
+    const long long l0 = g_launches;
+    DDRL_CUDA(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(n->cap_stream);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &g);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != DDRL_OK || ce != cudaSuccess || !g || cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      g_launches = l0;
+      n->graphs_off = true;
+      if (out) *out = nullptr;
+      return body(s);
+    }
+    if (n->graphs.size() >= 8) {             // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < n->graphs.size(); ++i) if (n->graphs[i].used < n->graphs[lru].used) lru = i;
+      cudaGraphExecDestroy(n->graphs[lru].exec);
+      cudaGraphDestroy(n->graphs[lru].graph);
+      n->graphs.erase(n->graphs.begin() + lru);
+    }
+    ddrl_net::GraphEntry ne;
+    ne.key = key; ne.graph = g; ne.exec = exec;
+    ne.launches = g_launches - l0;
+    g_launches = l0;
+    n->graphs.push_back(ne);
+    e = &n->graphs.back();
+  }
+  e->used = ++n->graph_clock;
+  if (out) *out = e;
+  else {
+    DDRL_CUDA(cudaGraphLaunch(e->exec, s));
+    g_launches += e->launches;
+  }
   return DDRL_OK;
 }
 
@@ -973,8 +1148,10 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
     if (t3) {
       ddrl_net* nn = const_cast<ddrl_net*>(n);
       TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &ctx.amax_a));
-      // a data gradient that fills only a channel slice of a wider tensor does not describe that tensor's amax
-      if (!sub) ctx.amax_out = amax_out_slot(nn, dx, (long long)mb * g.H * g.W, g.C, g.C);
+      // a data gradient that fills a channel slice of a wider tensor (the towers' halves of the fused first conv's output
+      // gradient) accumulates into the slot of the WHOLE tensor: every slice is written in this pass by a tracked producer,
+      // so after the last of them the slot holds the tensor's amax (atomicMax; zeroed at the start of the pass)
+      ctx.amax_out = amax_out_slot(nn, dx, (long long)mb * g.H * g.W, sub ? ctot : g.C, sub ? ctot : g.C);
     }
     if (dx && t.df[gi].on)
       TRY(conv_dgrad_fused_tc2(g, l.N, t.df[gi], dy, dx, mask_act ? mask_act + 2 : 0, mask_act ? x : nullptr, mb, s, ctot, coff,
@@ -1086,8 +1263,7 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
   const Lin &l0 = t0.L[0], &l1 = t1.L[0];
   const long long M = (long long)mb * g.Ho * g.Wo;
   float* dy = t0.buf[9];
-  TRY(colsum_add(dy, 2 * l0.N, M, l0.N, db_of(n, l0), s));
-  TRY(colsum_add(dy + l0.N, 2 * l0.N, M, l1.N, db_of(n, l1), s));
+  TRY(colsum_add(dy, 2 * l0.N, M, l0.N + l1.N, db_of(n, l0), s, db_of(n, l1), l0.N));     // ONE pass over the fused gradient
   if (n->s2d_train) {
     // weight gradient of both towers in the space-to-depth K order: dW0s2d [2 Cout, K] (the twin of w0s2d in the gradient
     // half of the packed arena), un-permuted per tower after the micro-batch loop
@@ -1205,6 +1381,11 @@ extern "C" int ddrl_net_create(const ddrl_net_desc* desc, ddrl_net** out) {
 
 extern "C" int ddrl_net_destroy(ddrl_net* n) {
   if (!n) return DDRL_OK;
+  graphs_clear(n);
+  for (int k = 0; k < 3; ++k) n->prep[k].clear();
+  n->unprep.clear();
+  if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
+  if (n->sumsq_dev) cudaFree(n->sumsq_dev);
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
   if (n->split_base) cudaFree(n->split_base);
@@ -1236,6 +1417,8 @@ extern "C" int ddrl_net_bind(ddrl_net* n, float* params, float* grads, float* ad
   if (!n || !params) return DDRL_E_ARG;
   n->params = params; n->grads = grads; n->am = adam_m; n->av = adam_v;
   n->dirty = true;
+  graphs_clear(n);
+  n->prep_ready = false;
   if (!n->packed_base) TRY(alloc_packed(n));
   return DDRL_OK;
 }
@@ -1246,6 +1429,7 @@ extern "C" int ddrl_net_set_extra_critics(ddrl_net* n, int count, const float* c
   if (count > 0 && !n->d.shared) return DDRL_E_UNSUPPORTED;     // an unshared extra critic owns an encoder: a net of its own
   if (count > 0 && (!w || !b)) return DDRL_E_ARG;
   n->extra.clear();
+  graphs_clear(n);
   for (int k = 0; k < count; ++k) {
     if (!w[k] || !b[k]) return DDRL_E_ARG;
     const int on = in_loss ? in_loss[k] : 0;
@@ -1336,25 +1520,15 @@ extern "C" int ddrl_net_encode(ddrl_net* n, const float* const* obs, int n_obs, 
   return DDRL_OK;
 }
 
-extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
-                                 const float* actions, const float* old_logp, const float* adv, const float* returns,
-                                 const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream) {
-  if (!n || !hp || B_local < 0 || B_global < B_local || B_global < 1) return DDRL_E_ARG;
-  if (!n->params || !n->grads) return DDRL_E_STATE;
-  cudaStream_t s = (cudaStream_t)stream;
+namespace ddrl {
+// zero the gradients, then per micro-batch: forward (act = data.actions), fused loss, heads and encoders backward; finally
+// the packed weight gradients are un-permuted into the reference layout
+static int backward_body(ddrl_net* n, const float* const* obs, int B_local, int B_global, const float* actions,
+                         const float* old_logp, const float* adv, const float* returns, const ddrl_ppo_hparams* hp, bool reuse_obs,
+                         cudaStream_t s) {
   // zero the flat grads (+ loss tail) and the packed grads: everything below accumulates
   DDRL_CUDA(cudaMemsetAsync(n->grads, 0, sizeof(float) * (size_t)(n->P + 8), s));
   if (n->packed_base) DDRL_CUDA(cudaMemsetAsync(n->packed_base + n->packed_grad_off, 0, n->packed_grad_bytes, s));
-  if (B_local == 0) return DDRL_OK;
-  TRY(check_obs(n, obs, n_obs));
-  if (!actions || !old_logp || !adv || !returns) return DDRL_E_ARG;
-  const char* ws_before = n->ws.base;
-  TRY(ensure_workspace(n, B_local, true));
-  if (n->dirty) TRY(repack(n, s));
-  const bool single = B_local <= n->MB;
-  const bool reuse_obs = obs_unchanged && single && ws_before == n->ws.base && n->cols_obs0 == obs[0] && n->cols_rows == B_local;
-  n->cols_obs0 = single ? obs[0] : nullptr;
-  n->cols_rows = single ? B_local : -1;
   const int A = n->d.act_dim, F = n->d.feat;
   const float invB = 1.0f / (float)B_global;
   float* loss_sums = n->grads + n->P;
@@ -1394,22 +1568,42 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
     if (n->fuse0) TRY(fused_conv0_bwd(n, mb, s));
   }
   // packed weight grads -> reference layout
-  if (n->s2d_train) {
-    const ConvGeom& g = n->towers[0].g[0];
-    const float* dw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(n->w0s2d) + n->packed_grad_off);
-    for (int k = 0; k < 2; ++k) {
-      const Lin& l = n->towers[k].L[0];
-      TRY(unpack_grad_s2d(dw + (size_t)k * l.N * l.ldw, n->grads + n->T[l.w_t].offset, l.N, g.C, g.KH, g.KW, g.stride, l.ldw, s));
-    }
-  }
-  for (auto& t : n->towers)
-    for (auto& l : t.L)
-      if (l.packed) {
-        if (n->s2d_train && &l == &t.L[0]) continue;         // done above from the fused space-to-depth gradient
-        if (l.s2d_s && !l.s2d_fwd_only) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
-        else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
-      }
+  if (prep_fused(n) && n->prep_ready) TRY(n->unprep.launch("prep_unpack_kernel", s));
+  else TRY(unpack_emit(n, s));
   return DDRL_OK;
+}
+}  // namespace ddrl
+
+extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
+                                 const float* actions, const float* old_logp, const float* adv, const float* returns,
+                                 const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream) {
+  if (!n || !hp || B_local < 0 || B_global < B_local || B_global < 1) return DDRL_E_ARG;
+  if (!n->params || !n->grads) return DDRL_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B_local == 0) {
+    DDRL_CUDA(cudaMemsetAsync(n->grads, 0, sizeof(float) * (size_t)(n->P + 8), s));
+    if (n->packed_base) DDRL_CUDA(cudaMemsetAsync(n->packed_base + n->packed_grad_off, 0, n->packed_grad_bytes, s));
+    return DDRL_OK;
+  }
+  TRY(check_obs(n, obs, n_obs));
+  if (!actions || !old_logp || !adv || !returns) return DDRL_E_ARG;
+  const char* ws_before = n->ws.base;
+  TRY(ensure_workspace(n, B_local, true));
+  if (n->dirty) TRY(repack(n, s));
+  const bool single = B_local <= n->MB;
+  const bool reuse_obs = obs_unchanged && single && ws_before == n->ws.base && n->cols_obs0 == obs[0] && n->cols_rows == B_local;
+  n->cols_obs0 = single ? obs[0] : nullptr;
+  n->cols_rows = single ? B_local : -1;
+  // iterations 2..10 of one learn call: same launches, same pointers -> one graph launch
+  if (reuse_obs && n->extra.empty() && graphs_enabled(n)) {
+    const std::string key = graph_key("bwd", {obs[0], n_obs > 1 ? obs[1] : nullptr, n_obs > 2 ? obs[2] : nullptr, actions, old_logp,
+                                              adv, returns, n->params, n->grads, n->ws.base},
+                                      {B_local, B_global}, hp, sizeof(*hp));
+    return run_graphed(n, key, s, [&](cudaStream_t cs) {
+      return backward_body(n, obs, B_local, B_global, actions, old_logp, adv, returns, hp, true, cs);
+    });
+  }
+  return backward_body(n, obs, B_local, B_global, actions, old_logp, adv, returns, hp, reuse_obs, s);
 }
 
 // debugging aid (not part of the public header): copies workspace buffer `idx` of tower `tower` to `out`
@@ -1430,10 +1624,8 @@ __global__ void finish_losses_kernel(const float* __restrict__ sums, float v_coe
 }
 }  // namespace ddrl
 
-extern "C" int ddrl_net_clip_adam(ddrl_net* n, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream) {
-  if (!n || !hp || step < 1) return DDRL_E_ARG;
-  if (!n->params || !n->grads || !n->am || !n->av) return DDRL_E_STATE;
-  cudaStream_t s = (cudaStream_t)stream;
+namespace ddrl {
+static int clip_adam_body(ddrl_net* n, int step, const ddrl_ppo_hparams* hp, float* loss4_out, cudaStream_t s) {
   if (loss4_out) {
     finish_losses_kernel<<<1, 1, 0, s>>>(n->grads + n->P, hp->v_coef, hp->ent_coef, loss4_out);
     DDRL_LAUNCHED("finish_losses_kernel");
@@ -1442,8 +1634,48 @@ extern "C" int ddrl_net_clip_adam(ddrl_net* n, int step, const ddrl_ppo_hparams*
   float lr[2];
   if (n->d.shared) lr[0] = hp->lr;
   else { lr[0] = hp->lr_actor; lr[1] = hp->lr_critic; }
-  TRY(clip_adam_launch(n->params, n->grads, n->am, n->av, n->P, sb, lr, n->nseg, step, hp, nullptr, s));
+  TRY(clip_adam_launch(n->params, n->grads, n->am, n->av, n->P, sb, lr, n->nseg, step, hp, nullptr, s, n->sumsq_dev));
   TRY(repack(n, s));
   return DDRL_OK;
+}
+}  // namespace ddrl
+
+extern "C" int ddrl_net_clip_adam(ddrl_net* n, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream) {
+  if (!n || !hp || step < 1) return DDRL_E_ARG;
+  if (!n->params || !n->grads || !n->am || !n->av) return DDRL_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!n->sumsq_dev) DDRL_CUDA(cudaMalloc(&n->sumsq_dev, sizeof(double)));
+  // the optimiser step + weight re-preparation (~50 small launches on forked side streams) replays as one graph; only the
+  // step-dependent scalars of the clip+Adam node change between replays.  The first step of a net runs on the stream (it
+  // also performs the one-time allocations a capture must not contain).
+  if (step > 1 && !n->dirty && n->packed_base && graphs_enabled(n)) {
+    const std::string key = graph_key("adam", {loss4_out, n->params, n->grads, n->am, n->av}, {}, hp, sizeof(*hp));
+    ddrl_net::GraphEntry* e = nullptr;
+    TRY(run_graphed(n, key, s, [&](cudaStream_t cs) { return clip_adam_body(n, step, hp, loss4_out, cs); }, &e));
+    if (!e) return DDRL_OK;                       // capture failed: the body already ran on the stream
+    if (!e->adam_node) {
+      size_t cnt = 0;
+      DDRL_CUDA(cudaGraphGetNodes(e->graph, nullptr, &cnt));
+      std::vector<cudaGraphNode_t> nodes(cnt);
+      DDRL_CUDA(cudaGraphGetNodes(e->graph, nodes.data(), &cnt));
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == clip_adam_kernel_func()) { e->adam_node = nd; break; }
+      }
+      if (!e->adam_node) { n->graphs_off = true; graphs_clear(n); return clip_adam_body(n, step, hp, loss4_out, s); }
+    }
+    long long sb[3] = {n->seg_begin[0], n->seg_begin[1], n->seg_begin[2]};
+    float lr[2];
+    if (n->d.shared) lr[0] = hp->lr;
+    else { lr[0] = hp->lr_actor; lr[1] = hp->lr_critic; }
+    TRY(clip_adam_update_node(e->exec, e->adam_node, sb, lr, n->nseg, step, hp));
+    DDRL_CUDA(cudaGraphLaunch(e->exec, s));
+    g_launches += e->launches;
+    n->dirty = false;
+    return DDRL_OK;
+  }
+  return clip_adam_body(n, step, hp, loss4_out, s);
 }
 

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "prep_kernels.cuh"
 #include "tc_ptx.cuh"
 
 namespace ddrl {
@@ -856,19 +857,16 @@ int tc2_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, float* dWp,
 // hi = rn_tf32(w), lo = rn_tf32(w - hi): the weight operand's split, once per optimiser step
 __global__ void __launch_bounds__(256) split_hi_lo_kernel(const float4* __restrict__ w, uint4* __restrict__ hi,
                                                           uint4* __restrict__ lo, long long n4) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 x = w[i];
-    uint4 h, l;
-    h.x = tf32_rn(x.x); h.y = tf32_rn(x.y); h.z = tf32_rn(x.z); h.w = tf32_rn(x.w);
-    l.x = tf32_rn(x.x - __uint_as_float(h.x)); l.y = tf32_rn(x.y - __uint_as_float(h.y));
-    l.z = tf32_rn(x.z - __uint_as_float(h.z)); l.w = tf32_rn(x.w - __uint_as_float(h.w));
-    hi[i] = h; lo[i] = l;
-  }
+  split_hi_lo_body(w, hi, lo, n4, blockIdx.x, gridDim.x);
 }
 int split_hi_lo(const float* w, float* hi, float* lo, long long n, cudaStream_t s) {
   if (n % 4 != 0 || !al16(w) || !al16(hi) || !al16(lo)) return DDRL_E_ARG;
   if (n == 0) return DDRL_OK;
   const long long n4 = n / 4;
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_SPLIT_HILO; j.a = w; j.b = hi; j.c = lo; j.total = n4; j.vblocks = prep_blocks(n4);
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   const int blocks = (int)std::min<long long>((n4 + 255) / 256, 8LL * kNumSMs);
   split_hi_lo_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(w), reinterpret_cast<uint4*>(hi),
                                             reinterpret_cast<uint4*>(lo), n4);

@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "layer_ops.h"
+#include "prep_kernels.cuh"
 #include "tc_ptx.cuh"
 
 namespace ddrl {
@@ -44,7 +45,7 @@ constexpr int T3_CHUNK = 4;                   // K blocks per TMEM main-accumula
 // two of ten splitter instructions per element pair (forward convs 5 % faster), but rows 2^-20 below the tensor's amax
 // drop from 22 to ~10 significant bits and micro-batched runs stop being bit-identical to single-shot ones (the power-of-two
 // scale is otherwise exact, so the split mantissas do not depend on it): not adopted.
-constexpr float T3_LO = 2048.f, T3_LO_INV = 1.f / 2048.f;
+// (T3_LO / T3_LO_INV and t3_scale live in prep_kernels.cuh: the weight-preparation kernels share them)
 
 // Optional role-level accounting (build with -DTC3_TIMING, scratch/tc3_roles.py): cycles each warp role of the forward
 // kernel spends in each of its phases, accumulated over every launch.  [role*8 + k]; k = 7 is the role's lifetime.
@@ -88,25 +89,6 @@ struct Tc3Args {
   float* colsum;                              // weight gradient: optional db[n] += sum_r dy[r, n] (bias gradient), fused into the dy conversion
   TcTap tap;
 };
-
-// power-of-two scale that maps amax into [2^13, 2^14) and its inverse, from the exponent bits (amax = 0 or denormal: the
-// clamp keeps both finite; inf / nan inputs poison the result either way)
-__host__ __device__ __forceinline__ void t3_scale(float amax, float& s, float& inv) {
-#ifdef __CUDA_ARCH__
-  int e = (__float_as_int(amax) >> 23) & 0xff;
-#else
-  uint32_t bits; memcpy(&bits, &amax, 4);
-  int e = (int)((bits >> 23) & 0xff);
-#endif
-  if (amax == 0.f) e = 127 + 13;
-  e = e < 14 ? 14 : (e > 253 ? 253 : e);
-  const uint32_t sb = (uint32_t)(267 - e) << 23, ib = (uint32_t)(e - 13) << 23;
-#ifdef __CUDA_ARCH__
-  s = __uint_as_float(sb); inv = __uint_as_float(ib);
-#else
-  memcpy(&s, &sb, 4); memcpy(&inv, &ib, 4);
-#endif
-}
 
 // (x0, x1) * s -> packed fp16 hi pair and packed fp16 lo' pair (saturating: a stale amax gives a wrong, finite result)
 template <bool SCALED = true>
@@ -1235,36 +1217,23 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
 }
 
 // ---------------------------------------------------------------- operand preparation
-// amax|x| over a [rows, cols] view (row stride ld) -> atomicMax on the bits of *slot (the caller zeroes the slot)
+// amax|x| over a [rows, cols] view (row stride ld) -> atomicMax on the bits of *slot (the caller zeroes the slot); body in
+// prep_kernels.cuh
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
                                                    unsigned int* __restrict__ slot) {
-  float m = 0.f;
-  if (cols == ld && (cols & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    const long long n4 = rows * cols / 4;
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-      const float4 v = x4[i];
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-  } else {
-    const long long n = rows * cols;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-      const long long r = i / cols;
-      m = fmaxf(m, fabsf(x[r * ld + (i - r * cols)]));
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float sm[8];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
-    if (m > 0.f) atomicMax(slot, __float_as_uint(m));
-  }
+  amax_body(x, rows, cols, ld, slot, blockIdx.x, gridDim.x);
 }
 int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s) {
   if (!slot || rows < 0 || cols < 0) return DDRL_E_ARG;
+  if (g_prep_rec) {
+    // recorded for the multi-job kernel: the zeroing of the slot belongs to the PREVIOUS phase (the caller keeps a second
+    // recorder for it), so only the reduction is recorded here
+    if (rows == 0 || cols == 0) return DDRL_OK;
+    if (ld > 0x7fffffffLL) return DDRL_E_ARG;
+    PrepJob j{}; j.type = PREP_AMAX; j.a = x; j.b = slot; j.total = rows; j.i[0] = cols; j.i[1] = (int)ld;
+    j.vblocks = prep_blocks(rows * cols, 1024);
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   if (zero_first) DDRL_CUDA(cudaMemsetAsync(slot, 0, sizeof(float), s));
   if (rows == 0 || cols == 0) return DDRL_OK;
   if (!x) return DDRL_E_ARG;
@@ -1275,30 +1244,21 @@ int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot
   return DDRL_OK;
 }
 
-// weights w [N, ldw] fp32 (K valid columns) -> hi / lo' [N, ld16] fp16 with the scale of *amax; optionally the transposed
-// pair hiT / loT [K, ldT16] (the K-major weight operand of a linear layer's data gradient).  Padding columns are zero.
+// weights w [N, ldw] fp32 -> scaled fp16 hi / lo' (+ transposed pair); body in prep_kernels.cuh
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, int N, int K, int ldw, const float* __restrict__ amax,
                                                         __half* __restrict__ hi, __half* __restrict__ lo, int ld16,
                                                         __half* __restrict__ hiT, __half* __restrict__ loT, int ldT16) {
-  float s, inv;
-  t3_scale(*amax, s, inv);
-  const long long n = (long long)N * ld16;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld16), k = (int)(i - (long long)r * ld16);
-    __half h = __float2half_rn(0.f), l = h;
-    if (k < K) {
-      const float y = w[(long long)r * ldw + k] * s;
-      h = __float2half_rn(y);
-      l = __float2half_rn((y - __half2float(h)) * T3_LO);
-      if (hiT) { hiT[(long long)k * ldT16 + r] = h; loT[(long long)k * ldT16 + r] = l; }
-    }
-    hi[i] = h; lo[i] = l;
-  }
+  split_f16_body(w, N, K, ldw, amax, hi, lo, ld16, hiT, loT, ldT16, blockIdx.x, gridDim.x);
 }
 int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT, int ldT16,
               cudaStream_t s) {
   if (!w || !amax || !hi || !lo || N < 1 || K < 1 || ld16 < K) return DDRL_E_ARG;
   const long long n = (long long)N * ld16;
+  if (g_prep_rec) {
+    PrepJob j{}; j.type = PREP_SPLIT_F16; j.a = w; j.b = hi; j.c = lo; j.d = hiT; j.e = loT; j.amax = amax; j.total = n;
+    j.i[0] = N; j.i[1] = K; j.i[2] = ldw; j.i[3] = ld16; j.i[4] = ldT16; j.vblocks = prep_blocks(n);
+    return prep_record(j) ? DDRL_OK : DDRL_E_STATE;
+  }
   const int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * kNumSMs);
   split_f16_kernel<<<blocks, 256, 0, s>>>(w, N, K, ldw, amax, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ld16,
                                           reinterpret_cast<__half*>(hiT), reinterpret_cast<__half*>(loT), ldT16);

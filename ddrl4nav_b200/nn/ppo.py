@@ -171,7 +171,7 @@ class PPO(Basenn):
             holder = Critic(last_input_dim=feat, pre=None)
             holder.critic_linear = c.critic_linear               # the SAME parameters: p.data re-points into aux's flat buffer
             actor = CategoricalActor(1, last_input_dim=feat, pre=None)
-            aux = PPO(actor, holder, c.pre, None, self.config, None)
+            aux = PPO(actor, holder, c.pre, None, None, None)      # no config: no Redis connection of its own
             aux.gemm_mode = self.gemm_mode
             aux.hp = kernels.make_hparams(
                 ppo_clip=self.hp.ppo_clip, dual_clip=self.hp.dual_clip, v_coef=1.0, ent_coef=0.0,

@@ -242,6 +242,46 @@ def test_add_critic_gail_matches_reference_golden(golden_dir, kind, B):
                        [l3[k] for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss")], rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("kind,B", [("pong", 21), ("navimg", 9), ("navlaser", 5)])
+def test_graph_replay_matches_stream_launches(monkeypatch, kind, B):
+    """Iterations 2..N of a learn call replay two CUDA graphs (backward; optimiser step + weight re-preparation, with the
+    step-dependent Adam scalars rewritten per replay).  They must do what the stream launches do (DDRL_NO_GRAPH=1)."""
+    from ddrl4nav_b200 import kernels
+    from ddrl4nav_b200.data import Experience
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    exp = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                     values=ret.numpy()[None])
+    exp.to_tensor(device=DEV)
+
+    def run(no_graph):
+        if no_graph:
+            monkeypatch.setenv("DDRL_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("DDRL_NO_GRAPH", raising=False)
+        net, _, _ = make(kind, TRAINING_ITER_TIME=5)
+        ds = [s.to(DEV) for s in states]
+        # gradient of the SAME parameters three times: stream launches, graph capture + first launch, graph replay
+        gs = []
+        for i in range(3):
+            net.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV), obs_unchanged=i > 0)
+            gs.append(net.flat_grads().clone())
+        kernels.launch_count_reset()
+        losses = [[l[k] for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss")] for l, _, _ in net.learn(exp)]
+        return gs, np.array(losses), net._flat.clone(), net._m.clone(), kernels.launch_count()
+
+    g_graph, l_graph, p_graph, m_graph, n_graph = run(False)
+    g_eager, l_eager, p_eager, m_eager, n_eager = run(True)
+    assert n_graph == n_eager            # replayed kernel nodes are counted like stream launches
+    for g in g_graph[1:] + g_eager[1:]:
+        assert rel_err(g, g_graph[0]) < 5e-6
+    assert np.allclose(l_graph[0], l_eager[0], rtol=1e-6, atol=1e-7)
+    assert np.allclose(l_graph, l_eager, rtol=2e-3, atol=2e-4), (l_graph, l_eager)
+    # Adam's first moment after 5 steps is a smooth function of the gradients (the parameters themselves move by
+    # ~lr * sign(g) per step on noise-level gradients): it pins the per-step scalars of the replayed optimiser node
+    assert rel_err(m_graph, m_eager) < 2e-3
+    assert float((p_graph - p_eager).abs().max()) < 5 * 1e-3 * 5      # <= (steps x largest lr) apart anywhere
+
+
 def test_micro_batching_equals_single_shot(monkeypatch):
     spec, params, states, a, old, adv, ret = _learn_case("pong", 21)
     net, _, _ = make("pong")
