@@ -78,7 +78,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: an integer round-trip hides the address space from
+  // the compiler, which then emits generic LD / ST (long-scoreboard, L1TEX path) for every shared-memory access below
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -148,7 +148,9 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   using Cfg = T2Cfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: an integer round-trip hides the address space from
+  // the compiler, which then emits generic LD / ST (long-scoreboard, L1TEX path) for every shared-memory access below
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
   uint64_t* bar_full = bars;                  // [S]  TMA landed
   uint64_t* bar_empty = bars + S;             // [S]  MMAs that read the stage retired

@@ -51,7 +51,7 @@ constexpr int T3_CHUNK = 4;                   // K blocks per TMEM main-accumula
 // kernel spends in each of its phases, accumulated over every launch.  [role*8 + k]; k = 7 is the role's lifetime.
 // roles: 0 producer {empty} | 1 chunk MMA {mfree, aready, issue+commit} | 2 corr MMA {cfree, aready, issue+commit} |
 //        3 splitter warp 4 {full, afree, lds+split, st+wait::st} | 4 epilogue warp 0 {mfull, cfull, stores, drain}
-__device__ unsigned long long g_tc3_wait[64];
+__device__ unsigned long long g_tc3_wait[96];   // weight-gradient kernel: roles 5 producer | 6 chunk MMA | 7 splitter warp 4 | 8 epilogue warp 0
 #ifdef TC3_TIMING
 #define T3_T0 const long long _t0 = clock64()
 #define T3_ACC(acc) acc += clock64() - _t0
@@ -149,7 +149,9 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   using Cfg = T3Cfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: an integer round-trip hides the address space from
+  // the compiler, which then emits generic LD / ST (long-scoreboard, L1TEX path) for every shared-memory access below
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* bar_full = bars;                  // [S]  TMA landed
   uint64_t* bar_empty = bars + S;             // [S]  MMAs that read the stage (and its TMEM slot) retired
@@ -801,7 +803,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = T3WCfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: an integer round-trip hides the address space from
+  // the compiler, which then emits generic LD / ST (long-scoreboard, L1TEX path) for every shared-memory access below
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + S;
@@ -822,8 +826,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_async_smem();
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 4); }
-    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4); mbar_init(smem_u32(bar_afree + a), 2); }
+    // a stage is consumed / a slot is produced by the 4 gather warps of one splitter group AND the NEPI conversion warps
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 4 + Cfg::NEPI); }
+    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4 + Cfg::NEPI); mbar_init(smem_u32(bar_afree + a), 2); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -861,9 +866,10 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     int pb = 0, pj = 0;
     if (tapA) { pb = kb0 / tp.tpi; pj = kb0 - pb * tp.tpi; }
+    T3_ROLE_BEGIN
     for (int i = 0; i < nkb; ++i) {
       const uint32_t s = i % S;
-      mbar_wait_long(smem_u32(bar_empty + s), ((i / S) & 1) ^ 1);
+      T3_WAITL(smem_u32(bar_empty + s), ((i / S) & 1) ^ 1, w0);
       if (elect_one()) {
         const uint32_t full = smem_u32(bar_full + s);
         const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, b_dst = a_dst + Cfg::A_BYTES;
@@ -897,6 +903,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (tapA && ++pj == tp.tpi) { pj = 0; ++pb; }
     }
+    T3_ROLE_END(5, true);
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers
     const bool chunk_role = warp == 1;
@@ -906,14 +913,16 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t b16_base = smem_u32(smem) + Cfg::B16_OFF;
     const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
     uint32_t ch = 0;
+    T3_ROLE_BEGIN
     for (int i = 0; i < nkb; ++i) {
       const uint32_t a = i % SA;
       const uint32_t buf = ch & 1;
       const bool first_in_chunk = (i % T3_CHUNK) == 0;
       const bool last_in_chunk = (i % T3_CHUNK) == T3_CHUNK - 1 || i == nkb - 1;
-      if (chunk_role && first_in_chunk) mbar_wait(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1);
-      mbar_wait(smem_u32(bar_aready + a), (i / SA) & 1);
+      if (chunk_role && first_in_chunk) T3_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0);
+      T3_WAIT(smem_u32(bar_aready + a), (i / SA) & 1, w1);
       tc_fence_after();
+      T3_SECTION_BEGIN;
       if (elect_one()) {
         // MN-major 128B-swizzled fp16 tiles: 64-column groups 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO);
         // one k step = 16 rows = 2 KB
@@ -942,32 +951,121 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       __syncwarp();
+      T3_SECTION_END(w2);
       if (last_in_chunk) ++ch;
     }
+    T3_ROLE_END(6, chunk_role);
   } else if (warp >= 4 && warp < Cfg::EPI0) {
-    // ============================================================ splitters: dy tile -> fp16 tiles, A columns -> TMEM
+    // ============================================================ splitters: A columns (transposing gather) -> TMEM
+    // Measured (profiles/r2p_tc3_roles.txt): with the dy conversion in these warps they were busy 87 % of the kernel while the
+    // MMA issuers waited 68 % and the epilogue warps 96 %: the conversion now runs in the epilogue warps.
     const int q = (warp - 4) & 3, grp = (warp - 4) >> 2;
-    const int st_tid = (threadIdx.x - 128) & 127;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    float sA, sA_inv, sB, sB_inv;
+    float sA, sA_inv;
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
-    t3_scale(__ldg(g.amax_b), sB, sB_inv);
-    // bias gradient: every conversion task of this thread covers the same 8 columns (128 threads, BN / 8 tasks per row),
-    // so the column sums of the dy tiles ride along in 8 registers (only the CTAs of the first M block contribute)
-    const bool unit_a = sA == 1.f;
-    const bool do_colsum = g.colsum != nullptr && blockIdx.x == 0;
-    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    T3_ROLE_BEGIN
     for (int i = 0; i < nkb; ++i) {
       if ((i % Cfg::NSG) != grp) continue;
       const int s = i % S, a = i % SA;
-      mbar_wait(smem_u32(bar_full + s), (i / S) & 1);
-      // the slot (TMEM columns + fp16 dy tiles) was last read by K block i - SA
-      if (i >= SA) mbar_wait(smem_u32(bar_afree + a), ((i / SA) - 1) & 1);
+      T3_WAIT(smem_u32(bar_full + s), (i / S) & 1, w0);
+      // the TMEM slot was last read by K block i - SA
+      if (i >= SA) T3_WAIT(smem_u32(bar_afree + a), ((i / SA) - 1) & 1, w1);
       tc_fence_after();
+      T3_SECTION_BEGIN;
+      const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      // A: thread = k column `lane` of slice q; gathers it over the 64 rows of the box, pairs of rows -> fp16x2
+      const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
+      const uint8_t* sp = st + q * Cfg::A_SUB + (lane & 3) * 4;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int pp = hf * 32 + 2 * p;
+          const float x0 = *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
+          const float x1 = *reinterpret_cast<const float*>(sp + (pp + 1) * 128 + (((lane >> 2) ^ ((pp + 1) & 7)) << 4));
+          // always the scaled form (s = 1 multiplies exactly): a per-pair `unit scale` branch made every pair its own basic
+          // block -- 2 LDS, branch, a 6-deep dependent conversion chain, branch -- with no overlap between pairs: ~80 clk per
+          // pair, 5000 clk per K block, the splitters 85 % busy and the tensor pipe 18 % (profiles/r2p_tc3_roles.txt)
+          t3_split2<true>(x0, x1, sA, hi[p], lo[p]);
+        }
+#ifdef TC3_TIMING
+        { const long long _q0 = clock64();
+#endif
+        tmem_st16(ta + hf * 16, hi);
+        tmem_st16(ta + 32 + hf * 16, lo);
+#ifdef TC3_TIMING
+          w3 += clock64() - _q0; }
+#endif
+      }
+#ifdef TC3_TIMING
+      const long long _q1 = clock64();
+#endif
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(smem_u32(bar_empty + s)); mbar_arrive(smem_u32(bar_aready + a)); }
+#ifdef TC3_TIMING
+      w3 += clock64() - _q1;
+#endif
+      T3_SECTION_END(w2);
+    }
+    T3_ROLE_END(7, warp == 4);
+  } else if (warp >= Cfg::EPI0) {
+    // ============================================================ dy conversion + drain + atomic accumulate
+    // Per K block these 8 warps turn the landed dy tile (fp32) into the MMA's fp16 hi / lo' tiles; after the last K block of
+    // chunk c they drain chunk c - 1 (its MMAs only depend on conversions that are already done, so the wait cannot
+    // deadlock, and the chunk MMA stream gets its buffer back one chunk ahead of needing it).
+    const int e = warp - Cfg::EPI0;
+    const int q = e & 3, half = e >> 2;
+    const int et = e * 32 + lane;                               // conversion thread 0 .. 255
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const uint32_t col0 = half * Cfg::COLS;
+    float sA, sA_inv, sB, sB_inv;
+    t3_scale(__ldg(g.amax_a), sA, sA_inv);
+    t3_scale(__ldg(g.amax_b), sB, sB_inv);
+    // bias gradient: every conversion task of this thread covers the same 8 columns (256 threads, BN / 8 tasks per row),
+    // so the column sums of the dy tiles ride along in 8 registers (only the CTAs of the first M block contribute)
+    const bool do_colsum = g.colsum != nullptr && blockIdx.x == 0;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[Cfg::COLS];
+#pragma unroll
+    for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
+    const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
+    T3_ROLE_BEGIN
+    // BN = 128: 64 accumulator registers per thread stay live across the conversion loop, so the drain reads TMEM 16
+    // columns at a time (32 would not fit the 96-register budget of a 640-thread CTA without spilling)
+    constexpr int LDW = BN <= 64 ? 32 : 16;
+    auto drain = [&](int c) {
+      const int buf = c & 1;
+      T3_WAITL(smem_u32(bar_mfull + buf), (c >> 1) & 1, w0);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += LDW) {
+        float v[LDW];
+        const uint32_t ta = tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0;
+        if (LDW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
+#pragma unroll
+        for (int j = 0; j < LDW; ++j) acc[j0 + j] += v[j];
+        if (Cfg::FOLD) {
+          if (LDW == 32) tmem_ld32(ta + BN, v); else tmem_ld16(ta + BN, v);
+#pragma unroll
+          for (int j = 0; j < LDW; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
+    };
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S, a = i % SA;
+      T3_WAIT(smem_u32(bar_full + s), (i / S) & 1, w3);
+      // the fp16 dy tiles of slot a were last read by K block i - SA
+      if (i >= SA) T3_WAIT(smem_u32(bar_afree + a), ((i / SA) - 1) & 1, w3);
       const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
       uint8_t* b16 = smem + Cfg::B16_OFF + a * Cfg::B16_BYTES;
       // dy tile: task = (row r, 8 consecutive columns): 2 swizzled 16-byte fp32 chunks -> 1 chunk of hi + 1 chunk of lo'
-      for (int v = st_tid; v < T3_BK * (BN / 8); v += 128) {
+      for (int v = et; v < T3_BK * (BN / 8); v += Cfg::NEPI * 32) {
         const int r = v / (BN / 8), c8 = v - r * (BN / 8);
         const uint8_t* src = st + Cfg::A_BYTES + (c8 >> 2) * Cfg::A_SUB + r * 128;
         const float4 x0 = *reinterpret_cast<const float4*>(src + ((((c8 & 3) * 2) ^ (r & 7)) << 4));
@@ -983,30 +1081,17 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *reinterpret_cast<uint4*>(dst + (BN / 64) * Cfg::B16_TILE) = l;
       }
       fence_async_smem();
-      // A: thread = k column `lane` of slice q; gathers it over the 64 rows of the box, pairs of rows -> fp16x2
-      const uint32_t ta = tmem_base + t_lane + Cfg::TM_A + a * 64;
-      const uint8_t* sp = st + q * Cfg::A_SUB + (lane & 3) * 4;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int pp = hf * 32 + 2 * p;
-          const float x0 = *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
-          const float x1 = *reinterpret_cast<const float*>(sp + (pp + 1) * 128 + (((lane >> 2) ^ ((pp + 1) & 7)) << 4));
-          if (unit_a) t3_split2<false>(x0, x1, 1.f, hi[p], lo[p]);
-          else t3_split2<true>(x0, x1, sA, hi[p], lo[p]);
-        }
-        tmem_st16(ta + hf * 16, hi);
-        tmem_st16(ta + 32 + hf * 16, lo);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(smem_u32(bar_empty + s)); mbar_arrive(smem_u32(bar_aready + a)); }
+      if ((i % T3_CHUNK) == T3_CHUNK - 1 && i >= T3_CHUNK) drain(i / T3_CHUNK - 1);
+    }
+    // chunks not drained inside the loop: the last full-or-partial one, and the one before it when the tail was partial
+    {
+      const int drained = nkb >= 2 * T3_CHUNK ? nkb / T3_CHUNK - 1 : 0;      // chunks 0 .. drained - 1 are done
+      for (int c = drained; c < nch; ++c) drain(c);
     }
     if (do_colsum) {
-      // threads with equal (st_tid mod BN/8) hold partial sums of the same 8 columns: lanes l, l + BN/8, ... of a warp
+      // threads with equal (et mod BN/8) hold partial sums of the same 8 columns: lanes l, l + BN/8, ... of a warp
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = cs[k];
@@ -1020,48 +1105,17 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int k = 0; k < 8; ++k) if (col + k < g.N) atomicAdd(g.colsum + col + k, cs[k]);
       }
     }
-  } else if (warp >= Cfg::EPI0) {
-    // ============================================================ drain + atomic accumulate
-    const int e = warp - Cfg::EPI0;
-    const int q = e & 3, half = e >> 2;
-    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    const uint32_t col0 = half * Cfg::COLS;
-    float sA, sA_inv, sB, sB_inv;
-    t3_scale(__ldg(g.amax_a), sA, sA_inv);
-    t3_scale(__ldg(g.amax_b), sB, sB_inv);
-    float acc[Cfg::COLS];
-#pragma unroll
-    for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
-    const int nch = (nkb + T3_CHUNK - 1) / T3_CHUNK;
-    for (int c = 0; c < nch; ++c) {
-      const int buf = c & 1;
-      mbar_wait_long(smem_u32(bar_mfull + buf), (c >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
-        if (Cfg::FOLD) {
-          tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
-    }
     if (nkb > 0) {
-      mbar_wait(smem_u32(bar_cfull), 0);
+      T3_WAIT(smem_u32(bar_cfull), 0, w1);
       tc_fence_after();
+      T3_SECTION_BEGIN;
 #pragma unroll
-      for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+      for (int j0 = 0; j0 < Cfg::COLS; j0 += LDW) {
+        float v[LDW];
+        if (LDW == 32) tmem_ld32(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
+        else tmem_ld16(tmem_base + t_lane + Cfg::TM_CORR + col0 + j0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+        for (int j = 0; j < LDW; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
       }
       const int r = q * 32 + lane;
       if (m0 + r < g.M) {
@@ -1072,7 +1126,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (col < g.N) atomicAdd(crow + (long long)col * g.sCn, (acc[j] * sA_inv) * sB_inv);
         }
       }
+      T3_SECTION_END(w2);
     }
+    T3_ROLE_END(8, warp == Cfg::EPI0);
   }
   tc_fence_before();
   __syncthreads();
@@ -1270,7 +1326,7 @@ int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi
 
 // debugging aid (not part of the public header): role counters of the tc3 forward kernel (all zero unless built -DTC3_TIMING)
 extern "C" int ddrl_tc3_timing_read(unsigned long long* out64, int reset) {
-  if (out64) DDRL_CUDA(cudaMemcpyFromSymbol(out64, ddrl::g_tc3_wait, sizeof(unsigned long long) * 64));
+  if (out64) DDRL_CUDA(cudaMemcpyFromSymbol(out64, ddrl::g_tc3_wait, sizeof(unsigned long long) * 96));
   if (reset) {
     unsigned long long z[64] = {0};
     DDRL_CUDA(cudaMemcpyToSymbol(ddrl::g_tc3_wait, z, sizeof(z)));
