@@ -446,29 +446,42 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           cb = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb;
           cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
         }
+        // branch-free per element: the bias of the panel's 32 columns is fetched up front (index clamped, so every load is
+        // legal and all 32 are in flight together), the activation is two selects on kernel-uniform predicates.  (A per-element
+        // `if (col < N) { if (bias) ...; if (act == ..) ... }` compiled to 32 serialised LDG -> branch -> FADD blocks.)
+        const bool relu = g.act == 1;
+        const float slope = g.act == 2 ? 0.01f : 1.f;
 #pragma unroll
         for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
           const int colb = n0 + col0 + p0;
+          float bv[32];
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bv[j] = __ldg(g.bias + min(colb + j, g.N - 1));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+          }
+          // the staging panels are free once the previous TMA stores have READ them (same issuing thread as below)
+          if (e == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int col = colb + 4 * c + k;
-              float x = acc[p0 + 4 * c + k];
-              if (col < g.N) {
-                if (g.bias != nullptr) x += __ldg(g.bias + col);
-                if (g.act == 1) x = fmaxf(x, 0.f);
-                else if (g.act == 2) x = x > 0.f ? x : 0.01f * x;
-                if (rvalid) run_max = fmaxf(run_max, fabsf(x));
-              }
+              float x = acc[p0 + 4 * c + k] + bv[4 * c + k];
+              const float neg = relu ? 0.f : slope * x;
+              x = x > 0.f ? x : neg;
+              const bool live = rvalid && (colb + 4 * c + k) < g.N;
+              run_max = fmaxf(run_max, live ? fabsf(x) : 0.f);
               o[k] = x;
             }
             *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
           }
           fence_async_smem();
           asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
-          if (e == 0 && elect_one()) {
+          if (e == 0 && lane == 0) {
 #pragma unroll
             for (int h = 0; h < Cfg::NEPI / 4; ++h) {
               const int col = n0 + h * Cfg::COLS + p0;
@@ -483,9 +496,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                              : "memory");
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");     // staging reusable
         }
       } else if (g.vec_store) {
         // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
@@ -601,6 +612,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       T3_SECTION_END(w2);
     }
     T3_ROLE_END(4, warp == Cfg::EPI0);
+    if (g.tma_store && e == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (g.amax_out != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
@@ -646,9 +658,12 @@ static int launch3_bn(int bn, const Tc3Maps& m, const Tc3Args& g, dim3 grid, cud
     default: return launch3<32>(m, g, grid, s);
   }
 }
-// measured (profiles/r2f_*): the tile stores through TMA are correct but 10-15 % slower than the per-warp coalesced stores
-// (two CTA-wide epilogue barriers per tile), so they are opt-in
-static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_TMA_STORE"); return e && e[0] == '1'; }();
+// Forward outputs (no activation mask, one pixel class) leave through TMA tile stores: ~120 instead of ~700 instructions
+// per warp and 32 x 32 panel -- the N = 64 conv kernels issue 2.5 of 4 instructions per clock, so epilogue instructions are
+// the currency (profiles/r2u_*).  The first version of this path (profiles/r2f_*) lost 10-15 % to per-element bias loads that
+// compiled to 32 serialised LDG / branch blocks and to waiting for the TMA read-out inside the tile.  DDRL_TC3_TMA_STORE=0
+// selects the per-warp coalesced stores.
+static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_TMA_STORE"); return !(e && e[0] == '0'); }();
 
 static inline int pick_bn3(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
