@@ -101,10 +101,10 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
                  float* amax_out, cudaStream_t s, const TcTap* cls = nullptr);
 // db (optional): bias gradient db[n] += sum_r dy[r, n], fused into the kernel's dy conversion (no separate column-sum pass)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
-              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db = nullptr);
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0);
 bool tc3_conv_wgrad_supported(const ConvOp& o);
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s, float* db = nullptr);
+                   cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0);
 int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s);
 int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT,
               int ldT16, cudaStream_t s);

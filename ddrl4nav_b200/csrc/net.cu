@@ -182,6 +182,15 @@ static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_G
 
 static void graphs_clear(ddrl_net* n);
 
+// The tc3 weight gradient sums the dy columns (bias gradient) while its epilogue warps convert the dy tiles: those warps are
+// idle 90 % of the kernel, so the separate column-sum pass over dy (5.8 % of a Pong step) disappears.  (While the
+// conversion lived in the splitter warps -- that kernel's critical role -- the fused sums cost what they saved, profiles/r2h_*.)
+// DDRL_TC3_FUSE_COLSUM=0 brings the separate pass back.
+static inline bool fuse_colsum() {
+  static const bool on = [] { const char* e = getenv("DDRL_TC3_FUSE_COLSUM"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // ---- amax registry of the tc3 engine -------------------------------------------------------------------------------
 // A view is (pointer, rows, cols, row stride); contiguous views are keyed by (pointer, element count) so that a conv
 // output [B*Ho*Wo, C] and the next layer's [B, Ho*Wo*C] read of it are the same key.  Only EXACT matches are trusted:
@@ -488,10 +497,7 @@ static int lin_bwd(const ddrl_net* n, const Lin& l, const float* x, int ldx, flo
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 && ldx % 4 == 0 && ldy % 4 == 0;
   const bool thin = l.K <= 36 && thin_supported(M, l.N, l.K, x, ldx, dy, ldy);
   const bool w3 = !thin && tc3_mode(n) && al && l.K >= 32 && !getenv("DDRL_TC3_NO_WGRAD");
-  // DDRL_TC3_FUSE_COLSUM=1: the tc3 weight gradient sums the dy columns while it converts the dy tiles.  Measured
-  // (profiles/r2h_*): the splitter warps are that kernel's critical role, so the fused sums cost what the separate pass
-  // saves (weight gradients +2.0 ms, column sums -2.1 ms per Pong step): off by default
-  static const bool fuse_cs = [] { const char* e = getenv("DDRL_TC3_FUSE_COLSUM"); return e && e[0] == '1'; }();
+  const bool fuse_cs = fuse_colsum();
   if (!(w3 && fuse_cs)) TRY(colsum_add(dy, ldy, M, l.N, db_of(n, l), s));
   if (thin)
     TRY(thin_wgrad(x, ldx, dy, dW_of(n, l), l.ldw, M, l.N, l.K, s));
@@ -1122,8 +1128,9 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
       const float *amx = nullptr, *amy = nullptr;
       TRY(amax_in_slot(nn, cols, (long long)mb * g.H * g.W, g.C, g.C, s, &amx, true));
       TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
-      TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
-      return tc3_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s);
+      if (!fuse_colsum()) TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
+      return tc3_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s,
+                            fuse_colsum() ? db_of(n, l) : nullptr);
     }
     TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
     if (tc2_mode(n)) return tc2_conv_wgrad(conv_op_fwd(g, cols, g.C, 0, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s);
@@ -1132,13 +1139,15 @@ static int conv_bwd(const ddrl_net* n, const Tower& t, int gi, int li, const flo
   if (t.implicit[gi]) {
     const bool sub = gi == 1 && t.in1_ctot;
     const int ctot = sub ? t.in1_ctot : g.C, coff = sub ? t.in1_coff : 0;
-    TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
-    if (tc3_mode(n) && tc3_conv_wgrad_supported(conv_op_fwd(g, x, ctot, coff, mb)) && !getenv("DDRL_TC3_NO_WGRAD")) {
+    const bool w3 = tc3_mode(n) && tc3_conv_wgrad_supported(conv_op_fwd(g, x, ctot, coff, mb)) && !getenv("DDRL_TC3_NO_WGRAD");
+    if (!(w3 && fuse_colsum())) TRY(colsum_add(dy, l.N, M, l.N, db_of(n, l), s));
+    if (w3) {
       ddrl_net* nn = const_cast<ddrl_net*>(n);
       const float *amx = nullptr, *amy = nullptr;
       TRY(amax_in_slot(nn, x, (long long)mb * g.H * g.W, ctot, ctot, s, &amx));
       TRY(amax_in_slot(nn, dy, M, l.N, l.N, s, &amy));
-      TRY(tc3_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s));
+      TRY(tc3_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, amx, amy, dW_of(n, l), l.ldw, s,
+                         fuse_colsum() ? db_of(n, l) : nullptr));
     } else {
       if (tc2_mode(n)) TRY(tc2_conv_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
       else TRY(conv_tc_wgrad(conv_op_fwd(g, x, ctot, coff, mb), dy, l.N, l.N, dW_of(n, l), l.ldw, s));
@@ -1263,7 +1272,9 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
   const Lin &l0 = t0.L[0], &l1 = t1.L[0];
   const long long M = (long long)mb * g.Ho * g.Wo;
   float* dy = t0.buf[9];
-  TRY(colsum_add(dy, 2 * l0.N, M, l0.N + l1.N, db_of(n, l0), s, db_of(n, l1), l0.N));     // ONE pass over the fused gradient
+  const bool w3 = tc3_mode(n) && !getenv("DDRL_TC3_NO_WGRAD");
+  const bool fcs = fuse_colsum() && (n->s2d_train || w3);
+  if (!fcs) TRY(colsum_add(dy, 2 * l0.N, M, l0.N + l1.N, db_of(n, l0), s, db_of(n, l1), l0.N));     // ONE pass over the fused gradient
   if (n->s2d_train) {
     // weight gradient of both towers in the space-to-depth K order: dW0s2d [2 Cout, K] (the twin of w0s2d in the gradient
     // half of the packed arena), un-permuted per tower after the micro-batch loop
@@ -1272,13 +1283,15 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
     TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &amx, true));
     TRY(amax_in_slot(n, dy, M, 2 * l0.N, 2 * l0.N, s, &amy));
     float* dw = reinterpret_cast<float*>(reinterpret_cast<char*>(n->w0s2d) + n->packed_grad_off);
-    return tc3_conv_wgrad(o, dy, 2 * l0.N, 2 * l0.N, amx, amy, dw, l0.ldw, s);
+    return tc3_conv_wgrad(o, dy, 2 * l0.N, 2 * l0.N, amx, amy, dw, l0.ldw, s, fcs ? db_of(n, l0) : nullptr, fcs ? db_of(n, l1) : nullptr,
+                          l0.N);
   }
-  if (tc3_mode(n) && !getenv("DDRL_TC3_NO_WGRAD")) {
+  if (w3) {
     const float *amx = nullptr, *amy = nullptr;
     TRY(amax_in_slot(n, t0.buf[0], M, l0.K, g.ldc, s, &amx, true));
     TRY(amax_in_slot(n, dy, M, 2 * l0.N, 2 * l0.N, s, &amy));
-    return tc3_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, amx, amy, l0.dwp, l0.ldw, s);
+    return tc3_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, amx, amy, l0.dwp, l0.ldw, s, fcs ? db_of(n, l0) : nullptr,
+                     fcs ? db_of(n, l1) : nullptr, l0.N);
   }
   return tc2_wgrad(l0.K, 2 * l0.N, M, t0.buf[0], g.ldc, dy, 2 * l0.N, l0.dwp, l0.ldw, s);
 }

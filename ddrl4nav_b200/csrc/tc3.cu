@@ -87,6 +87,8 @@ struct Tc3Args {
   const float* amax_b;
   float* amax_out;                            // optional: running amax of the stored output (atomicMax on the bits)
   float* colsum;                              // weight gradient: optional db[n] += sum_r dy[r, n] (bias gradient), fused into the dy conversion
+  float* colsum2;                             // columns >= colsum_split go to colsum2[n - colsum_split] (two layers behind one fused dy)
+  int colsum_split;
   TcTap tap;
 };
 
@@ -1117,7 +1119,11 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane < BN / 8) {
         const int col = n0 + lane * 8;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (col + k < g.N) atomicAdd(g.colsum + col + k, cs[k]);
+        for (int k = 0; k < 8; ++k)
+          if (col + k < g.N) {
+            const int c = col + k;
+            atomicAdd((g.colsum2 != nullptr && c >= g.colsum_split) ? g.colsum2 + (c - g.colsum_split) : g.colsum + c, cs[k]);
+          }
       }
     }
     if (nkb > 0) {
@@ -1192,7 +1198,7 @@ static void wgrad3_splits(Tc3Args& g, int tiles) {
 
 // dW[n*ldw + k] += sum_r dy[r, n] * x[r, k]     (x [rows, Kx], dy [rows, N]; accumulates atomically)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
-              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db) {
+              const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db, float* db2, int db_split) {
   if (Kx < 1 || N < 1 || rows < 1 || !al16(x) || !al16(dy) || ldx % 4 != 0 || ldy % 4 != 0 || rows > 0x7fffffffLL)
     return DDRL_E_UNSUPPORTED;
   if (!amax_x || !amax_dy) return DDRL_E_ARG;
@@ -1207,7 +1213,7 @@ int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const floa
   memset(&g, 0, sizeof(g));
   g.C = dW; g.M = Kx; g.N = N; g.K = (int)rows; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
   g.kb_total = (int)ceil_div64(rows, T3_BK);
-  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db;
+  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db; g.colsum2 = db2; g.colsum_split = db_split;
   const int tiles = ceil_div(Kx, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(Kx, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
@@ -1237,7 +1243,7 @@ static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn
 }
 
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s, float* db) {
+                   cudaStream_t s, float* db, float* db2, int db_split) {
   if (!tc3_conv_wgrad_supported(o) || N < 1 || ldy % 4 != 0 || !al16(dy)) return DDRL_E_UNSUPPORTED;
   if (!amax_x || !amax_dy) return DDRL_E_ARG;
   int r = tc_get_encode();
@@ -1280,7 +1286,7 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   if (r != DDRL_OK) return r;
   g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
   g.kb_total = o.Bn * g.tap.tpi;
-  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db;
+  g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db; g.colsum2 = db2; g.colsum_split = db_split;
   const int tiles = ceil_div(K, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(K, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
