@@ -12,7 +12,7 @@ class Actor(nn.Module):
     DIST = None
 
     def __init__(self, **kwargs):
-        super().__init__()
+        nn.Module.__init__(self)           # not super(): with the reference's class in the MRO its __init__ must not run
         self.pre = kwargs["pre"]
         self.device = kwargs["device"]
 
@@ -39,12 +39,23 @@ class Actor(nn.Module):
         return pi, log_p
 
 
-class GaussionActor(Actor):
+def _reference_bases(name):
+    """When the host application is the reference (its `USTC_lab.nn` is already imported), our actor classes also derive
+    from the reference's class of the same name, so that the reference's own `isinstance(net.actor, GaussionActor /
+    CategoricalActor)` dispatch (server/forward.py:140-142) holds without patching anything.  Our class comes first in the
+    MRO and never calls the reference's __init__ / forward: only the type relation is inherited."""
+    import sys
+    ref = sys.modules.get("USTC_lab.nn")
+    cls = getattr(ref, name, None) if ref is not None else None
+    return (Actor, cls) if isinstance(cls, type) and cls is not Actor else (Actor,)
+
+
+class GaussionActor(*_reference_bases("GaussionActor")):
     DIST = "gaussian"
 
     def __init__(self, action_output_dim=1, device="cpu", soft_max_grid=True, last_input_dim=512, pre=None,
                  nn_dtype=torch.float32):
-        super().__init__(pre=pre, device=device)
+        Actor.__init__(self, pre=pre, device=device)
         self.actor_linear = nn.Linear(last_input_dim, action_output_dim)
         self.log_std = nn.Parameter(torch.full((action_output_dim,), -0.5, dtype=nn_dtype))
 
@@ -55,12 +66,12 @@ class GaussionActor(Actor):
         return pi.log_prob(act).sum(axis=-1)
 
 
-class CategoricalActor(Actor):
+class CategoricalActor(*_reference_bases("CategoricalActor")):
     DIST = "categorical"
 
     def __init__(self, action_output_dim, device="cpu", soft_max_grid=True, last_input_dim=512, pre=None,
                  nn_dtype=torch.float32):
-        super().__init__(pre=pre, device=device)
+        Actor.__init__(self, pre=pre, device=device)
         self.logits_net = None
         self.action_output_dim = action_output_dim
         self.actor_linear = nn.Linear(last_input_dim, action_output_dim)

@@ -121,3 +121,26 @@ def test_no_gpu_means_loud_failure():
         pytest.skip("GPU present")
     with pytest.raises(DDRLError):
         kernels.gae(torch.zeros(3, 1, 4), torch.zeros(2, 1, 4), torch.zeros(2, 1, 4, dtype=torch.uint8), [0.99], 0.95)
+
+
+def test_actors_are_instances_of_the_reference_classes_when_hosted_by_it():
+    """server/forward.py:140-142 dispatches on isinstance(net.actor, GaussionActor / CategoricalActor) with the REFERENCE's
+    classes: when the reference is the host application (imported first) our actors derive from them -- no patching."""
+    import subprocess
+    import sys
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference not mounted")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import ref_shim; ref_shim.import_reference()\n"
+        "import USTC_lab.nn as R\n"
+        "from ddrl4nav_b200.nn import GaussionActor, CategoricalActor\n"
+        "g = GaussionActor(action_output_dim=2, last_input_dim=512); c = CategoricalActor(6, last_input_dim=512)\n"
+        "assert isinstance(g, R.GaussionActor) and isinstance(c, R.CategoricalActor)\n"
+        "assert not isinstance(g, R.CategoricalActor) and not isinstance(c, R.GaussionActor)\n"
+        "assert [n for n, _ in g.named_parameters()] == ['log_std', 'actor_linear.weight', 'actor_linear.bias']\n"
+        "assert type(g).forward is not R.GaussionActor.forward and type(g).__mro__[1].__module__.startswith('ddrl4nav_b200')\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
