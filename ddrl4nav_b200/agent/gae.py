@@ -38,7 +38,9 @@ def accumulate_rewards(self, experiences: List, rewards_step: np.ndarray) -> Lis
     V, N = values.shape[1], values.shape[2]
     dones = np.broadcast_to(dones.reshape(T, -1, N), (T, V, N))
     rewards = np.broadcast_to(rewards.reshape(T, -1, N), (T, V, N))
-    gae = GAE(np.asarray(self.discounts, dtype=np.float32).reshape(-1), self.landa)
+    # schedule 4 (sequential in t, two env columns per thread): bit-exact with the reference's numpy loop -- an actor's rollout
+    # is a few hundred steps x a few envs, nothing the time-parallel default (<= 3e-7 relative) would speed up
+    gae = GAE(np.asarray(self.discounts, dtype=np.float32).reshape(-1), self.landa, algo=4)
     ret, adv = gae(torch.from_numpy(values).to(dev), torch.from_numpy(np.ascontiguousarray(rewards)).to(dev),
                    torch.from_numpy(np.ascontiguousarray(dones)).to(dev))
     ret, adv = ret.cpu().numpy(), adv.cpu().numpy()

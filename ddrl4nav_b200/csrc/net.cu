@@ -47,6 +47,7 @@ struct Lin {
   float* dwp = nullptr;          // packed weight gradient   (when packed and training)
   int s2d_s = 0, s2d_C = 0, s2d_KH = 0, s2d_KW = 0;   // space-to-depth first layer: packing follows pack_weight_s2d
   bool s2d_fwd_only = false;     // ... for the forward weights only: the weight gradient runs on the im2col matrix (k = c,kh,kw)
+  int seg = 0;                   // backward segment after which this layer's gradient is final (assign_segments)
 };
 
 struct Arena {
@@ -155,7 +156,22 @@ struct ddrl_net {
     cudaGraphNode_t adam_node = nullptr;
     long long launches = 0;
     unsigned long long used = 0;
+    // a body with segment cuts (the backward pass) is a CHAIN of graphs: pre[0], pre[1], ..., then `exec`
+    std::vector<cudaGraph_t> pre_graphs;
+    std::vector<cudaGraphExec_t> pre_execs;
+    std::vector<long long> pre_launches;
   };
+  // segment cuts of the backward pass (seg_cut): while a capture is running each cut closes the current graph and opens the
+  // next, so that a data-parallel learner can hand the gradients that are final after segment k to NCCL while segment k + 1
+  // runs (nn/ppo.py learn).  Outside a capture a cut does nothing and the pass ends with ONE un-permutation of everything.
+  struct Capture {
+    bool active = false, failed = false;
+    int seg = 0;
+    long long l0 = 0;
+    std::vector<cudaGraph_t> done;
+    std::vector<long long> launches;
+  } cap;
+  int n_bwd_seg = 1;               // segments of a captured backward pass (towers + 1)
   std::vector<GraphEntry> graphs;
   unsigned long long graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
@@ -164,6 +180,7 @@ struct ddrl_net {
   // weight preparation as three dependent multi-job launches (prep.cu): [re-packs + amax-slot zeroing] -> [amax + tf32
   // mirrors] -> [fp16 splits]; and the gradient un-permutation that ends a backward pass as one more
   PrepTable prep[3], unprep;
+  std::vector<PrepTable> unprep_seg;   // the gradient un-permutation split by backward segment
   bool prep_ready = false;
   static constexpr int kSide = 8;
   cudaStream_t side[kSide] = {};
@@ -890,9 +907,10 @@ static int repack_emit(ddrl_net* n, cudaStream_t s0, bool par, PhaseFn&& phase_b
   return DDRL_OK;
 }
 
-// gradient un-permutation (packed layout -> reference OIHW / [out, in]) of every packed layer
-static int unpack_emit(ddrl_net* n, cudaStream_t s) {
-  if (n->s2d_train) {
+// gradient un-permutation (packed layout -> reference OIHW / [out, in]) of every packed layer (seg < 0), or of the layers
+// whose gradient is final after backward segment `seg`
+static int unpack_emit(ddrl_net* n, cudaStream_t s, int seg = -1) {
+  if (n->s2d_train && (seg < 0 || seg == n->n_bwd_seg - 1)) {
     const ConvGeom& g = n->towers[0].g[0];
     const float* dw = reinterpret_cast<const float*>(reinterpret_cast<const char*>(n->w0s2d) + n->packed_grad_off);
     for (int k = 0; k < 2; ++k) {
@@ -904,10 +922,38 @@ static int unpack_emit(ddrl_net* n, cudaStream_t s) {
     for (auto& l : t.L)
       if (l.packed) {
         if (n->s2d_train && &l == &t.L[0]) continue;         // done above from the fused space-to-depth gradient
+        if (seg >= 0 && l.seg != seg) continue;
         if (l.s2d_s && !l.s2d_fwd_only) TRY(unpack_grad_s2d(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.s2d_C, l.s2d_KH, l.s2d_KW, l.s2d_s, l.ldw, s));
         else TRY(unpack_grad(l.dwp, n->grads + n->T[l.w_t].offset, l.N, l.I, l.J, l.ldw, s));
       }
   return DDRL_OK;
+}
+
+// Backward segments: tower t's backward is cut once, after the layers that hold most of its parameters (the linear stack on
+// top of the conv stack); what runs before the cut of tower t belongs to segment t, the rest of the tower to segment t + 1, the
+// cross-tower fused first conv (it runs after the last tower) to the last segment.  Segment k's gradients are final -- and
+// un-permuted into the flat buffer -- when segment k ends.
+static int tower_cut_layer(const Tower& t) {
+  switch (t.arch) {
+    case DDRL_ARCH_ATARI: return 3;                                  // fc 3136 -> 512 (6.4 of the tower's 6.7 MB)
+    case DDRL_ARCH_NAV: case DDRL_ARCH_NAVPED: return 3;             // fc2, fc1, fc0 (flat -> 512: 18.9 MB) run first
+    case DDRL_ARCH_NAV1D: return 6;
+    default: return 0;
+  }
+}
+static void assign_segments(ddrl_net* n) {
+  const int T = (int)n->towers.size();
+  n->n_bwd_seg = T + 1;
+  for (int ti = 0; ti < T; ++ti) {
+    Tower& t = n->towers[ti];
+    const int cut = tower_cut_layer(t);
+    for (int li = 0; li < (int)t.L.size(); ++li) {
+      // ATARI / MLP run their layers top down (L.size()-1 .. 0); the nav towers run fc2, fc1, fc0 first (indices >= cut;
+      // NAV1D: 8, 7, 6), then the conv stack and the laser branch
+      t.L[li].seg = li >= cut ? ti : ti + 1;
+      if (li == 0 && (t.fuse_role || n->s2d_train)) t.L[li].seg = T;
+    }
+  }
 }
 
 static bool prep_fused(const ddrl_net* n) {
@@ -919,13 +965,19 @@ static bool prep_fused(const ddrl_net* n) {
 // graph capture -- the first optimiser step and every `dirty` re-preparation go straight to the stream)
 static int prep_build(ddrl_net* n) {
   PrepRecorder rec[3], unrec;
+  assign_segments(n);
+  std::vector<PrepRecorder> unrec_seg(n->n_bwd_seg);
   struct Guard { ~Guard() { g_prep_rec = nullptr; } } guard;
   int rc = repack_emit(n, nullptr, false, [&](int k) { g_prep_rec = &rec[k]; return DDRL_OK; });
   if (rc == DDRL_OK && n->grads) { g_prep_rec = &unrec; rc = unpack_emit(n, nullptr); }
+  for (int k = 0; rc == DDRL_OK && n->grads && k < n->n_bwd_seg; ++k) { g_prep_rec = &unrec_seg[k]; rc = unpack_emit(n, nullptr, k); }
   g_prep_rec = nullptr;
   if (rc != DDRL_OK) return rc;
   for (int k = 0; k < 3; ++k) TRY(n->prep[k].upload(rec[k].jobs));
   TRY(n->unprep.upload(unrec.jobs));
+  for (auto& t : n->unprep_seg) t.clear();
+  n->unprep_seg.assign(n->n_bwd_seg, PrepTable());
+  for (int k = 0; k < n->n_bwd_seg; ++k) TRY(n->unprep_seg[k].upload(unrec_seg[k].jobs));
   n->prep_ready = true;
   return DDRL_OK;
 }
@@ -954,12 +1006,30 @@ static int repack(ddrl_net* n, cudaStream_t s0) {
 }
 
 // ---- CUDA-graph cache ------------------------------------------------------------------
+static void graph_entry_destroy(ddrl_net::GraphEntry& e) {
+  if (e.exec) cudaGraphExecDestroy(e.exec);
+  if (e.graph) cudaGraphDestroy(e.graph);
+  for (auto x : e.pre_execs) cudaGraphExecDestroy(x);
+  for (auto g : e.pre_graphs) cudaGraphDestroy(g);
+}
 static void graphs_clear(ddrl_net* n) {
-  for (auto& e : n->graphs) {
-    if (e.exec) cudaGraphExecDestroy(e.exec);
-    if (e.graph) cudaGraphDestroy(e.graph);
-  }
+  for (auto& e : n->graphs) graph_entry_destroy(e);
   n->graphs.clear();
+}
+// Segment cut of the backward pass (see ddrl_net::Capture): ends segment n->cap.seg.  Inside a capture the gradients of the
+// segment are un-permuted, the current graph is closed and the next one opened; outside it does nothing.
+static int seg_cut(ddrl_net* n, cudaStream_t s) {
+  ddrl_net::Capture& c = n->cap;
+  if (!c.active || c.failed || c.seg >= n->n_bwd_seg - 1 || (int)n->unprep_seg.size() != n->n_bwd_seg) return DDRL_OK;
+  TRY(n->unprep_seg[c.seg].launch("prep_unpack_kernel", s));
+  cudaGraph_t g = nullptr;
+  if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) { c.failed = true; return DDRL_E_CUDA; }
+  c.done.push_back(g);
+  c.launches.push_back(g_launches - c.l0);
+  c.l0 = g_launches;
+  ++c.seg;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { c.failed = true; return DDRL_E_CUDA; }
+  return DDRL_OK;
 }
 static bool graphs_enabled(ddrl_net* n) {
   const char* e = getenv("DDRL_NO_GRAPH");
@@ -986,13 +1056,29 @@ static int run_graphed(ddrl_net* n, const std::string& key, cudaStream_t s, F&& 
     if (!n->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
     TRY(side_init(n));
     const long long l0 = g_launches;
+    ddrl_net::Capture& c = n->cap;
+    c = ddrl_net::Capture();
+    c.l0 = l0;
     DDRL_CUDA(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
+    c.active = true;
     const int rc = body(n->cap_stream);
+    c.active = false;
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &g);
+    ddrl_net::GraphEntry ne;
+    bool ok = rc == DDRL_OK && ce == cudaSuccess && g && !c.failed;
+    for (size_t k = 0; ok && k < c.done.size(); ++k) {
+      cudaGraphExec_t x = nullptr;
+      ok = cudaGraphInstantiate(&x, c.done[k], 0) == cudaSuccess;
+      if (ok) ne.pre_execs.push_back(x);
+    }
     cudaGraphExec_t exec = nullptr;
-    if (rc != DDRL_OK || ce != cudaSuccess || !g || cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) {
+    ok = ok && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess;
+    if (!ok) {
       if (g) cudaGraphDestroy(g);
+      for (auto x : ne.pre_execs) cudaGraphExecDestroy(x);
+      for (auto d : c.done) cudaGraphDestroy(d);
+      c = ddrl_net::Capture();
       cudaGetLastError();
       g_launches = l0;
       n->graphs_off = true;
@@ -1002,13 +1088,14 @@ static int run_graphed(ddrl_net* n, const std::string& key, cudaStream_t s, F&& 
     if (n->graphs.size() >= 8) {             // evict the least recently used entry
       size_t lru = 0;
       for (size_t i = 1; i < n->graphs.size(); ++i) if (n->graphs[i].used < n->graphs[lru].used) lru = i;
-      cudaGraphExecDestroy(n->graphs[lru].exec);
-      cudaGraphDestroy(n->graphs[lru].graph);
+      graph_entry_destroy(n->graphs[lru]);
       n->graphs.erase(n->graphs.begin() + lru);
     }
-    ddrl_net::GraphEntry ne;
     ne.key = key; ne.graph = g; ne.exec = exec;
-    ne.launches = g_launches - l0;
+    ne.pre_graphs = c.done;
+    ne.pre_launches = c.launches;
+    ne.launches = g_launches - c.l0;
+    c = ddrl_net::Capture();
     g_launches = l0;
     n->graphs.push_back(ne);
     e = &n->graphs.back();
@@ -1016,6 +1103,10 @@ static int run_graphed(ddrl_net* n, const std::string& key, cudaStream_t s, F&& 
   e->used = ++n->graph_clock;
   if (out) *out = e;
   else {
+    for (size_t k = 0; k < e->pre_execs.size(); ++k) {
+      DDRL_CUDA(cudaGraphLaunch(e->pre_execs[k], s));
+      g_launches += e->pre_launches[k];
+    }
     DDRL_CUDA(cudaGraphLaunch(e->exec, s));
     g_launches += e->launches;
   }
@@ -1186,6 +1277,7 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
     case DDRL_ARCH_ATARI: {
       // t.dh = dL/dh (linear has no activation); every conv output went through leaky_relu (atari_encoder.py:26-28)
       TRY(lin_bwd(n, t.L[3], b[5], 3136, t.dh, 512, b[6], 3136, 3136, ACT_LEAKY, b[5], mb, s));
+      TRY(seg_cut(n, s));
       TRY(conv_bwd(n, t, 2, 2, b[3], b[4], b[6], b[7], b[8], ACT_LEAKY, mb, s));
       TRY(conv_bwd(n, t, 1, 1, b[1], b[2], b[8], b[7], b[9], ACT_LEAKY, mb, s));
       if (!t.fuse_role) TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], b[9], nullptr, nullptr, 0, mb, s));   // else: fused_conv0_bwd
@@ -1206,6 +1298,7 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
       TRY(lin_bwd(n, t.L[Lfc2], b[10], 512, t.dh, 512, df1, 512, 512, ACT_RELU, b[10], mb, s));
       TRY(lin_bwd(n, t.L[Lfc1], b[9], ldcat, df1, 512, dcat, ldcat, img_off + 512, ACT_RELU, b[9], mb, s));
       TRY(lin_bwd(n, t.L[Lfc0], b[8], flat, dcat + img_off, ldcat, dp3, flat, flat, 0, nullptr, mb, s));
+      TRY(seg_cut(n, s));
       // ReLU' of the conv outputs is folded into pool_bwd (a > 0 test)
       TRY(pool_bwd(dp3, t.idx[2], b[7], dz3, mb, g2->Ho, g2->Wo, 256, s));
       TRY(conv_bwd(n, t, 2, 2, b[5], b[6], dz3, dcols, dp2, 0, mb, s));
@@ -1224,7 +1317,8 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
     }
     case DDRL_ARCH_MLP: {
       TRY(act_bwd(t.dh, t.feat, t.h, t.feat, mb, t.feat, ACT_RELU, s));
-      return lin_bwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.dh, t.feat, nullptr, 0, 0, 0, nullptr, mb, s);
+      TRY(lin_bwd(n, t.L[0], obs[0] + row0 * t.in_ch, t.in_ch, t.dh, t.feat, nullptr, 0, 0, 0, nullptr, mb, s));
+      return seg_cut(n, s);
     }
   }
   return DDRL_E_ARG;
@@ -1397,6 +1491,7 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   graphs_clear(n);
   for (int k = 0; k < 3; ++k) n->prep[k].clear();
   n->unprep.clear();
+  for (auto& t : n->unprep_seg) t.clear();
   if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
   if (n->sumsq_dev) cudaFree(n->sumsq_dev);
   if (n->ws.base) cudaFree(n->ws.base);
@@ -1581,25 +1676,48 @@ static int backward_body(ddrl_net* n, const float* const* obs, int B_local, int 
     if (n->fuse0) TRY(fused_conv0_bwd(n, mb, s));
   }
   // packed weight grads -> reference layout
-  if (prep_fused(n) && n->prep_ready) TRY(n->unprep.launch("prep_unpack_kernel", s));
+  if (n->cap.active && n->cap.seg > 0) TRY(n->unprep_seg[n->cap.seg].launch("prep_unpack_kernel", s));   // earlier segments: at their cuts
+  else if (prep_fused(n) && n->prep_ready) TRY(n->unprep.launch("prep_unpack_kernel", s));
   else TRY(unpack_emit(n, s));
   return DDRL_OK;
 }
 }  // namespace ddrl
 
-extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
-                                 const float* actions, const float* old_logp, const float* adv, const float* returns,
-                                 const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream) {
+// seg < 0: the whole pass.  seg >= 0: segment `seg` only (seg 0 validates, prepares and -- when the pass is not replayable as
+// a graph chain -- runs everything and reports one segment).
+static int backward_impl(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global, const float* actions,
+                         const float* old_logp, const float* adv, const float* returns, const ddrl_ppo_hparams* hp,
+                         int obs_unchanged, int seg, int* nseg_out, cudaStream_t s) {
   if (!n || !hp || B_local < 0 || B_global < B_local || B_global < 1) return DDRL_E_ARG;
   if (!n->params || !n->grads) return DDRL_E_STATE;
-  cudaStream_t s = (cudaStream_t)stream;
+  if (nseg_out) *nseg_out = 1;
   if (B_local == 0) {
+    if (seg > 0) return DDRL_E_ARG;
     DDRL_CUDA(cudaMemsetAsync(n->grads, 0, sizeof(float) * (size_t)(n->P + 8), s));
     if (n->packed_base) DDRL_CUDA(cudaMemsetAsync(n->packed_base + n->packed_grad_off, 0, n->packed_grad_bytes, s));
     return DDRL_OK;
   }
   TRY(check_obs(n, obs, n_obs));
   if (!actions || !old_logp || !adv || !returns) return DDRL_E_ARG;
+  const std::string key = graph_key("bwd", {obs[0], n_obs > 1 ? obs[1] : nullptr, n_obs > 2 ? obs[2] : nullptr, actions, old_logp,
+                                            adv, returns, n->params, n->grads, n->ws.base},
+                                    {B_local, B_global}, hp, sizeof(*hp));
+  auto launch_seg = [&](ddrl_net::GraphEntry* e, int k) {
+    const int pre = (int)e->pre_execs.size();
+    if (k < 0 || k > pre) return (int)DDRL_E_ARG;
+    DDRL_CUDA(cudaGraphLaunch(k < pre ? e->pre_execs[k] : e->exec, s));
+    g_launches += k < pre ? e->pre_launches[k] : e->launches;
+    return (int)DDRL_OK;
+  };
+  if (seg > 0) {
+    // later segments of the chain segment 0 of this very call sequence launched
+    for (auto& g : n->graphs)
+      if (g.key == key) {
+        if (nseg_out) *nseg_out = (int)g.pre_execs.size() + 1;
+        return launch_seg(&g, seg);
+      }
+    return DDRL_E_STATE;
+  }
   const char* ws_before = n->ws.base;
   TRY(ensure_workspace(n, B_local, true));
   if (n->dirty) TRY(repack(n, s));
@@ -1607,16 +1725,43 @@ extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs
   const bool reuse_obs = obs_unchanged && single && ws_before == n->ws.base && n->cols_obs0 == obs[0] && n->cols_rows == B_local;
   n->cols_obs0 = single ? obs[0] : nullptr;
   n->cols_rows = single ? B_local : -1;
-  // iterations 2..10 of one learn call: same launches, same pointers -> one graph launch
+  // iterations 2..10 of one learn call: same launches, same pointers -> one chain of graph launches
   if (reuse_obs && n->extra.empty() && graphs_enabled(n)) {
-    const std::string key = graph_key("bwd", {obs[0], n_obs > 1 ? obs[1] : nullptr, n_obs > 2 ? obs[2] : nullptr, actions, old_logp,
-                                              adv, returns, n->params, n->grads, n->ws.base},
-                                      {B_local, B_global}, hp, sizeof(*hp));
-    return run_graphed(n, key, s, [&](cudaStream_t cs) {
+    ddrl_net::GraphEntry* e = nullptr;
+    TRY(run_graphed(n, key, s, [&](cudaStream_t cs) {
       return backward_body(n, obs, B_local, B_global, actions, old_logp, adv, returns, hp, true, cs);
-    });
+    }, seg < 0 ? nullptr : &e));
+    if (seg < 0 || !e) return DDRL_OK;             // launched whole / capture failed: the body already ran on the stream
+    if (nseg_out) *nseg_out = (int)e->pre_execs.size() + 1;
+    return launch_seg(e, 0);
   }
   return backward_body(n, obs, B_local, B_global, actions, old_logp, adv, returns, hp, reuse_obs, s);
+}
+
+extern "C" int ddrl_net_backward(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
+                                 const float* actions, const float* old_logp, const float* adv, const float* returns,
+                                 const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream) {
+  return backward_impl(n, obs, n_obs, B_local, B_global, actions, old_logp, adv, returns, hp, obs_unchanged, -1, nullptr,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int ddrl_net_backward_segment(ddrl_net* n, const float* const* obs, int n_obs, int B_local, int B_global,
+                                         const float* actions, const float* old_logp, const float* adv, const float* returns,
+                                         const ddrl_ppo_hparams* hp, int obs_unchanged, int segment, int* n_segments,
+                                         void* stream) {
+  if (segment < 0 || !n_segments) return DDRL_E_ARG;
+  return backward_impl(n, obs, n_obs, B_local, B_global, actions, old_logp, adv, returns, hp, obs_unchanged, segment, n_segments,
+                       (cudaStream_t)stream);
+}
+
+// backward segment after which the gradient of parameter tensor `index` is final in the flat gradient buffer
+extern "C" int ddrl_net_tensor_segment(const ddrl_net* n, int index) {
+  if (!n || index < 0 || index >= (int)n->T.size()) return DDRL_E_ARG;
+  if (index == n->t_aw || index == n->t_ab || index == n->t_cw || index == n->t_cb || index == n->t_logstd) return 0;
+  for (auto& t : n->towers)
+    for (auto& l : t.L)
+      if (l.w_t == index || l.b_t == index) return l.seg;
+  return n->n_bwd_seg - 1;
 }
 
 // debugging aid (not part of the public header): copies workspace buffer `idx` of tower `tower` to `out`

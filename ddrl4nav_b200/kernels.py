@@ -5,7 +5,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import PPOHparams, check, current_stream, ptr, require_cuda
+from ._lib import DDRLError, PPOHparams, check, current_stream, ptr, require_cuda
 
 
 def make_hparams(ppo_clip=0.2, dual_clip=3.0, v_coef=1.0, ent_coef=0.05, max_grad_norm=0.5, clip_grad=True,
@@ -38,7 +38,10 @@ def gae(values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, gamma:
     assert rewards.shape[0] >= T and dones.shape[0] >= T and tuple(rewards.shape[1:]) == (V, N)
     ret = torch.empty((T, V, N), dtype=torch.float32, device=values.device)
     adv = torch.empty((T, N), dtype=torch.float32, device=values.device)
-    g = (C.c_float * V)(*[float(x) for x in gamma])
+    gamma = [float(x) for x in gamma]
+    if len(gamma) != V:
+        raise DDRLError("gae: %d discounts for %d value rows (agent/agent.py:79 builds one per value row)" % (len(gamma), V))
+    g = (C.c_float * V)(*gamma)
     check(lib.ddrl_gae_f32(ptr(values), ptr(rewards), ptr(dones), g, float(lam), T, V, N, ptr(ret), ptr(adv), algo,
                            current_stream()), "ddrl_gae_f32")
     return ret, adv
@@ -62,6 +65,11 @@ def gae_tempo(values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, 
     assert rewards.shape[0] >= T and dones.shape[0] >= T and durations.shape[0] >= T and tuple(rewards.shape[1:]) == (V, N)
     tab = [float(x) for x in table]
     assert 1 <= len(tab) <= 101
+    if T > 0:
+        # the reference indexes the table with the duration and raises IndexError outside it (agent/agent.py:151)
+        lo, hi = int(durations[:T].min()), int(durations[:T].max())
+        if lo < 0 or hi >= len(tab):
+            raise IndexError("gae_tempo: durations span [%d, %d] but the discount table has %d entries" % (lo, hi, len(tab)))
     dt = torch.float64 if out_f64 else torch.float32
     ret = torch.empty((T, V, N), dtype=dt, device=values.device)
     adv = torch.empty((T, N), dtype=dt, device=values.device)

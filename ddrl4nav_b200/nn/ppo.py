@@ -72,6 +72,7 @@ class PPO(Basenn):
         self._extra_key = None          # pointers the engine holds for the extra value heads (shared mode)
         self._extra_scratch = None      # per extra head: this iteration's (dw, db), written by the engine
         self._aux = []                  # one value-only engine per extra critic that owns an encoder (unshared mode)
+        self._seg_runs = None           # per backward segment: flat gradient ranges final after it (data-parallel overlap)
 
     # ------------------------------------------------------------------ engine plumbing
     def _encoder(self):
@@ -223,6 +224,7 @@ class PPO(Basenn):
                 p.data = view
                 p.grad = None
         self._flat, self._offsets = flat, offsets
+        self._seg_runs = None
         self._P = P
         check(lib.ddrl_net_bind(h, ptr(flat), ptr(self._grads), ptr(self._m), ptr(self._v)), "ddrl_net_bind")
         # stand-alone encoder calls (enc(states) -> [B, 512]) run on this engine's towers
@@ -346,10 +348,8 @@ class PPO(Basenn):
         dist.broadcast_params(self._flat, src=src, group=self._dp_group)
         self._weights_changed()
 
-    def backward_only(self, states, advs, actions, old_logps, returns, b_global=None, obs_unchanged=False):
-        """forward + fused loss + backward for the local rows; grads (scaled 1/B_global) stay in flat_grads()."""
-        self._ensure_engine()
-        lib = _lib.load()
+    def _bwd_args(self, states, advs, actions, old_logps, returns, b_global, obs_unchanged):
+        """Device-side argument list shared by ddrl_net_backward / ddrl_net_backward_segment (+ the tensors it points into)."""
         keep, arr, n_obs, B = self._obs_ptrs(states)
         dev = self._flat.device
         f = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
@@ -364,8 +364,19 @@ class PPO(Basenn):
             returns = ret
         else:
             returns = rows[0].contiguous()     # data.values is [V,B]; the PPO critic uses row 0 (ppo.py:95)
-        check(lib.ddrl_net_backward(self._h, arr, n_obs, B, int(b_global or B), ptr(actions), ptr(old_logps), ptr(advs),
-                                    ptr(returns), C.byref(self.hp), int(bool(obs_unchanged)), current_stream()), "ddrl_net_backward")
+        args = (self._h, arr, n_obs, B, int(b_global or B), ptr(actions), ptr(old_logps), ptr(advs), ptr(returns),
+                C.byref(self.hp), int(bool(obs_unchanged)))
+        return args, (keep, advs, actions, old_logps, returns, rows), B
+
+    def backward_only(self, states, advs, actions, old_logps, returns, b_global=None, obs_unchanged=False):
+        """forward + fused loss + backward for the local rows; grads (scaled 1/B_global) stay in flat_grads()."""
+        self._ensure_engine()
+        lib = _lib.load()
+        args, held, B = self._bwd_args(states, advs, actions, old_logps, returns, b_global, obs_unchanged)
+        keep, rows = held[0], held[-1]
+        dev = self._flat.device
+        V = len(self._critics)
+        check(lib.ddrl_net_backward(*args, current_stream()), "ddrl_net_backward")
         if V > 1 and self.prenet is not None:
             self._extra_grads_to_params()
         if V > 1 and self.prenet is None and self.gail_critic:
@@ -383,6 +394,66 @@ class PPO(Basenn):
                 p.grad = g.clone() if p.grad is None else p.grad.add_(g)
             self._grads[self._P + 1] += aux._grads[aux._P + 1] / (self._dp_world if self._dp_world > 1 else 1)
         return B
+
+    # ------------------------------------------------------------------ data-parallel learner: all-reduce under the backward
+    def _segment_runs(self, nseg):
+        """Per backward segment k: the contiguous [lo, hi) runs of the flat gradient buffer that are final once segment k has
+        run (ddrl_net_tensor_segment); the loss sums in the tail travel with the last segment."""
+        if self._seg_runs is None or len(self._seg_runs) != nseg:
+            lib = _lib.load()
+            sizes = [p.numel() for _, p in self.named_parameters()]
+            runs = [[] for _ in range(nseg)]
+            for i, (o, sz) in enumerate(zip(self._offsets, sizes)):
+                k = min(max(lib.ddrl_net_tensor_segment(self._h, i), 0), nseg - 1)
+                if runs[k] and runs[k][-1][1] == o:
+                    runs[k][-1][1] = o + sz
+                else:
+                    runs[k].append([o, o + sz])
+            last = runs[nseg - 1]
+            if last and last[-1][1] == self._P:
+                last[-1][1] = self._P + 4
+            else:
+                last.append([self._P, self._P + 4])
+            self._seg_runs = [[(lo, hi) for lo, hi in r] for r in runs]
+        return self._seg_runs
+
+    def _backward_allreduce(self, data, b_global, obs_unchanged):
+        """One iteration's backward + gradient all-reduce of a data-parallel learner.  The backward runs as a chain of
+        segments (ddrl_net_backward_segment); the gradient ranges that are final after segment k go to NCCL (its own stream)
+        while segment k + 1 computes, so only the last segment's small leftovers are reduced in the open.  Falls back to one
+        all-reduce after the whole pass when the pass cannot be cut (first iteration of a learn call, extra critics)."""
+        import torch.distributed as tdist
+        if len(self._critics) > 1 or os.environ.get("DDRL_DP_OVERLAP", "1") == "0":
+            self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global, obs_unchanged)
+            dist.allreduce_grads(self._grads, self._P, self._dp_group)
+            return
+        self._ensure_engine()
+        lib = _lib.load()
+        args, held, _ = self._bwd_args(data.states, data.advs, data.actions, data.old_logps, data.values, b_global, obs_unchanged)
+        nseg = C.c_int(1)
+        works = []
+        k = 0
+        while True:
+            check(lib.ddrl_net_backward_segment(*args, k, C.byref(nseg), current_stream()), "ddrl_net_backward_segment")
+            if nseg.value <= 1:
+                dist.allreduce_grads(self._grads, self._P, self._dp_group)
+                break
+            runs = self._segment_runs(nseg.value)[k]
+            if k == nseg.value - 1 and len(runs) > 1:
+                # the last segment leaves several small ranges: they travel as ONE message
+                parts = [self._grads[lo:hi] for lo, hi in runs]
+                packed = torch.cat(parts)
+                tdist.all_reduce(packed, group=self._dp_group)
+                torch._foreach_copy_(parts, list(packed.split([hi - lo for lo, hi in runs])))
+            else:
+                for lo, hi in runs:
+                    works.append(tdist.all_reduce(self._grads[lo:hi], group=self._dp_group, async_op=True))
+            k += 1
+            if k >= nseg.value:
+                break
+        for w in works:
+            w.wait()
+        del held
 
     def optimizer_step(self):
         lib = _lib.load()
@@ -402,10 +473,11 @@ class PPO(Basenn):
             b_global = dist.global_rows(b_local, self._flat.device, self._dp_group)
         for it in range(self.training_iter_time):
             start_time = time.time()
-            self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global,
-                               obs_unchanged=it > 0)
             if self._dp_world > 1:
-                dist.allreduce_grads(self._grads, self._P, self._dp_group)
+                self._backward_allreduce(data, b_global, obs_unchanged=it > 0)
+            else:
+                self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global,
+                                   obs_unchanged=it > 0)
             loss4 = self.optimizer_step().tolist()          # ONE 16-byte D2H per iteration (reference: four .item())
             self.update_time += 1
             loss_log = {"PpoTotalLoss": loss4[0], "ActorLoss": loss4[1], "VLoss": loss4[2], "EntLoss": loss4[3],

@@ -259,6 +259,16 @@ int ddrl_net_encode(ddrl_net* net, const float* const* obs, int n_obs, int B, in
 int ddrl_net_backward(ddrl_net* net, const float* const* obs, int n_obs, int B_local, int B_global,
                       const float* actions, const float* old_logp, const float* adv, const float* returns,
                       const ddrl_ppo_hparams* hp, int obs_unchanged, void* stream);
+/* The same pass in SEGMENTS, for a data-parallel learner that overlaps the gradient all-reduce with the rest of the
+ * backward (nn/ppo.py:113-123 runs the actor and the critic backward one after the other; server/backward.py:167 "TODO multi
+ * GPU").  Call with segment = 0, 1, ..., *n_segments - 1 in order and the SAME arguments; after segment k returns (stream
+ * order), every parameter tensor i with ddrl_net_tensor_segment(net, i) == k holds its final gradient in the flat buffer
+ * and may be reduced on another stream while segment k + 1 runs.  A pass that cannot be cut (first iteration of a learn
+ * call, micro-batched rows, extra critics) runs whole in segment 0 and reports *n_segments = 1. */
+int ddrl_net_backward_segment(ddrl_net* net, const float* const* obs, int n_obs, int B_local, int B_global,
+                              const float* actions, const float* old_logp, const float* adv, const float* returns,
+                              const ddrl_ppo_hparams* hp, int obs_unchanged, int segment, int* n_segments, void* stream);
+int ddrl_net_tensor_segment(const ddrl_net* net, int index);
 /* second half (nn/ppo.py:115-129): global-norm clip + the two (or one) Adam steps; then refreshes
  * the packed weights.  loss4_out (device, 4 floats, optional) = {total, actor, v, entropy}. */
 int ddrl_net_clip_adam(ddrl_net* net, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream);

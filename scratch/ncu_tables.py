@@ -56,30 +56,46 @@ def hbm(out, files):
                 mt / 1e3, mb / mt if mt else 0))
 
 
+UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
+        "Kbyte/block": 1e3, "byte/block": 1.0, "Mbyte/block": 1e6}
+
+
 def tc(out, path):
+    """--page raw --csv of an `ncu --set full` capture: one row per launch.  The raw page scales every column to its own
+    unit (second header row): durations are normalised to us, byte counts to bytes."""
     hdr, data = rows_of(path)
     units, data = data[0], data[1:]
 
     def col(name):
         return [i for i, h in enumerate(hdr) if h == name or h.endswith("." + name)][0]
-    cols = [("us", "gpu__time_duration.sum", 1e-3), ("tensor pipe active %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 1),
+
+    def val(r, name):
+        i = col(name)
+        try:
+            return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
+        except (ValueError, IndexError):
+            return float("nan")
+    cols = [("us", "gpu__time_duration.sum", 1), ("tensor pipe active %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 1),
+            ("SM busy %", "sm__throughput.avg.pct_of_peak_sustained_elapsed", 1), ("issue slots busy %", "sm__inst_issued.avg.pct_of_peak_sustained_active", 1),
             ("DRAM read MB", "dram__bytes_read.sum", 1e-6), ("DRAM write MB", "dram__bytes_write.sum", 1e-6),
             ("L2->SM MB", "l1tex__m_xbar2l1tex_read_bytes.sum", 1e-6), ("L2 hit %", "lts__t_sector_hit_rate.pct", 1),
             ("grid", "launch__grid_size", 1), ("regs", "launch__registers_per_thread", 1), ("smem KB", "launch__shared_mem_per_block_dynamic", 1e-3)]
+    cols = [c for c in cols if any(h == c[1] or h.endswith("." + c[1]) for h in hdr)]
     ki = col("Kernel Name")
+    tot_b = tot_us = 0.0
     with open(out, "w") as fh:
         fh.write("| # | kernel | " + " | ".join(c[0] for c in cols) + " | L2->SM TB/s | DRAM TB/s |\n")
         fh.write("|---|---|" + "---|" * (len(cols) + 2) + "\n")
         for i, r in enumerate(data):
-            vals = []
-            for _, c, sc in cols:
-                try:
-                    vals.append(float(r[col(c)].replace(",", "")) * sc)
-                except (ValueError, IndexError):
-                    vals.append(float("nan"))
-            us = vals[0]
-            fh.write("| %d | `%s` | " % (i, short(r[ki])) + " | ".join("%.1f" % v for v in vals) +
-                     " | %.2f | %.2f |\n" % (vals[4] / us, (vals[2] + vals[3]) / us))
+            vals = {c[0]: val(r, c[1]) * c[2] for c in cols}
+            us = vals["us"]
+            dram = vals["DRAM read MB"] + vals["DRAM write MB"]
+            tot_b += dram
+            tot_us += us
+            fh.write("| %d | `%s` | " % (i, short(r[ki])) + " | ".join("%.1f" % vals[c[0]] for c in cols) +
+                     " | %.2f | %.2f |\n" % (vals["L2->SM MB"] / us, dram / us))
+        fh.write("\n%d launches: %.1f us in total (serialised, cold cache), DRAM read+write %.1f MB in total = %.1f MB per launch\n" %
+                 (len(data), tot_us, tot_b, tot_b / max(len(data), 1)))
 
 
 def launch_list(out, path):

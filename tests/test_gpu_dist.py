@@ -20,7 +20,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, B, q):
+def _worker(rank, world, port, B, q, kind="pong", overlap="1", iters=2):
+    import os
+    os.environ["DDRL_DP_OVERLAP"] = overlap
     import torch.distributed as tdist
     from ddrl4nav_b200 import dist
     from ddrl4nav_b200.data import Experience
@@ -28,11 +30,11 @@ def _worker(rank, world, port, B, q):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     tdist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=dev)
-    spec = R.SPECS["pong"]
+    spec = R.SPECS[kind]
     params = R.init_params(spec, seed=3)
-    states = R.synth_states("pong", B, seed=4)
+    states = R.synth_states(kind, B, seed=4)
     a, old, adv, ret = R.synth_learn_batch(spec, params, states, seed=5)
-    net = make_net("pong", device=None, TRAINING_ITER_TIME=2)
+    net = make_net(kind, device=None, TRAINING_ITER_TIME=iters)
     net.load_state_dict(params if rank == 0 else R.init_params(spec, seed=99))   # rank 1 starts different on purpose
     net = net.to(dev)
     net.enable_data_parallel()
@@ -45,7 +47,7 @@ def _worker(rank, world, port, B, q):
     flat = net._flat.detach().cpu()
     if rank == 0:
         # single-GPU full batch on the same device
-        ref = make_net("pong", device=None, TRAINING_ITER_TIME=2)
+        ref = make_net(kind, device=None, TRAINING_ITER_TIME=iters)
         ref.load_state_dict(params)
         ref = ref.to(dev)
         full = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
@@ -60,11 +62,15 @@ def _worker(rank, world, port, B, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_learn_equals_single_gpu():
+@pytest.mark.parametrize("kind,B,overlap,iters", [("pong", 16, "1", 2), ("pong", 16, "0", 2), ("pong", 37, "1", 4), ("navimg", 11, "1", 3),
+                                                  ("navlaser", 6, "1", 3)])
+def test_two_gpu_learn_equals_single_gpu(kind, B, overlap, iters):
+    """overlap = "1": iterations 2.. run the backward as a chain of segments and reduce each segment's gradient ranges on
+    the NCCL stream while the next segment computes (PPO._backward_allreduce); "0": one all-reduce after the whole pass."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 16, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q, kind, overlap, iters)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(2)]
@@ -73,9 +79,11 @@ def test_two_gpu_learn_equals_single_gpu():
     r0 = [g for g in got if g[0] != "rank1"][0]
     r1 = [g for g in got if g[0] == "rank1"][0]
     logs, rlogs, flat0, flat_ref = r0
-    for l, r in zip(logs, rlogs):
+    assert len(logs) == iters
+    for i, (l, r) in enumerate(zip(logs, rlogs)):
+        tol = 2e-5 if i < 2 else 2e-3         # later iterations inherit Adam's sign-like first steps on noise-level gradients
         for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss"):
-            assert abs(l[k] - r[k]) <= 2e-5 * max(1.0, abs(r[k])), (k, l[k], r[k])
+            assert abs(l[k] - r[k]) <= tol * max(1.0, abs(r[k])), (i, k, l[k], r[k])
     assert np.array_equal(flat0, r1[1])                       # replicas stay bit-identical
     d = np.abs(flat0 - flat_ref)
-    assert (d > 3e-4).mean() < 1e-3                           # Adam step-1 sign flips on noise-level grads only
+    assert (d > 3e-4 * iters).mean() < 1e-3                   # Adam step-1 sign flips on noise-level grads only

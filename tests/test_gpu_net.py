@@ -282,6 +282,53 @@ def test_graph_replay_matches_stream_launches(monkeypatch, kind, B):
     assert float((p_graph - p_eager).abs().max()) < 5 * 1e-3 * 5      # <= (steps x largest lr) apart anywhere
 
 
+@pytest.mark.parametrize("kind,B", [("pong", 21), ("navimg", 9), ("navlaser", 5)])
+def test_backward_segments_finalise_their_gradient_ranges(kind, B):
+    """ddrl_net_backward_segment (the data-parallel learner's overlap hook): the chain of segments equals the whole pass, and
+    the flat-gradient ranges reported for segment k (ddrl_net_tensor_segment) already hold their FINAL values when segment k
+    has run -- so a reduction of those ranges may overlap segment k + 1."""
+    import ctypes as C
+    from ddrl4nav_b200 import _lib
+    from ddrl4nav_b200._lib import check, current_stream
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    net, _, _ = make(kind)
+    ds = [s.to(DEV) for s in states]
+    dv = [t.to(DEV) for t in (adv, a, old, ret)]
+    net.backward_only(ds, dv[0], dv[1], dv[2], dv[3])                       # stream launches; stages the observations
+    g_whole = net.flat_grads().clone()
+    lib = _lib.load()
+    args, held, _ = net._bwd_args(ds, dv[0], dv[1], dv[2], dv[3], None, True)
+    nseg = C.c_int(0)
+    for rep in range(2):                                                      # capture + first launch, then replay
+        snaps = []
+        k = 0
+        while True:
+            check(lib.ddrl_net_backward_segment(*args, k, C.byref(nseg), current_stream()), "segment")
+            snaps.append(net._grads.clone())
+            k += 1
+            if k >= nseg.value:
+                break
+        final = snaps[-1]
+        assert rel_err(final[:net._P], g_whole) < 5e-6
+        if GEMM_MODE == "simt" and nseg.value == 1:
+            continue
+        assert nseg.value == (2 if spec.shared else 3), nseg.value
+        runs = net._segment_runs(nseg.value)
+        covered = torch.zeros(net._P + 4, dtype=torch.bool)
+        for k, rk in enumerate(runs):
+            for lo, hi in rk:
+                assert not covered[lo:hi].any()
+                covered[lo:hi] = True
+                assert torch.equal(snaps[k][lo:hi], final[lo:hi]), (kind, k, lo, hi)
+        assert covered.all()
+        # the big linear layers are final before the last segment (that is what makes the overlap worth it)
+        early = sum(hi - lo for rk in runs[:-1] for lo, hi in rk)
+        assert early > 0.6 * net._P
+    # the plain entry point replays the same chain
+    net.backward_only(ds, dv[0], dv[1], dv[2], dv[3], obs_unchanged=True)
+    assert rel_err(net.flat_grads(), g_whole) < 5e-6
+
+
 def test_micro_batching_equals_single_shot(monkeypatch):
     spec, params, states, a, old, adv, ret = _learn_case("pong", 21)
     net, _, _ = make("pong")
