@@ -233,9 +233,14 @@ def run_ours(args):
     lib = _lib.load()
 
     net = make_net(args.workload, device=dev, gemm_mode=args.gemm_mode, TRAINING_ITER_TIME=ITERS)
+    collective = "none (1 GPU)"
     if dist is not None:
         net.enable_data_parallel()
         net.broadcast_parameters(0)
+        collective = ("own peer-memory all-reduce kernel (NVSwitch multicast)" if net._peer and net._peer["mc"] else
+                      "own peer-memory all-reduce kernel (peer loads/stores)" if net._peer else "NCCL all_reduce")
+        if os.environ.get("DDRL_DP_OVERLAP") == "1":
+            collective = "NCCL all_reduce per backward segment, under the backward"
     # ---- synthetic rollout shard of this rank (different rows per rank), host + device copies
     states_h, adv_h, ret_h = synth_batch_host(args.workload, B, seed=100 + rank)
     states_d = [s.to(dev) for s in states_h]
@@ -445,7 +450,7 @@ def run_ours(args):
                 args.gemm_mode, "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B * world, "iters_per_step": ITERS,
-                       "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode,
+                       "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode, "collective": collective,
                        "l2": "inputs larger than L2 (%.0f MB observations per GPU)" % (B * wl["obs_bytes"] / 1e6)},
             "e2e": {"value": round(e2e_value, 1), "unit": "learner sample-iterations/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 16 * ITERS},

@@ -44,6 +44,13 @@ inline void prof_work(double w) { if (g_prof_on) g_prof_work = w; }
     if (::ddrl::g_prof_on) ::ddrl::prof_record(name);             \
   } while (0)
 
+// function attributes (dynamic shared-memory opt-in) are per DEVICE: a once-per-process flag would leave a second GPU of the
+// same process unconfigured ("invalid argument" at its first launch)
+inline int current_device_index() {
+  int d = 0;
+  return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64 ? d : 0;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

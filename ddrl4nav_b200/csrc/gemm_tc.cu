@@ -410,7 +410,8 @@ bool gemm_tc_supported(int form, int M, int N, int K, const float* A, int lda, c
 template <int BN>
 static int launch_tc(int form, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
-  static bool attr_done[3] = {false, false, false};
+  static bool attr_done_dev[64][3] = {};
+  bool* attr_done = attr_done_dev[current_device_index()];
 #define TC_LAUNCH(AMN, BMN)                                                                                              \
   do {                                                                                                                   \
     if (!attr_done[form]) {                                                                                              \

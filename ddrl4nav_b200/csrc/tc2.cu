@@ -651,7 +651,8 @@ template <int BN, int MODE, bool B_MN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const Tc2Args& g, dim3 grid,
                    cudaStream_t s, const CUtensorMap* ta2 = nullptr) {
   using Cfg = T2Cfg<BN>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device_index()];
   if (!attr_done) {
     DDRL_CUDA(cudaFuncSetAttribute(tc2_kernel<BN, MODE, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;

@@ -635,7 +635,8 @@ struct Tc3Maps { CUtensorMap a, bhi, blo, a2, c, c2; };
 template <int BN>
 static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s) {
   using Cfg = T3Cfg<BN>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device_index()];
   if (!attr_done) {
     DDRL_CUDA(cudaFuncSetAttribute(tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
@@ -1163,7 +1164,8 @@ template <int BN>
 static int launch3w(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2, const Tc3Args& g,
                     dim3 grid, cudaStream_t s) {
   using Cfg = T3WCfg<BN>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device_index()];
   if (!attr_done) {
     DDRL_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;

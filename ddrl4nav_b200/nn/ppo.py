@@ -15,6 +15,7 @@ buffers of the same layout, so the data-parallel learner all-reduces one buffer 
 clip+Adam kernel walks it once.  No autograd graph is ever built.
 """
 import ctypes as C
+import functools
 import os
 import time
 
@@ -26,6 +27,19 @@ from torch.distributions.normal import Normal
 from .. import _lib, dist, kernels
 from .._lib import DDRLError, NetDesc, check, current_stream, ptr
 from .base import Basenn
+
+
+def _on_device(fn):
+    """Engine calls run with the NET's device current: the C ABI allocates and launches on the current device, and
+    current_stream() is the current device's stream -- a net on cuda:1 must not depend on the caller's set_device."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        p = next(self.parameters(), None)
+        if p is None or p.device.type != "cuda":
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(p.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 def _cfg(obj, name, default):
@@ -72,6 +86,8 @@ class PPO(Basenn):
         self._extra_key = None          # pointers the engine holds for the extra value heads (shared mode)
         self._extra_scratch = None      # per extra head: this iteration's (dw, db), written by the engine
         self._aux = []                  # one value-only engine per extra critic that owns an encoder (unshared mode)
+        self._peer = None               # peer-memory all-reduce state (enable_data_parallel)
+        self._peer_error = None
         self._seg_runs = None           # per backward segment: flat gradient ranges final after it (data-parallel overlap)
 
     # ------------------------------------------------------------------ engine plumbing
@@ -210,7 +226,10 @@ class PPO(Basenn):
         with torch.cuda.device(dev):
             flat = torch.empty(P, dtype=torch.float32, device=dev)
             old_m, old_v = self._m, self._v
-            self._grads = torch.zeros(P + 8, dtype=torch.float32, device=dev)
+            if self._peer is not None and self._peer["grads"].numel() == P + 8 and self._peer["grads"].device == dev:
+                self._grads = self._peer["grads"].zero_()      # the symmetric-memory buffer the peer all-reduce works on
+            else:
+                self._grads = torch.zeros(P + 8, dtype=torch.float32, device=dev)
             self._m = torch.zeros(P, dtype=torch.float32, device=dev)
             self._v = torch.zeros(P, dtype=torch.float32, device=dev)
             if old_m is not None and old_m.numel() == P:       # keep Adam state across a .to()/re-flatten
@@ -279,6 +298,7 @@ class PPO(Basenn):
         return keep, arr, n_obs, B
 
     # ------------------------------------------------------------------ Forward module
+    @_on_device
     def act(self, states, draw=None, play_mode=False, want_pi=False):
         """Fused compute body of ForwardThread.run (server/forward.py:128-146).
 
@@ -310,6 +330,7 @@ class PPO(Basenn):
         out = (actions, logps, values.view(V, B, 1))
         return out + (pi,) if want_pi else out
 
+    @_on_device
     def encode(self, states, tower=0):
         """Features [B, feat] of one encoder tower (0 = prenet / actor.pre, 1 = critic.pre): the stand-alone encoder
         forward of the reference (nn/atari_encoder.py:25-32, nn/nav_encoder.py:35-43,115-128)."""
@@ -335,14 +356,70 @@ class PPO(Basenn):
         return (pi, log_p), [values[k].view(-1, 1) for k in range(values.shape[0])]
 
     # ------------------------------------------------------------------ Backward module
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, collective=None):
         """Shard each full-batch iteration over the ranks of `group` (one process per GPU): local grads are
-        pre-scaled by 1/B_global, one NCCL all-reduce(sum) of the flat grad buffer (+ loss sums) per
-        iteration, then the identical fused clip+Adam on every rank (ddrl4nav_b200/dist.py)."""
+        pre-scaled by 1/B_global, one all-reduce(sum) of the flat grad buffer (+ loss sums) per iteration, then the
+        identical fused clip+Adam on every rank (ddrl4nav_b200/dist.py).
+
+        collective: "peer" (default; DDRL_DP_COLLECTIVE) = this library's own all-reduce kernel over NVLink / NVSwitch peer
+        memory (ddrl_peer_allreduce_f32: the gradient buffer moves into symmetric memory; NVSwitch multicast reduces in the
+        switch); "nccl" = torch.distributed's all_reduce.  Falls back to "nccl" -- on every rank together -- when symmetric
+        memory cannot be set up (CPU groups, no peer access)."""
         import torch.distributed as tdist
         self._dp_group = group if group is not None else tdist.group.WORLD
         self._dp_world = tdist.get_world_size(self._dp_group)
+        self._peer = None
+        collective = collective or os.environ.get("DDRL_DP_COLLECTIVE", "peer")
+        if self._dp_world > 1 and collective == "peer":
+            self._setup_peer_allreduce()
 
+    @_on_device
+    def _setup_peer_allreduce(self):
+        import torch.distributed as tdist
+        self._ensure_engine()
+        lib = _lib.load()
+        dev = self._flat.device
+        ok, st = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            if self._dp_world > 8:
+                raise DDRLError("the peer all-reduce covers the GPUs of one box (<= 8 ranks)")
+            g = symm_mem.empty(self._P + 8, dtype=torch.float32, device=dev)
+            f = symm_mem.empty(lib.ddrl_peer_allreduce_flag_bytes() // 4, dtype=torch.int32, device=dev)
+            g.zero_()
+            f.zero_()
+            hg = symm_mem.rendezvous(g, self._dp_group)
+            hf = symm_mem.rendezvous(f, self._dp_group)
+            W = self._dp_world
+            st = dict(grads=g, flags=f, handles=(hg, hf), rank=int(hg.rank), world=W, seq=0,
+                      bufs=(C.c_void_p * W)(*[int(p) for p in hg.buffer_ptrs]),
+                      flag_ptrs=(C.c_void_p * W)(*[int(p) for p in hf.buffer_ptrs]),
+                      mc=C.c_void_p(int(hg.multicast_ptr)) if int(hg.multicast_ptr or 0) and os.environ.get("DDRL_DP_MULTICAST", "1") != "0" else None)
+        except Exception as e:  # noqa: BLE001
+            ok, self._peer_error = 0, repr(e)
+        # all ranks take the same path: one rank without symmetric memory sends everybody to NCCL
+        t = torch.tensor([ok], dtype=torch.int32, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MIN, group=self._dp_group)       # also orders the zeroed flags before any kernel
+        torch.cuda.synchronize(dev)
+        if int(t.item()) != 1:
+            return
+        st["grads"].copy_(self._grads)
+        self._grads = st["grads"]
+        check(lib.ddrl_net_bind(self._h, ptr(self._flat), ptr(self._grads), ptr(self._m), ptr(self._v)), "ddrl_net_bind")
+        self._peer = st
+
+    def _allreduce_grads(self):
+        """Sum of grads[0 : P+4] over the ranks, in place: the peer-memory kernel when the buffer is symmetric, else NCCL."""
+        st = self._peer
+        if st is not None and st["grads"] is self._grads:
+            st["seq"] += 1
+            count = (self._P + 4 + 3) // 4 * 4                 # the buffer holds P + 8 floats
+            check(_lib.load().ddrl_peer_allreduce_f32(st["bufs"], st["mc"], st["flag_ptrs"], st["rank"], st["world"], 0, count,
+                                                      st["seq"], current_stream()), "ddrl_peer_allreduce_f32")
+        else:
+            dist.allreduce_grads(self._grads, self._P, self._dp_group)
+
+    @_on_device
     def broadcast_parameters(self, src=0):
         self._ensure_engine()
         dist.broadcast_params(self._flat, src=src, group=self._dp_group)
@@ -368,6 +445,7 @@ class PPO(Basenn):
                 C.byref(self.hp), int(bool(obs_unchanged)))
         return args, (keep, advs, actions, old_logps, returns, rows), B
 
+    @_on_device
     def backward_only(self, states, advs, actions, old_logps, returns, b_global=None, obs_unchanged=False):
         """forward + fused loss + backward for the local rows; grads (scaled 1/B_global) stay in flat_grads()."""
         self._ensure_engine()
@@ -417,15 +495,20 @@ class PPO(Basenn):
             self._seg_runs = [[(lo, hi) for lo, hi in r] for r in runs]
         return self._seg_runs
 
+    @_on_device
     def _backward_allreduce(self, data, b_global, obs_unchanged):
-        """One iteration's backward + gradient all-reduce of a data-parallel learner.  The backward runs as a chain of
-        segments (ddrl_net_backward_segment); the gradient ranges that are final after segment k go to NCCL (its own stream)
-        while segment k + 1 computes, so only the last segment's small leftovers are reduced in the open.  Falls back to one
-        all-reduce after the whole pass when the pass cannot be cut (first iteration of a learn call, extra critics)."""
+        """One iteration's backward + gradient all-reduce of a data-parallel learner.
+
+        Default: the whole backward, then ONE launch of the peer-memory all-reduce kernel (_allreduce_grads).
+        DDRL_DP_OVERLAP=1: the backward runs as a chain of segments (ddrl_net_backward_segment); the gradient ranges that are
+        final after segment k go to NCCL (its own stream) while segment k + 1 computes, so only the last segment's small
+        leftovers are reduced in the open.  Measured on 2 B200s (profiles/r2x_*): no gain -- every kernel of this engine is
+        one wave of 148 CTAs with statically assigned tiles, so the SMs NCCL's CTAs occupy stretch the kernel they overlap by
+        the collective's own duration; kept as an option for boxes where the collective is the larger term."""
         import torch.distributed as tdist
-        if len(self._critics) > 1 or os.environ.get("DDRL_DP_OVERLAP", "1") == "0":
+        if len(self._critics) > 1 or os.environ.get("DDRL_DP_OVERLAP", "0") != "1":
             self.backward_only(data.states, data.advs, data.actions, data.old_logps, data.values, b_global, obs_unchanged)
-            dist.allreduce_grads(self._grads, self._P, self._dp_group)
+            self._allreduce_grads()
             return
         self._ensure_engine()
         lib = _lib.load()
@@ -436,7 +519,7 @@ class PPO(Basenn):
         while True:
             check(lib.ddrl_net_backward_segment(*args, k, C.byref(nseg), current_stream()), "ddrl_net_backward_segment")
             if nseg.value <= 1:
-                dist.allreduce_grads(self._grads, self._P, self._dp_group)
+                self._allreduce_grads()
                 break
             runs = self._segment_runs(nseg.value)[k]
             if k == nseg.value - 1 and len(runs) > 1:
@@ -455,6 +538,7 @@ class PPO(Basenn):
             w.wait()
         del held
 
+    @_on_device
     def optimizer_step(self):
         lib = _lib.load()
         self._adam_step += 1

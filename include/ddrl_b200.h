@@ -269,6 +269,17 @@ int ddrl_net_backward_segment(ddrl_net* net, const float* const* obs, int n_obs,
                               const float* actions, const float* old_logp, const float* adv, const float* returns,
                               const ddrl_ppo_hparams* hp, int obs_unchanged, int segment, int* n_segments, void* stream);
 int ddrl_net_tensor_segment(const ddrl_net* net, int index);
+/* Gradient all-reduce (sum) of a data-parallel learner over NVLink / NVSwitch peer memory, as ONE kernel of this library
+ * (the reference is single-device: server/backward.py:167 "TODO multi GPU"; nn/ppo.py:113-129 is the step it feeds).
+ * peer_bufs[p]: rank p's buffer as mapped into THIS process (peer_bufs[rank] = the local one); multicast_buf: the NVSwitch
+ * multicast address of the same buffers, or NULL (plain peer loads / stores); peer_flags[p]: rank p's barrier-flag block
+ * (ddrl_peer_allreduce_flag_bytes() bytes, zeroed once, used by nothing else).  Reduces elements [offset, offset + count)
+ * (both multiples of 4) in place on every rank: rank r owns slice r, reduces it once and stores the result to all ranks,
+ * so replicas hold identical bits.  seq: strictly increasing per call (> 0), identical on all ranks.  Every rank of the
+ * group must make the same call; the kernel spins until its peers arrive. */
+int ddrl_peer_allreduce_flag_bytes(void);
+int ddrl_peer_allreduce_f32(float* const* peer_bufs, float* multicast_buf, void* const* peer_flags, int rank, int world,
+                            int64_t offset, int64_t count, uint32_t seq, void* stream);
 /* second half (nn/ppo.py:115-129): global-norm clip + the two (or one) Adam steps; then refreshes
  * the packed weights.  loss4_out (device, 4 floats, optional) = {total, actor, v, entropy}. */
 int ddrl_net_clip_adam(ddrl_net* net, int step, const ddrl_ppo_hparams* hp, float* loss4_out, void* stream);
