@@ -23,7 +23,7 @@ struct AdamSegs {
   int n;
 };
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out, DetSeq det) {
   __shared__ double scratch[32];
   double acc = 0.0;
   const long long n4 = n >> 2;
@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += (double)(g[i] * g[i]);
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) {
+    if (det.ctr) det_enter(det.ctr, blockIdx.x);
+    atomicAdd(out, acc);
+    if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
+  }
 }
 
 struct AdamScalars {
@@ -136,8 +140,9 @@ int clip_adam_launch(float* params, const float* grads, float* m, float* v, long
   AdamScalars sc;
   adam_host_scalars(seg_begin, seg_lr, nseg, step, hp, segs, sc);
   DDRL_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), s));
-  const int blocks = (int)std::min<long long>(ceil_div64(n, 256 * 4), 4 * kNumSMs);
-  sumsq_kernel<<<blocks, 256, 0, s>>>(grads, n, sumsq_scratch);
+  const DetSeq det = det_seq(1);
+  const int blocks = (int)std::min<long long>(ceil_div64(n, 256 * 4), det.ctr ? kDetMaxParts : 4 * kNumSMs);
+  sumsq_kernel<<<blocks, 256, 0, s>>>(grads, n, sumsq_scratch, det);
   prof_work(4.0 * n);
   DDRL_LAUNCHED("sumsq_kernel");
   const int blocks2 = (int)std::min<long long>(ceil_div64(n, 256 * 4), 8 * kNumSMs);

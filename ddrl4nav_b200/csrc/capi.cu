@@ -12,6 +12,26 @@ namespace ddrl {
 thread_local char g_cuda_err[256] = {0};
 long long g_launches = 0;
 
+// ---- deterministic mode ------------------------------------------------------------------
+bool g_deterministic = [] { const char* e = getenv("DDRL_DETERMINISTIC"); return e && e[0] == '1'; }();
+static unsigned int* g_det_pool[64] = {};
+static size_t g_det_next[64] = {};
+constexpr size_t kDetPool = 1 << 16;
+unsigned int* det_counters(int n) {
+  const int dev = current_device_index();
+  if (n < 1 || (size_t)n > kDetPool) return nullptr;
+  if (!g_det_pool[dev]) {
+    if (cudaMalloc(&g_det_pool[dev], kDetPool * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_det_pool[dev], 0, kDetPool * sizeof(unsigned int));
+  }
+  // round robin: counters reset themselves when their chain completes, and a range comes round again only after 65536
+  // later counters have been handed to kernels that run after this one (stream order)
+  if (g_det_next[dev] + n > kDetPool) g_det_next[dev] = 0;
+  unsigned int* p = g_det_pool[dev] + g_det_next[dev];
+  g_det_next[dev] += n;
+  return p;
+}
+
 // ---- per-kernel-class device timing ------------------------------------------------------
 bool g_prof_on = false;
 double g_prof_work = 0.0;
@@ -43,6 +63,12 @@ void prof_record(const char* name) {
 }  // namespace ddrl
 
 extern "C" int ddrl_version(void) { return 100; }
+
+extern "C" int ddrl_set_deterministic(int on) {
+  const int was = ddrl::g_deterministic ? 1 : 0;
+  ddrl::g_deterministic = on != 0;
+  return was;
+}
 
 extern "C" const char* ddrl_error_string(int code) {
   switch (code) {

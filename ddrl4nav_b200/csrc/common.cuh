@@ -81,6 +81,32 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return v;
 }
 
+// ---- deterministic mode (ddrl_set_deterministic / DDRL_DETERMINISTIC=1) ----------------------------------------------------
+// Every cross-block floating-point accumulation of the tc3 path (split-K weight gradients, bias gradients, loss sums, the
+// gradient norm) adds its block partials with atomicAdd: the ORDER of those adds, hence the last bits of the sum, changes
+// from run to run.  In deterministic mode the blocks that add to the same destination take turns in block order: block
+// `rank` waits until the destination's turn counter reads `rank`, adds, passes the turn on (the last one resets it).  Blocks
+// are dispatched in linear block-id order and the reduction dimension is never the fastest grid dimension, so the block a
+// waiter waits for is always resident or done.  Launchers cap the number of parts (chain length) in this mode.
+struct DetSeq { unsigned int* ctr; };          // ctr == nullptr: unordered atomics (default)
+extern bool g_deterministic;
+unsigned int* det_counters(int n);             // n zeroed, self-cleaning turn counters (device pointer; nullptr on failure)
+inline DetSeq det_seq(int n) { DetSeq d{nullptr}; if (g_deterministic) d.ctr = det_counters(n); return d; }
+constexpr int kDetMaxParts = 64;
+
+__device__ __forceinline__ void det_enter(unsigned int* c, unsigned int rank) {      // ONE thread; follow with a block barrier
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    if (v != rank) __nanosleep(32);
+  } while (v != rank);
+}
+__device__ __forceinline__ void det_leave(unsigned int* c, unsigned int rank, unsigned int nparts) {   // after a block barrier; ONE thread
+  __threadfence();
+  const unsigned int nxt = rank + 1 == nparts ? 0u : rank + 1;
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c), "r"(nxt) : "memory");
+}
+
 // streaming (read-once) loads/stores: keep L1 clean for the data that is reused
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;

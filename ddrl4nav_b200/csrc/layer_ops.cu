@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(float* __restrict__ dy, in
 
 // ---------------------------------------------------------------- bias gradient: db[n] += sum_rows dy[r, n]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int ld, long long rows, int N,
-                                                     float* __restrict__ db, long long rows_per_block) {
+                                                     float* __restrict__ db, long long rows_per_block, DetSeq det) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int n = blockIdx.x * 32 + tx;
@@ -297,14 +297,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += part[k][tx];
-    atomicAdd(db + n, s);
+    part[0][tx] = s;
+  }
+  // deterministic mode: the row blocks of one column group add in block order (turn counter per blockIdx.x)
+  if (det.ctr && threadIdx.x == 0) det_enter(det.ctr + blockIdx.x, blockIdx.y);
+  __syncthreads();
+  if (ty == 0 && n < N) atomicAdd(db + n, part[0][tx]);
+  if (det.ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) det_leave(det.ctr + blockIdx.x, blockIdx.y, gridDim.y);
   }
 }
 
 // float4 variant: thread = (row lane, 4 columns); 4 rows in flight per thread; N % 4 == 0, N <= 1024, 16-byte aligned rows
 __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__ dy, int ld4, long long rows, int n4,
                                                       float* __restrict__ db, long long rows_per_block,
-                                                      float* __restrict__ db2, int split4) {
+                                                      float* __restrict__ db2, int split4, DetSeq det) {
   __shared__ float4 part[256];
   const int ry = 256 / n4;                                // row lanes per block (n4 is a power-of-two divisor of 256 or < 256)
   const int tx = threadIdx.x % n4, ty = threadIdx.x / n4;
@@ -324,6 +332,7 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__
     }
   }
   part[threadIdx.x] = acc;
+  if (det.ctr && threadIdx.x == 0) det_enter(det.ctr, blockIdx.x);      // deterministic mode: row blocks add in block order
   __syncthreads();
   if (ty == 0) {
     float4 sum = part[tx];
@@ -335,6 +344,10 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__
     float* out = (db2 != nullptr && tx >= split4) ? db2 + 4 * (tx - split4) : db + 4 * tx;
     atomicAdd(out, sum.x); atomicAdd(out + 1, sum.y);
     atomicAdd(out + 2, sum.z); atomicAdd(out + 3, sum.w);
+  }
+  if (det.ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
 
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
 // dW[n, k] += sum_b dy[b, n] * x[b, k] ; db[n] += sum_b dy[b, n].  grid = (ceil(K/256), row chunks, N)
 __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x,
                                                            int ldx, int B, int N, int K, float* __restrict__ dW,
-                                                           float* __restrict__ db, int rows_per_block) {
+                                                           float* __restrict__ db, int rows_per_block, DetSeq det) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(B, r0 + rows_per_block);
@@ -404,8 +417,20 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
       acc = fmaf(d, x[(size_t)r * ldx + k], acc);
       accb += d;
     }
+  }
+  // deterministic mode: the row chunks of one (k block, n) add in chunk order
+  unsigned int* turn = det.ctr ? det.ctr + (size_t)blockIdx.z * gridDim.x + blockIdx.x : nullptr;
+  if (turn) {
+    if (threadIdx.x == 0) det_enter(turn, blockIdx.y);
+    __syncthreads();
+  }
+  if (k < K) {
     atomicAdd(dW + (size_t)n * K + k, acc);
     if (db && k == 0) atomicAdd(db + n, accb);
+  }
+  if (turn) {
+    __syncthreads();
+    if (threadIdx.x == 0) det_leave(turn, blockIdx.y, gridDim.y);
   }
 }
 
@@ -531,7 +556,7 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(const float4* __restrict_
 }
 template <int K4, int NC4>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
-                                                         float* __restrict__ dW, int ldw, long long M, int K) {
+                                                         float* __restrict__ dW, int ldw, long long M, int K, DetSeq det) {
   constexpr int RL = 256 / NC4;
   __shared__ float red[NC4 * 4 * K4 * 4];
   const int c4 = threadIdx.x % NC4, rl = threadIdx.x / NC4;
@@ -591,9 +616,17 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restric
     }
     __syncthreads();
   }
+  if (det.ctr) {                                         // deterministic mode: the blocks add in block order
+    if (threadIdx.x == 0) det_enter(det.ctr, blockIdx.x);
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < NV; i += 256) {
     const int n = i / (K4 * 4), k = i % (K4 * 4);
     if (k < K) atomicAdd(dW + (size_t)n * ldw + k, red[i]);
+  }
+  if (det.ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
 
@@ -693,20 +726,22 @@ int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaSt
   if (N % 4 == 0 && ld % 4 == 0 && N <= 1024 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
     const int n4 = N / 4;
     const int ry = std::max(1, 256 / n4);
-    long long chunks = std::max<long long>(1, std::min<long long>((rows + 16LL * ry - 1) / (16LL * ry), 8LL * kNumSMs));
+    const DetSeq det = det_seq(1);
+    long long chunks = std::max<long long>(1, std::min<long long>((rows + 16LL * ry - 1) / (16LL * ry), det.ctr ? kDetMaxParts : 8LL * kNumSMs));
     const long long rpb = (rows + chunks - 1) / chunks;
     chunks = (rows + rpb - 1) / rpb;
     if (n4 <= 256) {
-      colsum4_kernel<<<(unsigned)chunks, 256, 0, s>>>(reinterpret_cast<const float4*>(dy), ld / 4, rows, n4, db, rpb, db2, split / 4);
+      colsum4_kernel<<<(unsigned)chunks, 256, 0, s>>>(reinterpret_cast<const float4*>(dy), ld / 4, rows, n4, db, rpb, db2, split / 4, det);
       DDRL_LAUNCHED("colsum_kernel");
       return DDRL_OK;
     }
   }
   const int nb = ceil_div(N, 32);
-  long long chunks = std::max<long long>(1, std::min<long long>((rows + 255) / 256, (4LL * kNumSMs + nb - 1) / nb));
+  const DetSeq det = det_seq(nb);
+  long long chunks = std::max<long long>(1, std::min<long long>((rows + 255) / 256, det.ctr ? kDetMaxParts : (4LL * kNumSMs + nb - 1) / nb));
   const long long rpb = (rows + chunks - 1) / chunks;
   chunks = (rows + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(nb, (unsigned)chunks), 256, 0, s>>>(dy, ld, rows, N, db, rpb);
+  colsum_kernel<<<dim3(nb, (unsigned)chunks), 256, 0, s>>>(dy, ld, rows, N, db, rpb, det);
   DDRL_LAUNCHED("colsum_kernel");
   return DDRL_OK;
 }
@@ -739,7 +774,7 @@ bool thin_supported(long long M, int N, int K, const float* x, int ldx, const fl
 #define DDRL_THIN_DISPATCH(KERNEL, ...)                                                        \
   do {                                                                                         \
     const int k4 = ldx / 4, nc4 = N / 4;                                                       \
-    const int grid = (int)std::min<long long>((M + 256 / nc4 - 1) / (256 / nc4), 8LL * kNumSMs); \
+    const int grid = (int)std::min<long long>((M + 256 / nc4 - 1) / (256 / nc4), thin_grid_cap); \
     if (nc4 == 16 && k4 == 3) KERNEL<3, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);                \
     else if (nc4 == 16 && k4 == 9) KERNEL<9, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);           \
     else KERNEL<2, 8><<<grid, 256, 0, s>>>(__VA_ARGS__);                                      \
@@ -748,6 +783,7 @@ int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias
              cudaStream_t s) {
   if (!thin_supported(M, N, K, x, ldx, y, N)) return DDRL_E_UNSUPPORTED;
   prof_work(4.0 * (double)M * (ldx + N));
+  const long long thin_grid_cap = 8LL * kNumSMs;
   DDRL_THIN_DISPATCH(thin_fwd_kernel, reinterpret_cast<const float4*>(x), W, ldw, bias, reinterpret_cast<float4*>(y), M, K, act);
   DDRL_LAUNCHED("thin_fwd_kernel");
   return DDRL_OK;
@@ -755,7 +791,9 @@ int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias
 int thin_wgrad(const float* x, int ldx, const float* dy, float* dW, int ldw, long long M, int N, int K, cudaStream_t s) {
   if (!thin_supported(M, N, K, x, ldx, dy, N)) return DDRL_E_UNSUPPORTED;
   prof_work(4.0 * (double)M * (ldx + N));
-  DDRL_THIN_DISPATCH(thin_wgrad_kernel, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), dW, ldw, M, K);
+  const DetSeq det = det_seq(1);
+  const long long thin_grid_cap = det.ctr ? kDetMaxParts : 8LL * kNumSMs;
+  DDRL_THIN_DISPATCH(thin_wgrad_kernel, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), dW, ldw, M, K, det);
   DDRL_LAUNCHED("thin_wgrad_kernel");
   return DDRL_OK;
 }
@@ -820,10 +858,11 @@ int skinny_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int N
                  cudaStream_t s) {
   if (B == 0) return DDRL_OK;
   const int kb = ceil_div(K, 256);
-  int chunks = std::max(1, std::min(ceil_div(B, 64), ceil_div(4 * kNumSMs, kb * N)));
+  const DetSeq det = det_seq(kb * N);
+  int chunks = std::max(1, std::min(ceil_div(B, 64), det.ctr ? kDetMaxParts : ceil_div(4 * kNumSMs, kb * N)));
   const int rpb = ceil_div(B, chunks);
   chunks = ceil_div(B, rpb);
-  skinny_wgrad_kernel<<<dim3(kb, chunks, N), 256, 0, s>>>(dy, ldy, x, ldx, B, N, K, dW, db, rpb);
+  skinny_wgrad_kernel<<<dim3(kb, chunks, N), 256, 0, s>>>(dy, ldy, x, ldx, B, N, K, dW, db, rpb, det);
   DDRL_LAUNCHED("skinny_wgrad_kernel");
   return DDRL_OK;
 }

@@ -60,7 +60,7 @@ __device__ __forceinline__ float value_loss(float R, float v, int smooth_l1, flo
 __global__ void __launch_bounds__(128) ppo_loss_categorical_kernel(
     const float* __restrict__ logits, int ld, const float* __restrict__ actions, const float* __restrict__ old_logp,
     const float* __restrict__ adv, const float* __restrict__ returns, const float* __restrict__ v, int B, int A,
-    LossParams hp, float* __restrict__ dlogits, int ld_d, float* __restrict__ dv, float* __restrict__ loss_sums) {
+    LossParams hp, float* __restrict__ dlogits, int ld_d, float* __restrict__ dv, float* __restrict__ loss_sums, DetSeq det) {
   __shared__ float scratch[32];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l_actor = 0.f, l_v = 0.f, l_ent = 0.f;
@@ -114,9 +114,11 @@ __global__ void __launch_bounds__(128) ppo_loss_categorical_kernel(
   l_v = block_sum(l_v, scratch);
   l_ent = block_sum(l_ent, scratch);
   if (threadIdx.x == 0) {
+    if (det.ctr) det_enter(det.ctr, blockIdx.x);         // deterministic mode: the blocks add in block order
     atomicAdd(loss_sums + 0, l_actor);
     atomicAdd(loss_sums + 1, l_v);
     atomicAdd(loss_sums + 2, l_ent);
+    if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
 
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(128) ppo_loss_gaussian_kernel(
     const float* __restrict__ mu, int ld, const float* __restrict__ log_std, const float* __restrict__ actions,
     const float* __restrict__ old_logp, const float* __restrict__ adv, const float* __restrict__ returns,
     const float* __restrict__ v, int B, int A, LossParams hp, float* __restrict__ dmu, int ld_d,
-    float* __restrict__ dv, float* __restrict__ dlog_std, float* __restrict__ loss_sums) {
+    float* __restrict__ dv, float* __restrict__ dlog_std, float* __restrict__ loss_sums, DetSeq det) {
   __shared__ float scratch[32];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l_actor = 0.f, l_v = 0.f, l_ent = 0.f;
@@ -162,20 +164,21 @@ __global__ void __launch_bounds__(128) ppo_loss_gaussian_kernel(
   l_actor = block_sum(l_actor, scratch);
   l_v = block_sum(l_v, scratch);
   l_ent = block_sum(l_ent, scratch);
+  float tls[8];
+  for (int j = 0; j < A && j < 8; ++j) tls[j] = block_sum(dls[j], scratch);
   if (threadIdx.x == 0) {
+    if (det.ctr) det_enter(det.ctr, blockIdx.x);         // deterministic mode: the blocks add in block order
     atomicAdd(loss_sums + 0, l_actor);
     atomicAdd(loss_sums + 1, l_v);
     atomicAdd(loss_sums + 2, l_ent);
-  }
-  for (int j = 0; j < A && j < 8; ++j) {
-    const float t = block_sum(dls[j], scratch);
-    if (threadIdx.x == 0) atomicAdd(dlog_std + j, t);
+    for (int j = 0; j < A && j < 8; ++j) atomicAdd(dlog_std + j, tls[j]);
+    if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
 
 // value loss of one extra critic head (nn/ppo.py:97-104)
 __global__ void __launch_bounds__(128) value_loss_kernel(const float* __restrict__ returns, const float* __restrict__ v, int B,
-                                                         LossParams hp, float* __restrict__ dv, float* __restrict__ loss_sums) {
+                                                         LossParams hp, float* __restrict__ dv, float* __restrict__ loss_sums, DetSeq det) {
   __shared__ float scratch[32];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l_v = 0.f;
@@ -185,7 +188,11 @@ __global__ void __launch_bounds__(128) value_loss_kernel(const float* __restrict
     dv[b] = dl * hp.inv_B * (hp.shared ? hp.v_coef : 1.f);
   }
   l_v = block_sum(l_v, scratch);
-  if (threadIdx.x == 0) atomicAdd(loss_sums + 1, l_v);
+  if (threadIdx.x == 0) {
+    if (det.ctr) det_enter(det.ctr, blockIdx.x);
+    atomicAdd(loss_sums + 1, l_v);
+    if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
+  }
 }
 
 static LossParams make_params(const ddrl_ppo_hparams* hp, float inv_B, int shared) {
@@ -208,7 +215,7 @@ extern "C" int ddrl_ppo_loss_categorical(const float* logits, int ld, const floa
   if (!logits || !actions || !old_logp || !adv || !returns || !v || !dlogits || !dv || !loss_sums) return DDRL_E_ARG;
   ppo_loss_categorical_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
       logits, ld, actions, old_logp, adv, returns, v, B, A, make_params(hp, inv_B_global, shared), dlogits, ld_d, dv,
-      loss_sums);
+      loss_sums, det_seq(1));
   prof_work((8.0 * A + 24.0) * B);
   DDRL_LAUNCHED("ppo_loss_categorical_kernel");
   return DDRL_OK;
@@ -220,7 +227,7 @@ extern "C" int ddrl_value_loss(const float* returns, const float* v, int B, floa
   if (B == 0) return DDRL_OK;
   if (!returns || !v || !dv || !loss_sums) return DDRL_E_ARG;
   value_loss_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(returns, v, B, make_params(hp, inv_B_global, shared), dv,
-                                                                         loss_sums);
+                                                                         loss_sums, det_seq(1));
   prof_work(12.0 * B);
   DDRL_LAUNCHED("value_loss_kernel");
   return DDRL_OK;
@@ -236,7 +243,7 @@ extern "C" int ddrl_ppo_loss_gaussian(const float* mu, int ld, const float* log_
     return DDRL_E_ARG;
   ppo_loss_gaussian_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
       mu, ld, log_std, actions, old_logp, adv, returns, v, B, A, make_params(hp, inv_B_global, shared), dmu, ld_d, dv,
-      dlog_std, loss_sums);
+      dlog_std, loss_sums, det_seq(1));
   prof_work((12.0 * A + 20.0) * B);
   DDRL_LAUNCHED("ppo_loss_gaussian_kernel");
   return DDRL_OK;

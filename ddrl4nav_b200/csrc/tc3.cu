@@ -89,6 +89,7 @@ struct Tc3Args {
   float* colsum;                              // weight gradient: optional db[n] += sum_r dy[r, n] (bias gradient), fused into the dy conversion
   float* colsum2;                             // columns >= colsum_split go to colsum2[n - colsum_split] (two layers behind one fused dy)
   int colsum_split;
+  unsigned int* det_ctr;                      // weight gradient, deterministic mode: turn counters, one per (M block, N tile)
   TcTap tap;
 };
 
@@ -808,7 +809,8 @@ struct T3WCfg {
   static constexpr int NBARS = 2 * STAGES + 2 * SA + 6;
   static constexpr int B16_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = B16_OFF + SA * B16_BYTES;
-  static constexpr int SMEM = 1024 + BAR_OFF + 256;
+  static constexpr int CS_OFF = BAR_OFF + 256;                    // deterministic mode: [NEPI][BN] bias-gradient partials
+  static constexpr int SMEM = 1024 + CS_OFF + NEPI * BN * 4;
   static_assert(NBARS * 8 + 16 <= 256, "barrier block");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
@@ -1108,6 +1110,10 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int drained = nkb >= 2 * T3_CHUNK ? nkb / T3_CHUNK - 1 : 0;      // chunks 0 .. drained - 1 are done
       for (int c = drained; c < nch; ++c) drain(c);
     }
+    // deterministic mode (g.det_ctr): the K splits of one tile add in split order -- a turn counter per (M block, N tile) --
+    // and the 8 conversion warps' bias-gradient partials meet in shared memory in warp order instead of by atomics
+    unsigned int* turn = g.det_ctr ? g.det_ctr + (size_t)blockIdx.y * gridDim.x + blockIdx.x : nullptr;
+    float* cs_red = reinterpret_cast<float*>(smem + Cfg::CS_OFF);
     if (do_colsum) {
       // threads with equal (et mod BN/8) hold partial sums of the same 8 columns: lanes l, l + BN/8, ... of a warp
 #pragma unroll
@@ -1120,11 +1126,13 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane < BN / 8) {
         const int col = n0 + lane * 8;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (col + k < g.N) {
+        for (int k = 0; k < 8; ++k) {
+          if (turn) cs_red[e * BN + lane * 8 + k] = cs[k];
+          else if (col + k < g.N) {
             const int c = col + k;
             atomicAdd((g.colsum2 != nullptr && c >= g.colsum_split) ? g.colsum2 + (c - g.colsum_split) : g.colsum + c, cs[k]);
           }
+        }
       }
     }
     if (nkb > 0) {
@@ -1139,6 +1147,18 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < LDW; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
       }
+      if (turn) {
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");        // cs_red complete
+        if (e == 0 && lane == 0) det_enter(turn, blockIdx.z);
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
+        if (do_colsum && et < BN && n0 + et < g.N) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < Cfg::NEPI; ++w) v += cs_red[w * BN + et];
+          const int c = n0 + et;
+          atomicAdd((g.colsum2 != nullptr && c >= g.colsum_split) ? g.colsum2 + (c - g.colsum_split) : g.colsum + c, v);
+        }
+      }
       const int r = q * 32 + lane;
       if (m0 + r < g.M) {
         float* crow = g.C + (long long)(m0 + r) * g.sCm;
@@ -1147,6 +1167,10 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int col = n0 + col0 + j;
           if (col < g.N) atomicAdd(crow + (long long)col * g.sCn, (acc[j] * sA_inv) * sB_inv);
         }
+      }
+      if (turn) {
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
+        if (e == 0 && lane == 0) det_leave(turn, blockIdx.z, gridDim.z);
       }
       T3_SECTION_END(w2);
     }
@@ -1219,6 +1243,7 @@ int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const floa
   const int tiles = ceil_div(Kx, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(Kx, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  g.det_ctr = det_seq((int)(grid.x * grid.y)).ctr;
   return bn == 128 ? launch3w<128>(ta, tb, ta, tb, g, grid, s) : launch3w<64>(ta, tb, ta, tb, g, grid, s);
 }
 
@@ -1292,6 +1317,7 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   const int tiles = ceil_div(K, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(K, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
+  g.det_ctr = det_seq((int)(grid.x * grid.y)).ctr;
   return bn == 128 ? launch3w<128>(ta, tb, ta2, tb2, g, grid, s) : launch3w<64>(ta, tb, ta2, tb2, g, grid, s);
 }
 
