@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) {
     if (det.ctr) det_enter(det.ctr, blockIdx.x);
-    atomicAdd(out, acc);
+    det_add(det.ctr != nullptr, out, acc);
     if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }

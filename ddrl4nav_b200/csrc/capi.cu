@@ -67,6 +67,7 @@ extern "C" int ddrl_version(void) { return 100; }
 extern "C" int ddrl_set_deterministic(int on) {
   const int was = ddrl::g_deterministic ? 1 : 0;
   ddrl::g_deterministic = on != 0;
+  if (on) ddrl::det_counters(1);     // allocate the current device's counter pool now: never inside a graph capture
   return was;
 }
 

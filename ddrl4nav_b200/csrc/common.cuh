@@ -107,6 +107,14 @@ __device__ __forceinline__ void det_leave(unsigned int* c, unsigned int rank, un
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c), "r"(nxt) : "memory");
 }
 
+// the add itself: inside a turn the destination belongs to this block alone, so it is a plain L2 read-modify-write (stores that
+// the block barrier + the leader's fence publish, like any grid-synchronisation pattern); outside deterministic mode, atomicAdd
+template <typename T>
+__device__ __forceinline__ void det_add(bool ordered, T* p, T v) {
+  if (ordered) __stcg(p, __ldcg(p) + v);
+  else atomicAdd(p, v);
+}
+
 // streaming (read-once) loads/stores: keep L1 clean for the data that is reused
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;

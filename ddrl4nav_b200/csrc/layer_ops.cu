@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   // deterministic mode: the row blocks of one column group add in block order (turn counter per blockIdx.x)
   if (det.ctr && threadIdx.x == 0) det_enter(det.ctr + blockIdx.x, blockIdx.y);
   __syncthreads();
-  if (ty == 0 && n < N) atomicAdd(db + n, part[0][tx]);
+  if (ty == 0 && n < N) det_add(det.ctr != nullptr, db + n, part[0][tx]);
   if (det.ctr) {
     __syncthreads();
     if (threadIdx.x == 0) det_leave(det.ctr + blockIdx.x, blockIdx.y, gridDim.y);
@@ -342,8 +342,9 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__
     }
     // columns [0, 4 split4) -> db, the rest -> db2 (two layers' biases behind ONE pass over a fused [rows, N0 + N1] gradient)
     float* out = (db2 != nullptr && tx >= split4) ? db2 + 4 * (tx - split4) : db + 4 * tx;
-    atomicAdd(out, sum.x); atomicAdd(out + 1, sum.y);
-    atomicAdd(out + 2, sum.z); atomicAdd(out + 3, sum.w);
+    const bool ord = det.ctr != nullptr;
+    det_add(ord, out, sum.x); det_add(ord, out + 1, sum.y);
+    det_add(ord, out + 2, sum.z); det_add(ord, out + 3, sum.w);
   }
   if (det.ctr) {
     __syncthreads();
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
     __syncthreads();
   }
   if (k < K) {
-    atomicAdd(dW + (size_t)n * K + k, acc);
-    if (db && k == 0) atomicAdd(db + n, accb);
+    det_add(turn != nullptr, dW + (size_t)n * K + k, acc);
+    if (db && k == 0) det_add(turn != nullptr, db + n, accb);
   }
   if (turn) {
     __syncthreads();
@@ -622,7 +623,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float4* __restric
   }
   for (int i = threadIdx.x; i < NV; i += 256) {
     const int n = i / (K4 * 4), k = i % (K4 * 4);
-    if (k < K) atomicAdd(dW + (size_t)n * ldw + k, red[i]);
+    if (k < K) det_add(det.ctr != nullptr, dW + (size_t)n * ldw + k, red[i]);
   }
   if (det.ctr) {
     __syncthreads();

@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(128) ppo_loss_categorical_kernel(
   l_ent = block_sum(l_ent, scratch);
   if (threadIdx.x == 0) {
     if (det.ctr) det_enter(det.ctr, blockIdx.x);         // deterministic mode: the blocks add in block order
-    atomicAdd(loss_sums + 0, l_actor);
-    atomicAdd(loss_sums + 1, l_v);
-    atomicAdd(loss_sums + 2, l_ent);
+    det_add(det.ctr != nullptr, loss_sums + 0, l_actor);
+    det_add(det.ctr != nullptr, loss_sums + 1, l_v);
+    det_add(det.ctr != nullptr, loss_sums + 2, l_ent);
     if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(128) ppo_loss_gaussian_kernel(
   for (int j = 0; j < A && j < 8; ++j) tls[j] = block_sum(dls[j], scratch);
   if (threadIdx.x == 0) {
     if (det.ctr) det_enter(det.ctr, blockIdx.x);         // deterministic mode: the blocks add in block order
-    atomicAdd(loss_sums + 0, l_actor);
-    atomicAdd(loss_sums + 1, l_v);
-    atomicAdd(loss_sums + 2, l_ent);
-    for (int j = 0; j < A && j < 8; ++j) atomicAdd(dlog_std + j, tls[j]);
+    det_add(det.ctr != nullptr, loss_sums + 0, l_actor);
+    det_add(det.ctr != nullptr, loss_sums + 1, l_v);
+    det_add(det.ctr != nullptr, loss_sums + 2, l_ent);
+    for (int j = 0; j < A && j < 8; ++j) det_add(det.ctr != nullptr, dlog_std + j, tls[j]);
     if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) value_loss_kernel(const float* __restrict
   l_v = block_sum(l_v, scratch);
   if (threadIdx.x == 0) {
     if (det.ctr) det_enter(det.ctr, blockIdx.x);
-    atomicAdd(loss_sums + 1, l_v);
+    det_add(det.ctr != nullptr, loss_sums + 1, l_v);
     if (det.ctr) det_leave(det.ctr, blockIdx.x, gridDim.x);
   }
 }

@@ -371,8 +371,13 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     T2_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       for (int i = 0; i < nkb; ++i, ++it) {
-        if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
         const int s = it % S, a = it % SA;
+        if ((int)(it % Cfg::NSG) != grp) {                         // the groups take K blocks round-robin
+          // every group follows every phase of the stage barrier: a parity wait that skips a phase (S not a multiple of
+          // NSG) is satisfied by the phase before the skipped one (see tc3.cu)
+          if (S % Cfg::NSG != 0) T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
+          continue;
+        }
         T2_WAIT(smem_u32(bar_full + s), (it / S) & 1, w0);
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
 #ifdef TC2_TIMING

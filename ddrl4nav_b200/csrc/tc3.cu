@@ -309,8 +309,14 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     T3_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       for (int i = 0; i < nkb; ++i, ++it) {
-        if ((int)(it % Cfg::NSG) != grp) continue;                 // the groups take K blocks round-robin
         const int s = it % S, a = it % SA;
+        if ((int)(it % Cfg::NSG) != grp) {                         // the groups take K blocks round-robin
+          // ... but every group follows EVERY phase of the stage barriers: when S is not a multiple of NSG a group meets a
+          // stage only on every other use, and a parity wait that skips a phase is satisfied by the phase BEFORE the skipped
+          // one -- the group would read the stage while the skipped block's (or its own block's) TMA is still in flight
+          if (S % Cfg::NSG != 0) T3_WAITL(smem_u32(bar_full + s), (it / S) & 1, w0);
+          continue;
+        }
         T3_WAITL(smem_u32(bar_full + s), (it / S) & 1, w0);
         T3_SECTION_BEGIN;
         const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
@@ -985,8 +991,13 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
     T3_ROLE_BEGIN
     for (int i = 0; i < nkb; ++i) {
-      if ((i % Cfg::NSG) != grp) continue;
       const int s = i % S, a = i % SA;
+      if ((i % Cfg::NSG) != grp) {
+        // follow every phase of the stage barrier (see the forward kernel): with S = 3 stages and 2 groups a group meets a
+        // stage on every other use, and its parity wait would be satisfied by the phase before the one it skipped
+        if (S % Cfg::NSG != 0) T3_WAIT(smem_u32(bar_full + s), (i / S) & 1, w0);
+        continue;
+      }
       T3_WAIT(smem_u32(bar_full + s), (i / S) & 1, w0);
       // the TMEM slot was last read by K block i - SA
       if (i >= SA) T3_WAIT(smem_u32(bar_afree + a), ((i / SA) - 1) & 1, w1);
@@ -1156,7 +1167,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int w = 0; w < Cfg::NEPI; ++w) v += cs_red[w * BN + et];
           const int c = n0 + et;
-          atomicAdd((g.colsum2 != nullptr && c >= g.colsum_split) ? g.colsum2 + (c - g.colsum_split) : g.colsum + c, v);
+          det_add(true, (g.colsum2 != nullptr && c >= g.colsum_split) ? g.colsum2 + (c - g.colsum_split) : g.colsum + c, v);
         }
       }
       const int r = q * 32 + lane;
@@ -1165,7 +1176,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < Cfg::COLS; ++j) {
           const int col = n0 + col0 + j;
-          if (col < g.N) atomicAdd(crow + (long long)col * g.sCn, (acc[j] * sA_inv) * sB_inv);
+          if (col < g.N) det_add(turn != nullptr, crow + (long long)col * g.sCn, (acc[j] * sA_inv) * sB_inv);
         }
       }
       if (turn) {
@@ -1243,7 +1254,7 @@ int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const floa
   const int tiles = ceil_div(Kx, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(Kx, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
-  g.det_ctr = det_seq((int)(grid.x * grid.y)).ctr;
+  g.det_ctr = getenv("DDRL_DET_SKIP_WGRAD") ? nullptr : det_seq((int)(grid.x * grid.y)).ctr;
   return bn == 128 ? launch3w<128>(ta, tb, ta, tb, g, grid, s) : launch3w<64>(ta, tb, ta, tb, g, grid, s);
 }
 

@@ -23,6 +23,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def set_deterministic(on: bool = True) -> bool:
+    """Run-to-run bit-reproducible gradients / losses on the default engine (ddrl_set_deterministic); returns the previous setting."""
+    return bool(_lib.load().ddrl_set_deterministic(1 if on else 0))
+
+
 def gae(values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, gamma: Sequence[float], lam: float,
         algo: int = 0):
     """values [T+1,V,N] f32, rewards [>=T,V,N] f32, dones [>=T,V,N] u8 -> (returns [T,V,N], advs [T,N]).

@@ -81,6 +81,12 @@ const char* ddrl_last_cuda_error(void);
 /* number of kernels this library has launched since load / since reset (bench gpu_launches) */
 int64_t ddrl_launch_count(void);
 void ddrl_launch_count_reset(void);
+/* Deterministic mode (also DDRL_DETERMINISTIC=1 in the environment): every cross-block floating-point accumulation of the
+ * default (tc3) path -- split-K weight gradients and the bias gradients fused into them, loss sums, the gradient norm, the
+ * small-layer weight gradients -- adds its block partials in BLOCK ORDER instead of by unordered atomicAdd, so two runs on
+ * the same inputs produce the same bits (the reference's CPU path is run-to-run deterministic, nn/ppo.py:108-129).  Costs a
+ * few per cent (shorter reduction grids, serialised final adds).  Returns the previous setting. */
+int ddrl_set_deterministic(int on);
 /* per-kernel-class device timing for bench.py's roofline line: between start and stop every launch
  * on `stream` is followed by a CUDA event; stop writes "kernel_name ms launches work\n" lines
  * (work = algorithmic flops for GEMMs, bytes for the streaming kernels that declare them). */

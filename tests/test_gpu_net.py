@@ -331,6 +331,51 @@ def test_backward_segments_finalise_their_gradient_ranges(kind, B):
     assert rel_err(net.flat_grads(), g_whole) < 5e-6
 
 
+@pytest.mark.parametrize("kind,B", [("pong", 300), ("navimg", 70), ("navlaser", 33)])
+def test_deterministic_mode_is_bit_reproducible(kind, B):
+    """ddrl_set_deterministic(1): two backward passes on the same inputs give the same BITS (split-K weight gradients, fused
+    bias gradients, loss sums and the gradient norm add their block partials in block order), and so do two whole learn()
+    trajectories from identical nets; results stay within the usual tolerance of the default (unordered) mode."""
+    if GEMM_MODE != "tc3":
+        pytest.skip("deterministic mode covers the default (tc3) engine")
+    from ddrl4nav_b200 import kernels
+    from ddrl4nav_b200.data import Experience
+    spec, params, states, a, old, adv, ret = _learn_case(kind, B)
+    ds = [s.to(DEV) for s in states]
+    dv = [t.to(DEV) for t in (adv, a, old, ret)]
+    net, _, _ = make(kind)
+    net.backward_only(ds, dv[0], dv[1], dv[2], dv[3])
+    g_default = net._grads.clone()
+    was = kernels.set_deterministic(True)
+    try:
+        grads = []
+        for i in range(3):                     # stream launches, graph capture + first launch, graph replay
+            net.backward_only(ds, dv[0], dv[1], dv[2], dv[3], obs_unchanged=i > 0)
+            grads.append(net._grads.clone())
+        names = [n for n, _ in net.named_parameters()] + ["<loss sums>"]
+        bounds = list(net._offsets) + [net._P, net._P + 8]
+        for i in (1, 2):
+            bad = [(names[k], int((grads[0][bounds[k]:bounds[k + 1]] != grads[i][bounds[k]:bounds[k + 1]]).sum()),
+                    float((grads[0][bounds[k]:bounds[k + 1]] - grads[i][bounds[k]:bounds[k + 1]]).abs().max()),
+                    float(grads[0][bounds[k]:bounds[k + 1]].abs().max()))
+                   for k in range(len(names)) if not torch.equal(grads[0][bounds[k]:bounds[k + 1]], grads[i][bounds[k]:bounds[k + 1]])]
+            assert not bad, (i, bad)
+        assert rel_err(grads[0][:net._P], g_default[:net._P]) < 1e-5
+        runs = []
+        for rep in range(2):
+            n2, _, _ = make(kind, TRAINING_ITER_TIME=4)
+            exp = Experience(states=[s.numpy() for s in states], advs=adv.numpy(), actions=a.numpy(), old_logps=old.numpy(),
+                             values=ret.numpy()[None])
+            exp.to_tensor(device=DEV)
+            losses = [[l[k] for k in ("PpoTotalLoss", "ActorLoss", "VLoss", "EntLoss")] for l, _, _ in n2.learn(exp)]
+            runs.append((losses, n2._flat.clone(), n2._m.clone(), n2._v.clone()))
+        assert runs[0][0] == runs[1][0]
+        for x, y in zip(runs[0][1:], runs[1][1:]):
+            assert torch.equal(x, y)
+    finally:
+        kernels.set_deterministic(was)
+
+
 def test_micro_batching_equals_single_shot(monkeypatch):
     spec, params, states, a, old, adv, ret = _learn_case("pong", 21)
     net, _, _ = make("pong")
