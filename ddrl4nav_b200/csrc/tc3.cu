@@ -82,6 +82,7 @@ struct Tc3Args {
   int kb_total, kb_per_split;                 // K blocks of 64 (tap mode: pairs of 32-channel slices)
   int act, atomic, vec_store;
   int tma_store;                              // outputs leave through TMA tile stores of the staged panels (tmC / tmC2)
+  int tma_mask;                               // ... and the activation mask (act >= 3) ARRIVES through TMA, into the same panels (tmM / tmM2)
   int m_tiles, n_tiles;
   const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
   const float* amax_b;
@@ -131,7 +132,7 @@ struct T3Cfg {
   // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
   static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN, TM_A = FOLD ? 5 * BN : 3 * BN;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int NBARS = 2 * STAGES + SA + 6;
+  static constexpr int NBARS = 2 * STAGES + SA + 7;
   // epilogue staging: NEPI/4 panels of 128 rows x 32 fp32 columns (128-byte rows, 128B swizzle = the box layout of a TMA
   // tile store; warp e owns rows [32 (e & 3), +32) of panel e >> 2), 1024-byte aligned
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
@@ -148,7 +149,8 @@ template <int BN>
 __global__ void __launch_bounds__(T3Cfg<BN>::THREADS, 1)
 tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
            const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmA2,
-           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, Tc3Args g) {
+           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+           const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmM2, Tc3Args g) {
   using Cfg = T3Cfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
@@ -163,12 +165,14 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint64_t* bar_mfree = bar_mfull + 2;        // [2] drained
   uint64_t* bar_cfull = bar_mfull + 4;        // correction accumulator complete (tile end)
   uint64_t* bar_cfree = bar_mfull + 5;        // read by the epilogue
+  uint64_t* bar_mask = bar_mfull + 6;         // activation-mask panels landed in the staging area (TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcTap& tp = g.tap;
   const bool tapA = tp.mode != 0;
 
   if (warp == 0 && lane == 0) {
+    mbar_init(smem_u32(bar_mask), 1);
     for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
     for (int a = 0; a < SA; ++a) mbar_init(smem_u32(bar_aready + a), 4);
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
@@ -373,11 +377,54 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
     t3_scale(__ldg(g.amax_b), sB, sB_inv);
     float run_max = 0.f;
-    uint32_t ch = 0, tl = 0;
+    uint32_t ch = 0, tl = 0, mround = 0;
     T3_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
       const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
       const int m0 = mt * T3_BM, n0 = nt * BN;
+      // tile-level coordinates of the TMA epilogue (stores, and -- data gradients -- the mask panels that arrive the same way)
+      int cy = 0, cb = 0;
+      if (tapA) {
+        const bool ph2 = mt >= tp.tiles1;
+        cb = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb;
+        cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+      }
+      const bool masked = g.tma_store && g.tma_mask;
+      const bool leader = e == 0 && lane == 0;
+      const bool fusedT = tapA && tp.ncls > 1;
+      const uint32_t box_bytes = tapA ? (uint32_t)(mt >= tp.tiles1 ? tp.rows2 : tp.rows) * 128u : 16384u;
+      // global coordinates of the panel that starts at column `col`: a panel of the fused stride-parity gradient belongs to
+      // one pixel class, whose offset is the start of a strided box
+      auto coords = [&](int col, int& c0, int& c1, int& c2, int& c3) {
+        c0 = col; c1 = 0; c2 = cy; c3 = cb;
+        if (fusedT) {
+          const int qq = col / tp.cls_cols;
+          c0 = col - qq * tp.cls_cols; c1 = tp.cls_ix[qq]; c2 = tp.out_s * cy + tp.cls_iy[qq];
+        }
+      };
+      auto load_masks = [&](int p0) {           // leader only, after the previous stores have read the panels
+        uint32_t live = 0;
+#pragma unroll
+        for (int h = 0; h < Cfg::NEPI / 4; ++h) live += (n0 + h * Cfg::COLS + p0 < g.N) ? 1u : 0u;
+        mbar_expect_tx(smem_u32(bar_mask), live * box_bytes);
+#pragma unroll
+        for (int h = 0; h < Cfg::NEPI / 4; ++h) {
+          const int col = n0 + h * Cfg::COLS + p0;
+          if (col >= g.N) continue;
+          const uint32_t dst = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
+          if (!tapA) tma_load_2d(&tmM, smem_u32(bar_mask), dst, col, m0);
+          else {
+            int c0, c1, c2, c3;
+            coords(col, c0, c1, c2, c3);
+            tma_load_4d(mt >= tp.tiles1 ? &tmM2 : &tmM, smem_u32(bar_mask), dst, c0, c1, c2, c3);
+          }
+        }
+      };
+      // the first round's mask panels travel while the accumulators are drained
+      if (masked && leader) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        load_masks(0);
+      }
       float acc[Cfg::COLS];
 #pragma unroll
       for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
@@ -447,14 +494,11 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (g.tma_store) {
         // TMA path: bias + activation in registers, the warp's 32 rows x 32 columns into its slice of the swizzled panel,
         // then ONE elected thread stores the whole tile panel(s) with a tensor-map box that mirrors the load-side box
-        // (rows past the tensor's extents are clipped by the TMA unit: no per-row addressing, no per-element stores)
+        // (rows past the tensor's extents are clipped by the TMA unit: no per-row addressing, no per-element stores).
+        // Data gradients (g.tma_mask): the activation derivative needs the layer input at the very positions the panel is
+        // stored to, so the SAME box is first loaded into the panel (tmM / tmM2), transformed in place and stored back; the
+        // fused stride-parity gradient is one strided box per 32-column panel (a panel belongs to one pixel class).
         float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
-        int cy = 0, cb = 0;
-        if (tapA) {
-          const bool ph2 = mt >= tp.tiles1;
-          cb = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb;
-          cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
-        }
         // branch-free per element: the bias of the panel's 32 columns is fetched up front (index clamped, so every load is
         // legal and all 32 are in flight together), the activation is two selects on kernel-uniform predicates.  (A per-element
         // `if (col < N) { if (bias) ...; if (act == ..) ... }` compiled to 32 serialised LDG -> branch -> FADD blocks.)
@@ -472,25 +516,39 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             for (int j = 0; j < 32; ++j) bv[j] = 0.f;
           }
           // the staging panels are free once the previous TMA stores have READ them (same issuing thread as below)
-          if (e == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (leader && !(masked && p0 == 0)) {          // (round 0 of a masked tile: done before the drain)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (masked) load_masks(p0);
+          }
           asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
+          if (masked) {
+            mbar_wait(smem_u32(bar_mask), mround & 1);
+            ++mround;
+          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
+            float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
+            float4 mk4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (masked) mk4 = *reinterpret_cast<const float4*>(slot);
+            const float mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               float x = acc[p0 + 4 * c + k] + bv[4 * c + k];
-              const float neg = relu ? 0.f : slope * x;
-              x = x > 0.f ? x : neg;
+              if (masked) x = mk[k] > 0.f ? x : neg_slope * x;
+              else {
+                const float neg = relu ? 0.f : slope * x;
+                x = x > 0.f ? x : neg;
+              }
               const bool live = rvalid && (colb + 4 * c + k) < g.N;
               run_max = fmaxf(run_max, live ? fabsf(x) : 0.f);
               o[k] = x;
             }
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
           }
           fence_async_smem();
           asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
-          if (e == 0 && lane == 0) {
+          if (leader) {
 #pragma unroll
             for (int h = 0; h < Cfg::NEPI / 4; ++h) {
               const int col = n0 + h * Cfg::COLS + p0;
@@ -499,10 +557,13 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               if (!tapA)
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                              ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(src), "r"(col), "r"(m0) : "memory");
-              else
+              else {
+                int c0, c1, c2, c3;
+                coords(col, c0, c1, c2, c3);
                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(mt >= tp.tiles1 ? &tmC2 : &tmC)), "r"(src), "r"(col), "r"(0), "r"(cy), "r"(cb)
+                             ::"l"(reinterpret_cast<uint64_t>(mt >= tp.tiles1 ? &tmC2 : &tmC)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                              : "memory");
+              }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -637,7 +698,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------- host side
-struct Tc3Maps { CUtensorMap a, bhi, blo, a2, c, c2; };
+struct Tc3Maps { CUtensorMap a, bhi, blo, a2, c, c2, m, m2; };
 
 template <int BN>
 static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s) {
@@ -648,7 +709,7 @@ static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s
     DDRL_CUDA(cudaFuncSetAttribute(tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, g);
+  tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, m.m, m.m2, g);
   prof_work(2.0 * g.M * (double)g.N * g.K * (g.tap.work_scale > 0.f ? g.tap.work_scale : 1.f));   // algorithmic flops
   if (g_prof_on && g_prof_shapes) {
     char nm[96];
@@ -674,6 +735,9 @@ static int launch3_bn(int bn, const Tc3Maps& m, const Tc3Args& g, dim3 grid, cud
 // compiled to 32 serialised LDG / branch blocks and to waiting for the TMA read-out inside the tile.  DDRL_TC3_TMA_STORE=0
 // selects the per-warp coalesced stores.
 static const bool g_t3_tma_store = [] { const char* e = getenv("DDRL_TC3_TMA_STORE"); return !(e && e[0] == '0'); }();
+// ... and so do data gradients: the activation mask travels INTO the staging panels by TMA (same boxes as the stores), the
+// fused stride-parity gradient stores one strided box per pixel class.  DDRL_TC3_TMA_DGRAD=0: per-warp mask loads + stores.
+static const bool g_t3_tma_dgrad = [] { const char* e = getenv("DDRL_TC3_TMA_DGRAD"); return !(e && e[0] == '0'); }();
 
 static inline int pick_bn3(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -715,15 +779,20 @@ int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, cons
   g.m_tiles = ceil_div(M, T3_BM); g.n_tiles = ceil_div(N, bn);
   g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
   g.vec_store = (ldc % 4 == 0 && al16(C) && (!mask || al16(mask))) ? 1 : 0;
-  if (g.vec_store && act < 3 && g_t3_tma_store) {
-    // output tiles leave through TMA: boxes of 128 rows x 32 columns of C [M, N]
+  if (g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad)) {
+    // output tiles leave through TMA: boxes of 128 rows x 32 columns of C [M, N]; the mask of a data gradient (same
+    // layout as C) arrives through the same boxes
     const unsigned long long dims[2] = {(unsigned long long)N, (unsigned long long)M};
     const unsigned long long strides[1] = {(unsigned long long)ldc * 4};
     const unsigned box[2] = {32u, (unsigned)T3_BM}, estr[2] = {1u, 1u};
-    if (tc_encode_tiled(&mp.c, false, 2, C, dims, strides, box, estr, true) == DDRL_OK) g.tma_store = 1;
+    int rs = tc_encode_tiled(&mp.c, false, 2, C, dims, strides, box, estr, true);
+    if (rs == DDRL_OK && act >= 3) rs = tc_encode_tiled(&mp.m, false, 2, mask, dims, strides, box, estr, true);
+    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = act >= 3 ? 1 : 0; }
   }
   if (!g.tma_store) mp.c = mp.a;
   mp.c2 = mp.c;
+  if (!g.tma_mask) mp.m = mp.c;
+  mp.m2 = mp.m;
   dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
   return launch3_bn(bn, mp, g, grid, s);
 }
@@ -765,22 +834,36 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
   g.n_tiles = ceil_div(N, bn);
   g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
   g.vec_store = (osb % 4 == 0 && osy % 4 == 0 && osx % 4 == 0 && al16(out) && (!mask || al16(mask))) ? 1 : 0;
-  if (g.vec_store && act < 3 && g.tap.ncls <= 1 && g_t3_tma_store) {
+  const bool classes = g.tap.ncls > 1;
+  // fused stride-parity gradient through TMA: every 32-column panel belongs to ONE pixel class (cls_cols % 32 == 0), whose
+  // pixels (out_s*y + iy, out_s*x + ix) are a strided box of the output; needs the dense [B, out_H, out_W, ct] layout
+  const long long ct = classes && g.tap.out_s > 0 ? osx / g.tap.out_s : 0;
+  const bool classes_ok = classes && g_t3_tma_dgrad && g.tap.cls_cols % 32 == 0 && g.tap.out_W > 1 && g.tap.ncls == g.tap.out_s * g.tap.out_s &&
+                          ct > 0 && osx == ct * g.tap.out_s && osy == (long long)g.tap.out_s * g.tap.out_W * ct &&
+                          osb == (long long)g.tap.out_H * g.tap.out_W * ct;
+  if (g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad) && (!classes || classes_ok)) {
     // output tiles leave through TMA: the store box (32 columns x Xn pixels x ny rows x nb images of out[b, y, x, n])
-    // mirrors the load-side pixel box, one map per tiling phase
-    const unsigned long long dims[4] = {(unsigned long long)N, (unsigned long long)o.Xn, (unsigned long long)o.Yn, (unsigned long long)o.Bn};
-    const unsigned long long strides[3] = {(unsigned long long)osx * 4, (unsigned long long)osy * 4, (unsigned long long)osb * 4};
-    const unsigned estr[4] = {1u, 1u, 1u, 1u};
-    const unsigned box1[4] = {32u, (unsigned)o.Xn, (unsigned)g.tap.ny, (unsigned)g.tap.nb};
+    // mirrors the load-side pixel box, one map per tiling phase; the mask of a data gradient arrives through the same boxes
+    const int es = classes ? g.tap.out_s : 1;
+    const unsigned long long dims[4] = {(unsigned long long)(classes ? g.tap.cls_cols : N), (unsigned long long)(classes ? g.tap.out_W : o.Xn),
+                                        (unsigned long long)(classes ? g.tap.out_H : o.Yn), (unsigned long long)o.Bn};
+    const unsigned long long strides[3] = {(unsigned long long)(osx / es) * 4, (unsigned long long)(osy / es) * 4, (unsigned long long)osb * 4};
+    const unsigned estr[4] = {1u, (unsigned)es, (unsigned)es, 1u};
+    auto boxdim = [&](int n) { return (unsigned)((n - 1) * es + 1); };
+    const unsigned box1[4] = {32u, boxdim(o.Xn), boxdim(g.tap.ny), (unsigned)g.tap.nb};
+    const unsigned box2[4] = {32u, boxdim(o.Xn), boxdim(g.tap.ny2 > 0 ? g.tap.ny2 : 1), (unsigned)(g.tap.nb2 > 0 ? g.tap.nb2 : 1)};
     int rs = tc_encode_tiled(&mp.c, false, 4, out, dims, strides, box1, estr, true);
-    if (rs == DDRL_OK && ph2) {
-      const unsigned box2[4] = {32u, (unsigned)o.Xn, (unsigned)g.tap.ny2, (unsigned)g.tap.nb2};
-      rs = tc_encode_tiled(&mp.c2, false, 4, out, dims, strides, box2, estr, true);
+    if (rs == DDRL_OK && ph2) rs = tc_encode_tiled(&mp.c2, false, 4, out, dims, strides, box2, estr, true);
+    if (rs == DDRL_OK && act >= 3) {
+      rs = tc_encode_tiled(&mp.m, false, 4, mask, dims, strides, box1, estr, true);
+      if (rs == DDRL_OK && ph2) rs = tc_encode_tiled(&mp.m2, false, 4, mask, dims, strides, box2, estr, true);
     }
-    if (rs == DDRL_OK) g.tma_store = 1;
+    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = act >= 3 ? 1 : 0; }
   }
   if (!g.tma_store) mp.c = mp.a;
   if (!g.tma_store || !ph2) mp.c2 = mp.c;
+  if (!g.tma_mask) mp.m = mp.c;
+  if (!g.tma_mask || !ph2) mp.m2 = mp.m;
   dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
   return launch3_bn(bn, mp, g, grid, s);
 }
