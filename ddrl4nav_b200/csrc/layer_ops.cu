@@ -435,6 +435,106 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
   }
 }
 
+// Register-tiled forms of the three head kernels for the common shapes (K <= 512, N <= 8 -- the 6-way / 2-d / 1-wide heads on
+// the 512-wide feature): every operand element is read ONCE per block (the general kernels above re-read x per output
+// column and decompose a flat index with 64-bit divisions per element: 15 - 30 us per launch on 8192 rows, 2.3 % of a
+// Pong step).
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_fwd_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, int B, int N, int K,
+                                                             float* __restrict__ y, int ldy) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* xr = x + (size_t)warp * ldx;
+  float xv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) xv[j] = (lane + 32 * j) < K ? xr[lane + 32 * j] : 0.f;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    if (n < N) {
+      const float* w = W + (size_t)n * K;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if ((lane + 32 * j) < K) acc = fmaf(xv[j], __ldg(w + lane + 32 * j), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) y[(size_t)warp * ldy + n] = acc + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+// dx[b, 4 k4 ..] (+)= sum_n dy[b, n] * W[n, 4 k4 ..]: thread = (row lane, 4 consecutive k), its N x 4 weights in registers
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_dgrad_reg_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ W,
+                                                               int B, int N, int K, float* __restrict__ dx, int ldx, int accumulate) {
+  const int k4n = K >> 2;                                 // float4 columns per row (K % 4 == 0, k4n <= 256)
+  const int k4 = threadIdx.x % k4n, rl = threadIdx.x / k4n, rpb = 256 / k4n;
+  if (rl >= rpb) return;
+  float4 w[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    w[n] = n < N ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long b = (long long)blockIdx.x * rpb + rl; b < B; b += (long long)gridDim.x * rpb) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < N) {
+        const float d = __ldg(dy + b * ldy + n);
+        acc.x = fmaf(d, w[n].x, acc.x); acc.y = fmaf(d, w[n].y, acc.y); acc.z = fmaf(d, w[n].z, acc.z); acc.w = fmaf(d, w[n].w, acc.w);
+      }
+    }
+    float4* p = reinterpret_cast<float4*>(dx + b * ldx) + k4;
+    if (accumulate) { const float4 o = *p; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    *p = acc;
+  }
+}
+// dW[n, k] += sum_b dy[b, n] * x[b, k]; db[n] += sum_b dy[b, n]: thread = one k, N accumulators; grid = (K / 256, row chunks)
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_wgrad_reg_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x,
+                                                               int ldx, int B, int N, int K, float* __restrict__ dW,
+                                                               float* __restrict__ db, int rows_per_block, DetSeq det) {
+  __shared__ float sdy[64 * NMAX];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(B, r0 + rows_per_block);
+  float acc[NMAX], accb = 0.f;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  for (int t0 = r0; t0 < r1; t0 += 64) {
+    const int nr = min(64, r1 - t0);
+    for (int i = threadIdx.x; i < nr * NMAX; i += 256) {
+      const int r = i / NMAX, n = i - r * NMAX;
+      sdy[i] = n < N ? __ldg(dy + (size_t)(t0 + r) * ldy + n) : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float xv = __ldg(x + (size_t)(t0 + r) * ldx + k);
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) acc[n] = fmaf(sdy[r * NMAX + n], xv, acc[n]);
+      }
+    }
+    if (db && blockIdx.x == 0 && (int)threadIdx.x < N)
+      for (int r = 0; r < nr; ++r) accb += sdy[r * NMAX + threadIdx.x];
+    __syncthreads();
+  }
+  // deterministic mode: the row chunks of one k block add in chunk order
+  unsigned int* turn = det.ctr ? det.ctr + blockIdx.x : nullptr;
+  if (turn) {
+    if (threadIdx.x == 0) det_enter(turn, blockIdx.y);
+    __syncthreads();
+  }
+  if (k < K) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) det_add(turn != nullptr, dW + (size_t)n * K + k, acc[n]);
+  }
+  if (db && blockIdx.x == 0 && (int)threadIdx.x < N) det_add(turn != nullptr, db + threadIdx.x, accb);
+  if (turn) {
+    __syncthreads();
+    if (threadIdx.x == 0) det_leave(turn, blockIdx.y, gridDim.y);
+  }
+}
+
 // ---------------------------------------------------------------- space-to-depth (first-layer strided convs)
 // A valid (pad 0) convolution of an NCHW observation whose kernel extents and image extents are multiples of its stride s
 // (NatureCNN conv1: 8x8 stride 4 on 84x84, nn/atari_encoder.py:16) equals a stride-1 convolution with a (KH/s) x (KW/s)
@@ -841,9 +941,16 @@ int copy2d(const float* src, int ld_s, float* dst, int ld_d, long long rows, int
   DDRL_LAUNCHED("copy2d_kernel");
   return DDRL_OK;
 }
+static const bool g_skinny_reg = [] { const char* e = getenv("DDRL_SKINNY_GENERAL"); return !(e && e[0] == '1'); }();
 int skinny_fwd(const float* x, int ldx, const float* W, const float* bias, int B, int N, int K, float* y, int ldy,
                cudaStream_t s) {
   if (B == 0) return DDRL_OK;
+  if (g_skinny_reg && K <= 512 && N <= 8) {
+    if (N == 1) skinny_fwd_reg_kernel<1><<<ceil_div(B, 8), 256, 0, s>>>(x, ldx, W, bias, B, N, K, y, ldy);
+    else skinny_fwd_reg_kernel<8><<<ceil_div(B, 8), 256, 0, s>>>(x, ldx, W, bias, B, N, K, y, ldy);
+    DDRL_LAUNCHED("skinny_fwd_kernel");
+    return DDRL_OK;
+  }
   skinny_fwd_kernel<<<ceil_div(B, 8), 256, 0, s>>>(x, ldx, W, bias, B, N, K, y, ldy);
   DDRL_LAUNCHED("skinny_fwd_kernel");
   return DDRL_OK;
@@ -851,6 +958,15 @@ int skinny_fwd(const float* x, int ldx, const float* W, const float* bias, int B
 int skinny_dgrad(const float* dy, int ldy, const float* W, int B, int N, int K, float* dx, int ldx, int accumulate,
                  cudaStream_t s) {
   if (B == 0) return DDRL_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && ldx % 4 == 0;
+  if (g_skinny_reg && al && K % 4 == 0 && K <= 1024 && N <= 8) {
+    const int rpb = 256 / (K / 4);
+    const int grid = (int)std::min<long long>(ceil_div(B, rpb), 16LL * kNumSMs);
+    if (N == 1) skinny_dgrad_reg_kernel<1><<<grid, 256, 0, s>>>(dy, ldy, W, B, N, K, dx, ldx, accumulate);
+    else skinny_dgrad_reg_kernel<8><<<grid, 256, 0, s>>>(dy, ldy, W, B, N, K, dx, ldx, accumulate);
+    DDRL_LAUNCHED("skinny_dgrad_kernel");
+    return DDRL_OK;
+  }
   skinny_dgrad_kernel<<<grid_for((long long)B * K), 256, 0, s>>>(dy, ldy, W, B, N, K, dx, ldx, accumulate);
   DDRL_LAUNCHED("skinny_dgrad_kernel");
   return DDRL_OK;
@@ -859,6 +975,16 @@ int skinny_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int N
                  cudaStream_t s) {
   if (B == 0) return DDRL_OK;
   const int kb = ceil_div(K, 256);
+  if (g_skinny_reg && N <= 8) {
+    const DetSeq det = det_seq(kb);
+    int chunks = std::max(1, std::min(ceil_div(B, 64), det.ctr ? kDetMaxParts : ceil_div(4 * kNumSMs, kb)));
+    const int rpb = ceil_div(ceil_div(B, chunks), 64) * 64;
+    chunks = ceil_div(B, rpb);
+    if (N == 1) skinny_wgrad_reg_kernel<1><<<dim3(kb, chunks), 256, 0, s>>>(dy, ldy, x, ldx, B, N, K, dW, db, rpb, det);
+    else skinny_wgrad_reg_kernel<8><<<dim3(kb, chunks), 256, 0, s>>>(dy, ldy, x, ldx, B, N, K, dW, db, rpb, det);
+    DDRL_LAUNCHED("skinny_wgrad_kernel");
+    return DDRL_OK;
+  }
   const DetSeq det = det_seq(kb * N);
   int chunks = std::max(1, std::min(ceil_div(B, 64), det.ctr ? kDetMaxParts : ceil_div(4 * kNumSMs, kb * N)));
   const int rpb = ceil_div(B, chunks);
