@@ -569,20 +569,26 @@ __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, f
 }
 // C == 4, W % 4 == 0 (NatureCNN frames): 128-bit loads and stores, BANDS bands in flight per block iteration.  One output
 // float4 = the 4 channels of one (i, j) position.
-template <int BANDS>
-__global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int s,
-                                                     long long sb, long long bands) {
+// CH / CW / CS > 0: the frame size and stride as compile-time constants (NatureCNN: 84 x 84, stride 4).  The kernel decomposes a
+// flat slot index with seven integer divisions per 16-byte access; with run-time divisors that was 45 % of its issue slots
+// (64 % busy) and it ran at 2.9 TB/s (profiles/r3g_*) -- constant divisors compile to multiply-shift.
+template <int BANDS, int CH = 0, int CW = 0, int CS = 0>
+__global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x, float* __restrict__ out, int H_, int W_, int s_,
+                                                     long long sb, long long bands, unsigned int* __restrict__ amax_slot) {
   extern __shared__ float4 band4[];                     // [BANDS][4*s][W/4]
   float* band = reinterpret_cast<float*>(band4);
+  const int H = CH > 0 ? CH : H_, W = CW > 0 ? CW : W_, s = CS > 0 ? CS : s_;
   const int H2 = H / s, W2 = W / s, W4 = W / 4, rows = 4 * s, C2 = s * s * 4;
   const int n_in4 = rows * W4, n_out4 = W2 * s * s;
+  float run_max = 0.f;
   for (long long bd0 = (long long)blockIdx.x * BANDS; bd0 < bands; bd0 += (long long)gridDim.x * BANDS) {
     const int nb = (int)min((long long)BANDS, bands - bd0);
     for (int e = threadIdx.x; e < nb * n_in4; e += blockDim.x) {
       const int k = e / n_in4, r4 = e - k * n_in4;
       const int ci = r4 / W4, w4 = r4 - ci * W4;        // ci = c*s + i
       const int c = ci / s, i = ci - c * s;
-      const long long bd = bd0 + k, b = bd / H2;
+      const long long bd = bd0 + k;
+      const long long b = CH > 0 ? (long long)((unsigned int)bd / (unsigned int)H2) : bd / H2;      // (bands < 2^31 whenever CH > 0)
       const int Y = (int)(bd - b * H2);
       band4[e] = __ldg(reinterpret_cast<const float4*>(x + b * sb + (long long)c * H * W + (long long)(Y * s + i) * W) + w4);
     }
@@ -594,8 +600,14 @@ __global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x
       const float* bp = band + (size_t)k * rows * W + i * W + X * s + j;
       const float4 v = make_float4(bp[0], bp[(size_t)s * W], bp[(size_t)2 * s * W], bp[(size_t)3 * s * W]);
       reinterpret_cast<float4*>(out + (bd0 + k) * (long long)W2 * C2)[r4] = v;
+      run_max = fmaxf(run_max, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     __syncthreads();
+  }
+  if (amax_slot != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+    if ((threadIdx.x & 31) == 0 && run_max > 0.f) atomicMax(amax_slot, __float_as_uint(run_max));
   }
 }
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ w, float* __restrict__ dst, int O, int C, int KH,
@@ -899,23 +911,33 @@ int thin_wgrad(const float* x, int ldx, const float* dy, float* dW, int ldw, lon
   return DDRL_OK;
 }
 #undef DDRL_THIN_DISPATCH
-int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s) {
+int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s, float* amax_slot) {
   if (g.order != 1 || g.sw != 1 || g.stride < 1 || g.H % g.stride || g.W % g.stride) return DDRL_E_ARG;
   const long long bands = (long long)B * (g.H / g.stride);
   if (bands == 0) return DDRL_OK;
   const size_t smem = sizeof(float) * (size_t)g.C * g.stride * g.W;
   if (smem > 48 * 1024) return DDRL_E_UNSUPPORTED;
   prof_work(8.0 * (double)B * g.C * g.H * g.W);
+  unsigned int* am = reinterpret_cast<unsigned int*>(amax_slot);
   if (g.C == 4 && g.W % 4 == 0 && g.sb % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
       4 * smem <= 48 * 1024) {
     constexpr int BANDS = 4;
     const long long groups = (bands + BANDS - 1) / BANDS;
-    s2d_c4_kernel<BANDS><<<(int)std::min<long long>(groups, 8LL * kNumSMs), 256, BANDS * smem, s>>>(x, out, g.H, g.W, g.stride, g.sb, bands);
+    const int grid = (int)std::min<long long>(groups, 8LL * kNumSMs);
+    if (g.H == 84 && g.W == 84 && g.stride == 4 && bands < (1LL << 31))
+      s2d_c4_kernel<BANDS, 84, 84, 4><<<grid, 256, BANDS * smem, s>>>(x, out, g.H, g.W, g.stride, g.sb, bands, am);
+    else
+      s2d_c4_kernel<BANDS><<<grid, 256, BANDS * smem, s>>>(x, out, g.H, g.W, g.stride, g.sb, bands, am);
     DDRL_LAUNCHED("s2d_kernel");
     return DDRL_OK;
   }
   s2d_kernel<<<(int)std::min<long long>(bands, 16LL * kNumSMs), 256, smem, s>>>(x, out, g.C, g.H, g.W, g.stride, g.sb, bands);
   DDRL_LAUNCHED("s2d_kernel");
+  if (amax_slot) {                               // generic layout: the reduction runs as a pass of its own
+    const int rc = amax_f32(out, (long long)B * (g.H / g.stride) * (g.W / g.stride), g.C * g.stride * g.stride,
+                            (long long)g.C * g.stride * g.stride, amax_slot, false, s);
+    if (rc != DDRL_OK) return rc;
+  }
   return DDRL_OK;
 }
 static int record_s2d(const float* src, float* dst, int O, int C, int KH, int KW, int stride, int ld, int unpack) {

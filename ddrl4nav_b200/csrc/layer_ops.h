@@ -169,7 +169,9 @@ int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias
              cudaStream_t s);
 int thin_wgrad(const float* x, int ldx, const float* dy, float* dW, int ldw, long long M, int N, int K, cudaStream_t s);
 // first-layer strided valid convs as stride-1 convs over the space-to-depth observation (layer_ops.cu)
-int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s);
+// amax_slot (optional, tc3 engine): the kernel also leaves max|x| of the frames it moves there (atomicMax on the bits; the
+// caller zeroes the slot) -- the scale of the first conv's activation operand, without a pass of its own over the tensor
+int space_to_depth(const ConvGeom& g, const float* x, float* out, int B, cudaStream_t s, float* amax_slot = nullptr);
 int pack_weight_s2d(const float* w_oihw, float* dst, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s);
 int unpack_grad_s2d(const float* src, float* dst_oihw, int O, int C, int KH, int KW, int stride, int ld, cudaStream_t s);
 int copy2d(const float* src, int ld_s, float* dst, int ld_d, long long rows, int colsN, cudaStream_t s);

@@ -1340,9 +1340,22 @@ static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0,
   const ConvGeom& g = t0.g[0];
   const Lin& l = t0.L[0];
   if (n->fuse_s2d && (n->s2d_train || (!train && !n->ws_train))) {
-    if (!cols_cached) TRY(space_to_depth(g, obs[0] + row0 * g.sb, n->s2dbuf, mb, s));
     const ConvGeom& gs = t0.gs;
     const ConvOp o = conv_op_fwd(gs, n->s2dbuf, gs.C, 0, mb);
+    if (!cols_cached) {
+      // tc3: the staging kernel leaves the operand's amax in its (persistent) slot on the way -- no reduction pass of its own
+      float* slot = nullptr;
+      if (tc3_mode(n) && n->w16_s2d.hi && n->amax_dev) {
+        const std::string key = amax_key(n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot);
+        const int si = amax_slot_index(n, key, true);
+        if (si >= 0) {
+          slot = n->amax_dev + si;
+          DDRL_CUDA(cudaMemsetAsync(slot, 0, sizeof(float), s));
+          n->amax_keys[key].epoch = n->amax_epoch;
+        }
+      }
+      TRY(space_to_depth(g, obs[0] + row0 * g.sb, n->s2dbuf, mb, s, slot));
+    }
     const int N2 = 2 * l.N;
     if (tc3_mode(n) && n->w16_s2d.hi) {
       const float* ama = nullptr;
