@@ -220,8 +220,10 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
 // The ReLU derivative is folded into the index (4 = "no gradient": the window maximum is <= 0), so the backward pass
 // reads only dout (a quarter of da) and one index byte per element -- 21 B per 4 da elements instead of 37.
 __global__ void __launch_bounds__(256) pool_fwd_vec4_kernel(const float4* __restrict__ a, float4* __restrict__ out,
-                                                            uchar4* __restrict__ idx, int H, int W, int C4, unsigned total) {
+                                                            uchar4* __restrict__ idx, int H, int W, int C4, unsigned total,
+                                                            unsigned int* __restrict__ amax_slot) {
   const int Ho = H / 2, Wo = W / 2;
+  float run_max = 0.f;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned c = i % C4;
     unsigned t = i / C4;
@@ -244,11 +246,15 @@ __global__ void __launch_bounds__(256) pool_fwd_vec4_kernel(const float4* __rest
 #undef DDRL_POOL1
     out[i] = best;
     if (idx) idx[i] = bi;
+    run_max = fmaxf(run_max, fmaxf(fmaxf(fabsf(best.x), fabsf(best.y)), fmaxf(fabsf(best.z), fabsf(best.w))));
   }
+  if (amax_slot != nullptr) amax_commit(amax_slot, run_max);
 }
 __global__ void __launch_bounds__(256) pool_bwd_vec4_kernel(const float4* __restrict__ dout, const uchar4* __restrict__ idx,
-                                                            float4* __restrict__ da, int H, int W, int C4, unsigned total) {
+                                                            float4* __restrict__ da, int H, int W, int C4, unsigned total,
+                                                            unsigned int* __restrict__ amax_slot) {
   const int Ho = H / 2, Wo = W / 2;
+  float run_max = 0.f;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned c = i % C4;
     unsigned t = i / C4;
@@ -264,7 +270,11 @@ __global__ void __launch_bounds__(256) pool_bwd_vec4_kernel(const float4* __rest
     p[(size_t)W * C4] = DDRL_SEL(2);
     p[(size_t)W * C4 + C4] = DDRL_SEL(3);
 #undef DDRL_SEL
+    // what reaches da is g where the argmax survived the ReLU (k < 4), zero elsewhere
+    run_max = fmaxf(run_max, fmaxf(fmaxf(k.x < 4 ? fabsf(g.x) : 0.f, k.y < 4 ? fabsf(g.y) : 0.f),
+                                   fmaxf(k.z < 4 ? fabsf(g.z) : 0.f, k.w < 4 ? fabsf(g.w) : 0.f)));
   }
+  if (amax_slot != nullptr) amax_commit(amax_slot, run_max);
 }
 
 // dy *= act'(y) from the activation OUTPUT y: relu: y>0 ; leaky: y>0 ? 1 : 0.01 (y==0 -> 0.01)
@@ -604,11 +614,7 @@ __global__ void __launch_bounds__(256) s2d_c4_kernel(const float* __restrict__ x
     }
     __syncthreads();
   }
-  if (amax_slot != nullptr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
-    if ((threadIdx.x & 31) == 0 && run_max > 0.f) atomicMax(amax_slot, __float_as_uint(run_max));
-  }
+  if (amax_slot != nullptr) amax_commit(amax_slot, run_max);
 }
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ w, float* __restrict__ dst, int O, int C, int KH,
                                                        int KW, int s, int ld, int unpack) {
@@ -792,22 +798,25 @@ static inline bool pool_vec_ok(const void* p0, const void* p1, const void* p2, i
   return C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && total / 4 < 0x7fffffffLL &&
          ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p2) & 3) == 0;
 }
-int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s) {
+int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s, float* amax_slot) {
   const long long total = (long long)B * (H / 2) * (W / 2) * C;
   if (total == 0) return DDRL_OK;
   prof_work(4.0 * (double)B * H * W * C + 5.0 * total);
   if (pool_vec_ok(a, out, idx, H, W, C, total)) {
     pool_fwd_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<float4*>(out),
-                                                             reinterpret_cast<uchar4*>(idx), H, W, C / 4, (unsigned)(total / 4));
+                                                             reinterpret_cast<uchar4*>(idx), H, W, C / 4, (unsigned)(total / 4),
+                                                             reinterpret_cast<unsigned int*>(amax_slot));
     DDRL_LAUNCHED("pool_fwd_kernel");
     return DDRL_OK;
   }
   pool_fwd_kernel<<<grid_for(total), 256, 0, s>>>(a, out, idx, H, W, C, total);
   DDRL_LAUNCHED("pool_fwd_kernel");
+  if (amax_slot) return amax_f32(out, total / C, C, C, amax_slot, false, s);
   return DDRL_OK;
 }
 // `a` (the pooled layer's input) is no longer read: relu'(a) at the argmax is encoded in idx by pool_fwd
-int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s) {
+int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s,
+             float* amax_slot) {
   const long long total = (long long)B * H * W * C;
   if (total == 0) return DDRL_OK;
   const long long pooled = (long long)B * (H / 2) * (W / 2) * C;
@@ -815,12 +824,14 @@ int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, i
   if (pool_vec_ok(dout, da, idx, H, W, C, pooled)) {
     pool_bwd_vec4_kernel<<<grid_for(pooled / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(dout),
                                                               reinterpret_cast<const uchar4*>(idx), reinterpret_cast<float4*>(da),
-                                                              H, W, C / 4, (unsigned)(pooled / 4));
+                                                              H, W, C / 4, (unsigned)(pooled / 4),
+                                                              reinterpret_cast<unsigned int*>(amax_slot));
     DDRL_LAUNCHED("pool_bwd_kernel");
     return DDRL_OK;
   }
   pool_bwd_kernel<<<grid_for(total), 256, 0, s>>>(dout, idx, a, da, H, W, C, total);
   DDRL_LAUNCHED("pool_bwd_kernel");
+  if (amax_slot) return amax_f32(da, total / C, C, C, amax_slot, false, s);
   return DDRL_OK;
 }
 int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int colsN, int act, cudaStream_t s) {

@@ -156,8 +156,10 @@ bool gemm_tc_supported(int form, int M, int N, int K, const float* A, int lda, c
 // layer glue ----------------------------------------------------------------------------
 int im2col(const ConvGeom& g, const float* x, float* cols, int B, cudaStream_t s);
 int col2im(const ConvGeom& g, const float* dcols, float* dx, int B, cudaStream_t s);
-int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s);
-int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s);
+// amax_slot (optional, tc3 engine): max|output| is accumulated there on the way (atomicMax on the bits; zeroed by the caller)
+int pool_fwd(const float* a, float* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s, float* amax_slot = nullptr);
+int pool_bwd(const float* dout, const uint8_t* idx, const float* a, float* da, int B, int H, int W, int C, cudaStream_t s,
+             float* amax_slot = nullptr);
 int act_bwd(float* dy, int ld_dy, const float* y, int ld_y, long long rows, int colsN, int act, cudaStream_t s);
 // db2 != nullptr: columns [0, split) accumulate into db, [split, N) into db2 (one pass over a fused two-layer gradient)
 int colsum_add(const float* dy, int ld, long long rows, int N, float* db, cudaStream_t s, float* db2 = nullptr, int split = 0);

@@ -1172,12 +1172,16 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
         img = b[15];
       }
       const ConvGeom *g0 = &t.g[0], *g1 = &t.g[1], *g2 = &t.g[2];
+      // tc3: the pooling kernels leave max|output| in the operand's amax slot (no reduction pass of its own per tensor)
+      auto pool_slot = [&](const float* out, const ConvGeom* g, int C) {
+        return amax_out_slot(const_cast<ddrl_net*>(n), out, (long long)mb * (g->Ho / 2) * (g->Wo / 2), C, C);
+      };
       TRY(conv_block(n, t, 0, 0, img, b[0], b[1], mb, s, reuse_obs || t.borrow_cols));    // tower 0 ran first: its cols are current
-      TRY(pool_fwd(b[1], b[2], t.idx[0], mb, g0->Ho, g0->Wo, 64, s));
+      TRY(pool_fwd(b[1], b[2], t.idx[0], mb, g0->Ho, g0->Wo, 64, s, pool_slot(b[2], g0, 64)));
       TRY(conv_block(n, t, 1, 1, b[2], b[3], b[4], mb, s));
-      TRY(pool_fwd(b[4], b[5], t.idx[1], mb, g1->Ho, g1->Wo, 128, s));
+      TRY(pool_fwd(b[4], b[5], t.idx[1], mb, g1->Ho, g1->Wo, 128, s, pool_slot(b[5], g1, 128)));
       TRY(conv_block(n, t, 2, 2, b[5], b[6], b[7], mb, s));
-      TRY(pool_fwd(b[7], b[8], t.idx[2], mb, g2->Ho, g2->Wo, 256, s));
+      TRY(pool_fwd(b[7], b[8], t.idx[2], mb, g2->Ho, g2->Wo, 256, s, pool_slot(b[8], g2, 256)));
       const int flat = (g2->Ho / 2) * (g2->Wo / 2) * 256;
       const float* vec = obs[1];
       if (d1) {
@@ -1294,17 +1298,20 @@ static int tower_backward(ddrl_net* n, Tower& t, const float* const* obs, long l
             *dp1 = b[23], *dz1 = b[24];
       const int Lfc2 = d1 ? 8 : 5, Lfc1 = d1 ? 7 : 4, Lfc0 = d1 ? 6 : 3;
       const int img_off = d1 ? 256 : 0;
+      auto unpool_slot = [&](const float* da, const ConvGeom* g, int C) {
+        return amax_out_slot(n, da, (long long)mb * g->Ho * g->Wo, C, C);
+      };
       // fc2 (no activation) <- relu(fc1) <- relu(cat parts): each data gradient is multiplied by relu' of its target
       TRY(lin_bwd(n, t.L[Lfc2], b[10], 512, t.dh, 512, df1, 512, 512, ACT_RELU, b[10], mb, s));
       TRY(lin_bwd(n, t.L[Lfc1], b[9], ldcat, df1, 512, dcat, ldcat, img_off + 512, ACT_RELU, b[9], mb, s));
       TRY(lin_bwd(n, t.L[Lfc0], b[8], flat, dcat + img_off, ldcat, dp3, flat, flat, 0, nullptr, mb, s));
       TRY(seg_cut(n, s));
       // ReLU' of the conv outputs is folded into pool_bwd (a > 0 test)
-      TRY(pool_bwd(dp3, t.idx[2], b[7], dz3, mb, g2->Ho, g2->Wo, 256, s));
+      TRY(pool_bwd(dp3, t.idx[2], b[7], dz3, mb, g2->Ho, g2->Wo, 256, s, unpool_slot(dz3, g2, 256)));
       TRY(conv_bwd(n, t, 2, 2, b[5], b[6], dz3, dcols, dp2, 0, mb, s));
-      TRY(pool_bwd(dp2, t.idx[1], b[4], dz2, mb, g1->Ho, g1->Wo, 128, s));
+      TRY(pool_bwd(dp2, t.idx[1], b[4], dz2, mb, g1->Ho, g1->Wo, 128, s, unpool_slot(dz2, g1, 128)));
       TRY(conv_bwd(n, t, 1, 1, b[2], b[3], dz2, dcols, dp1, 0, mb, s));
-      TRY(pool_bwd(dp1, t.idx[0], b[1], dz1, mb, g0->Ho, g0->Wo, 64, s));
+      TRY(pool_bwd(dp1, t.idx[0], b[1], dz1, mb, g0->Ho, g0->Wo, 64, s, unpool_slot(dz1, g0, 64)));
       TRY(conv_bwd(n, t, 0, 0, nullptr, b[0], dz1, nullptr, nullptr, 0, mb, s));
       if (d1) {
         // laser branch: fc_1d+relu <- conv1d2 <- conv1d1, no activation between the convs (nav_encoder.py:109-110)
