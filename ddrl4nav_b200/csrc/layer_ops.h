@@ -98,13 +98,17 @@ int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, cons
              cudaStream_t s);
 int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, int N, const float* amax_a, const float* amax_b,
                  const float* bias, int act, const float* mask, float* out, long long osb, long long osy, long long osx,
-                 float* amax_out, cudaStream_t s, const TcTap* cls = nullptr);
+                 float* amax_out, cudaStream_t s, const TcTap* cls = nullptr, const void* a_hi16 = nullptr, const void* a_lo16 = nullptr);
+// a_hi16 / a_lo16 (optional, conv launches): the activation operand pre-split into fp16 planes by tc3_presplit (same layout as
+// o.a with 2-byte elements, scaled by t3_scale(*amax_a)); needs Cin % 64 == 0.  Both MMA operands are then plain TMA loads.
+int tc3_presplit(const float* x, long long n, const float* amax, void* hi, void* lo, cudaStream_t s);
 // db (optional): bias gradient db[n] += sum_r dy[r, n], fused into the kernel's dy conversion (no separate column-sum pass)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
               const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0);
 bool tc3_conv_wgrad_supported(const ConvOp& o);
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0);
+                   cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0, const void* a_hi16 = nullptr,
+                   const void* a_lo16 = nullptr);
 int amax_f32(const float* x, long long rows, int cols, long long ld, float* slot, bool zero_first, cudaStream_t s);
 int split_f16(const float* w, int N, int K, int ldw, const float* amax, void* hi, void* lo, int ld16, void* hiT, void* loT,
               int ldT16, cudaStream_t s);

@@ -126,6 +126,11 @@ struct ddrl_net {
   // the 3.4 GB im2col matrix and its two HBM-bound passes per iteration are gone (DDRL_NO_S2D_TRAIN=1 keeps the im2col GEMM)
   bool s2d_train = false;
   float* s2dbuf = nullptr;       // [MB, H/s, W/s, s*s*C] space-to-depth observation of the micro-batch
+  // ... and its fp16 split (tc3 engine, DDRL_NO_PRESPLIT=1 turns it off): planes hi [MB, ...] | lo' [MB, ...], written once per
+  // staged micro-batch by tc3_presplit.  The first conv and its weight gradient (20 launches per learn call on the same
+  // observation) then take both MMA operands straight from TMA: no per-use split, no splitter warps in those launches.
+  void* s2d16 = nullptr;
+  size_t s2d16_plane = 0;        // bytes per plane
   float* w0s2d = nullptr;        // [2 x Cout, K] both towers' conv1 weights in the space-to-depth K order (packed arena)
   float* bias0c = nullptr;       // its concatenated bias [2 x Cout]
   // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
@@ -607,7 +612,9 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   for (auto& t : n->towers) per += tower_bytes_per_sample(t, train);
   per += (size_t)(n->ldA * 2 + 2 + 8) * 4;
   const size_t s2d_floats = (n->fuse_s2d && (!train || n->s2d_train)) ? (size_t)n->towers[0].g[0].C * n->towers[0].g[0].H * n->towers[0].g[0].W : 0;
-  per += s2d_floats * 4;
+  const bool s2d_split = s2d_floats && tc3_mode(n) && s2d_floats % 8 == 0 && !getenv("DDRL_NO_PRESPLIT") &&
+                         (train || !getenv("DDRL_NO_PRESPLIT_INFER"));
+  per += s2d_floats * 4 * (s2d_split ? 2 : 1);
   const char* env_gb = getenv("DDRL_WS_GB");
   const char* env_mb = getenv("DDRL_MICRO_BATCH");
   const double budget = (env_gb ? atof(env_gb) : 24.0) * (double)(1ull << 30);
@@ -636,7 +643,7 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   }
   total += 4 * (((size_t)n->ldA * mb * 4 + 255) & ~size_t(255)) + 4096;
   total += 2 * (((size_t)kMaxExtra * mb * 4 + 255) & ~size_t(255));
-  total += (s2d_floats * mb * 4 + 255) & ~size_t(255);
+  total += ((s2d_floats * mb * 4 + 255) & ~size_t(255)) * (s2d_split ? 2 : 1);
   if (cudaMalloc(&n->ws.base, total) != cudaSuccess) {
     cudaGetLastError();
     n->ws.base = nullptr; n->MB = 0;
@@ -654,6 +661,8 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
     t.dh = train ? n->ws.take((size_t)t.feat * mb) : nullptr;
   }
   n->s2dbuf = s2d_floats ? n->ws.take(s2d_floats * mb) : nullptr;
+  n->s2d16 = s2d_split ? n->ws.take(s2d_floats * mb) : nullptr;
+  n->s2d16_plane = s2d_floats * mb * 2;
   if (n->towers.size() == 2 && n->towers[1].borrow_cols) {
     Tower &t0 = n->towers[0], &t1 = n->towers[1];
     t1.buf[0] = t0.buf[0];
@@ -1367,9 +1376,15 @@ static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0,
     if (tc3_mode(n) && n->w16_s2d.hi) {
       const float* ama = nullptr;
       TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &ama, true));
+      const void *p_hi = nullptr, *p_lo = nullptr;
+      if (n->s2d16 && o.Cin % 64 == 0) {
+        p_hi = n->s2d16; p_lo = reinterpret_cast<const char*>(n->s2d16) + n->s2d16_plane;
+        if (!cols_cached)
+          TRY(tc3_presplit(n->s2dbuf, (long long)mb * o.Hin * o.Win * o.Ctot, ama, n->s2d16, reinterpret_cast<char*>(n->s2d16) + n->s2d16_plane, s));
+      }
       return tc3_conv_fwd(o, n->w16_s2d.hi, n->w16_s2d.lo, n->w16_s2d.ld, N2, ama, n->w16_s2d.amax, n->bias0c, l.act, nullptr, t0.buf[1],
                           (long long)o.Yn * o.Xn * N2, (long long)o.Xn * N2, N2,
-                          amax_out_slot(n, t0.buf[1], (long long)mb * o.Yn * o.Xn, N2, N2), s);
+                          amax_out_slot(n, t0.buf[1], (long long)mb * o.Yn * o.Xn, N2, N2), s, nullptr, p_hi, p_lo);
     }
     return tc2_conv_fwd(o, hi_of(n, n->w0s2d), lo_of(n, n->w0s2d), l.ldw, N2, n->bias0c, l.act, nullptr, t0.buf[1], (long long)o.Yn * o.Xn * N2,
                         (long long)o.Xn * N2, N2, s);
@@ -1397,8 +1412,9 @@ static int fused_conv0_bwd(ddrl_net* n, int mb, cudaStream_t s) {
     TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &amx, true));
     TRY(amax_in_slot(n, dy, M, 2 * l0.N, 2 * l0.N, s, &amy));
     float* dw = reinterpret_cast<float*>(reinterpret_cast<char*>(n->w0s2d) + n->packed_grad_off);
+    const bool psw = n->s2d16 && o.Cin % 64 == 0 && !getenv("DDRL_NO_PRESPLIT_WGRAD");
     return tc3_conv_wgrad(o, dy, 2 * l0.N, 2 * l0.N, amx, amy, dw, l0.ldw, s, fcs ? db_of(n, l0) : nullptr, fcs ? db_of(n, l1) : nullptr,
-                          l0.N);
+                          l0.N, psw ? n->s2d16 : nullptr, psw ? reinterpret_cast<const char*>(n->s2d16) + n->s2d16_plane : nullptr);
   }
   if (w3) {
     const float *amx = nullptr, *amy = nullptr;

@@ -58,7 +58,12 @@ __device__ unsigned long long g_tc3_wait[96];   // weight-gradient kernel: roles
 #define T3_WAIT(bar, par, acc) do { T3_T0; mbar_wait(bar, par); T3_ACC(acc); } while (0)
 #define T3_WAITL(bar, par, acc) do { T3_T0; mbar_wait_long(bar, par); T3_ACC(acc); } while (0)
 #define T3_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0, w3 = 0; const long long role_t0 = clock64();
-#define T3_ROLE_END(role, cond) do { if ((cond) && lane == 0) { \
+#ifdef TC3_TIMING_PS            // account only the launches whose activation operand is pre-split
+#define T3_TCOND (g.presplit != 0)
+#else
+#define T3_TCOND true
+#endif
+#define T3_ROLE_END(role, cond) do { if ((cond) && T3_TCOND && lane == 0) { \
     atomicAdd(&g_tc3_wait[(role) * 8 + 0], (unsigned long long)w0); atomicAdd(&g_tc3_wait[(role) * 8 + 1], (unsigned long long)w1); \
     atomicAdd(&g_tc3_wait[(role) * 8 + 2], (unsigned long long)w2); atomicAdd(&g_tc3_wait[(role) * 8 + 3], (unsigned long long)w3); \
     atomicAdd(&g_tc3_wait[(role) * 8 + 7], (unsigned long long)(clock64() - role_t0)); } } while (0)
@@ -83,6 +88,12 @@ struct Tc3Args {
   int act, atomic, vec_store;
   int tma_store;                              // outputs leave through TMA tile stores of the staged panels (tmC / tmC2)
   int tma_mask;                               // ... and the activation mask (act >= 3) ARRIVES through TMA, into the same panels (tmM / tmM2)
+  // The activation operand was split ONCE, by its producer, into two fp16 planes (hi | lo', the tensor's layout with 2-byte
+  // elements, scaled by t3_scale(*amax_a)): both MMA operands are plain TMA loads, the A tiles stay in shared memory (SS
+  // MMAs) and the splitter warps have nothing to do.  Forward kernel: tmA / tmA2 = hi plane, tmM / tmM2 = lo' plane (such
+  // launches carry no activation mask); K blocks are one 64-channel slice of one tap.  Weight gradient: tmA / tmA2 = hi plane,
+  // tmAl / tmAl2 = lo' plane, the landed [64 pixels x 64 channels] boxes ARE the MN-major A tiles.
+  int presplit;
   int m_tiles, n_tiles;
   const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
   const float* amax_b;
@@ -111,6 +122,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 template <int BN>
@@ -195,7 +215,8 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   const int tile_step = (int)gridDim.x, tile_first = (int)blockIdx.x;
   const int nkb = g.kb_total;
   // tap mode with an odd slice count: the last K block holds ONE 32-channel slice (2 k steps)
-  const bool odd_tail = tapA && (tp.nslices & 1);
+  const bool ps = g.presplit != 0;
+  const bool odd_tail = tapA && !ps && (tp.nslices & 1);
 
   if (warp == 0) {
     // ============================================================ TMA producer
@@ -218,7 +239,19 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const uint32_t full = smem_u32(bar_full + s);
           const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
           const int k = i * T3_BK;
-          if (!tapA) {
+          if (ps) {
+            // pre-split operand: [hi tile | lo' tile], 128 rows x 64 halfs each (tap mode: tp.cpb counts 64-channel slices)
+            if (!tapA) {
+              mbar_expect_tx(full, Cfg::A_BYTES + 2u * Cfg::B_BYTES);
+              tma_load_2d(&tmA, full, a_dst, k, m0);
+              tma_load_2d(&tmM, full, a_dst + Cfg::A_SUB, k, m0);
+            } else {
+              const uint32_t box = (uint32_t)(ph2 ? tp.rows2 : tp.rows) * 128u;
+              mbar_expect_tx(full, 2u * box + 2u * Cfg::B_BYTES);
+              tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 64, kw - tp.px, y0 + kh, b0);
+              tma_load_4d(ph2 ? &tmM2 : &tmM, full, a_dst + Cfg::A_SUB, tp.c_off + cc * 64, kw - tp.px, y0 + kh, b0);
+            }
+          } else if (!tapA) {
             mbar_expect_tx(full, Cfg::A_BYTES + 2u * Cfg::B_BYTES);
             tma_load_2d(&tmA, full, a_dst, k, m0);
             tma_load_2d(&tmA, full, a_dst + Cfg::A_SUB, k + 32, m0);
@@ -239,8 +272,10 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (tapA) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < 2; ++j) {
+            if (ps && j == 1) break;                  // pre-split: one (64-channel) slice per K block
             if (++cc == tp.cpb) { cc = 0; if (++kw == tp.KW) { kw = 0; ++kh; } }
+          }
         }
       }
     }
@@ -267,14 +302,37 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         else if (i == 0) T3_WAIT(smem_u32(bar_cfree), (tl & 1) ^ 1, w0);
         // ONE wait per K block: the splitters arrive on `aready` after they have seen the stage's TMA barrier, so the
         // weight tile of the stage is complete (and visible through the same release / acquire chain) as well
-        T3_WAIT(smem_u32(bar_aready + a), (it / SA) & 1, w1);
+        // (pre-split operand: nobody stands between the TMA and the MMAs -- both issuers wait for the stage itself)
+        if (ps) T3_WAIT(smem_u32(bar_full + s), (it / S) & 1, w1);
+        else T3_WAIT(smem_u32(bar_aready + a), (it / SA) & 1, w1);
         tc_fence_after();
         T3_SECTION_BEGIN;
         if (elect_one()) {
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
           const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
           const uint64_t dbh0 = umma_desc(b_hi, 16, 1024, 2);
-          if (chunk_role) {
+          if (ps) {
+            // A tiles in shared memory: K-major, 128 rows x 64 halfs, 128B swizzle -- the weight tile's own layout
+            const uint32_t sa_hi = smem_base + s * Cfg::STAGE_BYTES;
+            const uint64_t dah0 = umma_desc(sa_hi, 16, 1024, 2), dal0 = umma_desc(sa_hi + Cfg::A_SUB, 16, 1024, 2);
+            if (chunk_role) {
+              const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_f16_ss(t_main, dah0 + k4 * 2, dbh0 + k4 * 2, Cfg::FOLD ? idesc2 : idesc, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+              umma_commit(smem_u32(bar_empty + s));
+              if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+            } else {
+              const uint64_t dbl0 = umma_desc(b_lo, 16, 1024, 2);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_f16_ss(t_corr, dal0 + k4 * 2, dbh0 + k4 * 2, idesc, (i | k4) != 0 ? 1u : 0u);
+                if (!Cfg::FOLD) umma_f16_ss(t_corr, dah0 + k4 * 2, dbl0 + k4 * 2, idesc, 1u);
+              }
+              umma_commit(smem_u32(bar_empty + s));
+              if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
+            }
+          } else if (chunk_role) {
             const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -311,7 +369,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int row = q * 32 + lane;
     uint32_t it = 0;
     T3_ROLE_BEGIN
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int tile = ps ? total_tiles : tile_first; tile < total_tiles; tile += tile_step) {    // (pre-split operand: nothing to do)
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % S, a = it % SA;
         if ((int)(it % Cfg::NSG) != grp) {                         // the groups take K blocks round-robin
@@ -750,6 +808,46 @@ static int make_map_b16(CUtensorMap* m, const void* base, int K, int N, int ldb1
   return tc_encode_tiled(m, true, 2, base, dims, strides, box, estr, true);
 }
 
+// 4-D map over one fp16 plane of a pre-split NHWC tensor [Bn, H, W, Ctot]: box = 64 channels x nx pixels (every sx-th) x ny rows
+// (every sy-th) x nb images, 128B swizzle: the box lands as rows of 64 halfs = the K-major (forward) / MN-major (weight gradient)
+// fp16 operand tile
+static int make_map_nhwc16(CUtensorMap* m, const void* plane, const ConvOp& o, int nx, int ny, int nb) {
+  const unsigned long long dims[4] = {(unsigned long long)o.Ctot, (unsigned long long)o.Win, (unsigned long long)o.Hin, (unsigned long long)o.Bn};
+  const unsigned long long strides[3] = {(unsigned long long)o.Ctot * 2, (unsigned long long)o.Win * o.Ctot * 2,
+                                         (unsigned long long)o.Hin * o.Win * o.Ctot * 2};
+  const unsigned box[4] = {64u, (unsigned)((nx - 1) * o.sx + 1), (unsigned)((ny - 1) * o.sy + 1), (unsigned)nb};
+  const unsigned estr[4] = {1u, (unsigned)o.sx, (unsigned)o.sy, 1u};
+  return tc_encode_tiled(m, true, 4, plane, dims, strides, box, estr, true);
+}
+static inline bool presplit_ok(const ConvOp& o, const void* hi, const void* lo) {
+  return hi && lo && al16(hi) && al16(lo) && o.Cin % 64 == 0 && o.Ctot % 8 == 0 && o.c_off % 8 == 0;
+}
+
+// x [n] fp32 -> fp16 planes hi [n] | lo' [n] of x * t3_scale(*amax): the split every tc3 consumer of x would otherwise repeat per
+// use (forward taps, weight gradient), done once.  8 elements per thread and step.
+__global__ void __launch_bounds__(256) presplit_kernel(const float* __restrict__ x, long long n8, const float* __restrict__ amax,
+                                                       uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  float sA, sA_inv;
+  t3_scale(__ldg(amax), sA, sA_inv);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(x4 + 2 * i), b = __ldg(x4 + 2 * i + 1);
+    uint4 h, l;
+    t3_split2(a.x, a.y, sA, h.x, l.x); t3_split2(a.z, a.w, sA, h.y, l.y);
+    t3_split2(b.x, b.y, sA, h.z, l.z); t3_split2(b.z, b.w, sA, h.w, l.w);
+    hi[i] = h; lo[i] = l;
+  }
+}
+int tc3_presplit(const float* x, long long n, const float* amax, void* hi, void* lo, cudaStream_t s) {
+  if (!x || !amax || !hi || !lo || n < 0 || n % 8 != 0 || !al16(x) || !al16(hi) || !al16(lo)) return DDRL_E_ARG;
+  if (n == 0) return DDRL_OK;
+  const long long n8 = n / 8;
+  const int blocks = (int)std::min<long long>((n8 + 255) / 256, 16LL * kNumSMs);
+  presplit_kernel<<<blocks, 256, 0, s>>>(x, n8, amax, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo));
+  DDRL_LAUNCHED("presplit_kernel");
+  return DDRL_OK;
+}
+
 bool tc3_gemm_supported(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16) {
   if (M < 1 || N < 1 || K < 1) return false;
   if (!al16(A) || !al16(Bhi) || !al16(Blo) || lda % 4 != 0 || ldb16 % 8 != 0) return false;
@@ -799,9 +897,11 @@ int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, cons
 
 int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, int N, const float* amax_a, const float* amax_b,
                  const float* bias, int act, const float* mask, float* out, long long osb, long long osy, long long osx,
-                 float* amax_out, cudaStream_t s, const TcTap* cls) {
+                 float* amax_out, cudaStream_t s, const TcTap* cls, const void* a_hi16, const void* a_lo16) {
   if (!conv_tc_supported(o, false) || N < 1 || ldw16 % 8 != 0 || !al16(Whi) || !al16(Wlo)) return DDRL_E_UNSUPPORTED;
   if ((act >= 3 && !mask) || !amax_a || !amax_b) return DDRL_E_ARG;
+  const bool ps = a_hi16 != nullptr || a_lo16 != nullptr;
+  if (ps && (!presplit_ok(o, a_hi16, a_lo16) || act >= 3)) return DDRL_E_UNSUPPORTED;
   int r = tc_get_encode();
   if (r != DDRL_OK) return r;
   const int bn = pick_bn3(N);
@@ -820,16 +920,23 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
   }
   const int K = o.KH * o.KW * o.Cin;
   Tc3Maps mp;
-  r = tc_make_map_nhwc(&mp.a, o, o.Xn, g.tap.ny, g.tap.nb, false);
   const bool ph2 = g.tap.ny2 > 0;
-  if (r == DDRL_OK && ph2) r = tc_make_map_nhwc(&mp.a2, o, o.Xn, g.tap.ny2, g.tap.nb2, false);
+  if (ps) {
+    g.presplit = 1;
+    g.tap.cpb = o.Cin / 64; g.tap.nslices = o.KH * o.KW * g.tap.cpb;     // 64-channel slices, one per K block
+    r = make_map_nhwc16(&mp.a, a_hi16, o, o.Xn, g.tap.ny, g.tap.nb);
+    if (r == DDRL_OK && ph2) r = make_map_nhwc16(&mp.a2, a_hi16, o, o.Xn, g.tap.ny2, g.tap.nb2);
+  } else {
+    r = tc_make_map_nhwc(&mp.a, o, o.Xn, g.tap.ny, g.tap.nb, false);
+    if (r == DDRL_OK && ph2) r = tc_make_map_nhwc(&mp.a2, o, o.Xn, g.tap.ny2, g.tap.nb2, false);
+  }
   if (r == DDRL_OK) r = make_map_b16(&mp.bhi, Whi, K, N, ldw16, bn);
   if (r == DDRL_OK) r = make_map_b16(&mp.blo, Wlo, K, N, ldw16, bn);
   if (r != DDRL_OK) return r;
   if (!ph2) mp.a2 = mp.a;
   g.C = out; g.bias = bias; g.mask = mask; g.act = act;
   g.M = o.Bn * o.Yn * o.Xn; g.N = N; g.K = K; g.sCm = 0; g.sCn = 1;
-  g.kb_total = (g.tap.nslices + 1) / 2; g.kb_per_split = g.kb_total;
+  g.kb_total = ps ? g.tap.nslices : (g.tap.nslices + 1) / 2; g.kb_per_split = g.kb_total;
   g.m_tiles = ceil_div(o.Bn, g.tap.nb) * g.tap.tpi + (ph2 ? ceil_div(o.Bn, g.tap.nb2) : 0);
   g.n_tiles = ceil_div(N, bn);
   g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
@@ -864,6 +971,12 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
   if (!g.tma_store || !ph2) mp.c2 = mp.c;
   if (!g.tma_mask) mp.m = mp.c;
   if (!g.tma_mask || !ph2) mp.m2 = mp.m;
+  if (ps) {                                       // the mask slots carry the lo' plane
+    r = make_map_nhwc16(&mp.m, a_lo16, o, o.Xn, g.tap.ny, g.tap.nb);
+    if (r == DDRL_OK && ph2) r = make_map_nhwc16(&mp.m2, a_lo16, o, o.Xn, g.tap.ny2, g.tap.nb2);
+    if (r != DDRL_OK) return r;
+    if (!ph2) mp.m2 = mp.m;
+  }
   dim3 grid(std::min(g.m_tiles * g.n_tiles, kNumSMs), 1, 1);
   return launch3_bn(bn, mp, g, grid, s);
 }
@@ -908,7 +1021,8 @@ struct T3WCfg {
 template <int BN>
 __global__ void __launch_bounds__(T3WCfg<BN>::THREADS, 1)
 tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, Tc3Args g) {
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmAl2, Tc3Args g) {
   using Cfg = T3WCfg<BN>;
   constexpr int S = Cfg::STAGES, SA = Cfg::SA;
   extern __shared__ uint8_t smem_dyn[];
@@ -927,6 +1041,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcTap& tp = g.tap;
   const bool tapA = tp.mode != 0;
+  // pre-split activation operand (fp16 hi / lo' planes): the landed boxes are the MMA's MN-major A tiles, so the stage is
+  // released by the MMAs (2 commits) and the conversion warps, and the gather warps have nothing to do
+  const bool ps = g.presplit != 0;
 
   if (tapA) {
     // pixel-box K blocks shorter than 64 rows: the rows no box covers must read as zero
@@ -936,8 +1053,8 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 0 && lane == 0) {
     // a stage is consumed / a slot is produced by the 4 gather warps of one splitter group AND the NEPI conversion warps
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 4 + Cfg::NEPI); }
-    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), 4 + Cfg::NEPI); mbar_init(smem_u32(bar_afree + a), 2); }
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), (ps ? 2 : 4) + Cfg::NEPI); }
+    for (int a = 0; a < SA; ++a) { mbar_init(smem_u32(bar_aready + a), (ps ? 0 : 4) + Cfg::NEPI); mbar_init(smem_u32(bar_afree + a), 2); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -962,13 +1079,15 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ============================================================ TMA producer
     int sl_c[4] = {0, 0, 0, 0}, sl_x[4] = {0, 0, 0, 0}, sl_y[4] = {0, 0, 0, 0}, na = 0;
     if (tapA) {
+      // (pre-split: slices are 64 channels wide, two per M block; tp.cpb / tp.nslices count those)
+      const int spb = ps ? 2 : 4, sw = ps ? 64 : 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int sl = (int)blockIdx.x * 4 + j;
-        if (sl < tp.nslices) {
+        const int sl = (int)blockIdx.x * spb + j;
+        if (j < spb && sl < tp.nslices) {
           const int tap = sl / tp.cpb, cc = sl - tap * tp.cpb;
           const int kh = tap / tp.KW, kw = tap - kh * tp.KW;
-          sl_c[j] = tp.c_off + cc * 32; sl_x[j] = kw - tp.px; sl_y[j] = kh - tp.py;
+          sl_c[j] = tp.c_off + cc * sw; sl_x[j] = kw - tp.px; sl_y[j] = kh - tp.py;
           na = j + 1;
         }
       }
@@ -993,18 +1112,24 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // two pixel-box classes (64 pixels each): class 1 covers the columns right of wxw0
           const bool c1 = pj >= tp.wnb0;
           const int x0 = c1 ? tp.wxw0 : 0, yy0 = c1 ? (pj - tp.wnb0) * tp.wyh1 : pj * tp.wyh0;
-          mbar_expect_tx(full, (na + BN / 32) * 64 * 128);
+          mbar_expect_tx(full, ((ps ? 2 * na : na) + BN / 32) * 64 * 128);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (j < na) tma_load_4d(c1 ? &tmA2 : &tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+            if (j < na) {
+              tma_load_4d(c1 ? &tmA2 : &tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+              if (ps) tma_load_4d(c1 ? &tmAl2 : &tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+            }
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j) tma_load_4d(c1 ? &tmB2 : &tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, x0, yy0, pb);
         } else {
           const int yy0 = pj * tp.ny;
-          mbar_expect_tx(full, (na + BN / 32) * tp.rows * 128);
+          mbar_expect_tx(full, ((ps ? 2 * na : na) + BN / 32) * tp.rows * 128);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (j < na) tma_load_4d(&tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+            if (j < na) {
+              tma_load_4d(&tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+              if (ps) tma_load_4d(&tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+            }
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, yy0 * tp.Xn, pb);
         }
@@ -1038,7 +1163,35 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t b_hi = b16_base + a * Cfg::B16_BYTES, b_lo = b_hi + (BN / 64) * Cfg::B16_TILE;
         const uint32_t a_hi = tmem_base + Cfg::TM_A + a * 64, a_lo = a_hi + 32;
         const uint64_t dbh0 = umma_desc(b_hi, Cfg::B16_TILE, 1024, 2);
-        if (chunk_role) {
+        if (ps) {
+          // A from shared memory, MN-major (bit 15): the stage holds [hi slice 0 | hi slice 1 | lo' slice 0 | lo' slice 1], each
+          // 64 pixels (k) x 64 channels (m) in the dy tiles' own layout: 64-channel groups 8 KB apart, one k step = 2 KB
+          const uint32_t st_a = smem_u32(smem) + (i % S) * Cfg::STAGE_BYTES;
+          const uint64_t dah0 = umma_desc(st_a, Cfg::A_SUB, 1024, 2), dal0 = umma_desc(st_a + 2 * Cfg::A_SUB, Cfg::A_SUB, 1024, 2);
+          const uint32_t am = 1u << 15;
+          if (chunk_role) {
+            const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_f16_ss(t_main, dah0 + k4 * (2048 >> 4), dbh0 + k4 * (2048 >> 4), (Cfg::FOLD ? idesc2 : idesc) | am, (!first_in_chunk || k4 != 0) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(bar_empty + (i % S)));
+            umma_commit(smem_u32(bar_afree + a));
+            if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
+          } else {
+            const uint64_t dbl0 = umma_desc(b_lo, Cfg::B16_TILE, 1024, 2);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (k4 >= ksteps) break;
+              umma_f16_ss(t_corr, dal0 + k4 * (2048 >> 4), dbh0 + k4 * (2048 >> 4), idesc | am, (i | k4) != 0 ? 1u : 0u);
+              if (!Cfg::FOLD) umma_f16_ss(t_corr, dah0 + k4 * (2048 >> 4), dbl0 + k4 * (2048 >> 4), idesc | am, 1u);
+            }
+            umma_commit(smem_u32(bar_empty + (i % S)));
+            umma_commit(smem_u32(bar_afree + a));
+            if (i == nkb - 1) umma_commit(smem_u32(bar_cfull));
+          }
+        } else if (chunk_role) {
           const uint32_t t_main = tmem_base + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -1073,7 +1226,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float sA, sA_inv;
     t3_scale(__ldg(g.amax_a), sA, sA_inv);
     T3_ROLE_BEGIN
-    for (int i = 0; i < nkb; ++i) {
+    for (int i = ps ? nkb : 0; i < nkb; ++i) {                     // (pre-split operand: nothing to gather)
       const int s = i % S, a = i % SA;
       if ((i % Cfg::NSG) != grp) {
         // follow every phase of the stage barrier (see the forward kernel): with S = 3 stages and 2 groups a group meets a
@@ -1280,7 +1433,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN>
 static int launch3w(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2, const Tc3Args& g,
-                    dim3 grid, cudaStream_t s) {
+                    dim3 grid, cudaStream_t s, const CUtensorMap* tal = nullptr, const CUtensorMap* tal2 = nullptr) {
   using Cfg = T3WCfg<BN>;
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device_index()];
@@ -1288,7 +1441,7 @@ static int launch3w(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
     DDRL_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  tc3_wgrad_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, ta2, tb2, g);
+  tc3_wgrad_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, ta2, tb2, tal ? *tal : ta, tal2 ? *tal2 : ta2, g);
   prof_work(2.0 * g.M * (double)g.N * g.K);
   if (g_prof_on && g_prof_shapes) {
     char nm[96];
@@ -1364,9 +1517,11 @@ static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn
 }
 
 int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float* amax_x, const float* amax_dy, float* dWp, int ldw,
-                   cudaStream_t s, float* db, float* db2, int db_split) {
+                   cudaStream_t s, float* db, float* db2, int db_split, const void* a_hi16, const void* a_lo16) {
   if (!tc3_conv_wgrad_supported(o) || N < 1 || ldy % 4 != 0 || !al16(dy)) return DDRL_E_UNSUPPORTED;
   if (!amax_x || !amax_dy) return DDRL_E_ARG;
+  const bool ps = a_hi16 != nullptr || a_lo16 != nullptr;
+  if (ps && !presplit_ok(o, a_hi16, a_lo16)) return DDRL_E_UNSUPPORTED;
   int r = tc_get_encode();
   if (r != DDRL_OK) return r;
   const int bn = N > 64 ? 128 : 64;
@@ -1377,7 +1532,13 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   g.tap.rows = o.Xn * g.tap.ny;
   g.tap.kpad = (g.tap.rows + 15) & ~15;
   const int K = o.KH * o.KW * o.Cin;
-  CUtensorMap ta, tb, ta2, tb2;
+  CUtensorMap ta, tb, ta2, tb2, tal, tal2;
+  if (ps) { g.presplit = 1; g.tap.cpb = o.Cin / 64; g.tap.nslices = o.KH * o.KW * g.tap.cpb; }
+  auto map_a = [&](CUtensorMap* hi, CUtensorMap* lo, int nx, int ny) {
+    if (!ps) return tc_make_map_nhwc(hi, o, nx, ny, 1, false);
+    const int rr = make_map_nhwc16(hi, a_hi16, o, nx, ny, 1);
+    return rr != DDRL_OK ? rr : make_map_nhwc16(lo, a_lo16, o, nx, ny, 1);
+  };
   // K blocks of exactly 64 pixels from two box classes when the map width is a sum of two powers of two and that packs
   // the image into >= 10 % fewer K blocks than whole rows
   static const bool no_w2 = [] { const char* e = getenv("DDRL_TC2_NO_WGRAD_BOXES"); return e && e[0] == '1'; }();
@@ -1395,14 +1556,14 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
     }
   }
   if (g.tap.w2on) {
-    r = tc_make_map_nhwc(&ta, o, g.tap.wxw0, g.tap.wyh0, 1, false);
-    if (r == DDRL_OK) r = tc_make_map_nhwc(&ta2, o, g.tap.wxw1, g.tap.wyh1, 1, false);
+    r = map_a(&ta, &tal, g.tap.wxw0, g.tap.wyh0);
+    if (r == DDRL_OK) r = map_a(&ta2, &tal2, g.tap.wxw1, g.tap.wyh1);
     if (r == DDRL_OK) r = make_map_dy4w(&tb, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw0, g.tap.wyh0);
     if (r == DDRL_OK) r = make_map_dy4w(&tb2, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw1, g.tap.wyh1);
   } else {
-    r = tc_make_map_nhwc(&ta, o, o.Xn, g.tap.ny, 1, false);
+    r = map_a(&ta, &tal, o.Xn, g.tap.ny);
     if (r == DDRL_OK) r = make_map_dy3w(&tb, dy, ldy, N, (long long)o.Yn * o.Xn, o.Bn, g.tap.rows);
-    ta2 = ta; tb2 = tb;
+    ta2 = ta; tb2 = tb; tal2 = tal;
   }
   if (r != DDRL_OK) return r;
   g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
@@ -1412,6 +1573,7 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   wgrad3_splits(g, tiles);
   dim3 grid(ceil_div(K, T3_BM), ceil_div(N, bn), ceil_div(g.kb_total, g.kb_per_split));
   g.det_ctr = det_seq((int)(grid.x * grid.y)).ctr;
+  if (ps) return bn == 128 ? launch3w<128>(ta, tb, ta2, tb2, g, grid, s, &tal, &tal2) : launch3w<64>(ta, tb, ta2, tb2, g, grid, s, &tal, &tal2);
   return bn == 128 ? launch3w<128>(ta, tb, ta2, tb2, g, grid, s) : launch3w<64>(ta, tb, ta2, tb2, g, grid, s);
 }
 

@@ -392,7 +392,7 @@ def test_micro_batching_equals_single_shot(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"DDRL_S2D": "1"}, {"DDRL_NO_FUSE0": "1"}, {"DDRL_NO_IMPLICIT": "1"}, {"DDRL_NO_S2D_FWD": "1"},
-                                 {"DDRL_TC2_ONE_PHASE": "1"}])
+                                 {"DDRL_TC2_ONE_PHASE": "1"}, {"DDRL_NO_PRESPLIT": "1"}, {"DDRL_NO_PRESPLIT_WGRAD": "1"}])
 def test_engine_layer_variants_agree(monkeypatch, env):
     """Alternative layer lowerings of the same net (space-to-depth conv1, un-fused first convs, explicit im2col for
     every conv) must give the default lowering's forward values and gradients to fp32 rounding."""
@@ -409,6 +409,27 @@ def test_engine_layer_variants_agree(monkeypatch, env):
     assert rel_err(net2.flat_grads(), g0) < 1e-5
     _, _, v2 = net2.act(ds, play_mode=True)
     assert rel_err(v2, v0) < 1e-5
+
+
+def test_presplit_first_conv_equals_in_kernel_split(monkeypatch):
+    """tc3 engine, Pong: the staged observation is split ONCE into fp16 hi / lo' planes and the first conv (forward and
+    weight gradient) takes its activation tiles straight from TMA (SS MMAs).  Same split values, same K-block order, same
+    accumulation chunks as the in-kernel splitter path: forward values must be bit-equal, gradients equal up to the order
+    of the split-K atomics."""
+    if GEMM_MODE not in (None, "tc3"):
+        pytest.skip("pre-split operands are a tc3 lowering")
+    spec, params, states, a, old, adv, ret = _learn_case("pong", 37)
+    ds = [s.to(DEV) for s in states]
+    net, _, _ = make("pong")
+    net.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    g1 = net.flat_grads().clone()
+    a1, l1, v1 = net.act(ds, play_mode=True)
+    monkeypatch.setenv("DDRL_NO_PRESPLIT", "1")
+    net2, _, _ = make("pong")
+    net2.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
+    a2, l2, v2 = net2.act(ds, play_mode=True)
+    assert torch.equal(v1, v2) and torch.equal(a1, a2) and torch.equal(l1, l2)
+    assert rel_err(net2.flat_grads(), g1) < 2e-6
 
 
 def test_forward_module_streamed_chunks_equal_one_shot():
