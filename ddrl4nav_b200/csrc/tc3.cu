@@ -57,7 +57,7 @@ __device__ unsigned long long g_tc3_wait[96];   // weight-gradient kernel: roles
 #define T3_ACC(acc) acc += clock64() - _t0
 #define T3_WAIT(bar, par, acc) do { T3_T0; mbar_wait(bar, par); T3_ACC(acc); } while (0)
 #define T3_WAITL(bar, par, acc) do { T3_T0; mbar_wait_long(bar, par); T3_ACC(acc); } while (0)
-#define T3_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0, w3 = 0; const long long role_t0 = clock64();
+#define T3_ROLE_BEGIN long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0; const long long role_t0 = clock64();
 #ifdef TC3_TIMING_PS            // account only the launches whose activation operand is pre-split
 #define T3_TCOND (g.presplit != 0)
 #else
@@ -66,6 +66,8 @@ __device__ unsigned long long g_tc3_wait[96];   // weight-gradient kernel: roles
 #define T3_ROLE_END(role, cond) do { if ((cond) && T3_TCOND && lane == 0) { \
     atomicAdd(&g_tc3_wait[(role) * 8 + 0], (unsigned long long)w0); atomicAdd(&g_tc3_wait[(role) * 8 + 1], (unsigned long long)w1); \
     atomicAdd(&g_tc3_wait[(role) * 8 + 2], (unsigned long long)w2); atomicAdd(&g_tc3_wait[(role) * 8 + 3], (unsigned long long)w3); \
+    atomicAdd(&g_tc3_wait[(role) * 8 + 4], (unsigned long long)w4); atomicAdd(&g_tc3_wait[(role) * 8 + 5], (unsigned long long)w5); \
+    atomicAdd(&g_tc3_wait[(role) * 8 + 6], (unsigned long long)w6); \
     atomicAdd(&g_tc3_wait[(role) * 8 + 7], (unsigned long long)(clock64() - role_t0)); } } while (0)
 #define T3_SECTION_BEGIN const long long _s0 = clock64()
 #define T3_SECTION_END(acc) acc += clock64() - _s0
@@ -94,6 +96,10 @@ struct Tc3Args {
   // launches carry no activation mask); K blocks are one 64-channel slice of one tap.  Weight gradient: tmA / tmA2 = hi plane,
   // tmAl / tmAl2 = lo' plane, the landed [64 pixels x 64 channels] boxes ARE the MN-major A tiles.
   int presplit;
+  // forward kernel, one N tile and a K-block count that divides the stage count: K block i always lands in stage i mod nkb, so
+  // its weight tiles are loaded ONCE per CTA and stay there -- later tiles only stream the activation tiles (the short-K first
+  // conv moves 184 KB per tile through L2 otherwise and sits at the L2 throughput cap, profiles/r4c_roles_ps.txt)
+  int b_resident;
   int m_tiles, n_tiles;
   const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
   const float* amax_b;
@@ -157,7 +163,8 @@ struct T3Cfg {
   // tile store; warp e owns rows [32 (e & 3), +32) of panel e >> 2), 1024-byte aligned
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STG_OFF + NEPI * 4096;
-  static constexpr int SMEM = 1024 + BAR_OFF + 256;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;                 // the tile's BN bias values (zero past N), TMA epilogue
+  static constexpr int SMEM = 1024 + BIAS_OFF + BN * 4;
   static_assert(NBARS * 8 + 16 <= 256, "barrier block");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(TM_A + SA * 64 <= 512, "TMEM budget");
@@ -235,6 +242,8 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       for (int i = 0; i < nkb; ++i, ++it) {
         const uint32_t s = it % S;
         T3_WAITL(smem_u32(bar_empty + s), ((it / S) & 1) ^ 1, w0);
+        const bool load_b = !g.b_resident || it < (uint32_t)S;
+        const uint32_t b_tx = load_b ? 2u * Cfg::B_BYTES : 0u;
         if (elect_one()) {
           const uint32_t full = smem_u32(bar_full + s);
           const uint32_t a_dst = smem_u32(smem) + s * Cfg::STAGE_BYTES, bh_dst = a_dst + Cfg::A_BYTES, bl_dst = bh_dst + Cfg::B_BYTES;
@@ -242,23 +251,23 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           if (ps) {
             // pre-split operand: [hi tile | lo' tile], 128 rows x 64 halfs each (tap mode: tp.cpb counts 64-channel slices)
             if (!tapA) {
-              mbar_expect_tx(full, Cfg::A_BYTES + 2u * Cfg::B_BYTES);
+              mbar_expect_tx(full, Cfg::A_BYTES + b_tx);
               tma_load_2d(&tmA, full, a_dst, k, m0);
               tma_load_2d(&tmM, full, a_dst + Cfg::A_SUB, k, m0);
             } else {
               const uint32_t box = (uint32_t)(ph2 ? tp.rows2 : tp.rows) * 128u;
-              mbar_expect_tx(full, 2u * box + 2u * Cfg::B_BYTES);
+              mbar_expect_tx(full, 2u * box + b_tx);
               tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 64, kw - tp.px, y0 + kh, b0);
               tma_load_4d(ph2 ? &tmM2 : &tmM, full, a_dst + Cfg::A_SUB, tp.c_off + cc * 64, kw - tp.px, y0 + kh, b0);
             }
           } else if (!tapA) {
-            mbar_expect_tx(full, Cfg::A_BYTES + 2u * Cfg::B_BYTES);
+            mbar_expect_tx(full, Cfg::A_BYTES + b_tx);
             tma_load_2d(&tmA, full, a_dst, k, m0);
             tma_load_2d(&tmA, full, a_dst + Cfg::A_SUB, k + 32, m0);
           } else {
             const bool two = !(odd_tail && i == nkb - 1);
             const uint32_t box = (uint32_t)(ph2 ? tp.rows2 : tp.rows) * 128u;
-            mbar_expect_tx(full, (two ? 2u : 1u) * box + 2u * Cfg::B_BYTES);
+            mbar_expect_tx(full, (two ? 2u : 1u) * box + b_tx);
             tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
             if (two) {
               int cc2 = cc + 1, kw2 = kw, kh2 = kh;
@@ -266,8 +275,10 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst + Cfg::A_SUB, tp.c_off + cc2 * 32, kw2 - tp.px, y0 + kh2, b0);
             }
           }
-          tma_load_2d(&tmBhi, full, bh_dst, k, n0);
-          tma_load_2d(&tmBlo, full, bl_dst, k, n0);
+          if (load_b) {
+            tma_load_2d(&tmBhi, full, bh_dst, k, n0);
+            tma_load_2d(&tmBlo, full, bl_dst, k, n0);
+          }
         }
         __syncwarp();
         if (tapA) {
@@ -425,6 +436,85 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
     T3_ROLE_END(3, warp == 4);
+  } else if (warp == 2) {
+    // ============================================================ store warp (TMA epilogue only)
+    // Lane 0 owns every bulk-async group of the epilogue: per tile and 32-column round it waits until the previous stores have
+    // READ the staging panels, requests the round's activation-mask panels (data gradients; the first round's travel while the
+    // epilogue warps still drain the accumulators), meets the epilogue warps at "panels free", again at "panels complete", and
+    // stores the panels with tensor-map boxes that mirror the load-side boxes.
+    if (g.tma_store) {
+      const bool masked = g.tma_mask != 0;
+      const bool fusedT = tapA && tp.ncls > 1;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+        const int m0 = mt * T3_BM, n0 = nt * BN;
+        int cy = 0, cb = 0;
+        const bool ph2 = tapA && mt >= tp.tiles1;
+        if (tapA) {
+          cb = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb;
+          cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
+        }
+        const uint32_t box_bytes = tapA ? (uint32_t)(ph2 ? tp.rows2 : tp.rows) * 128u : 16384u;
+        // global coordinates of the panel that starts at column `col`: a panel of the fused stride-parity gradient belongs to
+        // one pixel class, whose offset is the start of a strided box
+        auto coords = [&](int col, int& c0, int& c1, int& c2, int& c3) {
+          c0 = col; c1 = 0; c2 = cy; c3 = cb;
+          if (fusedT) {
+            const int qq = col / tp.cls_cols;
+            c0 = col - qq * tp.cls_cols; c1 = tp.cls_ix[qq]; c2 = tp.out_s * cy + tp.cls_iy[qq];
+          }
+        };
+#pragma unroll 1
+        for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (masked) {
+              uint32_t live = 0;
+#pragma unroll
+              for (int h = 0; h < Cfg::NEPI / 4; ++h) live += (n0 + h * Cfg::COLS + p0 < g.N) ? 1u : 0u;
+              mbar_expect_tx(smem_u32(bar_mask), live * box_bytes);
+#pragma unroll
+              for (int h = 0; h < Cfg::NEPI / 4; ++h) {
+                const int col = n0 + h * Cfg::COLS + p0;
+                if (col >= g.N) continue;
+                const uint32_t dst = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
+                if (!tapA) tma_load_2d(&tmM, smem_u32(bar_mask), dst, col, m0);
+                else {
+                  int c0, c1, c2, c3;
+                  coords(col, c0, c1, c2, c3);
+                  tma_load_4d(ph2 ? &tmM2 : &tmM, smem_u32(bar_mask), dst, c0, c1, c2, c3);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32 + 32) : "memory");       // panels free
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32 + 32) : "memory");       // panels complete
+          if (lane == 0) {
+#pragma unroll
+            for (int h = 0; h < Cfg::NEPI / 4; ++h) {
+              const int col = n0 + h * Cfg::COLS + p0;
+              if (col >= g.N) continue;
+              const uint32_t src = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
+              if (!tapA)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(src), "r"(col), "r"(m0) : "memory");
+              else {
+                int c0, c1, c2, c3;
+                coords(col, c0, c1, c2, c3);
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(ph2 ? &tmC2 : &tmC)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                             : "memory");
+              }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
   } else if (warp >= Cfg::EPI0) {
     // ============================================================ drain + epilogue
     const int e = warp - Cfg::EPI0;
@@ -436,6 +526,21 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     t3_scale(__ldg(g.amax_b), sB, sB_inv);
     float run_max = 0.f;
     uint32_t ch = 0, tl = 0, mround = 0;
+    // result scale: both factors are powers of two, so one multiplication by their product is exact -- unless the product
+    // itself leaves the normal range (operands near 1e+-19), where the two-step form is kept
+    float s_pre = 1.f, s_out = sA_inv * sB_inv;
+    if (!(s_out >= 1e-30f && s_out <= 1e30f)) { s_pre = sA_inv; s_out = sB_inv; }
+    // tile row -> (pixel, row, image) inside the tile's box, for both tiling phases: once per kernel, not per tile (the four
+    // integer divisions were ~100 instructions of every tile's epilogue)
+    const int r = q * 32 + lane;
+    int ryb1 = 0, ryb2 = 0;                              // row | image << 16
+    if (tapA) {
+      const int t1 = r / tp.Xn;
+      ryb1 = (t1 % tp.ny) | ((t1 / tp.ny) << 16);
+      if (tp.ny2 > 0) ryb2 = (t1 % tp.ny2) | ((t1 / tp.ny2) << 16);
+    }
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+    const int et = e * 32 + lane;
     T3_ROLE_BEGIN
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tl) {
       const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
@@ -448,41 +553,9 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         cy = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
       }
       const bool masked = g.tma_store && g.tma_mask;
-      const bool leader = e == 0 && lane == 0;
-      const bool fusedT = tapA && tp.ncls > 1;
-      const uint32_t box_bytes = tapA ? (uint32_t)(mt >= tp.tiles1 ? tp.rows2 : tp.rows) * 128u : 16384u;
-      // global coordinates of the panel that starts at column `col`: a panel of the fused stride-parity gradient belongs to
-      // one pixel class, whose offset is the start of a strided box
-      auto coords = [&](int col, int& c0, int& c1, int& c2, int& c3) {
-        c0 = col; c1 = 0; c2 = cy; c3 = cb;
-        if (fusedT) {
-          const int qq = col / tp.cls_cols;
-          c0 = col - qq * tp.cls_cols; c1 = tp.cls_ix[qq]; c2 = tp.out_s * cy + tp.cls_iy[qq];
-        }
-      };
-      auto load_masks = [&](int p0) {           // leader only, after the previous stores have read the panels
-        uint32_t live = 0;
-#pragma unroll
-        for (int h = 0; h < Cfg::NEPI / 4; ++h) live += (n0 + h * Cfg::COLS + p0 < g.N) ? 1u : 0u;
-        mbar_expect_tx(smem_u32(bar_mask), live * box_bytes);
-#pragma unroll
-        for (int h = 0; h < Cfg::NEPI / 4; ++h) {
-          const int col = n0 + h * Cfg::COLS + p0;
-          if (col >= g.N) continue;
-          const uint32_t dst = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
-          if (!tapA) tma_load_2d(&tmM, smem_u32(bar_mask), dst, col, m0);
-          else {
-            int c0, c1, c2, c3;
-            coords(col, c0, c1, c2, c3);
-            tma_load_4d(mt >= tp.tiles1 ? &tmM2 : &tmM, smem_u32(bar_mask), dst, c0, c1, c2, c3);
-          }
-        }
-      };
-      // the first round's mask panels travel while the accumulators are drained
-      if (masked && leader) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        load_masks(0);
-      }
+      // the tile's bias values: requested now, parked in shared memory after the drain (the load's latency hides behind it)
+      float bias_r = 0.f;
+      if (g.tma_store && et < BN && g.bias != nullptr && n0 + et < g.N) bias_r = __ldg(g.bias + n0 + et);
       float acc[Cfg::COLS];
 #pragma unroll
       for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
@@ -494,6 +567,15 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
         for (int j0 = 0; j0 < Cfg::COLS; j0 += 32) {
           float v[32];
+          if (Cfg::FOLD && c == 0) {
+            // first chunk of a tile: the main term lands in the (empty) accumulator registers directly, together with the
+            // hi*lo' term -- both loads in flight behind one wait
+            tmem_ld32x2(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0,
+                        tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + BN + col0 + j0, acc + j0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j0 + j] = fmaf(v[j], T3_LO_INV, acc[j0 + j]);
+            continue;
+          }
           tmem_ld32(tmem_base + t_lane + (buf ? Cfg::TM_MAIN1 : Cfg::TM_MAIN0) + col0 + j0, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j0 + j] += v[j];
@@ -520,34 +602,31 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(bar_cfree));
+      if (s_pre != 1.f) {
 #pragma unroll
-      for (int j = 0; j < Cfg::COLS; ++j) acc[j] = (acc[j] * sA_inv) * sB_inv;
+        for (int j = 0; j < Cfg::COLS; ++j) acc[j] *= s_pre;
+      }
       // ---- stores
       T3_SECTION_BEGIN;
-      const int r = q * 32 + lane;
-      bool rvalid;
-      long long roff;
-      if (tapA) {
-        const bool ph2 = mt >= tp.tiles1;
-        const int b0 = ph2 ? (mt - tp.tiles1) * tp.nb2 : (mt / tp.tpi) * tp.nb, y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
-        const int nyp = ph2 ? tp.ny2 : tp.ny;
-        const int x = r % tp.Xn, t2 = r / tp.Xn;
-        const int yy = t2 % nyp, bb = t2 / nyp;
-        rvalid = r < (ph2 ? tp.rows2 : tp.rows) && (b0 + bb) < tp.Bn && (y0 + yy) < tp.Yn;
-        roff = (long long)(b0 + bb) * tp.osb + (long long)(y0 + yy) * tp.osy + (long long)x * tp.osx;
-      } else {
-        rvalid = (m0 + r) < g.M;
-        roff = (long long)(m0 + r) * g.sCm;
-      }
+      const bool ph2e = tapA && mt >= tp.tiles1;
+      const int ryb = ph2e ? ryb2 : ryb1;
+      const bool rvalid = tapA ? (r < (ph2e ? tp.rows2 : tp.rows) && cb + (ryb >> 16) < tp.Bn && cy + (ryb & 0xffff) < tp.Yn)
+                               : (m0 + r) < g.M;
       const float neg_slope = g.act == 3 ? 0.f : 0.01f;
       // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
       const bool fused = tapA && tp.ncls > 1;
+      long long roff = 0;
       int py = 0, px = 0;
-      if (fused) {
-        const bool ph2 = mt >= tp.tiles1;
-        const int y0 = ph2 ? tp.y2 : (mt % tp.tpi) * tp.ny;
-        px = (r % tp.Xn) * tp.out_s;
-        py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
+      if (!g.tma_store) {                              // element addressing: only the per-warp store paths need it
+#pragma unroll
+        for (int j = 0; j < Cfg::COLS; ++j) acc[j] *= s_out;
+        if (tapA) {
+          const int xx = r % tp.Xn, yy = ryb & 0xffff, bb = ryb >> 16;
+          roff = (long long)(cb + bb) * tp.osb + (long long)(cy + yy) * tp.osy + (long long)xx * tp.osx;
+          if (fused) { px = xx * tp.out_s; py = (cy + yy) * tp.out_s; }
+        } else {
+          roff = (long long)(m0 + r) * g.sCm;
+        }
       }
       if (g.tma_store) {
         // TMA path: bias + activation in registers, the warp's 32 rows x 32 columns into its slice of the swizzled panel,
@@ -557,74 +636,85 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // stored to, so the SAME box is first loaded into the panel (tmM / tmM2), transformed in place and stored back; the
         // fused stride-parity gradient is one strided box per 32-column panel (a panel belongs to one pixel class).
         float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;
-        // branch-free per element: the bias of the panel's 32 columns is fetched up front (index clamped, so every load is
-        // legal and all 32 are in flight together), the activation is two selects on kernel-uniform predicates.  (A per-element
-        // `if (col < N) { if (bias) ...; if (act == ..) ... }` compiled to 32 serialised LDG -> branch -> FADD blocks.)
+        // Instruction count is what this path is bound by (profiles/r4b_roles_ps.txt: the epilogue warps of the short-K first
+        // conv are 94 % busy, two thirds of it here), so per element it is: one FFMA (result scale + bias), the activation as
+        // max(x, slope x), a share of an FMNMX3 for the running amax.  The tile's bias values sit in shared memory (zero past N:
+        // the accumulators of those columns are zero, so they store and max as zero without a per-element column test).
         const bool relu = g.act == 1;
         const float slope = g.act == 2 ? 0.01f : 1.f;
+        const bool has_bias = g.bias != nullptr;
+        if (et < BN) bias_s[et] = bias_r;               // read after the panel barrier below
+        // The TMA instructions themselves (read-out wait of the previous stores, mask-panel loads, tile stores) are issued by
+        // the STORE WARP (warp 2), which meets these warps at the two panel barriers of every round: ~150 single-lane
+        // instructions per tile that used to sit on the critical path of epilogue warp 0 -- and, through the accumulator
+        // barriers that need all epilogue warps, of the whole tile (profiles/r4e_roles_ps.txt).
 #pragma unroll
         for (int p0 = 0; p0 < Cfg::COLS; p0 += 32) {
-          const int colb = n0 + col0 + p0;
-          float bv[32];
-          if (g.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = __ldg(g.bias + min(colb + j, g.N - 1));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = 0.f;
-          }
-          // the staging panels are free once the previous TMA stores have READ them (same issuing thread as below)
-          if (leader && !(masked && p0 == 0)) {          // (round 0 of a masked tile: done before the drain)
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (masked) load_masks(p0);
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
+#ifdef TC3_TIMING
+          const long long _r0 = clock64();
+#endif
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32 + 32) : "memory");       // panels free (and mask loads issued)
+#ifdef TC3_TIMING
+          w3 += clock64() - _r0;                          // read-out wait of the previous tile's TMA stores + panel barrier
+#endif
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_s + col0 + p0);
+          float tmax = 0.f;
+          // operands of the whole round first (8 independent 16-byte loads in flight), then arithmetic and panel writes: the
+          // compiler does not move a shared-memory load above an earlier shared-memory store, so a load inside the write loop
+          // costs its full latency in every iteration
           if (masked) {
             mbar_wait(smem_u32(bar_mask), mround & 1);
             ++mround;
-          }
+            float4 mq[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
-            float4 mk4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (masked) mk4 = *reinterpret_cast<const float4*>(slot);
-            const float mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-            float o[4];
+            for (int c = 0; c < 8; ++c) mq[c] = *reinterpret_cast<const float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float x = acc[p0 + 4 * c + k] + bv[4 * c + k];
-              if (masked) x = mk[k] > 0.f ? x : neg_slope * x;
-              else {
-                const float neg = relu ? 0.f : slope * x;
-                x = x > 0.f ? x : neg;
+            for (int c = 0; c < 8; ++c) {
+              float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_bias) b4 = bias4[c];
+              const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, mk[4] = {mq[c].x, mq[c].y, mq[c].z, mq[c].w};
+              float o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float x = fmaf(acc[p0 + 4 * c + k], s_out, bv[k]);
+                o[k] = mk[k] > 0.f ? x : neg_slope * x;
               }
-              const bool live = rvalid && (colb + 4 * c + k) < g.N;
-              run_max = fmaxf(run_max, live ? fabsf(x) : 0.f);
-              o[k] = x;
+              tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+              *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            float4 bq[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bq[c] = bias4[c];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
+              const float bv[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+              float o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float x = fmaf(acc[p0 + 4 * c + k], s_out, bv[k]);
+                o[k] = fmaxf(x, relu ? 0.f : slope * x);          // relu / leaky (slope < 1) / identity (slope = 1)
+              }
+              tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+              *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
+            }
           }
+          run_max = fmaxf(run_max, rvalid ? tmax : 0.f);           // rows past the tile's box hold stale operands
+#ifdef TC3_TIMING
+          const long long _r1 = clock64();
+          w4 += _r1 - _r0;                                // ... + bias / activation / panel writes
+#endif
           fence_async_smem();
-          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32) : "memory");
-          if (leader) {
-#pragma unroll
-            for (int h = 0; h < Cfg::NEPI / 4; ++h) {
-              const int col = n0 + h * Cfg::COLS + p0;
-              if (col >= g.N) continue;
-              const uint32_t src = smem_u32(smem + Cfg::STG_OFF) + h * 16384;
-              if (!tapA)
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(src), "r"(col), "r"(m0) : "memory");
-              else {
-                int c0, c1, c2, c3;
-                coords(col, c0, c1, c2, c3);
-                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(mt >= tp.tiles1 ? &tmC2 : &tmC)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                             : "memory");
-              }
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
+#ifdef TC3_TIMING
+          const long long _r2 = clock64();
+          w5 += _r2 - _r1;                                // proxy fence
+#endif
+          asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI * 32 + 32) : "memory");       // panels complete: the store warp takes over
+#ifdef TC3_TIMING
+          w6 += clock64() - _r2;                          // panel-complete barrier
+#endif
         }
       } else if (g.vec_store) {
         // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
@@ -740,7 +830,6 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       T3_SECTION_END(w2);
     }
     T3_ROLE_END(4, warp == Cfg::EPI0);
-    if (g.tma_store && e == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (g.amax_out != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
@@ -767,7 +856,10 @@ static int launch3(const Tc3Maps& m, const Tc3Args& g, dim3 grid, cudaStream_t s
     DDRL_CUDA(cudaFuncSetAttribute(tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, m.m, m.m2, g);
+  static const bool no_bres = [] { const char* e = getenv("DDRL_TC3_NO_BRES"); return e && e[0] == '1'; }();
+  Tc3Args ga = g;
+  ga.b_resident = (!no_bres && g.n_tiles == 1 && g.kb_total >= 1 && Cfg::STAGES % g.kb_total == 0) ? 1 : 0;
+  tc3_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(m.a, m.bhi, m.blo, m.a2, m.c, m.c2, m.m, m.m2, ga);
   prof_work(2.0 * g.M * (double)g.N * g.K * (g.tap.work_scale > 0.f ? g.tap.work_scale : 1.f));   // algorithmic flops
   if (g_prof_on && g_prof_shapes) {
     char nm[96];

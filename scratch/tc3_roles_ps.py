@@ -16,7 +16,7 @@ lib = _lib.load()
 lib.ddrl_tc3_timing_read.restype = C.c_int
 lib.ddrl_tc3_timing_read.argtypes = [C.c_void_p, C.c_int]
 NAMES = {0: ("producer", ["empty"]), 1: ("mma-chunk", ["mfree", "full/aready", "issue+commit"]), 2: ("mma-corr", ["cfree", "full/aready", "issue+commit"]),
-         4: ("epilogue", ["mfull", "cfull", "stores"]),
+         4: ("epilogue", ["mfull", "cfull", "stores", "of which read-out wait + barrier", "...+ compute + panel writes", "proxy fence", "panel barrier"]),
          5: ("w-producer", ["empty"]), 6: ("w-mma-chunk", ["mfree", "aready", "issue+commit"]),
          8: ("w-epilogue", ["mfull", "cfull", "atomics", "full+afree"])}
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
