@@ -1084,9 +1084,10 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
 template <int BN>
 struct T3WCfg {
   static_assert(BN == 64 || BN == 128, "weight-gradient tiles are 64 or 128 columns");
-  static constexpr int A_SUB = T3_BK * 128;                      // one slice: 64 rows x 32 k fp32 = 8 KB
+  static constexpr int R_SUB = T3_BK * 128;                      // one raw slab: 64 rows x 32 fp32 = 8 KB
+  static constexpr int A_SUB = R_SUB;                            // one A slice: 64 rows x 32 k fp32, or 64 pixels x 64 halfs of a pre-split plane
   static constexpr int A_BYTES = 4 * A_SUB;
-  static constexpr int BRAW_BYTES = (BN / 32) * A_SUB;           // dy tile raw: slabs of 64 rows x 32 n
+  static constexpr int BRAW_BYTES = (BN / 32) * R_SUB;           // dy tile raw: slabs of 64 rows x 32 n
   static constexpr int STAGE_BYTES = A_BYTES + BRAW_BYTES;
   static constexpr int B16_TILE = T3_BK * 128;                   // 64 rows x 64 n halfs = 8 KB
   static constexpr int B16_BYTES = 2 * (BN / 64) * B16_TILE;     // [hi groups | lo groups]
@@ -1199,7 +1200,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j) tma_load_2d(&tmA, full, a_dst + j * Cfg::A_SUB, m0 + j * 32, k);
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, k);
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, k);
         } else if (tp.w2on) {
           // two pixel-box classes (64 pixels each): class 1 covers the columns right of wxw0
           const bool c1 = pj >= tp.wnb0;
@@ -1212,7 +1213,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (ps) tma_load_4d(c1 ? &tmAl2 : &tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], x0 * tp.sx + sl_x[j], yy0 * tp.sy + sl_y[j], pb);
             }
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_4d(c1 ? &tmB2 : &tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, x0, yy0, pb);
+          for (int j = 0; j < BN / 32; ++j) tma_load_4d(c1 ? &tmB2 : &tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, x0, yy0, pb);
         } else {
           const int yy0 = pj * tp.ny;
           mbar_expect_tx(full, ((ps ? 2 * na : na) + BN / 32) * tp.rows * 128);
@@ -1223,7 +1224,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (ps) tma_load_4d(&tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
             }
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::A_SUB, n0 + j * 32, yy0 * tp.Xn, pb);
+          for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, yy0 * tp.Xn, pb);
         }
       }
       __syncwarp();
@@ -1416,6 +1417,15 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
     };
+    constexpr int NT = T3_BK * (BN / 8) / (Cfg::NEPI * 32);       // conversion tasks per thread and K block
+    int t_src[NT], t_dst[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int v = et + t * Cfg::NEPI * 32;
+      const int r = v / (BN / 8), c8 = v - r * (BN / 8);
+      t_src[t] = (c8 >> 2) * Cfg::R_SUB + r * 128 + ((((c8 & 3) * 2) ^ (r & 7)) << 4);      // second chunk: this offset ^ 16
+      t_dst[t] = (c8 >> 3) * Cfg::B16_TILE + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
+    }
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S, a = i % SA;
       T3_WAIT(smem_u32(bar_full + s), (i / S) & 1, w3);
@@ -1424,18 +1434,20 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
       uint8_t* b16 = smem + Cfg::B16_OFF + a * Cfg::B16_BYTES;
       // dy tile: task = (row r, 8 consecutive columns): 2 swizzled 16-byte fp32 chunks -> 1 chunk of hi + 1 chunk of lo'
-      for (int v = et; v < T3_BK * (BN / 8); v += Cfg::NEPI * 32) {
-        const int r = v / (BN / 8), c8 = v - r * (BN / 8);
-        const uint8_t* src = st + Cfg::A_BYTES + (c8 >> 2) * Cfg::A_SUB + r * 128;
-        const float4 x0 = *reinterpret_cast<const float4*>(src + ((((c8 & 3) * 2) ^ (r & 7)) << 4));
-        const float4 x1 = *reinterpret_cast<const float4*>(src + ((((c8 & 3) * 2 + 1) ^ (r & 7)) << 4));
+      // (a thread's tasks sit at the same tile positions in every K block: offsets computed once, before the loop -- the
+      // per-task index arithmetic was 12 % of every weight-gradient launch, profiles/r4i_*)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const uint8_t* src = st + Cfg::A_BYTES + t_src[t];
+        const float4 x0 = *reinterpret_cast<const float4*>(src);
+        const float4 x1 = *reinterpret_cast<const float4*>(st + Cfg::A_BYTES + (t_src[t] ^ 16));
         uint4 h, l;
         t3_split2(x0.x, x0.y, sB, h.x, l.x); t3_split2(x0.z, x0.w, sB, h.y, l.y);
         t3_split2(x1.x, x1.y, sB, h.z, l.z); t3_split2(x1.z, x1.w, sB, h.w, l.w);
         if (do_colsum) {
           cs[0] += x0.x; cs[1] += x0.y; cs[2] += x0.z; cs[3] += x0.w; cs[4] += x1.x; cs[5] += x1.y; cs[6] += x1.z; cs[7] += x1.w;
         }
-        uint8_t* dst = b16 + (c8 >> 3) * Cfg::B16_TILE + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
+        uint8_t* dst = b16 + t_dst[t];
         *reinterpret_cast<uint4*>(dst) = h;
         *reinterpret_cast<uint4*>(dst + (BN / 64) * Cfg::B16_TILE) = l;
       }
