@@ -612,8 +612,10 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   for (auto& t : n->towers) per += tower_bytes_per_sample(t, train);
   per += (size_t)(n->ldA * 2 + 2 + 8) * 4;
   const size_t s2d_floats = (n->fuse_s2d && (!train || n->s2d_train)) ? (size_t)n->towers[0].g[0].C * n->towers[0].g[0].H * n->towers[0].g[0].W : 0;
+  // (training workspaces only: one inference pass uses the observation once, and the extra pass over it costs more than the
+  // first conv gains -- Forward 4.63 M vs 4.14 M actions/s, profiles/r4_notes.md; DDRL_PRESPLIT_INFER=1 forces it)
   const bool s2d_split = s2d_floats && tc3_mode(n) && s2d_floats % 8 == 0 && !getenv("DDRL_NO_PRESPLIT") &&
-                         (train || !getenv("DDRL_NO_PRESPLIT_INFER"));
+                         (train || getenv("DDRL_PRESPLIT_INFER"));
   per += s2d_floats * 4 * (s2d_split ? 2 : 1);
   const char* env_gb = getenv("DDRL_WS_GB");
   const char* env_mb = getenv("DDRL_MICRO_BATCH");
@@ -1377,7 +1379,7 @@ static int fused_conv0_fwd(ddrl_net* n, const float* const* obs, long long row0,
       const float* ama = nullptr;
       TRY(amax_in_slot(n, n->s2dbuf, (long long)mb * o.Hin * o.Win, o.Ctot, o.Ctot, s, &ama, true));
       const void *p_hi = nullptr, *p_lo = nullptr;
-      if (n->s2d16 && o.Cin % 64 == 0) {
+      if (n->s2d16 && o.Cin % 64 == 0 && (train || getenv("DDRL_PRESPLIT_INFER"))) {
         p_hi = n->s2d16; p_lo = reinterpret_cast<const char*>(n->s2d16) + n->s2d16_plane;
         if (!cols_cached)
           TRY(tc3_presplit(n->s2dbuf, (long long)mb * o.Hin * o.Win * o.Ctot, ama, n->s2d16, reinterpret_cast<char*>(n->s2d16) + n->s2d16_plane, s));

@@ -420,6 +420,7 @@ def test_presplit_first_conv_equals_in_kernel_split(monkeypatch):
         pytest.skip("pre-split operands are a tc3 lowering")
     spec, params, states, a, old, adv, ret = _learn_case("pong", 37)
     ds = [s.to(DEV) for s in states]
+    monkeypatch.setenv("DDRL_PRESPLIT_INFER", "1")        # inference passes take the in-kernel split by default (faster there)
     net, _, _ = make("pong")
     net.backward_only(ds, adv.to(DEV), a.to(DEV), old.to(DEV), ret.to(DEV))
     g1 = net.flat_grads().clone()
