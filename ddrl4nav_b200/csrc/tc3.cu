@@ -1215,16 +1215,28 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j) tma_load_4d(c1 ? &tmB2 : &tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, x0, yy0, pb);
         } else {
-          const int yy0 = pj * tp.ny;
-          mbar_expect_tx(full, ((ps ? 2 * na : na) + BN / 32) * tp.rows * 128);
+          // K blocks [0, tiles1): boxes of ny rows x nb images, tpi per image group; K blocks >= tiles1 (two-phase K tiling of
+          // small maps): the images' remaining rows [y2, Yn), nb2 images per box -- 9x9 maps: 7 rows x 1 image + 2 rows x 3
+          // images = 4 K blocks per 3 images instead of 6 (one of 63 and one of 18 pixels per image)
+          const int kb = kb0 + i;
+          const bool p2 = kb >= tp.tiles1;
+          int bb0, yy0;
+          if (!p2) { const int grp = kb / tp.tpi; bb0 = grp * tp.nb; yy0 = (kb - grp * tp.tpi) * tp.ny; }
+          else { bb0 = (kb - tp.tiles1) * tp.nb2; yy0 = tp.y2; }
+          mbar_expect_tx(full, ((ps ? 2 * na : na) + BN / 32) * (p2 ? tp.rows2 : tp.rows) * 128);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (j < na) {
-              tma_load_4d(&tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
-              if (ps) tma_load_4d(&tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], pb);
+              tma_load_4d(p2 ? &tmA2 : &tmA, full, a_dst + j * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], bb0);
+              if (ps) tma_load_4d(p2 ? &tmAl2 : &tmAl, full, a_dst + (2 + j) * Cfg::A_SUB, sl_c[j], sl_x[j], yy0 * tp.sy + sl_y[j], bb0);
             }
+          if (tp.nb == 1 && tp.ny2 == 0) {             // one image per box: dy rows are one run of pixels (3-D map)
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, yy0 * tp.Xn, pb);
+            for (int j = 0; j < BN / 32; ++j) tma_load_3d(&tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, yy0 * tp.Xn, bb0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_4d(p2 ? &tmB2 : &tmB, full, b_dst + j * Cfg::R_SUB, n0 + j * 32, 0, yy0, bb0);
+          }
         }
       }
       __syncwarp();
@@ -1419,10 +1431,15 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     constexpr int NT = T3_BK * (BN / 8) / (Cfg::NEPI * 32);       // conversion tasks per thread and K block
     int t_src[NT], t_dst[NT];
+    // two-phase K tiling with boxes of different heights: a stage's rows past the current box still hold the previous K
+    // block's dy pixels -- converted as zeros (the activation rows they meet are finite, so the products vanish)
+    const bool mask_rows = tapA && !tp.w2on && tp.ny2 > 0 && tp.rows2 != tp.rows;
+    int t_row[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int v = et + t * Cfg::NEPI * 32;
       const int r = v / (BN / 8), c8 = v - r * (BN / 8);
+      t_row[t] = r;
       t_src[t] = (c8 >> 2) * Cfg::R_SUB + r * 128 + ((((c8 & 3) * 2) ^ (r & 7)) << 4);      // second chunk: this offset ^ 16
       t_dst[t] = (c8 >> 3) * Cfg::B16_TILE + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
     }
@@ -1433,14 +1450,16 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (i >= SA) T3_WAIT(smem_u32(bar_afree + a), ((i / SA) - 1) & 1, w3);
       const uint8_t* st = smem + s * Cfg::STAGE_BYTES;
       uint8_t* b16 = smem + Cfg::B16_OFF + a * Cfg::B16_BYTES;
+      const int rows_blk = (kb0 + i) >= tp.tiles1 ? tp.rows2 : tp.rows;
       // dy tile: task = (row r, 8 consecutive columns): 2 swizzled 16-byte fp32 chunks -> 1 chunk of hi + 1 chunk of lo'
       // (a thread's tasks sit at the same tile positions in every K block: offsets computed once, before the loop -- the
       // per-task index arithmetic was 12 % of every weight-gradient launch, profiles/r4i_*)
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const uint8_t* src = st + Cfg::A_BYTES + t_src[t];
-        const float4 x0 = *reinterpret_cast<const float4*>(src);
-        const float4 x1 = *reinterpret_cast<const float4*>(st + Cfg::A_BYTES + (t_src[t] ^ 16));
+        float4 x0 = *reinterpret_cast<const float4*>(src);
+        float4 x1 = *reinterpret_cast<const float4*>(st + Cfg::A_BYTES + (t_src[t] ^ 16));
+        if (mask_rows && t_row[t] >= rows_blk) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
         uint4 h, l;
         t3_split2(x0.x, x0.y, sB, h.x, l.x); t3_split2(x0.z, x0.w, sB, h.y, l.y);
         t3_split2(x1.x, x1.y, sB, h.z, l.z); t3_split2(x1.z, x1.w, sB, h.w, l.w);
@@ -1613,10 +1632,10 @@ static int make_map_dy3w(CUtensorMap* m, const float* dy, int ldy, int N, long l
   const unsigned box[3] = {32u, (unsigned)rows, 1u}, estr[3] = {1u, 1u, 1u};
   return tc_encode_tiled(m, false, 3, dy, dims, strides, box, estr, true);
 }
-static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn, int Yn, int Bn, int xw, int yh) {
+static int make_map_dy4w(CUtensorMap* m, const float* dy, int ldy, int N, int Xn, int Yn, int Bn, int xw, int yh, int nb = 1) {
   const unsigned long long dims[4] = {(unsigned long long)N, (unsigned long long)Xn, (unsigned long long)Yn, (unsigned long long)Bn};
   const unsigned long long strides[3] = {(unsigned long long)ldy * 4, (unsigned long long)Xn * ldy * 4, (unsigned long long)Yn * Xn * ldy * 4};
-  const unsigned box[4] = {32u, (unsigned)xw, (unsigned)yh, 1u}, estr[4] = {1u, 1u, 1u, 1u};
+  const unsigned box[4] = {32u, (unsigned)xw, (unsigned)yh, (unsigned)nb}, estr[4] = {1u, 1u, 1u, 1u};
   return tc_encode_tiled(m, false, 4, dy, dims, strides, box, estr, true);
 }
 
@@ -1638,10 +1657,10 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   const int K = o.KH * o.KW * o.Cin;
   CUtensorMap ta, tb, ta2, tb2, tal, tal2;
   if (ps) { g.presplit = 1; g.tap.cpb = o.Cin / 64; g.tap.nslices = o.KH * o.KW * g.tap.cpb; }
-  auto map_a = [&](CUtensorMap* hi, CUtensorMap* lo, int nx, int ny) {
-    if (!ps) return tc_make_map_nhwc(hi, o, nx, ny, 1, false);
-    const int rr = make_map_nhwc16(hi, a_hi16, o, nx, ny, 1);
-    return rr != DDRL_OK ? rr : make_map_nhwc16(lo, a_lo16, o, nx, ny, 1);
+  auto map_a = [&](CUtensorMap* hi, CUtensorMap* lo, int nx, int ny, int nb = 1) {
+    if (!ps) return tc_make_map_nhwc(hi, o, nx, ny, nb, false);
+    const int rr = make_map_nhwc16(hi, a_hi16, o, nx, ny, nb);
+    return rr != DDRL_OK ? rr : make_map_nhwc16(lo, a_lo16, o, nx, ny, nb);
   };
   // K blocks of exactly 64 pixels from two box classes when the map width is a sum of two powers of two and that packs
   // the image into >= 10 % fewer K blocks than whole rows
@@ -1665,13 +1684,30 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
     if (r == DDRL_OK) r = make_map_dy4w(&tb, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw0, g.tap.wyh0);
     if (r == DDRL_OK) r = make_map_dy4w(&tb2, dy, ldy, N, o.Xn, o.Yn, o.Bn, g.tap.wxw1, g.tap.wyh1);
   } else {
-    r = map_a(&ta, &tal, o.Xn, g.tap.ny);
-    if (r == DDRL_OK) r = make_map_dy3w(&tb, dy, ldy, N, (long long)o.Yn * o.Xn, o.Bn, g.tap.rows);
-    ta2 = ta; tb2 = tb; tal2 = tal;
+    // two-phase K tiling (tc_tap_common's plan with 64-row boxes): multi-image boxes / a second box class for the rows a
+    // whole number of row blocks leaves over, when that packs the pixels into >= 5 % fewer K blocks
+    static const bool no_k2 = [] { const char* e = getenv("DDRL_TC3_NO_WGRAD_K2"); return e && e[0] == '1'; }();
+    if (!no_k2 && ldy == N) {
+      TcTap t2;
+      tc_tap_common(t2, o, T3_BK, true);
+      if (t2.nb > 1 || t2.ny2 > 0) {
+        g.tap.ny = t2.ny; g.tap.nb = t2.nb; g.tap.tpi = t2.tpi; g.tap.rows = t2.rows;
+        g.tap.y2 = t2.y2; g.tap.ny2 = t2.ny2; g.tap.nb2 = t2.nb2; g.tap.rows2 = t2.rows2; g.tap.tiles1 = t2.tiles1;
+        g.tap.kpad = (std::max(t2.rows, t2.ny2 > 0 ? t2.rows2 : 0) + 15) & ~15;
+      }
+    }
+    const bool p2 = g.tap.ny2 > 0;
+    r = map_a(&ta, &tal, o.Xn, g.tap.ny, g.tap.nb);
+    if (r == DDRL_OK)
+      r = (g.tap.nb == 1 && !p2) ? make_map_dy3w(&tb, dy, ldy, N, (long long)o.Yn * o.Xn, o.Bn, g.tap.rows)
+                                 : make_map_dy4w(&tb, dy, ldy, N, o.Xn, o.Yn, o.Bn, o.Xn, g.tap.ny, g.tap.nb);
+    if (r == DDRL_OK && p2) r = map_a(&ta2, &tal2, o.Xn, g.tap.ny2, g.tap.nb2);
+    if (r == DDRL_OK && p2) r = make_map_dy4w(&tb2, dy, ldy, N, o.Xn, o.Yn, o.Bn, o.Xn, g.tap.ny2, g.tap.nb2);
+    if (!p2) { ta2 = ta; tb2 = tb; tal2 = tal; }
   }
   if (r != DDRL_OK) return r;
   g.C = dWp; g.M = K; g.N = N; g.K = o.Bn * o.Yn * o.Xn; g.sCm = 1; g.sCn = ldw; g.atomic = 1;
-  g.kb_total = o.Bn * g.tap.tpi;
+  g.kb_total = g.tap.w2on ? o.Bn * g.tap.tpi : ceil_div(o.Bn, g.tap.nb) * g.tap.tpi + (g.tap.ny2 > 0 ? ceil_div(o.Bn, g.tap.nb2) : 0);
   g.amax_a = amax_x; g.amax_b = amax_dy; g.colsum = db; g.colsum2 = db2; g.colsum_split = db_split;
   const int tiles = ceil_div(K, T3_BM) * ceil_div(N, bn);
   wgrad3_splits(g, tiles);
