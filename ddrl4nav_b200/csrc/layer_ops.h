@@ -102,6 +102,11 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
 // a_hi16 / a_lo16 (optional, conv launches): the activation operand pre-split into fp16 planes by tc3_presplit (same layout as
 // o.a with 2-byte elements, scaled by t3_scale(*amax_a)); needs Cin % 64 == 0.  Both MMA operands are then plain TMA loads.
 int tc3_presplit(const float* x, long long n, const float* amax, void* hi, void* lo, cudaStream_t s);
+// sign-bit tensors (one bit per element, set where the activation is > 0): a relu / leaky forward launch that writes a
+// registered buffer densely also writes its bits; a data gradient whose mask points into a buffer with fresh bits reads those
+// instead of the fp32 activation (the net registers nothing when DDRL_NO_SIGNBITS=1)
+void tc3_signbits_register(const float* base, size_t elems, unsigned int* bits);
+void tc3_signbits_unregister(const float* base);
 // db (optional): bias gradient db[n] += sum_r dy[r, n], fused into the kernel's dy conversion (no separate column-sum pass)
 int tc3_wgrad(int Kx, int N, long long rows, const float* x, int ldx, const float* dy, int ldy, const float* amax_x,
               const float* amax_dy, float* dW, int ldw, cudaStream_t s, float* db = nullptr, float* db2 = nullptr, int db_split = 0);

@@ -131,6 +131,9 @@ struct ddrl_net {
   // observation) then take both MMA operands straight from TMA: no per-use split, no splitter warps in those launches.
   void* s2d16 = nullptr;
   size_t s2d16_plane = 0;        // bytes per plane
+  // activation buffers with a registered sign-bit tensor (tc3 engine, NatureCNN towers: the conv outputs whose leaky'
+  // the data gradients of the next layer need) -- see tc3_signbits_register
+  std::vector<const float*> signbit_bases;
   float* w0s2d = nullptr;        // [2 x Cout, K] both towers' conv1 weights in the space-to-depth K order (packed arena)
   float* bias0c = nullptr;       // its concatenated bias [2 x Cout]
   // observation-side im2col matrices in the workspace belong to (obs pointer, rows) of the last single-chunk backward
@@ -627,6 +630,8 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   mb = std::min(mb, std::max(B, 1));
   if (n->ws.base && n->MB >= mb && (n->ws_train || !train)) return DDRL_OK;
   graphs_clear(n);                  // captured launches point into the old workspace
+  for (const float* p : n->signbit_bases) tc3_signbits_unregister(p);
+  n->signbit_bases.clear();
   if (n->ws.base) { cudaDeviceSynchronize(); cudaFree(n->ws.base); n->ws.base = nullptr; }
   // the amax registry is keyed by workspace pointers: start over (persistent entries are re-created on demand)
   for (auto it = n->amax_keys.begin(); it != n->amax_keys.end();) it = it->second.persistent ? std::next(it) : n->amax_keys.erase(it);
@@ -646,6 +651,15 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   total += 4 * (((size_t)n->ldA * mb * 4 + 255) & ~size_t(255)) + 4096;
   total += 2 * (((size_t)kMaxExtra * mb * 4 + 255) & ~size_t(255));
   total += ((s2d_floats * mb * 4 + 255) & ~size_t(255)) * (s2d_split ? 2 : 1);
+  // sign-bit tensors of the NatureCNN conv outputs (1 bit per element)
+  const bool signbits = train && tc3_mode(n) && !getenv("DDRL_NO_SIGNBITS");
+  if (signbits)
+    for (auto& t : n->towers) {
+      if (t.arch != DDRL_ARCH_ATARI) continue;
+      std::vector<size_t> f, u8;
+      tower_sizes(t, train, f, u8);
+      for (int i : {1, 3, 5}) if (i < (int)f.size() && f[i]) total += ((f[i] * mb / 32 + 1) * 4 + 255) & ~size_t(255);
+    }
   if (cudaMalloc(&n->ws.base, total) != cudaSuccess) {
     cudaGetLastError();
     n->ws.base = nullptr; n->MB = 0;
@@ -665,6 +679,19 @@ static int ensure_workspace(ddrl_net* n, int B, bool train) {
   n->s2dbuf = s2d_floats ? n->ws.take(s2d_floats * mb) : nullptr;
   n->s2d16 = s2d_split ? n->ws.take(s2d_floats * mb) : nullptr;
   n->s2d16_plane = s2d_floats * mb * 2;
+  if (signbits)
+    for (auto& t : n->towers) {
+      if (t.arch != DDRL_ARCH_ATARI) continue;
+      std::vector<size_t> f, u8;
+      tower_sizes(t, train, f, u8);
+      for (int i : {1, 3, 5}) {
+        if (i >= (int)f.size() || !f[i] || !t.buf[i] || (f[i] * mb) % 32 != 0) continue;     // (a borrowed a1 has f = 0: its owner registers it)
+        float* w = n->ws.take(f[i] * mb / 32 + 1);
+        if (!w) continue;
+        tc3_signbits_register(t.buf[i], f[i] * mb, reinterpret_cast<unsigned int*>(w));
+        n->signbit_bases.push_back(t.buf[i]);
+      }
+    }
   if (n->towers.size() == 2 && n->towers[1].borrow_cols) {
     Tower &t0 = n->towers[0], &t1 = n->towers[1];
     t1.buf[0] = t0.buf[0];
@@ -1532,6 +1559,7 @@ extern "C" int ddrl_net_destroy(ddrl_net* n) {
   for (auto& t : n->unprep_seg) t.clear();
   if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
   if (n->sumsq_dev) cudaFree(n->sumsq_dev);
+  for (const float* p : n->signbit_bases) tc3_signbits_unregister(p);
   if (n->ws.base) cudaFree(n->ws.base);
   if (n->packed_base) cudaFree(n->packed_base);
   if (n->split_base) cudaFree(n->split_base);

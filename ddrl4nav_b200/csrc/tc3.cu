@@ -29,6 +29,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "layer_ops.h"
@@ -104,6 +106,13 @@ struct Tc3Args {
   const float* amax_a;                        // device scalars: amax of the activation operand / of the weight operand
   const float* amax_b;
   float* amax_out;                            // optional: running amax of the stored output (atomicMax on the bits)
+  // Sign bits of an activation tensor (TMA epilogue): one bit per element, word = element offset / 32, set where the stored
+  // activation is > 0.  A forward launch whose output has a registered bit tensor writes it (bits_out, one word per lane and
+  // 32-column round); the data gradient that needs that activation's derivative reads the words (bits_in, addressed like
+  // its own output) instead of loading the whole fp32 activation through the staging panels: 1/32 of the mask bytes and no
+  // TMA round trip inside the tile.
+  unsigned int* bits_out;
+  const unsigned int* bits_in;
   float* colsum;                              // weight gradient: optional db[n] += sum_r dy[r, n] (bias gradient), fused into the dy conversion
   float* colsum2;                             // columns >= colsum_split go to colsum2[n - colsum_split] (two layers behind one fused dy)
   int colsum_split;
@@ -534,6 +543,8 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // integer divisions were ~100 instructions of every tile's epilogue)
     const int r = q * 32 + lane;
     int ryb1 = 0, ryb2 = 0;                              // row | image << 16
+    const bool need_off = !g.tma_store || g.bits_out != nullptr || g.bits_in != nullptr;      // per-row element offsets
+    const int rx = (tapA && need_off) ? r % tp.Xn : 0;
     if (tapA) {
       const int t1 = r / tp.Xn;
       ryb1 = (t1 % tp.ny) | ((t1 / tp.ny) << 16);
@@ -556,6 +567,42 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       // the tile's bias values: requested now, parked in shared memory after the drain (the load's latency hides behind it)
       float bias_r = 0.f;
       if (g.tma_store && et < BN && g.bias != nullptr && n0 + et < g.N) bias_r = __ldg(g.bias + n0 + et);
+      const bool ph2e = tapA && mt >= tp.tiles1;
+      const int ryb = ph2e ? ryb2 : ryb1;
+      const bool rvalid = tapA ? (r < (ph2e ? tp.rows2 : tp.rows) && cb + (ryb >> 16) < tp.Bn && cy + (ryb & 0xffff) < tp.Yn)
+                               : (m0 + r) < g.M;
+      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
+      const bool fused = tapA && tp.ncls > 1;
+      long long roff = 0;                              // element offset of this thread's row in the output (mask) tensor
+      int py = 0, px = 0;
+      if (need_off) {
+        if (tapA) {
+          const int yy = ryb & 0xffff, bb = ryb >> 16;
+          roff = (long long)(cb + bb) * tp.osb + (long long)(cy + yy) * tp.osy + (long long)rx * tp.osx;
+          if (fused) { px = rx * tp.out_s; py = (cy + yy) * tp.out_s; }
+        } else {
+          roff = (long long)(m0 + r) * g.sCm;
+        }
+      }
+      // activation-derivative bits of the row's 32-column groups (data gradients): requested before the drain as well
+      uint32_t mw[Cfg::COLS / 32];
+#pragma unroll
+      for (int p = 0; p < Cfg::COLS / 32; ++p) mw[p] = 0u;
+      if (g.bits_in != nullptr && rvalid) {
+#pragma unroll
+        for (int p = 0; p < Cfg::COLS / 32; ++p) {
+          const int col = n0 + col0 + p * 32;
+          if (col >= g.N) continue;
+          long long eoff = roff + col;
+          bool inb = true;
+          if (fused) {
+            const int qq = col / tp.cls_cols;
+            inb = py + tp.cls_iy[qq] < tp.out_H && px + tp.cls_ix[qq] < tp.out_W;
+            eoff += tp.cls_off[qq] - (long long)qq * tp.cls_cols;
+          }
+          if (inb) mw[p] = __ldg(g.bits_in + (eoff >> 5));
+        }
+      }
       float acc[Cfg::COLS];
 #pragma unroll
       for (int j = 0; j < Cfg::COLS; ++j) acc[j] = 0.f;
@@ -608,25 +655,10 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
       // ---- stores
       T3_SECTION_BEGIN;
-      const bool ph2e = tapA && mt >= tp.tiles1;
-      const int ryb = ph2e ? ryb2 : ryb1;
-      const bool rvalid = tapA ? (r < (ph2e ? tp.rows2 : tp.rows) && cb + (ryb >> 16) < tp.Bn && cy + (ryb & 0xffff) < tp.Yn)
-                               : (m0 + r) < g.M;
       const float neg_slope = g.act == 3 ? 0.f : 0.01f;
-      // fused parity classes: tile pixel (py, px) -> input pixel (out_s*py + cls_iy, out_s*px + cls_ix) per column group
-      const bool fused = tapA && tp.ncls > 1;
-      long long roff = 0;
-      int py = 0, px = 0;
-      if (!g.tma_store) {                              // element addressing: only the per-warp store paths need it
+      if (!g.tma_store) {
 #pragma unroll
         for (int j = 0; j < Cfg::COLS; ++j) acc[j] *= s_out;
-        if (tapA) {
-          const int xx = r % tp.Xn, yy = ryb & 0xffff, bb = ryb >> 16;
-          roff = (long long)(cb + bb) * tp.osb + (long long)(cy + yy) * tp.osy + (long long)xx * tp.osx;
-          if (fused) { px = xx * tp.out_s; py = (cy + yy) * tp.out_s; }
-        } else {
-          roff = (long long)(m0 + r) * g.sCm;
-        }
       }
       if (g.tma_store) {
         // TMA path: bias + activation in registers, the warp's 32 rows x 32 columns into its slice of the swizzled panel,
@@ -659,6 +691,49 @@ tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #endif
           const float4* bias4 = reinterpret_cast<const float4*>(bias_s + col0 + p0);
           float tmax = 0.f;
+          if (g.bits_in != nullptr) {
+            // data gradient, activation derivative from the sign bits: no mask panel, the staging panel is write-only
+            const uint32_t w = mw[p0 / 32];
+            float4 bq[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bq[c] = has_bias ? bias4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
+              const float bv[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+              float o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float x = fmaf(acc[p0 + 4 * c + k], s_out, bv[k]);
+                o[k] = ((w >> (4 * c + k)) & 1u) ? x : neg_slope * x;
+              }
+              tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+              *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else if (g.bits_out != nullptr) {
+            // forward launch that also leaves the sign bits of what it stores (relu / leaky outputs)
+            uint32_t w = 0u;
+            float4 bq[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bq[c] = bias4[c];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float* slot = stg + lane * 32 + ((c ^ (lane & 7)) << 2);
+              const float bv[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+              float o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float x = fmaf(acc[p0 + 4 * c + k], s_out, bv[k]);
+                const bool pos = x > 0.f;
+                o[k] = pos ? x : (relu ? 0.f : slope * x);
+                if (pos) w |= 1u << (4 * c + k);
+              }
+              tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+              *reinterpret_cast<float4*>(slot) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            const int col = n0 + col0 + p0;
+            if (rvalid && col < g.N) g.bits_out[(roff + col) >> 5] = w;
+          } else
           // operands of the whole round first (8 independent 16-byte loads in flight), then arithmetic and panel writes: the
           // compiler does not move a shared-memory load above an earlier shared-memory store, so a load inside the write loop
           // costs its full latency in every iteration
@@ -940,6 +1015,48 @@ int tc3_presplit(const float* x, long long n, const float* amax, void* hi, void*
   return DDRL_OK;
 }
 
+// ---------------------------------------------------------------- sign-bit tensors of activations (see Tc3Args::bits_out)
+// The net registers a bit tensor per activation buffer whose derivative a data gradient will need.  `fresh` says that the
+// buffer's CURRENT contents were written by a launch that also wrote the bits: a consumer only trusts fresh bits, and any
+// tc3 launch that writes the buffer through another epilogue path clears the flag.
+struct SignBits { const float* base; size_t elems; unsigned int* bits; bool fresh; };
+static std::vector<SignBits> g_signbits;
+static std::mutex g_signbits_mu;
+void tc3_signbits_register(const float* base, size_t elems, unsigned int* bits) {
+  std::lock_guard<std::mutex> lk(g_signbits_mu);
+  for (auto& e : g_signbits)
+    if (e.base == base) { e.elems = elems; e.bits = bits; e.fresh = false; return; }
+  g_signbits.push_back({base, elems, bits, false});
+}
+void tc3_signbits_unregister(const float* base) {
+  std::lock_guard<std::mutex> lk(g_signbits_mu);
+  for (size_t i = 0; i < g_signbits.size(); ++i)
+    if (g_signbits[i].base == base) { g_signbits.erase(g_signbits.begin() + i); return; }
+}
+// producer side: `out` is exactly a registered buffer, written densely with row length N (a multiple of 32) through the TMA
+// epilogue of a relu / leaky launch -> its bit tensor (and the buffer counts as fresh); otherwise nullptr (and stale)
+static unsigned int* signbits_for_output(const float* out, bool eligible) {
+  std::lock_guard<std::mutex> lk(g_signbits_mu);
+  for (auto& e : g_signbits)
+    if (out >= e.base && out < e.base + e.elems) {
+      e.fresh = eligible && out == e.base;
+      return e.fresh ? e.bits : nullptr;
+    }
+  return nullptr;
+}
+// consumer side: `mask` points into a registered buffer with fresh bits, at a 32-element boundary -> the word that holds the
+// bit of element mask[0]
+static const unsigned int* signbits_for_mask(const float* mask) {
+  std::lock_guard<std::mutex> lk(g_signbits_mu);
+  if (!mask) return nullptr;
+  for (auto& e : g_signbits)
+    if (mask >= e.base && mask < e.base + e.elems) {
+      const size_t off = (size_t)(mask - e.base);
+      return (e.fresh && off % 32 == 0) ? e.bits + off / 32 : nullptr;
+    }
+  return nullptr;
+}
+
 bool tc3_gemm_supported(int M, int N, int K, const float* A, int lda, const void* Bhi, const void* Blo, int ldb16) {
   if (M < 1 || N < 1 || K < 1) return false;
   if (!al16(A) || !al16(Bhi) || !al16(Blo) || lda % 4 != 0 || ldb16 % 8 != 0) return false;
@@ -969,16 +1086,20 @@ int tc3_gemm(int M, int N, int K, const float* A, int lda, const void* Bhi, cons
   g.m_tiles = ceil_div(M, T3_BM); g.n_tiles = ceil_div(N, bn);
   g.amax_a = amax_a; g.amax_b = amax_b; g.amax_out = amax_out;
   g.vec_store = (ldc % 4 == 0 && al16(C) && (!mask || al16(mask))) ? 1 : 0;
-  if (g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad)) {
+  const bool tma_ok = g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad);
+  // data gradient whose activation has fresh sign bits (and a word-aligned layout): the mask is 1/32 of the bytes
+  const unsigned int* mbits = (tma_ok && act >= 3 && ldc % 32 == 0) ? signbits_for_mask(mask) : nullptr;
+  if (tma_ok) {
     // output tiles leave through TMA: boxes of 128 rows x 32 columns of C [M, N]; the mask of a data gradient (same
     // layout as C) arrives through the same boxes
     const unsigned long long dims[2] = {(unsigned long long)N, (unsigned long long)M};
     const unsigned long long strides[1] = {(unsigned long long)ldc * 4};
     const unsigned box[2] = {32u, (unsigned)T3_BM}, estr[2] = {1u, 1u};
     int rs = tc_encode_tiled(&mp.c, false, 2, C, dims, strides, box, estr, true);
-    if (rs == DDRL_OK && act >= 3) rs = tc_encode_tiled(&mp.m, false, 2, mask, dims, strides, box, estr, true);
-    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = act >= 3 ? 1 : 0; }
+    if (rs == DDRL_OK && act >= 3 && !mbits) rs = tc_encode_tiled(&mp.m, false, 2, mask, dims, strides, box, estr, true);
+    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = (act >= 3 && !mbits) ? 1 : 0; g.bits_in = mbits; }
   }
+  g.bits_out = signbits_for_output(C, g.tma_store && (act == 1 || act == 2) && ldc == N && N % 32 == 0);
   if (!g.tma_store) mp.c = mp.a;
   mp.c2 = mp.c;
   if (!g.tma_mask) mp.m = mp.c;
@@ -1040,7 +1161,12 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
   const bool classes_ok = classes && g_t3_tma_dgrad && g.tap.cls_cols % 32 == 0 && g.tap.out_W > 1 && g.tap.ncls == g.tap.out_s * g.tap.out_s &&
                           ct > 0 && osx == ct * g.tap.out_s && osy == (long long)g.tap.out_s * g.tap.out_W * ct &&
                           osb == (long long)g.tap.out_H * g.tap.out_W * ct;
-  if (g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad) && (!classes || classes_ok)) {
+  const bool tma_ok = g.vec_store && g_t3_tma_store && (act < 3 || g_t3_tma_dgrad) && (!classes || classes_ok);
+  const unsigned int* mbits = (tma_ok && act >= 3 && osb % 32 == 0 && osy % 32 == 0 && osx % 32 == 0 && (!classes || g.tap.cls_cols % 32 == 0))
+                                  ? signbits_for_mask(mask) : nullptr;
+  if (mbits && classes)
+    for (int q = 0; q < g.tap.ncls; ++q) if (g.tap.cls_off[q] % 32 != 0) mbits = nullptr;
+  if (tma_ok) {
     // output tiles leave through TMA: the store box (32 columns x Xn pixels x ny rows x nb images of out[b, y, x, n])
     // mirrors the load-side pixel box, one map per tiling phase; the mask of a data gradient arrives through the same boxes
     const int es = classes ? g.tap.out_s : 1;
@@ -1053,12 +1179,14 @@ int tc3_conv_fwd(const ConvOp& o, const void* Whi, const void* Wlo, int ldw16, i
     const unsigned box2[4] = {32u, boxdim(o.Xn), boxdim(g.tap.ny2 > 0 ? g.tap.ny2 : 1), (unsigned)(g.tap.nb2 > 0 ? g.tap.nb2 : 1)};
     int rs = tc_encode_tiled(&mp.c, false, 4, out, dims, strides, box1, estr, true);
     if (rs == DDRL_OK && ph2) rs = tc_encode_tiled(&mp.c2, false, 4, out, dims, strides, box2, estr, true);
-    if (rs == DDRL_OK && act >= 3) {
+    if (rs == DDRL_OK && act >= 3 && !mbits) {
       rs = tc_encode_tiled(&mp.m, false, 4, mask, dims, strides, box1, estr, true);
       if (rs == DDRL_OK && ph2) rs = tc_encode_tiled(&mp.m2, false, 4, mask, dims, strides, box2, estr, true);
     }
-    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = act >= 3 ? 1 : 0; }
+    if (rs == DDRL_OK) { g.tma_store = 1; g.tma_mask = (act >= 3 && !mbits) ? 1 : 0; g.bits_in = mbits; }
   }
+  g.bits_out = signbits_for_output(out, g.tma_store && !classes && (act == 1 || act == 2) && N % 32 == 0 && osx == N &&
+                                            osy == (long long)o.Xn * N && osb == (long long)o.Yn * o.Xn * N);
   if (!g.tma_store) mp.c = mp.a;
   if (!g.tma_store || !ph2) mp.c2 = mp.c;
   if (!g.tma_mask) mp.m = mp.c;
@@ -1686,7 +1814,8 @@ int tc3_conv_wgrad(const ConvOp& o, const float* dy, int ldy, int N, const float
   } else {
     // two-phase K tiling (tc_tap_common's plan with 64-row boxes): multi-image boxes / a second box class for the rows a
     // whole number of row blocks leaves over, when that packs the pixels into >= 5 % fewer K blocks
-    static const bool no_k2 = [] { const char* e = getenv("DDRL_TC3_NO_WGRAD_K2"); return e && e[0] == '1'; }();
+    const char* e_k2 = getenv("DDRL_TC3_NO_WGRAD_K2");
+    const bool no_k2 = e_k2 && e_k2[0] == '1';
     if (!no_k2 && ldy == N) {
       TcTap t2;
       tc_tap_common(t2, o, T3_BK, true);

@@ -392,7 +392,8 @@ def test_micro_batching_equals_single_shot(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"DDRL_S2D": "1"}, {"DDRL_NO_FUSE0": "1"}, {"DDRL_NO_IMPLICIT": "1"}, {"DDRL_NO_S2D_FWD": "1"},
-                                 {"DDRL_TC2_ONE_PHASE": "1"}, {"DDRL_NO_PRESPLIT": "1"}, {"DDRL_NO_PRESPLIT_WGRAD": "1"}])
+                                 {"DDRL_TC2_ONE_PHASE": "1"}, {"DDRL_NO_PRESPLIT": "1"}, {"DDRL_NO_PRESPLIT_WGRAD": "1"}, {"DDRL_NO_SIGNBITS": "1"},
+                                 {"DDRL_TC3_NO_WGRAD_K2": "1"}])
 def test_engine_layer_variants_agree(monkeypatch, env):
     """Alternative layer lowerings of the same net (space-to-depth conv1, un-fused first convs, explicit im2col for
     every conv) must give the default lowering's forward values and gradients to fp32 rounding."""
