@@ -389,7 +389,7 @@ def run_ours(args):
         arrs = [(a[:rows_w] * 255).astype(np.uint8) if (i == 0 and dt is np.uint8) else (a[:rows_w].astype(dt) if i == 0 else a[:rows_w])
                 for i, a in enumerate(f_np)]
         payload = torch.frombuffer(bytearray(encode_forward_payload(arrs, per_env)), dtype=torch.uint8).pin_memory()
-        sec_w = timed(lambda: fm.step_bytes_replies(payload, per_env), 3, 2, dist)
+        sec_w = timed(lambda: fm.step_bytes_replies(payload, per_env), 3, 4, dist)
         fwd_wire[tag] = {"value": round(world * rows_w * 3 / sec_w, 1), "rows_per_gpu": rows_w, "h2d_bytes_per_step": int(payload.numel()),
                          "d2h_bytes_per_step": int(lib.ddrl_easybytes_reply_bytes(per_env, 0 if wl_dist(args.workload) else 2, 1)) * (rows_w // per_env)}
         del payload, arrs
