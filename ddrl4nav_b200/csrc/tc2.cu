@@ -53,15 +53,6 @@ __device__ unsigned long long g_tc2_wait[32];
 #define T2_ROLE_END(role, cond)
 #endif
 
-// Timing experiments (scratch/tc2_exp.py; WRONG RESULTS, never defined in the product build): -DT2_EXP=<bitmask>
-//   1 wgrad: skip the dy (B) tile split   2 wgrad: skip the A gather loads   4 fwd: skip the epilogue's global stores
-//   8 fwd: skip the splitter's smem loads   16 skip tcgen05.wait::st   64 issue no MMA at all (commits only)
-//   128 every MMA with N = 16 (same instruction count, ~no tensor-pipe time)   256 corr stream issues nothing
-//   512 fwd: no B (weight) TMA loads   1024 fwd: no A (activation) TMA load
-#ifndef T2_EXP
-#define T2_EXP 0
-#endif
-
 struct Tc2Args {
   float* C;
   const float* bias;
@@ -80,55 +71,21 @@ struct T2Cfg {
   static constexpr int A_BYTES = T2_BM * T2_BK * 4;              // 16 KB raw activation tile (or 4 transposed slices)
   static constexpr int B_BYTES = BNS * T2_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;      // A raw | B hi | B lo
-#ifdef T2_NOFOLD
-  // Un-folded layout: accumulators [main0 | main1 | corr] = 3 BN TMEM columns leave room for more A slots.  The engine is
-  // bounded by the A-slot round trip (split -> tcgen05.st -> MMA -> commit -> slot free), not by MMA time
-  // (profiles/r1d_tc2_skeleton.md), so depth beats the saved MMA.
-  static constexpr int STAGES = BN <= 32 ? 7 : (BN <= 64 ? 6 : 4);
-#else
   static constexpr int STAGES = BN <= 32 ? 6 : (BN <= 64 ? 5 : 4);
-#endif
   // BN <= 64: hi*hi and hi*lo are ONE MMA of N' = 2 BN (B hi | B lo tiles are adjacent in shared memory) writing the
   // adjacent accumulators [main | corrB] of the current chunk buffer; lo*hi goes to corrA.  2 MMAs per k step instead
   // of 3 (every tf32 MMA with N <= 64 occupies the tensor pipe for ~45 cycles regardless of N, scratch/mma_bench.cu).
-#ifdef T2_NOFOLD
-  static constexpr bool FOLD = false;
-  static constexpr int SA = BN <= 32 ? 6 : (BN <= 64 ? 5 : 2);   // TMEM A slots (64 columns each: hi | lo)
-#else
+  // (Measured alternatives -- un-folded accumulators with more A slots, one MMA stream, a single chunk accumulator for
+  // BN = 128 -- are recorded in profiles/r1d_tc2_skeleton.md / r1c_tc2_experiments.txt; none was adopted.)
   static constexpr bool FOLD = BN <= 64;
-#ifdef T2_ONE_STREAM
-  // FOLD with ONE MMA stream: the lo*hi product accumulates into the corrB columns of the current chunk buffer (same
-  // issuing thread as the folded MMA that zero-initialises them, so program order = execution order).  No whole-tile
-  // correction accumulator: its single buffer serialised tile t+1's MMAs behind the epilogue's read of tile t, and its
-  // 64 columns now hold a 4th A slot.
-  static constexpr int SA = BN <= 32 ? 5 : (BN <= 64 ? 4 : 2);
-#else
-#ifdef T2_SINGLE128
-  // BN = 128 experiment: ONE chunk accumulator (the MMA stream waits for the previous chunk's drain) buys a 3rd A slot
-  static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 3);   // 4 stages of 48 KB: S > SA
-#else
   static constexpr int SA = BN <= 32 ? 4 : (BN <= 64 ? 3 : 2);   // TMEM A slots (64 columns each: hi | lo)
-#endif
-#endif
-#endif
-#ifdef T2_SINGLE128
-  static constexpr bool SINGLE = BN > 64;
-#else
-  static constexpr bool SINGLE = false;
-#endif
-#if defined(T2_ONE_STREAM) && !defined(T2_NOFOLD)
-  static constexpr bool ONE = BN <= 64;
-#else
-  static constexpr bool ONE = false;
-#endif
   static constexpr int NEPI = BN <= 32 ? 4 : 8;                  // 32 accumulator columns per epilogue thread (64 for BN = 128)
   static constexpr int NSG = BN <= 64 ? 2 : 1;                   // splitter groups (4 warps each), K blocks round-robin
   static constexpr int EPI0 = 4 + 4 * NSG;                       // first epilogue warp
   static constexpr int THREADS = (EPI0 + NEPI) * 32;
   static constexpr int COLS = BN / (NEPI / 4);                   // accumulator columns per epilogue thread
   // FOLD: [main0 | corrB0 | main1 | corrB1 | corrA | A slots]; else [main0 | main1 | corr | A slots]
-  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = SINGLE ? 0 : (FOLD ? 2 * BN : BN), TM_CORR = SINGLE ? BN : (FOLD ? 4 * BN : 2 * BN),
-                       TM_A = SINGLE ? 2 * BN : (ONE ? 4 * BN : (FOLD ? 5 * BN : 3 * BN));
+  static constexpr int TM_MAIN0 = 0, TM_MAIN1 = FOLD ? 2 * BN : BN, TM_CORR = FOLD ? 4 * BN : 2 * BN, TM_A = FOLD ? 5 * BN : 3 * BN;
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBARS = 2 * STAGES + SA + 6;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES + 256;      // epilogue staging: one swizzled 32 x 32 fp32 panel per warp
@@ -172,7 +129,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   }
   if (warp == 0 && lane == 0) {
     // stages and A slots are released by BOTH MMA issuers' commits
-    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), Cfg::ONE ? 1 : 2); }
+    for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 2); }
     for (int a = 0; a < SA; ++a) mbar_init(smem_u32(bar_aready + a), 4);
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(bar_mfull + b), 1); mbar_init(smem_u32(bar_mfree + b), Cfg::NEPI); }
     mbar_init(smem_u32(bar_cfull), 1);
@@ -244,16 +201,15 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                          bl_dst = bh_dst + Cfg::B_BYTES;
           const int k = (kb0 + i) * T2_BK;
           if (MODE == 0) {
-            const uint32_t bbytes = (T2_EXP & 512) ? 0u : 2u * Cfg::B_BYTES;
+            const uint32_t bbytes = 2u * Cfg::B_BYTES;
             if (!tapA) {
-              mbar_expect_tx(full, ((T2_EXP & 1024) ? 0 : Cfg::A_BYTES) + bbytes);
-              if (!(T2_EXP & 1024)) tma_load_2d(&tmA, full, a_dst, k, m0);
+              mbar_expect_tx(full, Cfg::A_BYTES + bbytes);
+              tma_load_2d(&tmA, full, a_dst, k, m0);
             } else {
-              mbar_expect_tx(full, ((T2_EXP & 1024) ? 0 : (ph2 ? tp.rows2 : tp.rows) * 128) + bbytes);
-              if (!(T2_EXP & 1024)) tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
+              mbar_expect_tx(full, (ph2 ? tp.rows2 : tp.rows) * 128 + bbytes);
+              tma_load_4d(ph2 ? &tmA2 : &tmA, full, a_dst, tp.c_off + cc * 32, kw - tp.px, y0 + kh, b0);
             }
-            if (T2_EXP & 512) {
-            } else if (!B_MN) {
+            if (!B_MN) {
               tma_load_2d(&tmBhi, full, bh_dst, k, n0);
               tma_load_2d(&tmBlo, full, bl_dst, k, n0);
             } else {
@@ -296,16 +252,16 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
     T2_ROLE_END(0, true);
-  } else if (warp == 1 || (warp == 3 && !Cfg::ONE)) {
+  } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers (one elected thread each)
     // warp 1: chunk buffers   main (+)= A_hi . B_hi          [FOLD: [main | corrB] (+)= A_hi . [B_hi ; B_lo], N' = 2 BN]
     // warp 3: whole tile      corr  += A_lo . B_hi           [!FOLD: ... + A_hi . B_lo]
     // The two streams write disjoint accumulators, so they need no ordering between them.
     const bool chunk_role = warp == 1;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
-                           ((uint32_t)(((T2_EXP & 128) ? 16 : BN) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
-                            ((uint32_t)(((T2_EXP & 128) ? 16 : 2 * BN) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+                            ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t t_corr = tmem_base + Cfg::TM_CORR;
     constexpr uint32_t kstep = B_MN ? (1024 >> 4) : (32 >> 4);      // start-address field increment per k step
@@ -320,8 +276,6 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (chunk_role) {
           if (first_in_chunk) {
             T2_WAIT(smem_u32(bar_mfree + buf), ((ch >> 1) & 1) ^ 1, w0);
-            // one physical accumulator: the previous chunk (other barrier of the pair) must be drained as well
-            if (Cfg::SINGLE && ch > 0) T2_WAIT(smem_u32(bar_mfree + ((ch - 1) & 1)), ((ch - 1) >> 1) & 1, w0);
           }
         }
         else if (i == 0) T2_WAIT(smem_u32(bar_cfree), (tl & 1) ^ 1, w0);
@@ -337,10 +291,8 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
               if (k4 >= ksteps) break;
-              if (!(T2_EXP & 64))
               umma_tf32_ts(t_main, a_hi + k4 * 8, dbh0 + k4 * kstep, Cfg::FOLD ? idesc2 : idesc,
                            (!first_in_chunk || k4 != 0) ? 1u : 0u);
-              if (Cfg::ONE && !(T2_EXP & 64)) umma_tf32_ts(t_main + BN, a_lo + k4 * 8, dbh0 + k4 * kstep, idesc, 1u);
             }
             umma_commit(smem_u32(bar_empty + s));            // retires the stage AND the TMEM A slot of this K block
             if (last_in_chunk) umma_commit(smem_u32(bar_mfull + buf));
@@ -349,7 +301,6 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int k4 = 0; k4 < T2_BK / 8; ++k4) {
               if (k4 >= ksteps) break;
-              if (T2_EXP & (64 | 256)) continue;
               umma_tf32_ts(t_corr, a_lo + k4 * 8, dbh0 + k4 * kstep, idesc, (i | k4) != 0 ? 1u : 0u);
               if (!Cfg::FOLD) umma_tf32_ts(t_corr, a_hi + k4 * 8, dbl0 + k4 * kstep, idesc, 1u);
             }
@@ -383,7 +334,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #ifdef TC2_TIMING
         const long long sp0 = clock64();
 #endif
-        if (MODE == 1 && !(T2_EXP & 1)) {
+        if (MODE == 1) {
           // raw dy tile: hi in place + lo twin; element-wise, so the TMA swizzle is preserved
           uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
           for (int v = st_tid; v < Cfg::B_BYTES / 16; v += 128) {
@@ -406,8 +357,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const uint8_t* rp = st + row * 128;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float4 v = (T2_EXP & 8) ? make_float4(1.f, 2.f, 3.f, (float)it)
-                                            : *reinterpret_cast<const float4*>(rp + (((hf * 4 + c) ^ (row & 7)) << 4));
+              const float4 v = *reinterpret_cast<const float4*>(rp + (((hf * 4 + c) ^ (row & 7)) << 4));
               const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[c * 4 + e], lo[c * 4 + e]);
@@ -418,8 +368,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
               const int pp = hf * 16 + p;
-              const float x = (T2_EXP & 2) ? (float)(it + pp)
-                                           : *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
+              const float x = *reinterpret_cast<const float*>(sp + pp * 128 + (((lane >> 2) ^ (pp & 7)) << 4));
               split_tf32(x, hi[p], lo[p]);
             }
           }
@@ -438,7 +387,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           tmem_st16(ta + hf * 16, hi);
           tmem_st16(ta + 32 + hf * 16, lo);
         }
-        if (!(T2_EXP & 16)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_aready + a));
@@ -482,7 +431,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(bar_mfree + buf));
       }
-      if (!Cfg::ONE) {
+      {
         T2_WAIT(smem_u32(bar_cfull), tl & 1, w1);
         tc_fence_after();
 #pragma unroll
@@ -525,9 +474,7 @@ tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         px = (r % tp.Xn) * tp.out_s;
         py = (y0 + (r / tp.Xn) % (ph2 ? tp.ny2 : tp.ny)) * tp.out_s;
       }
-      if (T2_EXP & 4) {
-        if (acc[0] == 123.456f) g.C[0] = acc[1];
-      } else if (MODE == 0 && g.vec_store) {
+      if (MODE == 0 && g.vec_store) {
         // Coalesced path: the warp's 32 rows x 32 columns go through a swizzled 4 KB staging panel, then every store
         // (and activation-mask load) instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
         float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + e * 1024;

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the T2_EXP / T2_NOFOLD / T2_ONE_STREAM / T2_SINGLE128 switches were removed from tc2.cu at the end of round 2 -- check out the round-1 tree to rebuild these experiments; results: profiles/r1d_tc2_skeleton.md)
 # builds ddrl4nav_b200/libddrl_exp<mask>.so for each T2_EXP mask given (timing experiments; see csrc/tc2.cu)
 cd "$(dirname "$0")/../ddrl4nav_b200/csrc" || exit 1
 mkdir -p build_exp
