@@ -22,7 +22,17 @@
 // Accumulation: the tensor core adds into fp32 with truncation (scratch/tc_acc.py), so `main` lives in TMEM only for 16
 // MMAs (4 K blocks) and is then added round-to-nearest into fp32 registers, exactly as in tc2.
 // Warp roles: 0 TMA producer | 1 MMA issuer (chunk accumulators) | 3 MMA issuer (whole-tile correction accumulator) |
-// 2 TMEM allocator | splitter groups of 4 warps | epilogue warps.
+// 2 TMEM allocator, then STORE WARP of the TMA epilogue (read-out waits, activation-mask loads, tile stores) | splitter
+// groups of 4 warps | epilogue warps.
+// Later additions (end of round 2; DESIGN.md section 5.1, profiles/r4_notes.md):
+//   * pre-split activation operands (Tc3Args::presplit): fp16 hi | lo' planes written once by tc3_presplit -> both MMA operands
+//     are plain TMA loads (SS MMAs; MN-major A in the weight gradient), the splitter warps idle;
+//   * resident weight tiles when the K blocks of a tile map one-to-one onto the stages (Tc3Args::b_resident);
+//   * sign-bit activation masks (Tc3Args::bits_out / bits_in): forward launches leave one bit per stored element, data
+//     gradients read those words instead of the fp32 activation;
+//   * weight gradient: two-phase K tiling of small maps (multi-image pixel boxes), conversion-task offsets hoisted.
+// What bounds the N = 64 launches now is L2 -> SM bandwidth (the fp32 tile is fetched once per tap): ncu shows 9.4-10 TB/s
+// on them (profiles/r4z_ncu_tc3_table.md).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
