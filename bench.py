@@ -216,6 +216,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host threads and the pinned buffers they allocate next to the GPU's PCIe root (ddrl4nav_b200.dist.bind_host_to_device);
+    # DDRL_NO_NUMA_BIND=1 leaves the placement to the scheduler
+    from ddrl4nav_b200.dist import bind_host_to_device
+    host_bind = None if os.environ.get("DDRL_NO_NUMA_BIND") == "1" else bind_host_to_device(local)
     dist = None
     saved_stdout = None
     if world > 1:
@@ -437,6 +441,8 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0 only, N=1 only): the oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if host_bind is not None:
+            os.sched_setaffinity(0, host_bind[0])         # the CPU leg runs on every core the process was given
         cpu = cpu_reference(args.workload, wl["cpu_batch"], iters=2, warm=1)
 
     if dist is not None:
@@ -451,7 +457,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows_per_gpu": B, "global_batch": B * world, "iters_per_step": ITERS,
                        "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode, "collective": collective,
-                       "l2": "inputs larger than L2 (%.0f MB observations per GPU)" % (B * wl["obs_bytes"] / 1e6)},
+                       "l2": "inputs larger than L2 (%.0f MB observations per GPU)" % (B * wl["obs_bytes"] / 1e6),
+                       "host_affinity": ("CPUs of NUMA node %d (the GPU's)" % host_bind[1]) if host_bind is not None else "unchanged"},
             "e2e": {"value": round(e2e_value, 1), "unit": "learner sample-iterations/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 16 * ITERS},
             "gpu_launches": int(launches),
