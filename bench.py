@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the driver's measurement contract for the DDRL4NAV actor-learner hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pong|navlaser|navimg] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pong|navlaser|navimg|navlaser3] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -40,6 +40,11 @@ WORKLOADS = {
     "navlaser": dict(batch=1024, fwd_batch=4096, cpu_batch=128, ref_batch=256, desc="robot-nav PPO learner, NavPreNet1D laser 1x960 + vec5 + "
                      "ped-map 3x48x48, unshared towers, 2-d Gaussian (BASELINE C2)",
                      flops_fwd=545.3e6, flops_learn=1562.6e6, obs_bytes=31508),
+    # NOT a reference configuration (SURVEY 8d asks for it beside C2, labelled): BASELINE's "3 x 960" laser wording -- the same
+    # stack with Conv1d(3, 32, 5, 2); 3-frame laser stacking is an env option only, no shipped encoder consumes it
+    "navlaser3": dict(batch=1024, fwd_batch=4096, cpu_batch=128, ref_batch=256, desc="NON-REFERENCE variant of C2: NavPreNet1D with a "
+                      "3x960 laser (Conv1d(3,32,5,2)) + vec5 + ped-map 3x48x48, unshared towers, 2-d Gaussian",
+                      flops_fwd=545.9e6, flops_learn=1563.8e6, obs_bytes=39188),
     # C5 = "nav image-env PPO (1x48x48 egocentric map), shared encoder, 28-way categorical"
     "navimg": dict(batch=2048, fwd_batch=8192, cpu_batch=256, ref_batch=1024, desc="nav image-env PPO learner, NavPreNet 1x48x48 + vec9, shared "
                    "encoder, 28-way categorical (BASELINE C5)",
@@ -138,8 +143,8 @@ def synth_states(kind, B, seed):
     g = torch.Generator().manual_seed(seed)
     if kind == "pong":
         return [torch.rand(B, 4, 84, 84, generator=g)]
-    if kind == "navlaser":
-        laser = torch.rand(B, 1, 960, generator=g)
+    if kind in ("navlaser", "navlaser3"):
+        laser = torch.rand(B, 3 if kind == "navlaser3" else 1, 960, generator=g)
         vec = torch.randn(B, 5, generator=g)
         occ = (torch.rand(B, 1, 48, 48, generator=g) < 0.03).float()
         vel = (torch.rand(B, 2, 48, 48, generator=g) - 0.5) * occ
@@ -160,7 +165,7 @@ def synth_batch_host(kind, B, seed):
 
 def wl_dist(kind):
     """True for the categorical (1-D action) workloads."""
-    return kind != "navlaser"
+    return kind not in ("navlaser", "navlaser3")
 
 
 def encode_forward_payload(arrays, per_env):
@@ -624,6 +629,13 @@ def main():
                     help="run ONE Forward tick (wire bytes in, replies out) and one GAE scan between cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "navlaser3":
+        # non-reference variant: the reference has no encoder for it, so there is no CPU arm to put beside it
+        args.no_cpu = True
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "navlaser3 is a non-reference variant (no reference encoder takes a 3x960 laser)"}), flush=True)
+            return 0
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

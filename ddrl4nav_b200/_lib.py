@@ -17,7 +17,7 @@ class DDRLError(RuntimeError):
 
 class NetDesc(C.Structure):
     _fields_ = [("arch", C.c_int32), ("in_ch", C.c_int32), ("act_dim", C.c_int32), ("dist", C.c_int32),
-                ("shared", C.c_int32), ("feat", C.c_int32), ("gemm_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("shared", C.c_int32), ("feat", C.c_int32), ("gemm_mode", C.c_int32), ("laser_ch", C.c_int32)]
 
 
 class PPOHparams(C.Structure):

@@ -893,7 +893,7 @@ bool thin_supported(long long M, int N, int K, const float* x, int ldx, const fl
   if (M < 1 || ldy != N || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return false;
   const int k4 = ldx / 4, nc4 = N / 4;
   if (ldx % 4 != 0 || N % 4 != 0 || K > ldx) return false;
-  return (nc4 == 16 && (k4 == 3 || k4 == 9)) || (nc4 == 8 && k4 == 2);
+  return (nc4 == 16 && (k4 == 3 || k4 == 9)) || (nc4 == 8 && (k4 == 2 || k4 == 4));
 }
 #define DDRL_THIN_DISPATCH(KERNEL, ...)                                                        \
   do {                                                                                         \
@@ -901,6 +901,7 @@ bool thin_supported(long long M, int N, int K, const float* x, int ldx, const fl
     const int grid = (int)std::min<long long>((M + 256 / nc4 - 1) / (256 / nc4), thin_grid_cap); \
     if (nc4 == 16 && k4 == 3) KERNEL<3, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);                \
     else if (nc4 == 16 && k4 == 9) KERNEL<9, 16><<<grid, 256, 0, s>>>(__VA_ARGS__);           \
+    else if (nc4 == 8 && k4 == 4) KERNEL<4, 8><<<grid, 256, 0, s>>>(__VA_ARGS__);  /* 3 x 960 laser variant: K = 15 */ \
     else KERNEL<2, 8><<<grid, 256, 0, s>>>(__VA_ARGS__);                                      \
   } while (0)
 int thin_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias, float* y, long long M, int N, int K, int act,

@@ -202,6 +202,9 @@ constexpr int kAmaxSlots = 1024, kAmaxWeights = 256;
 constexpr int kMaxExtra = 2;      // extra critic heads ("suppose 3 critic net at most", nn/ppo.py:93)
 // mode 3 (tc3) is a superset of mode 2: same lowering decisions; the tc2 kernels keep the launches tc3 does not take
 static inline bool tc3_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC3_F16; }
+// NavPreNet1D: channels of the laser observation [B, laser_ch, 960].  The reference's encoder takes 1 (nn/nav_encoder.py:87);
+// 3 is the NON-reference "3 x 960" variant SURVEY 8(d) asks to bench (3-frame laser stacking is an env option only)
+static inline int laser_ch_of(const ddrl_net* n) { return n->d.laser_ch > 0 ? n->d.laser_ch : 1; }
 static inline bool tc_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC_3XTF32 || n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
 static inline bool tc2_mode(const ddrl_net* n) { return n->d.gemm_mode == DDRL_GEMM_TC2_TMEM || tc3_mode(n); }
 
@@ -325,7 +328,7 @@ static void add_encoder_tensors(ddrl_net* n, const std::string& pre, int arch, i
       break;
     case DDRL_ARCH_NAV1D:
       conv("conv1", 64, in_ch, 7, 7); conv("conv2", 128, 64, 5, 5); conv("conv3", 256, 128, 3, 3);
-      add_tensor(n, pre + "conv1d1.weight", {32, 1, 5}); add_tensor(n, pre + "conv1d1.bias", {32});
+      add_tensor(n, pre + "conv1d1.weight", {32, laser_ch_of(n), 5}); add_tensor(n, pre + "conv1d1.bias", {32});
       add_tensor(n, pre + "conv1d2.weight", {32, 32, 3}); add_tensor(n, pre + "conv1d2.bias", {32});
       lin("fc_1d.0", 256, 7616); lin("fc0.0", 512, 6400); lin("fc1.0", 512, 773); lin("fc2", 512, 512);
       break;
@@ -391,12 +394,12 @@ static void build_tower(ddrl_net* n, Tower& t, const std::string& prefix, int ar
       t.g[0] = conv_geom(48, 48, in_ch, true, 7, 7, 1, 1);       // -> 44x44x64 -> pool 22
       t.g[1] = conv_geom(22, 22, 64, false, 5, 5, 1, 1);         // -> 20x20x128 -> pool 10
       t.g[2] = conv_geom(10, 10, 128, false, 3, 3, 1, 1);        // -> 10x10x256 -> pool 5
-      t.g[3] = conv_geom(1, 960, 1, true, 1, 5, 2, 0);           // laser conv1d1 -> 478 x 32
+      t.g[3] = conv_geom(1, 960, laser_ch_of(n), true, 1, 5, 2, 0);   // laser conv1d1 -> 478 x 32 (laser_ch = 1 in the reference)
       t.g[4] = conv_geom(1, 478, 32, false, 1, 3, 2, 0);         // laser conv1d2 -> 238 x 32
       t.L.push_back(make_lin(n, P("conv1"), 64, t.g[0].K, 1, t.g[0].K, ACT_RELU));
       t.L.push_back(make_lin(n, P("conv2"), 128, t.g[1].K, 25, 64, ACT_RELU));
       t.L.push_back(make_lin(n, P("conv3"), 256, t.g[2].K, 9, 128, ACT_RELU));
-      t.L.push_back(make_lin(n, P("conv1d1"), 32, 5, 1, 5, ACT_NONE));
+      t.L.push_back(make_lin(n, P("conv1d1"), 32, t.g[3].K, 1, t.g[3].K, ACT_NONE));
       t.L.push_back(make_lin(n, P("conv1d2"), 32, 96, 3, 32, ACT_NONE));
       t.L.push_back(make_lin(n, P("fc_1d.0"), 256, 7616, 238, 32, ACT_RELU));
       t.L.push_back(make_lin(n, P("fc0.0"), 512, 6400, 25, 256, ACT_RELU));
@@ -1224,7 +1227,7 @@ static int tower_forward(ddrl_net* n, Tower& t, const float* const* obs, long lo
       const float* vec = obs[1];
       if (d1) {
         // laser branch: conv1d1 -> conv1d2 (no activation between, nav_encoder.py:109-110) -> fc_1d+relu -> cat[:, 0:256]
-        const float* laser = obs[0] + row0 * 960;
+        const float* laser = obs[0] + row0 * t.g[3].sb;
         TRY(conv_block(n, t, 3, 3, laser, b[11], b[12], mb, s, reuse_obs || t.borrow_cols));
         TRY(conv_block(n, t, 4, 4, b[12], b[13], b[14], mb, s));
         TRY(lin_fwd(n, t.L[5], b[14], 7616, b[9], ldcat, mb, s));
@@ -1634,7 +1637,7 @@ extern "C" int64_t ddrl_net_obs_elems(const ddrl_net* n, int slot) {
     case DDRL_ARCH_MLP: return slot == 0 ? n->d.in_ch : 0;
     case DDRL_ARCH_NAV: return slot == 0 ? (int64_t)n->d.in_ch * 48 * 48 : (slot == 1 ? 9 : 0);
     case DDRL_ARCH_NAVPED: return slot == 0 ? (int64_t)(n->d.in_ch - 3) * 48 * 48 : (slot == 1 ? 9 : (slot == 2 ? 3 * 48 * 48 : 0));
-    case DDRL_ARCH_NAV1D: return slot == 0 ? 960 : (slot == 1 ? 5 : (slot == 2 ? (int64_t)n->d.in_ch * 48 * 48 : 0));
+    case DDRL_ARCH_NAV1D: return slot == 0 ? 960 * (int64_t)laser_ch_of(n) : (slot == 1 ? 5 : (slot == 2 ? (int64_t)n->d.in_ch * 48 * 48 : 0));
   }
   return 0;
 }

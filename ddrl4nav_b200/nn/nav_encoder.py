@@ -44,10 +44,12 @@ class NavPreNet1D(PreNet):
     ARCH = "nav1d"
     VEC = 5
 
-    def __init__(self, image_channel=1, last_output_dim=512):
+    def __init__(self, image_channel=1, last_output_dim=512, laser_channel=1):
+        # laser_channel: 1 in the reference (nav_encoder.py:87); 3 = the non-reference "3 x 960" bench variant
         super().__init__()
         _conv_stack(self, image_channel, (7, 5, 3))
-        self.conv1d1 = nn.Conv1d(1, 32, 5, 2, "valid")
+        self.laser_channel = int(laser_channel)
+        self.conv1d1 = nn.Conv1d(self.laser_channel, 32, 5, 2, "valid")
         self.conv1d2 = nn.Conv1d(32, 32, 3, 2, "valid")
         self.fc_1d = mlp([(32 * 238, 256, "relu")])
         self.fc0 = mlp([(256 * 5 * 5, 512, "relu")])

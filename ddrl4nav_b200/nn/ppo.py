@@ -101,7 +101,8 @@ class PPO(Basenn):
         if self.prenet is None and type(self.critic.pre) is not type(enc):
             raise DDRLError("unshared mode needs the same encoder family in actor.pre and critic.pre")
         return dict(arch=enc.ARCH, in_ch=enc.engine_in_ch(), act_dim=self.actor.actor_linear.out_features,
-                    dist=self.actor.DIST, shared=self.prenet is not None, feat=self.actor.actor_linear.in_features)
+                    dist=self.actor.DIST, shared=self.prenet is not None, feat=self.actor.actor_linear.in_features,
+                    laser_ch=int(getattr(enc, "laser_channel", 0)))
 
     def _destroy(self):
         if self._h is not None:
@@ -203,7 +204,7 @@ class PPO(Basenn):
         self._destroy()
         s = self._spec()
         desc = NetDesc(_lib.ARCH[s["arch"]], s["in_ch"], s["act_dim"], _lib.DIST[s["dist"]], int(s["shared"]), s["feat"],
-                       _lib.GEMM_MODE[self.gemm_mode], 0)
+                       _lib.GEMM_MODE[self.gemm_mode], s["laser_ch"])
         h = C.c_void_p()
         check(lib.ddrl_net_create(C.byref(desc), C.byref(h)), "ddrl_net_create")
         self._h = h

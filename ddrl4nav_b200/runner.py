@@ -54,6 +54,7 @@ _KINDS = {
     #  kind: (encoder factory, distribution, act_dim, shared)
     "pong": (lambda: AtariPreNet(4, 512), "categorical", 6, False),                 # BASELINE C1 / C4
     "navlaser": (lambda: NavPreNet1D(image_channel=3), "gaussian", 2, False),       # C2
+    "navlaser3": (lambda: NavPreNet1D(image_channel=3, laser_channel=3), "gaussian", 2, False),   # NON-reference 3 x 960 laser
     "navimg": (lambda: NavPreNet(image_channel=1), "categorical", 28, True),        # C5
     "navped": (lambda: NavPedPreNet(image_channel=4), "categorical", 28, True),
     "mlp": (lambda: MLPPreNet(4, 128), "categorical", 2, False),

@@ -57,7 +57,8 @@ typedef struct {
   int32_t shared;    /* SHARE_CNN_NET (config_nn.py:57; runner/utils.py:88-135) */
   int32_t feat;      /* AC_INPUT_DIM = 512 (MLP: last_output_dim) */
   int32_t gemm_mode; /* enum ddrl_gemm_mode */
-  int32_t reserved;
+  int32_t laser_ch;  /* DDRL_ARCH_NAV1D: channels of the laser observation; 0 or 1 = the reference's Conv1d(1, 32, 5, 2)
+                      * (nn/nav_encoder.py:87); 3 = the non-reference "3 x 960" variant.  Other architectures: 0 */
 } ddrl_net_desc;
 
 typedef struct {     /* config/config_nn.py:27-57; torch.optim.Adam defaults */

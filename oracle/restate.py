@@ -45,11 +45,15 @@ class NetSpec:
     dist: str            # 'categorical' | 'gaussian'
     shared: bool         # SHARE_CNN_NET
     feat: int = 512      # AC_INPUT_DIM (MLPPreNet: last_output_dim)
+    laser_ch: int = 1    # nav1d: Conv1d(laser_ch, 32, 5, 2); the reference has 1 (nn/nav_encoder.py:87)
 
 
 SPECS = {
     "pong": NetSpec("atari", 4, 6, "categorical", False),       # BASELINE config C1
     "navlaser": NetSpec("nav1d", 3, 2, "gaussian", False),      # C2
+    # NOT a reference configuration: the "3 x 960" laser wording of BASELINE (3-frame laser stacking is an env option,
+    # envs/cfg/old_cfg/image_ped_circle.yaml:25; no shipped encoder consumes it).  Same stack with Conv1d(3, 32, 5, 2)
+    "navlaser3": NetSpec("nav1d", 3, 2, "gaussian", False, 512, 3),
     "navimg": NetSpec("nav", 1, 28, "categorical", True),       # C5
     "navped": NetSpec("navped", 4, 28, "categorical", True),    # C5 "+ scan" variant: NavPedPreNet, cat(map, ped-map)
 }
@@ -74,7 +78,7 @@ class PPOHyper:
 # --------------------------------------------------------------------------------------
 # parameter tables (names / shapes / order = reference named_parameters())
 # --------------------------------------------------------------------------------------
-def encoder_param_shapes(arch: str, in_ch: int, feat: int = 512) -> List[Tuple[str, Tuple[int, ...]]]:
+def encoder_param_shapes(arch: str, in_ch: int, feat: int = 512, laser_ch: int = 1) -> List[Tuple[str, Tuple[int, ...]]]:
     if arch == "atari":      # nn/atari_encoder.py:12-23
         return [("conv1.weight", (32, in_ch, 8, 8)), ("conv1.bias", (32,)),
                 ("conv2.weight", (64, 32, 4, 4)), ("conv2.bias", (64,)),
@@ -91,7 +95,7 @@ def encoder_param_shapes(arch: str, in_ch: int, feat: int = 512) -> List[Tuple[s
         return [("conv1.weight", (64, in_ch, 7, 7)), ("conv1.bias", (64,)),
                 ("conv2.weight", (128, 64, 5, 5)), ("conv2.bias", (128,)),
                 ("conv3.weight", (256, 128, 3, 3)), ("conv3.bias", (256,)),
-                ("conv1d1.weight", (32, 1, 5)), ("conv1d1.bias", (32,)),
+                ("conv1d1.weight", (32, laser_ch, 5)), ("conv1d1.bias", (32,)),
                 ("conv1d2.weight", (32, 32, 3)), ("conv1d2.bias", (32,)),
                 ("fc_1d.0.weight", (256, 7616)), ("fc_1d.0.bias", (256,)),
                 ("fc0.0.weight", (512, 6400)), ("fc0.0.bias", (512,)),
@@ -106,7 +110,7 @@ def param_table(spec: NetSpec) -> List[Tuple[str, Tuple[int, ...]]]:
     """Full ``named_parameters()`` order of ``PPO`` (``nn/ppo.py:26-30``: prenet, actor, critic;
     ``nn/actor.py:12-16,52-56``: parameters before sub-modules, ``pre`` before ``actor_linear``;
     ``nn/critic.py:8-12``: ``critic_linear`` before ``pre``)."""
-    enc = encoder_param_shapes(spec.arch, spec.in_ch, spec.feat)
+    enc = encoder_param_shapes(spec.arch, spec.in_ch, spec.feat, spec.laser_ch)
     out: List[Tuple[str, Tuple[int, ...]]] = []
     if spec.shared:
         out += [("prenet." + n, s) for n, s in enc]
@@ -464,8 +468,8 @@ def synth_states(kind: str, B: int, seed: int = 0) -> List[Tensor]:
     g = torch.Generator().manual_seed(seed)
     if kind == "pong":
         return [torch.rand(B, 4, 84, 84, generator=g)]
-    if kind == "navlaser":
-        laser = torch.rand(B, 1, 960, generator=g)
+    if kind in ("navlaser", "navlaser3"):
+        laser = torch.rand(B, 3 if kind == "navlaser3" else 1, 960, generator=g)
         vec = torch.randn(B, 5, generator=g)
         occ = (torch.rand(B, 1, 48, 48, generator=g) < 0.03).float()
         vel = (torch.rand(B, 2, 48, 48, generator=g) - 0.5) * occ

@@ -114,7 +114,7 @@ def _oracle_grads(spec, params, states, adv, a, old, ret, flips=None):
 TIE_EPS = 1e-6      # an activation with |z| < TIE_EPS * max|z| of its layer is zero to within fp32 rounding: a tie
 
 
-@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("pong", 40), ("navped", 5)])
+@pytest.mark.parametrize("kind,B", [("pong", 8), ("navimg", 6), ("navlaser", 4), ("pong", 40), ("navped", 5), ("navlaser3", 4)])
 def test_backward_grads_match_oracle(kind, B):
     """Every parameter gradient within 2e-5 of its tensor's max.  relu / leaky_relu are not differentiable at 0, and a
     pre-activation that is zero to fp32 rounding (|z| < 1e-6 max|z|) may take either branch depending on summation
