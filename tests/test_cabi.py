@@ -68,6 +68,41 @@ def test_engine_param_table_is_reference_order(kind):
     assert lib.ddrl_net_create(C.byref(bad), C.byref(h)) == -1
 
 
+def test_laser_channel_variant_tables_agree():
+    """The NON-reference 3 x 960 laser variant (SURVEY 8d asks for it beside C2): the engine (ddrl_net_desc.laser_ch), the Python
+    mirror and the oracle agree on the parameter table; laser_ch = 0 / 1 is the reference's Conv1d(1, 32, 5, 2)."""
+    _lib = _ensure_built()
+    lib = _lib.load()
+    from ddrl4nav_b200.runner import make_net
+    spec = R.SPECS["navlaser3"]
+    assert spec.laser_ch == 3 and R.SPECS["navlaser"].laser_ch == 1
+    table = R.param_table(spec)
+    assert ("actor.pre.conv1d1.weight", (32, 3, 5)) in table
+    net = make_net("navlaser3", device=None)
+    assert [(n, tuple(p.shape)) for n, p in net.named_parameters()] == [(n, tuple(s)) for n, s in table]
+    name = C.create_string_buffer(128)
+    shape = (C.c_int64 * 4)()
+    ndim, off = C.c_int(), C.c_int64()
+    for laser_ch, want in ((3, table), (0, R.param_table(R.SPECS["navlaser"])), (1, R.param_table(R.SPECS["navlaser"]))):
+        desc = _lib.NetDesc(_lib.ARCH[spec.arch], spec.in_ch, spec.act_dim, _lib.DIST[spec.dist], 0, spec.feat, 0, laser_ch)
+        h = C.c_void_p()
+        assert lib.ddrl_net_create(C.byref(desc), C.byref(h)) == 0
+        assert lib.ddrl_net_num_tensors(h) == len(want)
+        for i, (n, shp) in enumerate(want):
+            assert lib.ddrl_net_tensor_info(h, i, name, 128, shape, C.byref(ndim), C.byref(off)) == 0
+            assert name.value.decode() == n and tuple(shape[k] for k in range(ndim.value)) == tuple(shp)
+        assert lib.ddrl_net_obs_elems(h, 0) == 960 * max(laser_ch, 1)
+        assert lib.ddrl_net_destroy(h) == 0
+
+
+def test_bind_host_to_device_is_harmless_without_a_gpu():
+    import os
+    from ddrl4nav_b200.dist import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_device(0) is None or os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
+
+
 @pytest.mark.parametrize("kind", ["pong", "navlaser", "navimg", "navped"])
 def test_mirror_modules_register_reference_order(kind):
     from ddrl4nav_b200.runner import make_net
